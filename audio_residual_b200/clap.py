@@ -1,0 +1,192 @@
+"""Mirror of the CLAP wrapper API the Audio-ResiDual drivers call, on top of libard_b200.so.
+
+* CLAP           <- clap_module/model.py (audio side only): encode_audio :589-590, audio_projection :539-543,
+                    get_audio_embedding :720-742, get_audio_output_dict :745-762.
+* CLAP_Module    <- hook.py: get_audio_embedding_from_data(x, use_tensor=False, data_fil="repeatpad") :158-192.
+* get_audio_features / batch_features <- training/data.py:402-506 (the reachable <= max_len branches), batched on device
+  instead of the reference's per-clip Python loop.
+Text towers, checkpoint download and tokenisers are out of scope (they need the network and are not on the path).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import weights as W
+from .htsat import HTSAT_Swin_Transformer, create_htsat_model
+
+AUDIO_CFG = {"audio_length": 1024, "clip_samples": 480000, "mel_bins": 64, "sample_rate": 48000, "window_size": 1024,
+             "hop_size": 480, "fmin": 50, "fmax": 14000, "class_num": 527, "model_type": "HTSAT"}
+
+
+def int16_to_float32(x):
+    """data.py:93-94"""
+    return (x / 32767.0).astype("float32")
+
+
+def float32_to_int16(x):
+    """data.py:97-99"""
+    x = np.clip(x, a_min=-1.0, a_max=1.0)
+    return (x * 32767.0).astype("int16")
+
+
+def _fill(wave, max_len, data_filling):
+    """data.py:469-496 for one clip (1-D tensor) with len <= max_len."""
+    n = wave.shape[0]
+    if n == max_len:
+        return wave
+    if data_filling == "repeatpad":
+        wave = wave.repeat(int(max_len / n))
+        return F.pad(wave, (0, max_len - wave.shape[0]), mode="constant", value=0)
+    if data_filling == "pad":
+        return F.pad(wave, (0, max_len - n), mode="constant", value=0)
+    if data_filling == "repeat":
+        return wave.repeat(int(max_len / n) + 1)[:max_len]
+    raise NotImplementedError(f"data_filling {data_filling} not implemented")
+
+
+def get_audio_features(sample, audio_data, max_len, data_truncating, data_filling, audio_cfg, require_grad=False):
+    """data.py:402-506 restricted to what the reference can reach: clips longer than max_len crash there
+    (np.random.integers does not exist, data.py:467), so they raise here too. `mel_fusion` is produced by the encoder's
+    on-device featuriser (CLAP_Module.fusion_mel), not per clip."""
+    if data_truncating not in ("rand_trunc", "fusion"):
+        raise NotImplementedError(f"data_truncating {data_truncating} not implemented")
+    if len(audio_data) > max_len:
+        raise AttributeError("module 'numpy.random' has no attribute 'integers' (reference data.py:467): clips longer than "
+                             "max_len are unreachable")
+    sample["waveform"] = _fill(audio_data, max_len, data_filling)
+    sample["longer"] = torch.tensor([False])
+    return sample
+
+
+def batch_features(x, max_len=480000, data_filling="repeatpad", device=None, do_pad_or_truncate=False):
+    """Batched get_audio_features: x is [B, T] (tensor/ndarray) or a list of 1-D clips of different lengths.
+    Returns a [B, max_len] float32 tensor on `device`."""
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(x)
+    if torch.is_tensor(x) and x.dim() == 2:
+        clips = x if x.shape[1] == max_len else [c for c in x]
+    else:
+        clips = [torch.as_tensor(c) for c in x]
+    if torch.is_tensor(clips):
+        out = clips
+    else:
+        if do_pad_or_truncate:
+            from .residual import pad_or_truncate
+            clips = [pad_or_truncate(c, max_len) for c in clips]
+        for c in clips:
+            if c.shape[0] > max_len:
+                raise AttributeError("clips longer than max_len are unreachable in the reference (data.py:467)")
+        out = torch.stack([_fill(c.float(), max_len, data_filling) for c in clips])
+    return out.to(device=device, dtype=torch.float32) if device is not None else out.float()
+
+
+class CLAP(nn.Module):
+    """Audio side of clap_module/model.py::CLAP."""
+
+    def __init__(self, embed_dim, audio_cfg, text_cfg=None, enable_fusion=False, fusion_type="None", joint_embed_shape=512,
+                 mlp_act="relu"):
+        super().__init__()
+        self.audio_cfg, self.enable_fusion, self.fusion_type = audio_cfg, enable_fusion, fusion_type
+        self.joint_embed_shape = joint_embed_shape
+        if audio_cfg.get("model_type", "HTSAT") != "HTSAT":
+            raise RuntimeError(f"Model config for {audio_cfg.get('model_type')} not found.")   # model.py:469-470
+        if mlp_act != "relu":
+            raise NotImplementedError("audio_projection activation other than ReLU")
+        self.audio_branch = create_htsat_model(audio_cfg, enable_fusion, fusion_type)
+        self.audio_projection = nn.Sequential(nn.Linear(embed_dim, joint_embed_shape), nn.ReLU(),
+                                              nn.Linear(joint_embed_shape, joint_embed_shape))
+        for p in self.parameters():
+            p.requires_grad = False
+
+    def __setattr__(self, name, value):
+        super().__setattr__(name, value)
+        if name in ("audio_branch", "audio_projection"):    # callers re-assign audio_branch (src/training.py:103)
+            ab = self._modules.get("audio_branch")
+            pj = self._modules.get("audio_projection")
+            if ab is not None and pj is not None:
+                object.__setattr__(ab, "_projection", pj)
+
+    def _input(self, data):
+        keys = data[0].keys()
+        return {k: torch.cat([d[k].unsqueeze(0) for d in data], dim=0) for k in keys}   # model.py:735-738
+
+    def encode_audio(self, audio, device=None):
+        return self.audio_branch(audio, mixup_lambda=None, device=device)
+
+    def get_audio_embedding(self, data):
+        """model.py:720-742: list of per-clip dicts (or an already batched dict) -> L2-normalised [N, joint] embeddings."""
+        inp = data if isinstance(data, dict) else self._input(data)
+        ab = self.audio_branch
+        if ab.enable_fusion:
+            out = ab.encode(mel_fusion=inp["mel_fusion"], want_audio_embed=True)
+        else:
+            out = ab.encode(waveform=inp["waveform"], want_audio_embed=True)
+        return out["audio_embed"]
+
+    def get_audio_output_dict(self, data):
+        """model.py:745-762 (fork addition)."""
+        inp = data if isinstance(data, dict) else self._input(data)
+        return self.encode_audio(inp)
+
+
+class CLAP_Module(nn.Module):
+    """hook.py::CLAP_Module, audio entry points only."""
+
+    def __init__(self, enable_fusion=False, device=None, amodel="HTSAT-tiny", tmodel="roberta"):
+        super().__init__()
+        if device is None:
+            device = "cuda:0"
+        name = amodel.split("-")[-1]
+        if name not in W.CONFIGS:
+            raise RuntimeError(f"Model config for {amodel} not found.")
+        cfg = W.CONFIGS[name]
+        audio_cfg = dict(AUDIO_CFG, model_name=name)
+        self.enable_fusion = enable_fusion
+        self.model_cfg = {"embed_dim": cfg["embed_dim"] * 8, "audio_cfg": audio_cfg}
+        self.model = CLAP(cfg["embed_dim"] * 8, audio_cfg, enable_fusion=enable_fusion,
+                          fusion_type="aff_2d" if enable_fusion else "None", joint_embed_shape=cfg["joint_dim"])
+        self.device = torch.device(device)
+        self.model.to(self.device)
+        self._htk = None
+
+    def load_state_dict_flat(self, sd):
+        """Load a flat dict with un-prefixed audio_branch keys + audio_projection.* keys (weights.make_state_dict layout,
+        i.e. the reference checkpoint's `audio_branch.` / `audio_projection.` tensors, factory.py:53-70)."""
+        ab = self.model.audio_branch
+        own = ab.state_dict()
+        ab.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
+        self.model.audio_projection.load_state_dict({k[len("audio_projection."):]: v for k, v in sd.items()
+                                                     if k.startswith("audio_projection.")})
+        self.model.to(self.device)
+        return self
+
+    def fusion_mel(self, wave, quantize=False):
+        """get_mel (data.py:363-399) for a batch on device, stacked 4x as data.py:497-501 does for clips <= 10 s."""
+        import ctypes as C
+        from . import lib as L
+        enc = self.model.audio_branch
+        h = enc._handle()
+        raise NotImplementedError("on-device fusion featuriser: scheduled with SURVEY §8(f) rank 1")
+
+    def get_audio_embedding_from_data(self, x, use_tensor=False, data_fil="repeatpad"):
+        """hook.py:158-192. use_tensor=False: numpy/tensor input, int16 round-trip first, returns numpy.
+        use_tensor=True: tensor input, no quantisation, returns a tensor."""
+        self.model.eval()
+        enc = self.model.audio_branch
+        wave = batch_features(x, 480000, data_fil, device=self.device)
+        if enc.enable_fusion:
+            out = enc.encode(mel_fusion=self.fusion_mel(wave, quantize=not use_tensor), want_audio_embed=True)
+        else:
+            out = enc.encode(waveform=wave, quantize=not use_tensor, want_audio_embed=True)
+        emb = out["audio_embed"]
+        if not use_tensor:
+            emb = emb.detach().cpu().numpy()
+        return emb
+
+
+def build_clap_module(model="tiny", state_dict=None, device="cuda:0", enable_fusion=False, seed=0):
+    """CLAP_Module with synthetic (or given) weights: the offline stand-in for hook.py's load_ckpt()."""
+    m = CLAP_Module(enable_fusion=enable_fusion, device=device, amodel=f"HTSAT-{model}")
+    sd = state_dict if state_dict is not None else W.make_state_dict(model, seed=seed)
+    return m.load_state_dict_flat(sd)

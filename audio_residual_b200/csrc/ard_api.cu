@@ -1,0 +1,564 @@
+// C ABI of libard_b200.so (see include/ard.h): handle management, weight packing from the reference's state_dict keys,
+// the encoder forward schedule, and the op-level entry points.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ard_internal.h"
+
+namespace ard {
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static thread_local int g_launches = 0;
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) {
+        if (strstr(what, "launch") != nullptr) ++g_launches;
+        return 0;
+    }
+    return set_error(ARD_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+void count_launch(int n) { g_launches += n; }
+
+// ------------------------------------------------------------------------------------------------ device buffers
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int ensure(size_t n) {
+        if (n <= bytes) return 0;
+        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) { p = nullptr; return set_error(ARD_ERR_CUDA, "cudaMalloc(%zu): %s", n, cudaGetErrorString(e)); }
+        bytes = n;
+        return 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct BlockW {
+    DevBuf ln1_g, ln1_b, ln2_g, ln2_b;
+    DevBuf qkv_w, qkv_b, proj_w, proj_b, proj_w_f32, fc1_w, fc1_b, fc2_w, fc2_b, rpb;
+    // ResiDual (src/residual.py:14-42) injected after this block's attention
+    bool has_res = false, lambda_set = false;
+    int K = 0;
+    std::vector<float> h_mean;
+    DevBuf res_basis, res_dmean, res_M, proj_w_fold, proj_b_fold, lam_ones;
+};
+struct LayerW {
+    std::vector<BlockW> blocks;
+    DevBuf mg_g, mg_b, mg_w;
+};
+
+}  // namespace ard
+
+using namespace ard;
+
+struct ard_handle {
+    ard_config cfg;
+    int nlayers = 4;
+    int num_sms = 148;
+    bool finalized = false;
+    std::map<std::string, std::vector<float>> host;   // raw state_dict tensors (fp32)
+    // front end
+    DevBuf window, twiddle, melw, mstart, mlen, bn_scale, bn_shift;
+    int band_max = 0;
+    DevBuf pe_w, pe_b, pe_g, pe_beta;
+    std::vector<LayerW> layers;
+    DevBuf norm_g, norm_b, tscam_w, tscam_b, p0_w, p0_b, p2_w, p2_b;
+    // workspace
+    DevBuf ws_logmel, ws_x, ws_y, ws_xn, ws_ao, ws_qkv, ws_h, ws_normed, ws_emb, ws_hid, ws_proj, ws_tscam_a, ws_tscam_y, ws_wave;
+    int last_launches = 0;
+};
+
+namespace ard {
+
+static int C_of(const ard_handle* h, int l) { return h->cfg.embed_dim << l; }
+static int R_of(int l) { return 64 >> l; }   // tokens per side
+
+static int upload(DevBuf& b, const void* src, size_t bytes) {
+    ARD_TRY(b.ensure(bytes));
+    ARD_CUDA(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+static int upload_f32(DevBuf& b, const std::vector<float>& v) { return upload(b, v.data(), v.size() * 4); }
+static int upload_bf16(DevBuf& b, const std::vector<float>& v) {
+    std::vector<__nv_bfloat16> t(v.size());
+    for (size_t i = 0; i < v.size(); ++i) t[i] = __float2bfloat16_rn(v[i]);
+    return upload(b, t.data(), t.size() * 2);
+}
+
+static int get(const ard_handle* h, const std::string& key, size_t numel, const std::vector<float>** out) {
+    auto it = h->host.find(key);
+    if (it == h->host.end()) return set_error(ARD_ERR_STATE, "weight '%s' was never set", key.c_str());
+    if (it->second.size() != numel)
+        return set_error(ARD_ERR_SHAPE, "weight '%s' has %zu elements, expected %zu", key.c_str(), it->second.size(), numel);
+    *out = &it->second;
+    return 0;
+}
+
+static int finalize(ard_handle* h, cudaStream_t) {
+    const ard_config& c = h->cfg;
+    const std::vector<float>* v = nullptr;
+    const std::vector<float>* v2 = nullptr;
+    // ---- front end
+    if (!c.enable_fusion) {
+        // window = row k=0 of the (cos * window) Conv1d kernel (torchlibrosa STFT: W_real[k, 0, n] = cos(2 pi k n / N) * win[n])
+        ARD_TRY(get(h, "spectrogram_extractor.stft.conv_real.weight", 513 * 1024, &v));
+        std::vector<float> win(v->begin(), v->begin() + 1024);
+        ARD_TRY(upload_f32(h->window, win));
+        std::vector<float> tw(2048);
+        for (int i = 0; i < 1024; ++i) {
+            const double a = -2.0 * M_PI * i / 1024.0;
+            tw[2 * i] = (float)cos(a);
+            tw[2 * i + 1] = (float)sin(a);
+        }
+        ARD_TRY(upload_f32(h->twiddle, tw));
+        ARD_TRY(get(h, "logmel_extractor.melW", 513 * 64, &v));
+        std::vector<int> st(64), ln(64);
+        int bmax = 1;
+        for (int m = 0; m < 64; ++m) {
+            int lo = 513, hi = -1;
+            for (int k = 0; k < 513; ++k)
+                if ((*v)[k * 64 + m] != 0.0f) { lo = k < lo ? k : lo; hi = k; }
+            if (hi < 0) { lo = 0; hi = 0; }
+            st[m] = lo; ln[m] = hi - lo + 1;
+            bmax = ln[m] > bmax ? ln[m] : bmax;
+        }
+        std::vector<float> band((size_t)64 * bmax, 0.f);
+        for (int m = 0; m < 64; ++m)
+            for (int q = 0; q < ln[m]; ++q) band[(size_t)m * bmax + q] = (*v)[(st[m] + q) * 64 + m];
+        h->band_max = bmax;
+        ARD_TRY(upload_f32(h->melw, band));
+        ARD_TRY(upload(h->mstart, st.data(), 64 * 4));
+        ARD_TRY(upload(h->mlen, ln.data(), 64 * 4));
+    }
+    {   // bn0 eval: y = (x - rm) / sqrt(rv + eps) * g + b  ->  scale, shift   (htsat.py:691, :900-902)
+        const std::vector<float>*g, *b, *rm, *rv;
+        ARD_TRY(get(h, "bn0.weight", 64, &g));
+        ARD_TRY(get(h, "bn0.bias", 64, &b));
+        ARD_TRY(get(h, "bn0.running_mean", 64, &rm));
+        ARD_TRY(get(h, "bn0.running_var", 64, &rv));
+        std::vector<float> sc(64), sh(64);
+        for (int i = 0; i < 64; ++i) {
+            const double s = (double)(*g)[i] / sqrt((double)(*rv)[i] + 1e-5);
+            sc[i] = (float)s;
+            sh[i] = (float)((double)(*b)[i] - (double)(*rm)[i] * s);
+        }
+        ARD_TRY(upload_f32(h->bn_scale, sc));
+        ARD_TRY(upload_f32(h->bn_shift, sh));
+    }
+    const int C0 = c.embed_dim;
+    ARD_TRY(get(h, "patch_embed.proj.weight", (size_t)C0 * 16, &v)); ARD_TRY(upload_f32(h->pe_w, *v));
+    ARD_TRY(get(h, "patch_embed.proj.bias", C0, &v)); ARD_TRY(upload_f32(h->pe_b, *v));
+    ARD_TRY(get(h, "patch_embed.norm.weight", C0, &v)); ARD_TRY(upload_f32(h->pe_g, *v));
+    ARD_TRY(get(h, "patch_embed.norm.bias", C0, &v)); ARD_TRY(upload_f32(h->pe_beta, *v));
+    // ---- swin layers
+    for (int l = 0; l < h->nlayers; ++l) {
+        const int C = C_of(h, l), nH = c.num_heads[l];
+        if (C % nH) return set_error(ARD_ERR_SHAPE, "layer %d: dim %d not divisible by heads %d", l, C, nH);
+        const int hd = C / nH;
+        const float qscale = 1.0f / sqrtf((float)hd);   // htsat.py:295 head_dim ** -0.5, folded into the q rows
+        for (int b = 0; b < c.depths[l]; ++b) {
+            BlockW& bw = h->layers[l].blocks[b];
+            char pfx[64];
+            snprintf(pfx, sizeof(pfx), "layers.%d.blocks.%d.", l, b);
+            const std::string p(pfx);
+            ARD_TRY(get(h, p + "norm1.weight", C, &v)); ARD_TRY(upload_f32(bw.ln1_g, *v));
+            ARD_TRY(get(h, p + "norm1.bias", C, &v)); ARD_TRY(upload_f32(bw.ln1_b, *v));
+            ARD_TRY(get(h, p + "norm2.weight", C, &v)); ARD_TRY(upload_f32(bw.ln2_g, *v));
+            ARD_TRY(get(h, p + "norm2.bias", C, &v)); ARD_TRY(upload_f32(bw.ln2_b, *v));
+            ARD_TRY(get(h, p + "attn.qkv.weight", (size_t)3 * C * C, &v));
+            ARD_TRY(get(h, p + "attn.qkv.bias", (size_t)3 * C, &v2));
+            {
+                std::vector<float> w(*v), bb(*v2);
+                for (size_t i = 0; i < (size_t)C * C; ++i) w[i] *= qscale;
+                for (int i = 0; i < C; ++i) bb[i] *= qscale;
+                ARD_TRY(upload_bf16(bw.qkv_w, w));
+                ARD_TRY(upload_f32(bw.qkv_b, bb));
+            }
+            ARD_TRY(get(h, p + "attn.proj.weight", (size_t)C * C, &v));
+            ARD_TRY(upload_bf16(bw.proj_w, *v));
+            ARD_TRY(upload_f32(bw.proj_w_f32, *v));
+            ARD_TRY(get(h, p + "attn.proj.bias", C, &v)); ARD_TRY(upload_f32(bw.proj_b, *v));
+            ARD_TRY(get(h, p + "mlp.fc1.weight", (size_t)4 * C * C, &v)); ARD_TRY(upload_bf16(bw.fc1_w, *v));
+            ARD_TRY(get(h, p + "mlp.fc1.bias", (size_t)4 * C, &v)); ARD_TRY(upload_f32(bw.fc1_b, *v));
+            ARD_TRY(get(h, p + "mlp.fc2.weight", (size_t)4 * C * C, &v)); ARD_TRY(upload_bf16(bw.fc2_w, *v));
+            ARD_TRY(get(h, p + "mlp.fc2.bias", C, &v)); ARD_TRY(upload_f32(bw.fc2_b, *v));
+            ARD_TRY(get(h, p + "attn.relative_position_bias_table", (size_t)225 * nH, &v)); ARD_TRY(upload_f32(bw.rpb, *v));
+            if (bw.has_res) {   // proj bias may have changed: refresh (b_proj - mean) and force a re-fold
+                std::vector<float> dm(C);
+                const std::vector<float>* pb;
+                ARD_TRY(get(h, p + "attn.proj.bias", C, &pb));
+                for (int i = 0; i < C; ++i) dm[i] = (*pb)[i] - bw.h_mean[i];
+                ARD_TRY(upload_f32(bw.res_dmean, dm));
+                bw.lambda_set = false;
+            }
+        }
+        if (l < h->nlayers - 1) {
+            char pfx[64];
+            snprintf(pfx, sizeof(pfx), "layers.%d.downsample.", l);
+            const std::string p(pfx);
+            ARD_TRY(get(h, p + "norm.weight", (size_t)4 * C, &v)); ARD_TRY(upload_f32(h->layers[l].mg_g, *v));
+            ARD_TRY(get(h, p + "norm.bias", (size_t)4 * C, &v)); ARD_TRY(upload_f32(h->layers[l].mg_b, *v));
+            ARD_TRY(get(h, p + "reduction.weight", (size_t)8 * C * C, &v)); ARD_TRY(upload_bf16(h->layers[l].mg_w, *v));
+        }
+    }
+    const int NF = C_of(h, h->nlayers - 1);
+    ARD_TRY(get(h, "norm.weight", NF, &v)); ARD_TRY(upload_f32(h->norm_g, *v));
+    ARD_TRY(get(h, "norm.bias", NF, &v)); ARD_TRY(upload_f32(h->norm_b, *v));
+    if (h->host.count("tscam_conv.weight")) {
+        ARD_TRY(get(h, "tscam_conv.weight", (size_t)ARD_CLASS_NUM * NF * 6, &v)); ARD_TRY(upload_bf16(h->tscam_w, *v));
+        ARD_TRY(get(h, "tscam_conv.bias", ARD_CLASS_NUM, &v)); ARD_TRY(upload_f32(h->tscam_b, *v));
+    }
+    if (h->host.count("audio_projection.0.weight")) {
+        const int J = c.joint_dim;
+        ARD_TRY(get(h, "audio_projection.0.weight", (size_t)J * NF, &v)); ARD_TRY(upload_f32(h->p0_w, *v));
+        ARD_TRY(get(h, "audio_projection.0.bias", J, &v)); ARD_TRY(upload_f32(h->p0_b, *v));
+        ARD_TRY(get(h, "audio_projection.2.weight", (size_t)J * J, &v)); ARD_TRY(upload_f32(h->p2_w, *v));
+        ARD_TRY(get(h, "audio_projection.2.bias", J, &v)); ARD_TRY(upload_f32(h->p2_b, *v));
+    }
+    h->finalized = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ forward schedule
+static int ensure_workspace(ard_handle* h, int B) {
+    const size_t MC = (size_t)B * 4096 * h->cfg.embed_dim;   // max over stages of tokens*channels
+    ARD_TRY(h->ws_x.ensure(MC * 4));
+    ARD_TRY(h->ws_y.ensure(MC * 4));
+    ARD_TRY(h->ws_xn.ensure(MC * 2));
+    ARD_TRY(h->ws_ao.ensure(MC * 2));
+    ARD_TRY(h->ws_qkv.ensure(MC * 3 * 2));
+    ARD_TRY(h->ws_h.ensure(MC * 4 * 2));
+    return 0;
+}
+
+static int ensure_fold(ard_handle* h, int l, int b, cudaStream_t s) {
+    BlockW& bw = h->layers[l].blocks[b];
+    if (!bw.has_res || bw.lambda_set) return 0;
+    // learnable initialises to ones (src/residual.py:27)
+    const int C = C_of(h, l);
+    std::vector<float> ones(bw.K, 1.0f);
+    ARD_TRY(upload_f32(bw.lam_ones, ones));
+    ARD_TRY(residual_fold(bw.proj_w_f32.as<float>(), bw.res_dmean.as<float>(), bw.res_basis.as<float>(), bw.lam_ones.as<float>(), C, bw.K,
+                          bw.res_M.as<float>(), bw.proj_w_fold.as<__nv_bfloat16>(), bw.proj_b_fold.as<float>(), s));
+    bw.lambda_set = true;
+    return 0;
+}
+
+// One Swin block on the residual stream held in X (fp32 [B*T, C]); Y is scratch. Result ends in X.
+//   plain  : htsat.py:439-482            patched: src/residual.py:58-98 (doubled shortcut + FFN)
+static int run_block(ard_handle* h, int l, int b, int B, float* X, float* Y, float* attn_out, float attn_scale, int attn_acc,
+                     float* res_out, long long res_bstride, int res_T, cudaStream_t s) {
+    BlockW& bw = h->layers[l].blocks[b];
+    const int C = C_of(h, l), R = R_of(l), T = R * R, nH = h->cfg.num_heads[l];
+    const long long M = (long long)B * T;
+    __nv_bfloat16* XN = h->ws_xn.as<__nv_bfloat16>();
+    __nv_bfloat16* AO = h->ws_ao.as<__nv_bfloat16>();
+    __nv_bfloat16* QKV = h->ws_qkv.as<__nv_bfloat16>();
+    __nv_bfloat16* Hb = h->ws_h.as<__nv_bfloat16>();
+    const int shift = (b % 2 == 0) ? 0 : 4;   // htsat.py:563
+
+    ARD_TRY(layernorm_bf16(X, bw.ln1_g.as<float>(), bw.ln1_b.as<float>(), XN, M, C, s));
+    GemmArgs g;
+    g.A = XN; g.lda = C; g.W = bw.qkv_w.as<__nv_bfloat16>(); g.ldw = C; g.out = QKV; g.ldo = 3 * C; g.out_bf16 = 1;
+    g.M = (int)M; g.N = 3 * C; g.K = C; g.bias = bw.qkv_b.as<float>();
+    ARD_TRY(gemm_bf16(g, h->num_sms, s));
+    AttnArgs a;
+    a.qkv = QKV; a.out = AO; a.bias_table = bw.rpb.as<float>(); a.attn_mean = attn_out; a.attn_scale = attn_scale; a.attn_accumulate = attn_acc;
+    a.B = B; a.H = R; a.W = R; a.C = C; a.nH = nH; a.shift = shift;
+    ARD_TRY(window_attention(a, s));
+    // proj (+ folded ResiDual) + shortcut:  Y = X + r,  aux = r = residual_x
+    ARD_TRY(ensure_fold(h, l, b, s));
+    g = GemmArgs();
+    g.A = AO; g.lda = C; g.ldw = C; g.out = Y; g.ldo = C; g.M = (int)M; g.N = C; g.K = C;
+    if (bw.has_res) { g.W = bw.proj_w_fold.as<__nv_bfloat16>(); g.bias = bw.proj_b_fold.as<float>(); }
+    else { g.W = bw.proj_w.as<__nv_bfloat16>(); g.bias = bw.proj_b.as<float>(); }
+    g.resid1 = X; g.ldr1 = C;
+    if (res_out) { g.aux = res_out; g.ld_aux = C; g.aux_T = T; g.aux_bstride = res_bstride; (void)res_T; }
+    ARD_TRY(gemm_bf16(g, h->num_sms, s));
+    // FFN: (Y) -> LN2 -> fc1+GELU -> fc2
+    auto ffn = [&](const float* in, float* out, const float* r1, const float* r2) -> int {
+        ARD_TRY(layernorm_bf16(in, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), XN, M, C, s));
+        GemmArgs f;
+        f.A = XN; f.lda = C; f.W = bw.fc1_w.as<__nv_bfloat16>(); f.ldw = C; f.out = Hb; f.ldo = 4 * C; f.out_bf16 = 1;
+        f.M = (int)M; f.N = 4 * C; f.K = C; f.bias = bw.fc1_b.as<float>(); f.act = ARD_ACT_GELU;
+        ARD_TRY(gemm_bf16(f, h->num_sms, s));
+        f = GemmArgs();
+        f.A = Hb; f.lda = 4 * C; f.W = bw.fc2_w.as<__nv_bfloat16>(); f.ldw = 4 * C; f.out = out; f.ldo = C;
+        f.M = (int)M; f.N = C; f.K = 4 * C; f.bias = bw.fc2_b.as<float>();
+        f.resid1 = r1; f.ldr1 = C; f.resid2 = r2; f.ldr2 = C;
+        return gemm_bf16(f, h->num_sms, s);
+    };
+    if (!bw.has_res) {
+        ARD_TRY(ffn(Y, X, Y, nullptr));            // x = x1 + mlp(norm2(x1))                       htsat.py:480
+    } else {
+        ARD_TRY(ffn(Y, Y, Y, X));                  // x3 = shortcut + (x1 + mlp(norm2(x1)))         src/residual.py:93,95
+        ARD_TRY(ffn(Y, X, Y, nullptr));            // x4 = x3 + mlp(norm2(x3))                      src/residual.py:96
+    }
+    return 0;
+}
+
+static int encoder_forward(ard_handle* h, const ard_forward_args* a, cudaStream_t s) {
+    if (!h->finalized) return set_error(ARD_ERR_STATE, "ard_finalize_weights has not been called");
+    const int B = a->B;
+    if (B <= 0) return set_error(ARD_ERR_SHAPE, "batch must be positive (got %d)", B);
+    if (!a->embedding) return set_error(ARD_ERR_SHAPE, "embedding output is required");
+    const int C0 = h->cfg.embed_dim;
+    ARD_TRY(ensure_workspace(h, B));
+    float* X = h->ws_x.as<float>();
+    float* Y = h->ws_y.as<float>();
+    // ---- front end
+    if (h->cfg.enable_fusion) {
+        if (!a->mel_fusion) return set_error(ARD_ERR_SHAPE, "fusion model expects mel_fusion input");
+        ARD_TRY(patch_embed_ln(a->mel_fusion, 4LL * ARD_FRAMES * 64, ARD_FRAMES, h->bn_scale.as<float>(), h->bn_shift.as<float>(),
+                               h->pe_w.as<float>(), h->pe_b.as<float>(), h->pe_g.as<float>(), h->pe_beta.as<float>(), X, B, C0, s));
+    } else {
+        if (!a->waveform) return set_error(ARD_ERR_SHAPE, "non-fusion model expects waveform input");
+        ARD_TRY(h->ws_logmel.ensure((size_t)B * ARD_FRAMES * 64 * 4));
+        MelBands mb{h->melw.as<float>(), h->mstart.as<int>(), h->mlen.as<int>(), h->band_max};
+        ARD_TRY(stft_logmel(a->waveform, B, ARD_CLIP_SAMPLES, h->window.as<float>(), h->twiddle.as<float2>(), mb, nullptr, nullptr,
+                            h->ws_logmel.as<float>(), a->quantize, s));
+        ARD_TRY(patch_embed_ln(h->ws_logmel.as<float>(), (long long)ARD_FRAMES * 64, ARD_FRAMES, h->bn_scale.as<float>(),
+                               h->bn_shift.as<float>(), h->pe_w.as<float>(), h->pe_b.as<float>(), h->pe_g.as<float>(), h->pe_beta.as<float>(),
+                               X, B, C0, s));
+    }
+    // ---- swin stages
+    for (int l = 0; l < h->nlayers; ++l) {
+        const int C = C_of(h, l), R = R_of(l), T = R * R, depth = h->cfg.depths[l];
+        for (int b = 0; b < depth; ++b) {
+            float* res = a->layers_residuals[l] ? a->layers_residuals[l] + (long long)b * T * C : nullptr;
+            // BasicLayer.forward (htsat.py:589-596): mean of the blocks' maps; residuals concatenated along tokens
+            ARD_TRY(run_block(h, l, b, B, X, Y, a->layers_attention[l], 1.0f / depth, b > 0, res, (long long)depth * T, T, s));
+        }
+        if (l < h->nlayers - 1) {   // PatchMerging (htsat.py:505-526)
+            __nv_bfloat16* Hb = h->ws_h.as<__nv_bfloat16>();
+            ARD_TRY(merge_layernorm_bf16(X, h->layers[l].mg_g.as<float>(), h->layers[l].mg_b.as<float>(), Hb, B, R, R, C, s));
+            GemmArgs g;
+            g.A = Hb; g.lda = 4 * C; g.W = h->layers[l].mg_w.as<__nv_bfloat16>(); g.ldw = 4 * C; g.out = Y; g.ldo = 2 * C;
+            g.M = B * (T / 4); g.N = 2 * C; g.K = 4 * C;
+            ARD_TRY(gemm_bf16(g, h->num_sms, s));
+            float* t = X; X = Y; Y = t;
+        }
+    }
+    // ---- tail
+    const int NF = C_of(h, h->nlayers - 1);
+    const bool need_tscam = a->framewise_output || a->clipwise_output || a->fine_grained_embedding;
+    float* normed = nullptr;
+    if (need_tscam) {
+        ARD_TRY(h->ws_normed.ensure((size_t)B * 64 * NF * 4));
+        normed = h->ws_normed.as<float>();
+    }
+    ARD_TRY(final_norm_mean(X, h->norm_g.as<float>(), h->norm_b.as<float>(), a->embedding, normed, B, 64, NF, s));
+    if (a->audio_embed) {
+        if (!h->p0_w.p) return set_error(ARD_ERR_STATE, "audio_projection weights were never set");
+        const int J = h->cfg.joint_dim;
+        ARD_TRY(h->ws_hid.ensure((size_t)B * J * 4));
+        ARD_TRY(h->ws_proj.ensure((size_t)B * J * 4));
+        ARD_TRY(linear_small(a->embedding, NF, h->p0_w.as<float>(), h->p0_b.as<float>(), h->ws_hid.as<float>(), J, B, J, NF, ARD_ACT_RELU, s));
+        ARD_TRY(linear_small(h->ws_hid.as<float>(), J, h->p2_w.as<float>(), h->p2_b.as<float>(), h->ws_proj.as<float>(), J, B, J, J, ARD_ACT_NONE, s));
+        ARD_TRY(l2_normalize(h->ws_proj.as<float>(), a->audio_embed, B, J, s));
+    }
+    if (need_tscam) {
+        if (a->fine_grained_embedding) ARD_TRY(fine_grained(normed, a->fine_grained_embedding, B, NF, s));
+        if (a->framewise_output || a->clipwise_output) {
+            if (!h->tscam_w.p) return set_error(ARD_ERR_STATE, "tscam_conv weights were never set");
+            const int ldy = 528;
+            ARD_TRY(h->ws_tscam_a.ensure((size_t)B * 32 * NF * 6 * 2));
+            ARD_TRY(h->ws_tscam_y.ensure((size_t)B * 32 * ldy * 4));
+            ARD_TRY(tscam_im2col(normed, h->ws_tscam_a.as<__nv_bfloat16>(), B, NF, s));
+            GemmArgs g;
+            g.A = h->ws_tscam_a.as<__nv_bfloat16>(); g.lda = 6LL * NF; g.W = h->tscam_w.as<__nv_bfloat16>(); g.ldw = 6LL * NF;
+            g.out = h->ws_tscam_y.as<float>(); g.ldo = ldy; g.M = B * 32; g.N = ARD_CLASS_NUM; g.K = 6 * NF; g.bias = h->tscam_b.as<float>();
+            ARD_TRY(gemm_bf16(g, h->num_sms, s));
+            ARD_TRY(tscam_finish(h->ws_tscam_y.as<float>(), ldy, a->framewise_output, a->clipwise_output, B, ARD_CLASS_NUM, s));
+        }
+    }
+    return 0;
+}
+
+}  // namespace ard
+
+// ================================================================================================== C ABI
+extern "C" {
+
+const char* ard_last_error(void) { return g_err; }
+int ard_version(void) { return 100; }
+
+int ard_create(const ard_config* cfg, ard_handle** out) {
+    if (!cfg || !out) return set_error(ARD_ERR_SHAPE, "null argument");
+    if (cfg->embed_dim != 96 && cfg->embed_dim != 128)
+        return set_error(ARD_ERR_SHAPE, "Import Model for embed_dim=%d not found (tiny=96, base=128)", cfg->embed_dim);   // htsat.py:1044-1045
+    ard_handle* h = new ard_handle();
+    h->cfg = *cfg;
+    h->layers.resize(4);
+    for (int l = 0; l < 4; ++l) {
+        if (cfg->depths[l] <= 0 || cfg->num_heads[l] <= 0) { delete h; return set_error(ARD_ERR_SHAPE, "bad depth/heads for layer %d", l); }
+        h->layers[l].blocks.resize(cfg->depths[l]);
+    }
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        delete h;
+        return set_error(ARD_ERR_CUDA, "no CUDA device: libard_b200 has no CPU fallback");
+    }
+    h->num_sms = sms;
+    *out = h;
+    return 0;
+}
+
+int ard_destroy(ard_handle* h) {
+    delete h;
+    return 0;
+}
+
+int ard_set_weight(ard_handle* h, const char* key, const float* data, long long numel) {
+    if (!h || !key || !data || numel <= 0) return set_error(ARD_ERR_SHAPE, "ard_set_weight: bad argument");
+    h->host[std::string(key)] = std::vector<float>(data, data + numel);
+    h->finalized = false;
+    return 0;
+}
+
+int ard_finalize_weights(ard_handle* h, void* stream) {
+    if (!h) return set_error(ARD_ERR_SHAPE, "null handle");
+    return finalize(h, (cudaStream_t)stream);
+}
+
+int ard_set_block_residual(ard_handle* h, int layer, int block, const float* mean, const float* basis, int K, int D) {
+    if (!h) return set_error(ARD_ERR_SHAPE, "null handle");
+    if (layer < 0 || layer >= h->nlayers) return set_error(ARD_ERR_SHAPE, "Layer index %d out of range for model with %d layers", layer, h->nlayers);  // src/residual.py:194-195
+    if (block < 0 || block >= h->cfg.depths[layer]) return set_error(ARD_ERR_SHAPE, "block index %d out of range", block);
+    const int C = C_of(h, layer);
+    if (D != C || K <= 0 || K > D) return set_error(ARD_ERR_SHAPE, "ResiDual basis [%d,%d] does not match layer width %d", K, D, C);
+    BlockW& bw = h->layers[layer].blocks[block];
+    bw.K = K;
+    bw.h_mean.assign(mean, mean + D);
+    ARD_TRY(upload(bw.res_basis, basis, (size_t)K * D * 4));
+    ARD_TRY(bw.res_M.ensure((size_t)C * C * 4));
+    ARD_TRY(bw.proj_w_fold.ensure((size_t)C * C * 2));
+    ARD_TRY(bw.proj_b_fold.ensure((size_t)C * 4));
+    char key[96];
+    snprintf(key, sizeof(key), "layers.%d.blocks.%d.attn.proj.bias", layer, block);
+    auto it = h->host.find(key);
+    if (it == h->host.end()) return set_error(ARD_ERR_STATE, "set weights before injecting ResiDual ('%s' missing)", key);
+    std::vector<float> dm(C);
+    for (int i = 0; i < C; ++i) dm[i] = it->second[i] - mean[i];
+    ARD_TRY(upload_f32(bw.res_dmean, dm));
+    bw.has_res = true;
+    bw.lambda_set = false;
+    return 0;
+}
+
+int ard_clear_block_residual(ard_handle* h, int layer, int block) {
+    if (!h || layer < 0 || layer >= h->nlayers || block < 0 || block >= h->cfg.depths[layer]) return set_error(ARD_ERR_SHAPE, "bad block index");
+    h->layers[layer].blocks[block].has_res = false;
+    return 0;
+}
+
+int ard_set_block_lambda(ard_handle* h, int layer, int block, const float* lambda_dev, void* stream) {
+    if (!h || layer < 0 || layer >= h->nlayers || block < 0 || block >= h->cfg.depths[layer]) return set_error(ARD_ERR_SHAPE, "bad block index");
+    if (!h->finalized) return set_error(ARD_ERR_STATE, "ard_finalize_weights has not been called");
+    BlockW& bw = h->layers[layer].blocks[block];
+    if (!bw.has_res) return set_error(ARD_ERR_STATE, "block (%d,%d) has no ResiDual injected", layer, block);
+    const int C = C_of(h, layer);
+    g_launches = 0;
+    ARD_TRY(residual_fold(bw.proj_w_f32.as<float>(), bw.res_dmean.as<float>(), bw.res_basis.as<float>(), lambda_dev, C, bw.K,
+                          bw.res_M.as<float>(), bw.proj_w_fold.as<__nv_bfloat16>(), bw.proj_b_fold.as<float>(), (cudaStream_t)stream));
+    bw.lambda_set = true;
+    return 0;
+}
+
+int ard_encoder_forward(ard_handle* h, const ard_forward_args* args, void* stream) {
+    if (!h || !args) return set_error(ARD_ERR_SHAPE, "null argument");
+    g_launches = 0;
+    const int rc = encoder_forward(h, args, (cudaStream_t)stream);
+    h->last_launches = g_launches;
+    return rc;
+}
+
+int ard_block_forward(ard_handle* h, int layer, int block, const float* x_in, int B, float* x_out, float* attn, float* residual_x,
+                      void* stream) {
+    if (!h || !x_in || !x_out) return set_error(ARD_ERR_SHAPE, "null argument");
+    if (!h->finalized) return set_error(ARD_ERR_STATE, "ard_finalize_weights has not been called");
+    if (layer < 0 || layer >= h->nlayers || block < 0 || block >= h->cfg.depths[layer]) return set_error(ARD_ERR_SHAPE, "bad block index");
+    if (B <= 0) return set_error(ARD_ERR_SHAPE, "batch must be positive");
+    cudaStream_t s = (cudaStream_t)stream;
+    g_launches = 0;
+    ARD_TRY(ensure_workspace(h, B));
+    const int C = C_of(h, layer), T = R_of(layer) * R_of(layer);
+    const size_t bytes = (size_t)B * T * C * 4;
+    float* X = h->ws_x.as<float>();
+    ARD_CUDA(cudaMemcpyAsync(X, x_in, bytes, cudaMemcpyDeviceToDevice, s));
+    ARD_TRY(run_block(h, layer, block, B, X, h->ws_y.as<float>(), attn, 1.0f, 0, residual_x, T, T, s));
+    ARD_CUDA(cudaMemcpyAsync(x_out, X, bytes, cudaMemcpyDeviceToDevice, s));
+    h->last_launches = g_launches;
+    return 0;
+}
+
+long long ard_workspace_bytes(const ard_handle* h) {
+    if (!h) return 0;
+    const DevBuf* bufs[] = {&h->ws_logmel, &h->ws_x, &h->ws_y, &h->ws_xn, &h->ws_ao, &h->ws_qkv, &h->ws_h, &h->ws_normed,
+                            &h->ws_emb, &h->ws_hid, &h->ws_proj, &h->ws_tscam_a, &h->ws_tscam_y, &h->ws_wave};
+    long long t = 0;
+    for (const DevBuf* b : bufs) t += (long long)b->bytes;
+    return t;
+}
+int ard_last_launch_count(const ard_handle* h) { return h ? h->last_launches : 0; }
+
+// ---------------------------------------------------------------- op-level entry points
+int ard_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int out_is_bf16, int M, int N,
+                  int K, const float* bias, int act, const float* resid1, long long ldr1, const float* resid2, long long ldr2,
+                  void* stream) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return set_error(ARD_ERR_CUDA, "no CUDA device");
+    GemmArgs g;
+    g.A = (const __nv_bfloat16*)A; g.lda = lda; g.W = (const __nv_bfloat16*)W; g.ldw = ldw; g.out = out; g.ldo = ldo; g.out_bf16 = out_is_bf16;
+    g.M = M; g.N = N; g.K = K; g.bias = bias; g.act = act; g.resid1 = resid1; g.ldr1 = ldr1; g.resid2 = resid2; g.ldr2 = ldr2;
+    return gemm_bf16(g, sms, (cudaStream_t)stream);
+}
+
+int ard_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int C, void* stream) {
+    return layernorm_bf16(x, gamma, beta, (__nv_bfloat16*)out_bf16, rows, C, (cudaStream_t)stream);
+}
+
+int ard_window_attention(const void* qkv_bf16, void* out_bf16, const float* bias_table, float* attn, float attn_scale, int accumulate,
+                         int B, int H, int W, int C, int nH, int shift, void* stream) {
+    AttnArgs a;
+    a.qkv = (const __nv_bfloat16*)qkv_bf16; a.out = (__nv_bfloat16*)out_bf16; a.bias_table = bias_table; a.attn_mean = attn;
+    a.attn_scale = attn_scale; a.attn_accumulate = accumulate; a.B = B; a.H = H; a.W = W; a.C = C; a.nH = nH; a.shift = shift;
+    return window_attention(a, (cudaStream_t)stream);
+}
+
+int ard_f32_to_bf16(const float* in, void* out_bf16, long long n, float scale, void* stream) {
+    return f32_to_bf16(in, (__nv_bfloat16*)out_bf16, n, scale, (cudaStream_t)stream);
+}
+
+int ard_quantize_waveform(const float* in, float* out, long long n, void* stream) { return quantize_waveform(in, out, n, (cudaStream_t)stream); }
+
+int ard_logmel(ard_handle* h, const float* wave, int B, int n_samples, int apply_bn, int quantize, float* out, void* stream) {
+    if (!h || !h->finalized) return set_error(ARD_ERR_STATE, "handle not finalised");
+    if (!h->window.p) return set_error(ARD_ERR_STATE, "front-end weights (spectrogram_extractor / logmel_extractor) were never set");
+    MelBands mb{h->melw.as<float>(), h->mstart.as<int>(), h->mlen.as<int>(), h->band_max};
+    return stft_logmel(wave, B, n_samples, h->window.as<float>(), h->twiddle.as<float2>(), mb, apply_bn ? h->bn_scale.as<float>() : nullptr,
+                       apply_bn ? h->bn_shift.as<float>() : nullptr, out, quantize, (cudaStream_t)stream);
+}
+
+int ard_stats_accumulate(const float* x, long long rows, int D, double* sum, double* sumsq, void* stream) {
+    return stats_accumulate(x, rows, D, sum, sumsq, (cudaStream_t)stream);
+}
+
+}  // extern "C"

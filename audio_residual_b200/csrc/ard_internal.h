@@ -1,0 +1,104 @@
+// Internal host-side declarations shared by the .cu translation units of libard_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/ard.h"
+
+namespace ard {
+
+typedef CUresult (*PFN_cuTensorMapEncodeTiled_local)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// records the message for ard_last_error() and returns `code`
+int set_error(int code, const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+#define ARD_CUDA(call)                                           \
+    do {                                                         \
+        if (int _rc = ::ard::check_cuda((call), #call)) return _rc; \
+    } while (0)
+#define ARD_TRY(call)                   \
+    do {                                \
+        if (int _rc = (call)) return _rc; \
+    } while (0)
+
+// ---------------------------------------------------------------- tcgen05 GEMM (gemm_tc.cu)
+struct GemmArgs {
+    const __nv_bfloat16* A = nullptr;  // [M, lda] row-major activations
+    long long lda = 0;
+    const __nv_bfloat16* W = nullptr;  // [N, ldw] row-major weights (nn.Linear layout)
+    long long ldw = 0;
+    void* out = nullptr;               // bf16 or fp32 [M, ldo]
+    long long ldo = 0;
+    int out_bf16 = 0;
+    int M = 0, N = 0, K = 0;
+    const float* bias = nullptr;
+    int act = 0;                       // ARD_ACT_*
+    const float* resid1 = nullptr;
+    long long ldr1 = 0;
+    const float* resid2 = nullptr;
+    long long ldr2 = 0;
+    float* aux = nullptr;              // fp32 copy of acc+bias before the residual adds (ResiDual/attention residual capture)
+    long long ld_aux = 0;
+    int aux_T = 0;
+    long long aux_bstride = 0;
+    int force_bn = 0;
+};
+int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream);
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
+
+// ---------------------------------------------------------------- row-wise kernels (rowwise.cu)
+// LayerNorm over the last dim C of x[rows, C] (fp32) -> bf16; two-pass variance like at::native layer_norm.
+int layernorm_bf16(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, long long rows, int C, cudaStream_t s);
+// PatchMerging gather (htsat.py:516-521) + LayerNorm(4C) -> bf16 [B*(H/2)*(W/2), 4C]
+int merge_layernorm_bf16(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int B, int H, int W, int C,
+                         cudaStream_t s);
+// final LayerNorm + token mean (htsat.py:797, :810-811): x[B, T, C] -> emb[B, C]; optionally the normalised tokens (fp32) too
+int final_norm_mean(const float* x, const float* gamma, const float* beta, float* emb, float* normed, int B, int T, int C, cudaStream_t s);
+int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, float scale, cudaStream_t s);
+int fill_f32(float* p, long long n, float v, cudaStream_t s);
+
+// ---------------------------------------------------------------- window attention (attn_window.cu)
+struct AttnArgs {
+    const __nv_bfloat16* qkv = nullptr;  // [B*T, 3C] token order (q already scaled by hd^-0.5)
+    __nv_bfloat16* out = nullptr;        // [B*T, C] token order
+    const float* bias_table = nullptr;   // [225, nH] relative_position_bias_table
+    float* attn_mean = nullptr;          // optional [B*nW, nH, 64, 64] fp32; accumulates p * attn_scale
+    float attn_scale = 1.0f;
+    int attn_accumulate = 0;             // 0: overwrite, 1: +=
+    int B = 0, H = 0, W = 0, C = 0, nH = 0, shift = 0;
+};
+int window_attention(const AttnArgs& a, cudaStream_t s);
+
+// ---------------------------------------------------------------- front end (frontend.cu)
+struct MelBands {            // banded view of logmel_extractor.melW [513,64]
+    const float* w = nullptr;   // [64, band_max] weights, zero padded
+    const int* start = nullptr; // [64]
+    const int* len = nullptr;   // [64]
+    int band_max = 0;
+};
+int stft_logmel(const float* wave, int B, int n_samples, const float* window, const float2* twiddle, const MelBands& mel,
+                const float* bn_scale, const float* bn_shift, float* out /*[B,frames,64]*/, int quantize, cudaStream_t s);
+int patch_embed_ln(const float* logmel /*[B,frames,64]*/, long long clip_stride, int frames, const float* bn_scale, const float* bn_shift,
+                   const float* w /*[C,16]*/, const float* bias, const float* gamma, const float* beta, float* out /*[B,4096,C]*/, int B,
+                   int C, cudaStream_t s);
+int quantize_waveform(const float* in, float* out, long long n, cudaStream_t s);
+
+// ---------------------------------------------------------------- heads (heads.cu)
+int linear_small(const float* x, int ldx, const float* W, const float* bias, float* y, int ldy, int B, int N, int K, int act, cudaStream_t s);
+int l2_normalize(const float* x, float* y, int B, int N, cudaStream_t s);
+int residual_fold(const float* proj_w, const float* dmean, const float* basis, const float* lam, int C, int K, float* Mtmp,
+                  __nv_bfloat16* w_out, float* b_out, cudaStream_t s);
+int tscam_im2col(const float* normed, __nv_bfloat16* A, int B, int C, cudaStream_t s);
+int tscam_finish(const float* y, int ldy, float* framewise, float* clipwise, int B, int NC, cudaStream_t s);
+int fine_grained(const float* normed, float* fine, int B, int C, cudaStream_t s);
+int stats_accumulate(const float* x, long long rows, int D, double* sum, double* sumsq, cudaStream_t s);
+
+// launch accounting (ard_last_launch_count)
+void count_launch(int n = 1);
+
+}  // namespace ard

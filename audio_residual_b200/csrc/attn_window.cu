@@ -1,0 +1,270 @@
+// Shifted-window attention core for HTSAT (8x8 = 64-token windows, head_dim 24 or 32).
+//
+// Reference: WindowAttention.forward  CLAP/src/laion_clap/clap_module/htsat.py:326-352  (q k^T + relative-position bias
+// + shift mask, softmax, attn @ v) together with the layout work SwinTransformerBlock.forward does around it
+// (torch.roll / window_partition before, window_reverse / torch.roll after: htsat.py:452-474). Here the layout work
+// costs nothing: qkv and the output both stay in TOKEN order in HBM and the cyclic shift + window gather/scatter is
+// pure address arithmetic in this kernel's loads and stores (the proj Linear that follows is per-token, so it commutes
+// with the permutation).
+//
+// One CTA (4 warps) per (clip, window, group of 4 heads). Each warp owns 16 query rows; the 64x64 score tile of one
+// head lives entirely in registers (mma.sync m16n8k16 bf16 fragments), bias/mask/softmax are applied in registers and
+// P feeds the second MMA directly from registers - S/P never touch shared or global memory unless the caller asks for
+// the attention maps (`attn`, the block-mean capture of BasicLayer.forward htsat.py:589-595).
+// The per-(window, head) problem is 64x64x24: far too small for a tcgen05 tile, and the kernel is bound by the softmax
+// ALU/MUFU work (4096 exp per head-window vs 0.4 MFLOP of MMA), so the register-resident mma.sync form is the right tool.
+#include "ard_common.cuh"
+#include "ard_internal.h"
+
+namespace ard {
+
+constexpr int AT_HEADS = 4;  // heads per CTA
+constexpr int AT_TILE_BYTES = 3 * AT_HEADS * 64 * 64;
+constexpr int AT_SMEM_BYTES = AT_TILE_BYTES + AT_HEADS * 232 * 4 + 2 * 64 * 4;
+
+ARD_DEVINL void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+ARD_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+ARD_DEVINL void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+ARD_DEVINL void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+ARD_DEVINL void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+ARD_DEVINL float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// smem tile of one head's Q, K or V: 64 rows x 64 bytes (head_dim padded to 32 bf16), 16-byte units XOR-swizzled by (row>>1)&3
+ARD_DEVINL uint32_t tile_off(int row, int unit) { return (uint32_t)(row * 64 + ((unit ^ ((row >> 1) & 3)) << 4)); }
+
+template <int HD>
+__global__ void __launch_bounds__(128) window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                               const float* __restrict__ bias_table, float* __restrict__ attn,
+                                                               float attn_scale, int attn_acc, int H, int W, int C, int nH, int shift) {
+    constexpr int UPH = HD / 8;             // 16-byte units per head row (3 or 4)
+    constexpr int UPR = AT_HEADS * UPH;     // units per (row, q|k|v) segment for this CTA's 4 heads
+    constexpr int NT_O = HD / 8;            // output n-tiles
+    extern __shared__ __align__(128) uint8_t dsm[];
+    uint8_t* tiles = dsm;                                               // [part][head][64 rows][64 B]
+    float (*tbl)[232] = reinterpret_cast<float (*)[232]>(dsm + AT_TILE_BYTES);
+    int* tok_row = reinterpret_cast<int*>(dsm + AT_TILE_BYTES + AT_HEADS * 232 * 4);   // window token -> global row (b*T + token)
+    int* tok_lab = tok_row + 64;                                        // shift-mask region label (htsat.py:414-437)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = nH / AT_HEADS;
+    const int nWw = W >> 3, nW = (H >> 3) * nWw;
+    const int g = blockIdx.x % G;
+    const int wflat = blockIdx.x / G;       // b*nW + w
+    const int w = wflat % nW;
+    const long long b = wflat / nW;
+    const int wh = w / nWw, ww = w % nWw;
+    const int T = H * W;
+
+    if (tid < 64) {
+        const int th = tid >> 3, tw = tid & 7;
+        const int hs = wh * 8 + th, ws = ww * 8 + tw;               // coordinates in the rolled image
+        const int h = (hs + shift) % H, wd = (ws + shift) % W;      // torch.roll(x, -shift): rolled[hs] = x[(hs+shift)%H]
+        tok_row[tid] = (int)(b * T + h * W + wd);
+        int lab = 0;
+        if (shift > 0) {
+            const int rh = hs < H - 8 ? 0 : (hs < H - shift ? 1 : 2);
+            const int rw = ws < W - 8 ? 0 : (ws < W - shift ? 1 : 2);
+            lab = rh * 3 + rw;
+        }
+        tok_lab[tid] = lab;
+    }
+    for (int i = tid; i < AT_HEADS * 225; i += 128) {
+        const int hh = i / 225, idx = i - hh * 225;
+        tbl[hh][idx] = __ldg(bias_table + idx * nH + g * AT_HEADS + hh);
+    }
+    __syncthreads();
+
+    // ---- gather q/k/v rows of this window (token order in HBM) into swizzled smem tiles
+    for (int i = tid; i < 64 * 3 * UPR; i += 128) {
+        const int u = i % UPR;
+        const int rp = i / UPR;
+        const int part = rp % 3, t = rp / 3;
+        const int hh = u / UPH, q = u - hh * UPH;
+        const __nv_bfloat16* src = qkv + (long long)tok_row[t] * (3 * C) + part * C + (g * AT_HEADS) * HD + u * 8;
+        cp_async16(tiles + (part * AT_HEADS + hh) * 4096 + tile_off(t, q), src);
+    }
+    if constexpr (HD == 24) {  // zero the padded k-dim unit (unit 3) of every tile
+        for (int i = tid; i < 3 * AT_HEADS * 64; i += 128) {
+            const int t = i & 63, ph = i >> 6;
+            *reinterpret_cast<uint4*>(tiles + ph * 4096 + tile_off(t, 3)) = make_uint4(0, 0, 0, 0);
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    const int r0 = warp * 16 + (lane >> 2);   // this thread's two query rows: r0 and r0 + 8
+    const int ih0 = r0 >> 3, iw0 = r0 & 7, ih1 = ih0 + 1;
+    // shift-mask bitmaps over this thread's 16 key columns
+    uint32_t neq0 = 0, neq1 = 0;
+    if (shift > 0) {
+        const int l0 = tok_lab[r0], l1 = tok_lab[r0 + 8];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int lj = tok_lab[nt * 8 + (lane & 3) * 2 + e];
+                neq0 |= (uint32_t)(lj != l0) << (nt * 2 + e);
+                neq1 |= (uint32_t)(lj != l1) << (nt * 2 + e);
+            }
+    }
+    const uint32_t tiles_u32 = smem_u32(tiles);
+    constexpr float LOG2E = 1.4426950408889634f;
+
+#pragma unroll 1
+    for (int hh = 0; hh < AT_HEADS; ++hh) {
+        const uint32_t qs = tiles_u32 + (0 * AT_HEADS + hh) * 4096;
+        const uint32_t ks = tiles_u32 + (1 * AT_HEADS + hh) * 4096;
+        const uint32_t vs = tiles_u32 + (2 * AT_HEADS + hh) * 4096;
+        // Q fragments: 16 rows x 32 (padded) k
+        uint32_t qa[2][4];
+#pragma unroll
+        for (int ksd = 0; ksd < 2; ++ksd)
+            ldmatrix_x4(qs + tile_off(warp * 16 + (lane & 15), ksd * 2 + (lane >> 4)), qa[ksd][0], qa[ksd][1], qa[ksd][2], qa[ksd][3]);
+        float s[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+            uint32_t kb0, kb1, kb2, kb3;
+            ldmatrix_x4(ks + tile_off(nt * 8 + (lane & 7), lane >> 3), kb0, kb1, kb2, kb3);
+            mma_bf16_16816(s[nt], qa[0][0], qa[0][1], qa[0][2], qa[0][3], kb0, kb1);
+            mma_bf16_16816(s[nt], qa[1][0], qa[1][1], qa[1][2], qa[1][3], kb2, kb3);
+        }
+        // + relative position bias (htsat.py:337-340) + shift mask (htsat.py:342-345), row max
+        float m0 = -INFINITY, m1 = -INFINITY;
+        const float* tb = tbl[hh];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int jw = (lane & 3) * 2 + e;
+                const int i0 = (ih0 - nt + 7) * 15 + (iw0 - jw + 7);
+                float v0 = s[nt][e] + tb[i0];
+                float v1 = s[nt][2 + e] + tb[i0 + 15];      // row r0+8: ih1 = ih0+1
+                if ((neq0 >> (nt * 2 + e)) & 1) v0 -= 100.0f;
+                if ((neq1 >> (nt * 2 + e)) & 1) v1 -= 100.0f;
+                s[nt][e] = v0;
+                s[nt][2 + e] = v1;
+                m0 = fmaxf(m0, v0);
+                m1 = fmaxf(m1, v1);
+            }
+        (void)ih1;
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        const float mb0 = m0 * LOG2E, mb1 = m1 * LOG2E;
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float p0 = ex2_approx(fmaf(s[nt][e], LOG2E, -mb0));
+                const float p1 = ex2_approx(fmaf(s[nt][2 + e], LOG2E, -mb1));
+                s[nt][e] = p0;
+                s[nt][2 + e] = p1;
+                sum0 += p0;
+                sum1 += p1;
+            }
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+        const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+
+        if (attn != nullptr) {   // capture of the softmax probabilities (layers_attention)
+            float* ap = attn + ((long long)wflat * nH + g * AT_HEADS + hh) * 4096;
+            const float c0 = inv0 * attn_scale, c1 = inv1 * attn_scale;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                float2* d0 = reinterpret_cast<float2*>(ap + r0 * 64 + nt * 8 + (lane & 3) * 2);
+                float2* d1 = reinterpret_cast<float2*>(ap + (r0 + 8) * 64 + nt * 8 + (lane & 3) * 2);
+                float2 a = make_float2(s[nt][0] * c0, s[nt][1] * c0);
+                float2 c = make_float2(s[nt][2] * c1, s[nt][3] * c1);
+                if (attn_acc) {
+                    const float2 o0 = *d0, o1 = *d1;
+                    a.x += o0.x; a.y += o0.y; c.x += o1.x; c.y += o1.y;
+                }
+                *d0 = a;
+                *d1 = c;
+            }
+        }
+
+        // O = P V  (P from registers as the A operand)
+        float o[NT_O][4];
+#pragma unroll
+        for (int nd = 0; nd < NT_O; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t a0 = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+            const uint32_t a1 = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+            const uint32_t a2 = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+            const uint32_t a3 = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+            const int krow = kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {     // pairs of 8-wide output tiles: (0,1) and (2,3)
+                uint32_t v0, v1, v2, v3;
+                ldmatrix_x4_trans(vs + tile_off(krow, np * 2 + (lane >> 4)), v0, v1, v2, v3);
+                mma_bf16_16816(o[np * 2], a0, a1, a2, a3, v0, v1);
+                if (np * 2 + 1 < NT_O) mma_bf16_16816(o[(np * 2 + 1) < NT_O ? (np * 2 + 1) : 0], a0, a1, a2, a3, v2, v3);
+            }
+        }
+        // normalise and park O (bf16) in this warp's own rows of the Q tile of head hh (nobody else reads them)
+        uint8_t* qt = tiles + (0 * AT_HEADS + hh) * 4096;
+#pragma unroll
+        for (int nd = 0; nd < NT_O; ++nd) {
+            *reinterpret_cast<uint32_t*>(qt + tile_off(r0, nd) + (lane & 3) * 4) = pack_bf16x2(o[nd][0] * inv0, o[nd][1] * inv0);
+            *reinterpret_cast<uint32_t*>(qt + tile_off(r0 + 8, nd) + (lane & 3) * 4) = pack_bf16x2(o[nd][2] * inv1, o[nd][3] * inv1);
+        }
+    }
+    __syncwarp();
+    // ---- scatter this warp's 16 output rows back to token order: (attn @ v).transpose(1,2).reshape(B_, N, C) htsat.py:354
+    for (int i = lane; i < 16 * UPR; i += 32) {
+        const int rr = warp * 16 + i / UPR;
+        const int u = i % UPR;
+        const int hh = u / UPH, q = u - hh * UPH;
+        const uint4 val = *reinterpret_cast<const uint4*>(tiles + (0 * AT_HEADS + hh) * 4096 + tile_off(rr, q));
+        *reinterpret_cast<uint4*>(out + (long long)tok_row[rr] * C + (g * AT_HEADS) * HD + u * 8) = val;
+    }
+}
+
+int window_attention(const AttnArgs& a, cudaStream_t s) {
+    if (a.B <= 0) return 0;
+    if (a.nH <= 0 || a.C % a.nH != 0) return set_error(ARD_ERR_SHAPE, "window_attention: C=%d not divisible by heads=%d", a.C, a.nH);
+    const int hd = a.C / a.nH;
+    if ((a.H % 8) || (a.W % 8) || (a.nH % AT_HEADS)) return set_error(ARD_ERR_SHAPE, "window_attention: H=%d W=%d nH=%d unsupported", a.H, a.W, a.nH);
+    int shift = a.shift;
+    if (a.H <= 8 || a.W <= 8) shift = 0;   // htsat.py:393-396
+    const long long blocks = (long long)a.B * (a.H / 8) * (a.W / 8) * (a.nH / AT_HEADS);
+    if (blocks > 0x7fffffffLL) return set_error(ARD_ERR_SHAPE, "window_attention: grid too large");
+    static bool attr_set = false;
+    if (!attr_set) {
+        ARD_CUDA(cudaFuncSetAttribute(window_attention_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+        ARD_CUDA(cudaFuncSetAttribute(window_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+        attr_set = true;
+    }
+    if (hd == 24)
+        window_attention_kernel<24><<<(unsigned)blocks, 128, AT_SMEM_BYTES, s>>>(a.qkv, a.out, a.bias_table, a.attn_mean, a.attn_scale, a.attn_accumulate,
+                                                                    a.H, a.W, a.C, a.nH, shift);
+    else if (hd == 32)
+        window_attention_kernel<32><<<(unsigned)blocks, 128, AT_SMEM_BYTES, s>>>(a.qkv, a.out, a.bias_table, a.attn_mean, a.attn_scale, a.attn_accumulate,
+                                                                    a.H, a.W, a.C, a.nH, shift);
+    else
+        return set_error(ARD_ERR_SHAPE, "window_attention: head_dim %d unsupported (24 or 32)", hd);
+    return check_cuda(cudaGetLastError(), "window_attention launch");
+}
+
+}  // namespace ard

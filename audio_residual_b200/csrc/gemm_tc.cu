@@ -1,0 +1,359 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:   out[M,N] = epilogue( A[M,K] (bf16) * W[N,K]^T (bf16) )
+//
+// This is the contraction engine behind every Linear on the HTSAT path (reference call sites:
+// WindowAttention.qkv / .proj htsat.py:330,354-355; Mlp.fc1 / .fc2 htsat.py:159-163; PatchMerging.reduction htsat.py:524;
+// ResiDual projections src/residual.py:38-40; audio_projection model.py:539-543).
+//
+//   warp 0      : TMA producer  (A tile 128x64 and W tile BNx64 per stage, SWIZZLE_128B, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BN, K=16 per instruction, fp32 accum in TMEM,
+//                 two accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warps 2..9  : epilogue. Warp w owns TMEM lanes 32*(w%4)..+31 (one output row per thread), pulls 32-column chunks with
+//                 tcgen05.ld, applies bias / exact-erf GELU / ReLU / up to two fp32 residual adds in registers, writes the chunk
+//                 into a swizzled shared-memory staging tile and hands it to a TMA store (no global store instructions).
+//
+// The contraction is tensor-core work; for the small-K layers of stages 0/1 (K = 96/192) the kernel is bound by the
+// epilogue's CUDA-core instructions and by HBM, so the epilogue is kept to a few instructions per element.
+#include "ard_common.cuh"
+#include "ard_internal.h"
+
+namespace ard {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_NEPI = 8;                       // epilogue warps
+constexpr int GEMM_THREADS = 64 + GEMM_NEPI * 32;  // 320
+constexpr int GEMM_CSTAGE_BYTES = 4096;            // one 32x32 fp32 chunk (bf16 uses half)
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int STAGES = (BN >= 256) ? 3 : 4;
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int CSTAGE_OFF = STAGES * STAGE_BYTES;
+    static constexpr int BIAS_OFF = CSTAGE_OFF + GEMM_NEPI * 2 * GEMM_CSTAGE_BYTES;
+    static constexpr int BAR_OFF = BIAS_OFF + GEMM_NEPI * 32 * 4;
+    static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;  // + alignment slack
+};
+
+struct GemmKernelParams {
+    int M, N, K;
+    const float* bias;   // [N] or null
+    int act;             // 0 none, 1 gelu(erf), 2 relu
+    const float* resid1; // fp32 [M, ldr1] or null
+    long long ldr1;
+    const float* resid2;
+    long long ldr2;
+    float* aux;          // optional fp32 copy of (acc+bias) BEFORE residual adds, row m -> aux[(m / aux_T) * aux_bstride + m % aux_T]
+    long long ld_aux;
+    int aux_T;
+    long long aux_bstride;
+};
+
+template <int BN, bool OUT_BF16>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const GemmKernelParams p) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+    uint64_t* empty_bar = full_bar + Cfg::STAGES;
+    uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m_blocks = (p.M + GEMM_BM - 1) / GEMM_BM;
+    const int n_blocks = (p.N + BN - 1) / BN;
+    const int num_tiles = m_blocks * n_blocks;
+    const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        for (int i = 0; i < Cfg::STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], GEMM_NEPI);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+                    tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t da = umma_desc_sw128(sa);
+                    const uint64_t db = umma_desc_sw128(sa + Cfg::A_BYTES);
+                    const int ksteps = min(GEMM_BK, p.K - kb * GEMM_BK) >> 4;
+                    for (int k = 0; k < ksteps; ++k)
+                        umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[as]);          // accumulator ready
+            }
+        }
+    } else {
+        // ===================================================== epilogue warps
+        const int ew = warp - 2;
+        const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int grp = ew >> 2;                   // column-chunk interleave group
+        constexpr int NGRP = GEMM_NEPI / 4;
+        constexpr int NCHUNK = BN / 32;
+        uint8_t* cst = smem + Cfg::CSTAGE_OFF + ew * 2 * GEMM_CSTAGE_BYTES;
+        float* bias_w = reinterpret_cast<float*>(smem + Cfg::BIAS_OFF) + ew * 32;
+        int buf = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            const int row = m_blk * GEMM_BM + quad * 32 + lane;
+            const bool row_ok = row < p.M;
+            // last chunk index handled by this group
+            int last_c = -1;
+            for (int c = grp; c < NCHUNK; c += NGRP) last_c = c;
+            for (int c = grp; c < NCHUNK; c += NGRP) {
+                const int col0 = n_blk * BN + c * 32;
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + as * 256 + c * 32 + ((uint32_t)(quad * 32) << 16), v);
+                // stage this chunk's bias while the TMEM load is in flight
+                __syncwarp();
+                bias_w[lane] = (p.bias != nullptr && col0 + lane < p.N) ? __ldg(p.bias + col0 + lane) : 0.0f;
+                __syncwarp();
+                tmem_ld_wait();
+                if (c == last_c) {                 // all TMEM reads of this tile by this warp are done
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[as]);
+                }
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias_w + j);
+                    f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
+                    f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                    f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+                    f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+                }
+                if (p.act == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                } else if (p.act == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+                }
+                if constexpr (!OUT_BF16) {
+                    if (p.aux != nullptr && row_ok) {
+                        float* ap = p.aux + ((long long)(row / p.aux_T) * p.aux_bstride + (row % p.aux_T)) * p.ld_aux + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (col0 + j < p.N) *reinterpret_cast<float4*>(ap + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    }
+                    if (p.resid1 != nullptr && row_ok) {
+                        const float* rp = p.resid1 + (long long)row * p.ldr1 + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (col0 + j < p.N) {
+                                const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+                                f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+                            }
+                        }
+                    }
+                    if (p.resid2 != nullptr && row_ok) {
+                        const float* rp = p.resid2 + (long long)row * p.ldr2 + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (col0 + j < p.N) {
+                                const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+                                f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+                            }
+                        }
+                    }
+                }
+                // staging buffer `buf` was last handed to TMA two chunks ago: make sure it has been read out
+                if (lane == 0) tma_store_wait_read<1>();
+                __syncwarp();
+                uint8_t* sbuf = cst + buf * GEMM_CSTAGE_BYTES;
+                if constexpr (OUT_BF16) {
+                    // row = 64 B (32 bf16), CU_TENSOR_MAP_SWIZZLE_64B: 16-byte unit index ^= (row >> 1) & 3
+                    uint8_t* rowp = sbuf + lane * 64;
+                    const int sw = (lane >> 1) & 3;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 u;
+                        u.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+                        u.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+                        u.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+                        u.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+                        *reinterpret_cast<uint4*>(rowp + ((q ^ sw) << 4)) = u;
+                    }
+                } else {
+                    // row = 128 B (32 fp32), CU_TENSOR_MAP_SWIZZLE_128B: 16-byte unit index ^= row & 7
+                    uint8_t* rowp = sbuf + lane * 128;
+                    const int sw = lane & 7;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4*>(rowp + ((q ^ sw) << 4)) =
+                            make_float4(f[q * 4 + 0], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmC, sbuf, col0, m_blk * GEMM_BM + quad * 32);
+                    tma_store_commit();
+                }
+                buf ^= 1;
+            }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_local g_encode = nullptr;
+
+static int ensure_encode() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) return set_error(ARD_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_local>(fn);
+    return 0;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+    if (int rc = ensure_encode()) return rc;
+    cuuint64_t gdim[2] = {inner, outer};
+    cuuint64_t gstride[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                            : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = g_encode(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(ARD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) base=%p inner=%llu outer=%llu stride=%llu", (int)r,
+                                            base, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes);
+    return 0;
+}
+
+template <int BN, bool OUT_BF16>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmKernelParams& kp, int num_sms,
+                       cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    auto kern = gemm_tc_kernel<BN, OUT_BF16>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return set_error(ARD_ERR_CUDA, "cudaFuncSetAttribute(gemm smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int tiles = ((kp.M + GEMM_BM - 1) / GEMM_BM) * ((kp.N + BN - 1) / BN);
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, kp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(ARD_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+static int pick_bn(int N) {
+    // widest tile that divides N (fewest re-reads of A); fall back to 128 with a clipped last tile.
+    if (N % 256 == 0) return 256;
+    if (N % 192 == 0) return 192;
+    if (N % 128 == 0) return 128;
+    if (N % 96 == 0) return 96;
+    return 128;
+}
+
+int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream) {
+    if (a.M <= 0 || a.N <= 0 || a.K <= 0 || (a.K % 16) != 0 || (a.lda % 8) != 0 || (a.ldw % 8) != 0)
+        return set_error(ARD_ERR_SHAPE, "gemm: bad shape M=%d N=%d K=%d lda=%lld ldw=%lld", a.M, a.N, a.K, a.lda, a.ldw);
+    if ((a.out_bf16 && (a.ldo % 8) != 0) || (!a.out_bf16 && (a.ldo % 4) != 0)) return set_error(ARD_ERR_SHAPE, "gemm: ldo alignment");
+    if (a.out_bf16 && (a.resid1 || a.resid2 || a.aux)) return set_error(ARD_ERR_SHAPE, "gemm: residual/aux need fp32 output");
+    const int BN = a.force_bn ? a.force_bn : pick_bn(a.N);
+    CUtensorMap ta, tb, tc;
+    if (int rc = make_tmap_2d(&ta, a.A, 2, a.K, a.M, (uint64_t)a.lda * 2, GEMM_BK, GEMM_BM, 128)) return rc;
+    if (int rc = make_tmap_2d(&tb, a.W, 2, a.K, a.N, (uint64_t)a.ldw * 2, GEMM_BK, BN, 128)) return rc;
+    if (a.out_bf16) {
+        if (int rc = make_tmap_2d(&tc, a.out, 2, a.N, a.M, (uint64_t)a.ldo * 2, 32, 32, 64)) return rc;
+    } else {
+        if (int rc = make_tmap_2d(&tc, a.out, 4, a.N, a.M, (uint64_t)a.ldo * 4, 32, 32, 128)) return rc;
+    }
+    GemmKernelParams kp;
+    kp.M = a.M; kp.N = a.N; kp.K = a.K;
+    kp.bias = a.bias; kp.act = a.act;
+    kp.resid1 = a.resid1; kp.ldr1 = a.ldr1; kp.resid2 = a.resid2; kp.ldr2 = a.ldr2;
+    kp.aux = a.aux; kp.ld_aux = a.ld_aux; kp.aux_T = a.aux_T > 0 ? a.aux_T : a.M; kp.aux_bstride = a.aux_bstride;
+#define ARD_GEMM_CASE(bn)                                                                                          \
+    case bn:                                                                                                       \
+        return a.out_bf16 ? launch_gemm<bn, true>(ta, tb, tc, kp, num_sms, stream) : launch_gemm<bn, false>(ta, tb, tc, kp, num_sms, stream);
+    switch (BN) {
+        ARD_GEMM_CASE(96)
+        ARD_GEMM_CASE(128)
+        ARD_GEMM_CASE(192)
+        ARD_GEMM_CASE(256)
+    }
+#undef ARD_GEMM_CASE
+    return set_error(ARD_ERR_SHAPE, "gemm: unsupported BN=%d", BN);
+}
+
+}  // namespace ard

@@ -1,0 +1,257 @@
+// Row-wise HBM-bound kernels: LayerNorm (-> bf16 GEMM operand), PatchMerging gather + LayerNorm, final norm + token mean,
+// dtype conversion, waveform quantisation. One warp per row, the row is held in registers, loads are coalesced/vectorised.
+#include "ard_common.cuh"
+#include "ard_internal.h"
+
+namespace ard {
+
+constexpr float LN_EPS = 1e-5f;
+
+ARD_DEVINL float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int VEC>
+ARD_DEVINL void load_vec(const float* p, float* r) {
+    if constexpr (VEC == 4) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+    } else if constexpr (VEC == 2) {
+        float2 t = *reinterpret_cast<const float2*>(p);
+        r[0] = t.x; r[1] = t.y;
+    } else {
+        r[0] = *p;
+    }
+}
+template <int VEC>
+ARD_DEVINL void store_bf16_vec(__nv_bfloat16* p, const float* r) {
+    if constexpr (VEC == 4) {
+        uint2 u;
+        u.x = pack_bf16x2(r[0], r[1]);
+        u.y = pack_bf16x2(r[2], r[3]);
+        *reinterpret_cast<uint2*>(p) = u;
+    } else if constexpr (VEC == 2) {
+        *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(r[0], r[1]);
+    } else {
+        *p = __float2bfloat16_rn(r[0]);
+    }
+}
+
+// Row r of the logical [rows, C] matrix; element offset e (multiple of VEC) -> source pointer.
+struct PlainRows {
+    const float* x;
+    int C;
+    ARD_DEVINL const float* at(long long row, int e) const { return x + row * C + e; }
+};
+// PatchMerging.forward htsat.py:516-521: logical row (b, i, j) of width 4*Cin = [x(2i,2j), x(2i+1,2j), x(2i,2j+1), x(2i+1,2j+1)]
+struct MergeRows {
+    const float* x;
+    int H, W, Cin;
+    ARD_DEVINL const float* at(long long row, int e) const {
+        const int W2 = W >> 1, H2 = H >> 1;
+        const int j = (int)(row % W2);
+        const long long t = row / W2;
+        const int i = (int)(t % H2);
+        const long long b = t / H2;
+        const int s = e / Cin, c = e - s * Cin;
+        const int hh = 2 * i + (s & 1), ww = 2 * j + (s >> 1);
+        return x + ((b * H + hh) * W + ww) * (long long)Cin + c;
+    }
+};
+
+template <int VEC, int NV, class Rows>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(Rows rows, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            __nv_bfloat16* __restrict__ out, long long nrows) {
+    constexpr int C = 32 * VEC * NV;
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    float v[NV][VEC];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) load_vec<VEC>(rows.at(row, (i * 32 + lane) * VEC), v[i]);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) s += v[i][k];
+    const float mean = warp_sum(s) * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const float d = v[i][k] - mean;
+            q = fmaf(d, d, q);
+        }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + LN_EPS);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int e = (i * 32 + lane) * VEC;
+        float g[VEC], b[VEC], o[VEC];
+        load_vec<VEC>(gamma + e, g);
+        load_vec<VEC>(beta + e, b);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) o[k] = fmaf((v[i][k] - mean) * rstd, g[k], b[k]);
+        store_bf16_vec<VEC>(out + row * C + e, o);
+    }
+}
+
+template <class Rows>
+static int launch_ln(Rows rows, const float* gamma, const float* beta, __nv_bfloat16* out, long long nrows, int C, cudaStream_t s) {
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((nrows + wpb - 1) / wpb);
+#define ARD_LN_CASE(c, vec, nv) \
+    case c: layernorm_rows_kernel<vec, nv, Rows><<<grid, wpb * 32, 0, s>>>(rows, gamma, beta, out, nrows); break;
+    switch (C) {
+        ARD_LN_CASE(96, 1, 3)
+        ARD_LN_CASE(128, 4, 1)
+        ARD_LN_CASE(192, 2, 3)
+        ARD_LN_CASE(256, 4, 2)
+        ARD_LN_CASE(384, 4, 3)
+        ARD_LN_CASE(512, 4, 4)
+        ARD_LN_CASE(768, 4, 6)
+        ARD_LN_CASE(1024, 4, 8)
+        ARD_LN_CASE(1536, 4, 12)
+        ARD_LN_CASE(2048, 4, 16)
+        default: return set_error(ARD_ERR_SHAPE, "layernorm: unsupported width C=%d", C);
+    }
+#undef ARD_LN_CASE
+    return check_cuda(cudaGetLastError(), "layernorm launch");
+}
+
+int layernorm_bf16(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, long long rows, int C, cudaStream_t s) {
+    if (rows <= 0) return 0;
+    return launch_ln(PlainRows{x, C}, gamma, beta, out, rows, C, s);
+}
+
+int merge_layernorm_bf16(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int B, int H, int W, int C,
+                         cudaStream_t s) {
+    if ((H & 1) || (W & 1)) return set_error(ARD_ERR_SHAPE, "x size (%d*%d) are not even.", H, W);  // htsat.py:512
+    const long long rows = (long long)B * (H / 2) * (W / 2);
+    return launch_ln(MergeRows{x, H, W, C}, gamma, beta, out, rows, 4 * C, s);
+}
+
+// ---------------------------------------------------------------------------------------------- final norm + token mean
+// forward_features tail, htsat.py:797 (self.norm) and :810-811 (avgpool over all tokens) : x[B, T, C] -> emb[B, C].
+// One CTA per clip, one warp per token (T = 64 tokens, 8 warps x 8 tokens).
+template <int VEC, int NV>
+__global__ void __launch_bounds__(256) final_norm_mean_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float* __restrict__ emb,
+                                                             float* __restrict__ normed, int T) {
+    constexpr int C = 32 * VEC * NV;
+    __shared__ float part[8][C];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long b = blockIdx.x;
+    float acc[NV][VEC];
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[i][k] = 0.f;
+    for (int t = warp; t < T; t += 8) {
+        const float* xr = x + (b * T + t) * C;
+        float v[NV][VEC];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) load_vec<VEC>(xr + (i * 32 + lane) * VEC, v[i]);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) s += v[i][k];
+        const float mean = warp_sum(s) * (1.0f / C);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const float d = v[i][k] - mean;
+                q = fmaf(d, d, q);
+            }
+        const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + LN_EPS);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int e = (i * 32 + lane) * VEC;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const float o = fmaf((v[i][k] - mean) * rstd, __ldg(gamma + e + k), __ldg(beta + e + k));
+                acc[i][k] += o;
+                if (normed) normed[(b * T + t) * C + e + k] = o;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) part[warp][(i * 32 + lane) * VEC + k] = acc[i][k];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += part[w][c];
+        emb[b * C + c] = s / (float)T;
+    }
+}
+
+int final_norm_mean(const float* x, const float* gamma, const float* beta, float* emb, float* normed, int B, int T, int C, cudaStream_t s) {
+    if (B <= 0) return 0;
+    switch (C) {
+        case 768: final_norm_mean_kernel<4, 6><<<B, 256, 0, s>>>(x, gamma, beta, emb, normed, T); break;
+        case 1024: final_norm_mean_kernel<4, 8><<<B, 256, 0, s>>>(x, gamma, beta, emb, normed, T); break;
+        default: return set_error(ARD_ERR_SHAPE, "final norm: unsupported width C=%d", C);
+    }
+    return check_cuda(cudaGetLastError(), "final_norm_mean launch");
+}
+
+// ---------------------------------------------------------------------------------------------- conversions
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n, float scale) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (; i + 3 < n; i += stride) {
+        const float4 v = *reinterpret_cast<const float4*>(in + i);
+        uint2 u;
+        u.x = pack_bf16x2(v.x * scale, v.y * scale);
+        u.y = pack_bf16x2(v.z * scale, v.w * scale);
+        *reinterpret_cast<uint2*>(out + i) = u;
+    }
+    if (i < n && i + 3 >= n)
+        for (long long k = i; k < n; ++k) out[k] = __float2bfloat16_rn(in[k] * scale);
+}
+
+int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, float scale, cudaStream_t s) {
+    if (n <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7)) return set_error(ARD_ERR_SHAPE, "f32_to_bf16: unaligned");
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    f32_to_bf16_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, out, n, scale);
+    return check_cuda(cudaGetLastError(), "f32_to_bf16 launch");
+}
+
+__global__ void fill_f32_kernel(float* p, long long n, float v) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+int fill_f32(float* p, long long n, float v, cudaStream_t s) {
+    if (n <= 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    fill_f32_kernel<<<(unsigned)blocks, 256, 0, s>>>(p, n, v);
+    return check_cuda(cudaGetLastError(), "fill launch");
+}
+
+// quantize_tensor, src/residual.py:210-212: clamp(-1,1) * 32767 -> int16 (truncation toward zero) -> float / 32767
+__global__ void quantize_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float c = fminf(fmaxf(in[i], -1.0f), 1.0f);
+        out[i] = truncf(c * 32767.0f) / 32767.0f;
+    }
+}
+int quantize_waveform(const float* in, float* out, long long n, cudaStream_t s) {
+    if (n <= 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    quantize_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, out, n);
+    return check_cuda(cudaGetLastError(), "quantize launch");
+}
+
+}  // namespace ard

@@ -1,0 +1,142 @@
+/*
+ * ard.h — C ABI of libard_b200.so: the B200 (sm_100a) implementation of Audio-ResiDual's HTSAT + ResiDual hot path.
+ *
+ * Drop-in boundary. The reference (arianna011/Audio-ResiDual) is pure Python/PyTorch and has NO foreign-function
+ * interface of its own, so each entry point below names the reference Python interface it replaces (paths relative to
+ * the reference root). The reference-side binding is a ctypes stub; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "device" is a CUDA device pointer owned by the caller (PyTorch
+ *     allocator on the reference side) and borrowed for the duration of the call; outputs are written in place.
+ *   - every function returns 0 on success or a negative ARD_ERR_* code; ard_last_error() returns the message of the
+ *     last failure on the calling thread. No exceptions, no exit(). The Python shim maps codes back to the exception
+ *     types the reference raises (ValueError / AssertionError / RuntimeError / NotImplementedError).
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream); calls are asynchronous.
+ *   - one ard_handle per device; a handle is not thread-safe, distinct handles are independent.
+ */
+#ifndef ARD_H_
+#define ARD_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARD_OK 0
+#define ARD_ERR_SHAPE (-1)    /* bad shape / index  -> ValueError or AssertionError (htsat.py:115,137,511; src/residual.py:194) */
+#define ARD_ERR_DTYPE (-2)
+#define ARD_ERR_CUDA (-3)     /* CUDA runtime/driver failure -> RuntimeError */
+#define ARD_ERR_STATE (-4)    /* weights missing / not finalised -> RuntimeError */
+#define ARD_ERR_KEY (-5)      /* unknown state_dict key -> KeyError */
+#define ARD_ERR_NOTIMPL (-6)  /* -> NotImplementedError (data.py:462-464,494-496) */
+
+#define ARD_ACT_NONE 0
+#define ARD_ACT_GELU 1  /* exact-erf GELU, htsat.py:151 */
+#define ARD_ACT_RELU 2  /* model.py:541 */
+
+#define ARD_MAX_LAYERS 4
+#define ARD_CLIP_SAMPLES 480000
+#define ARD_FRAMES 1001
+#define ARD_MEL_BINS 64
+#define ARD_WINDOW_TOKENS 64
+#define ARD_CLASS_NUM 527
+
+const char* ard_last_error(void);
+int ard_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Encoder handle: packed weights + workspace for HTSAT_Swin_Transformer (CLAP/src/laion_clap/clap_module/htsat.py:596-994)
+ * and CLAP.audio_projection (clap_module/model.py:539-543).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ard_handle ard_handle;
+
+typedef struct ard_config {
+    int embed_dim;                 /* 96 tiny / 128 base (htsat.py:1004,1017) */
+    int depths[ARD_MAX_LAYERS];    /* {2,2,6,2} / {2,2,12,2} */
+    int num_heads[ARD_MAX_LAYERS]; /* {4,8,16,32} */
+    int joint_dim;                 /* 512 (model.py joint_embed_shape) */
+    int enable_fusion;             /* 1: input is mel_fusion (htsat.py:883-894), 0: waveform (htsat.py:896-910) */
+} ard_config;
+
+int ard_create(const ard_config* cfg, ard_handle** out);
+int ard_destroy(ard_handle* h);
+
+/* Load one tensor of the reference checkpoint by its state_dict key, audio_branch keys un-prefixed
+ * ("layers.2.blocks.5.attn.qkv.weight", "bn0.running_var", "logmel_extractor.melW", ...) plus
+ * "audio_projection.{0,2}.{weight,bias}". `data` is float32, HOST memory, `numel` elements. Replaces
+ * nn.Module.load_state_dict on the audio branch (factory.py:53-70 key layout). Integer buffers
+ * (relative_position_index, num_batches_tracked) and attn_mask are derived, not loaded. */
+int ard_set_weight(ard_handle* h, const char* key, const float* data, long long numel);
+/* Derive packed device forms (bf16 GEMM operands, q-scale folded into qkv, BN0 folded to scale/shift, banded mel
+ * filters, FFT window). Must be called after all weights are set / whenever they change. */
+int ard_finalize_weights(ard_handle* h, void* stream);
+
+/* ResiDual injection: replaces patch_block_with_residual(block, residual) (src/residual.py:45-100) for block
+ * (layer, block). mean[D], basis[K,D] (rows = components, n_components slices rows: src/residual.py:20-26) are
+ * float32 HOST pointers. The patched block reproduces the reference's doubled shortcut/FFN (src/residual.py:91-96). */
+int ard_set_block_residual(ard_handle* h, int layer, int block, const float* mean, const float* basis, int K, int D);
+int ard_clear_block_residual(ard_handle* h, int layer, int block);
+/* lambda = ResiDual.learnable [K] (src/residual.py:27), float32 DEVICE pointer; re-derives the fused
+ * projection  W' = M W_proj, b' = (b_proj - mean) M  with  M = B^T diag(lambda) B. */
+int ard_set_block_lambda(ard_handle* h, int layer, int block, const float* lambda_dev, void* stream);
+
+typedef struct ard_forward_args {
+    const float* waveform;   /* device [B, 480000] fp32 (non-fusion route) */
+    const float* mel_fusion; /* device [B, 4, 1001, 64] fp32 (fusion route; only channel 0 is consumed, htsat.py:110-113) */
+    int B;
+    int quantize;            /* 1: apply quantize_tensor (src/residual.py:210-212) to the waveform on device first */
+    float* embedding;        /* device [B, 8*embed_dim]        output_dict['embedding'] (htsat.py:810-811,829) */
+    float* audio_embed;      /* device [B, joint_dim] or NULL  CLAP.get_audio_embedding (model.py:739-741) */
+    float* layers_residuals[ARD_MAX_LAYERS]; /* device [B, depth_l*T_l, C_l] or NULL  (htsat.py:596,831) */
+    float* layers_attention[ARD_MAX_LAYERS]; /* device [B*nW_l, nH_l, 64, 64] or NULL  block-mean (htsat.py:589-595,830) */
+    float* framewise_output; /* device [B, 1024, 527] or NULL (htsat.py:818,826) */
+    float* clipwise_output;  /* device [B, 527] or NULL (htsat.py:820-821,827) */
+    float* fine_grained_embedding; /* device [B, 1024, 8*embed_dim] or NULL (htsat.py:807-808,828) */
+} ard_forward_args;
+
+/* HTSAT_Swin_Transformer.forward (htsat.py:881-994) in eval mode + optional audio_projection/normalize. */
+int ard_encoder_forward(ard_handle* h, const ard_forward_args* args, void* stream);
+
+/* SwinTransformerBlock.forward (htsat.py:439-482) or the ResiDual-patched forward (src/residual.py:58-98) of block
+ * (layer, block) on x[B, T_l, C_l] fp32 device. Outputs (device, fp32): x_out [B,T,C]; attn [B*nW,nH,64,64] or NULL;
+ * residual_x [B,T,C] or NULL. x_out may alias x_in. */
+int ard_block_forward(ard_handle* h, int layer, int block, const float* x_in, int B, float* x_out, float* attn, float* residual_x,
+                      void* stream);
+
+/* Bytes of device workspace the handle currently holds (grown on demand by forward calls). */
+long long ard_workspace_bytes(const ard_handle* h);
+/* Number of kernels launched by the last ard_encoder_forward / ard_block_forward on this handle. */
+int ard_last_launch_count(const ard_handle* h);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Op-level entry points (the kernels behind the handle; also what the parity tests drive directly)
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* out[M,N] = act(A[M,K] W[N,K]^T + bias) (+ resid1 + resid2); A, W bf16 device; out bf16 or fp32.  nn.Linear semantics. */
+int ard_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int out_is_bf16, int M, int N,
+                  int K, const float* bias, int act, const float* resid1, long long ldr1, const float* resid2, long long ldr2,
+                  void* stream);
+/* nn.LayerNorm(C, eps=1e-5) over x[rows, C] fp32 -> bf16 (htsat.py:449,479 norm1/norm2). */
+int ard_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int C, void* stream);
+/* Shifted-window attention core of WindowAttention.forward (htsat.py:326-352) incl. roll/partition/reverse addressing
+ * (htsat.py:452-474): qkv bf16 [B*H*W, 3C] in token order (q pre-scaled) -> out bf16 [B*H*W, C] in token order.
+ * attn (optional fp32 [B*nW, nH, 64, 64]) receives attn_scale * softmax probabilities (+= if accumulate). */
+int ard_window_attention(const void* qkv_bf16, void* out_bf16, const float* bias_table, float* attn, float attn_scale, int accumulate,
+                         int B, int H, int W, int C, int nH, int shift, void* stream);
+/* fp32 -> bf16 conversion with scale (device). */
+int ard_f32_to_bf16(const float* in, void* out_bf16, long long n, float scale, void* stream);
+/* quantize_tensor (src/residual.py:210-212): clamp, *32767, truncate to int16, /32767; in place allowed. */
+int ard_quantize_waveform(const float* in, float* out, long long n, void* stream);
+
+/* Spectrogram + LogmelFilterBank + bn0 (htsat.py:898-902) on device: wave [B, n_samples] -> out [B, 1001, 64]
+ * (bn0 applied iff apply_bn). Uses the handle's window / mel filters / BN statistics. */
+int ard_logmel(ard_handle* h, const float* wave, int B, int n_samples, int apply_bn, int quantize, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * PCA sufficient statistics (replaces IncrementalPCA.partial_fit in compute_pca_components, src/residual.py:137-138):
+ * accumulates n += rows, sum[D] += sum_r x[r], sumsq[D,D] += x^T x in float64 on device. x fp32 [rows, D] device.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int ard_stats_accumulate(const float* x, long long rows, int D, double* sum, double* sumsq, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARD_H_ */

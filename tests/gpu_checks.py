@@ -1,0 +1,224 @@
+"""Parity checks of the CUDA path against the CPU oracle (oracle/htsat_oracle.py) and the committed golden vectors.
+
+Shared by tests/test_gpu_*.py (pytest -m gpu) and tools/gpu_debug.py (prints every metric without stopping).
+Every check returns a dict of named relative errors; `TOL` holds the stated tolerance for each.
+
+Tolerances (BASELINE.json north_star): bf16 tensor-core path rel. err <= 1e-2 on embeddings / per-layer outputs;
+fp32 CUDA-core pieces (front end, LayerNorm statistics, heads) <= 1e-4.  rel err = ||a-b||_2 / ||b||_2.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from audio_residual_b200 import lib as L  # noqa: E402
+from audio_residual_b200 import weights as W  # noqa: E402
+from oracle import htsat_oracle as O  # noqa: E402
+
+TOL_BF16 = 1e-2
+TOL_FP32 = 1e-4
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def golden_sample(t, n=4096):
+    f = t.detach().reshape(-1)
+    step = max(1, f.numel() // n)
+    while step > 1 and (step % 2 == 0 or step % 3 == 0):
+        step -= 1
+    return f[::step][:n].to(torch.float32).cpu()
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+# ---------------------------------------------------------------------------------------------------- op level
+def check_gemm(M, N, K, out_bf16, act=0, bias=True, nres=0, seed=0):
+    lib = L.load()
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(M, K, generator=g)
+    Wt = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) if bias else None
+    r1 = torch.randn(M, N, generator=g) if nres >= 1 else None
+    r2 = torch.randn(M, N, generator=g) if nres >= 2 else None
+    ref = bf16r(A) @ bf16r(Wt).t()
+    if b is not None:
+        ref = ref + b
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    elif act == 2:
+        ref = torch.relu(ref)
+    if r1 is not None:
+        ref = ref + r1
+    if r2 is not None:
+        ref = ref + r2
+    dev = "cuda"
+    Ad, Wd = A.to(dev, torch.bfloat16).contiguous(), Wt.to(dev, torch.bfloat16).contiguous()
+    ldo = N if (N % 8 == 0) else ((N + 7) // 8) * 8
+    out = torch.zeros(M, ldo, device=dev, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    bd = b.to(dev) if b is not None else None
+    r1d = r1.to(dev).contiguous() if r1 is not None else None
+    r2d = r2.to(dev).contiguous() if r2 is not None else None
+    L.check(lib.ard_gemm_bf16(L.ptr(Ad), K, L.ptr(Wd), K, L.ptr(out), ldo, int(out_bf16), M, N, K, L.ptr(bd), act,
+                              L.ptr(r1d), N, L.ptr(r2d), N, L.stream_ptr()))
+    torch.cuda.synchronize()
+    got = out[:, :N].float().cpu()
+    return rel(got, ref), (got - ref).abs().max().item()
+
+
+def check_layernorm(rows, Cdim, seed=0):
+    lib = L.load()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(rows, Cdim, generator=g) * 2 + 0.5
+    gm = 1 + 0.1 * torch.randn(Cdim, generator=g)
+    bt = 0.1 * torch.randn(Cdim, generator=g)
+    ref = torch.nn.functional.layer_norm(x, (Cdim,), gm, bt, 1e-5)
+    out = torch.empty(rows, Cdim, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.ard_layernorm_bf16(L.ptr(x.cuda()), L.ptr(gm.cuda()), L.ptr(bt.cuda()), L.ptr(out), rows, Cdim, L.stream_ptr()))
+    torch.cuda.synchronize()
+    return rel(out.float().cpu(), bf16r(ref)), rel(out.float().cpu(), ref)
+
+
+def check_window_attention(B, R, Cdim, nH, shift, seed=0):
+    """ard_window_attention vs the oracle's attention core on identical (bf16-rounded) qkv."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(seed)
+    hd = Cdim // nH
+    T = R * R
+    qkv = torch.randn(B * T, 3 * Cdim, generator=g)
+    qkv[:, :Cdim] *= hd ** -0.5           # q pre-scaled (the C path folds the scale into the qkv weights)
+    qkv = bf16r(qkv)
+    table = 0.5 * torch.randn(225, nH, generator=g)
+    # oracle: roll -> partition -> attention core -> reverse -> roll   (htsat.py:452-474, :326-352)
+    x = qkv.view(B, R, R, 3 * Cdim)
+    sh = shift if R > 8 else 0
+    if sh > 0:
+        x = torch.roll(x, shifts=(-sh, -sh), dims=(1, 2))
+        mask = O.shift_attn_mask(R, R, 8, sh)
+    else:
+        mask = None
+    xw = O.window_partition(x, 8).view(-1, 64, 3 * Cdim)
+    B_ = xw.shape[0]
+    q, k, v = xw.reshape(B_, 64, 3, nH, hd).permute(2, 0, 3, 1, 4)
+    attn = q @ k.transpose(-2, -1)
+    idx = O.relative_position_index()
+    attn = attn + table[idx.view(-1)].view(64, 64, -1).permute(2, 0, 1).unsqueeze(0)
+    if mask is not None:
+        nW = mask.shape[0]
+        attn = (attn.view(B_ // nW, nW, nH, 64, 64) + mask.unsqueeze(1).unsqueeze(0)).view(-1, nH, 64, 64)
+    attn = torch.softmax(attn, dim=-1)
+    o = (attn @ v).transpose(1, 2).reshape(B_, 64, Cdim)
+    o = O.window_reverse(o.view(-1, 8, 8, Cdim), 8, R, R)
+    if sh > 0:
+        o = torch.roll(o, shifts=(sh, sh), dims=(1, 2))
+    ref_out = o.reshape(B * T, Cdim)
+    qd = qkv.to("cuda", torch.bfloat16).contiguous()
+    out = torch.zeros(B * T, Cdim, device="cuda", dtype=torch.bfloat16)
+    cap = torch.zeros(B_, nH, 64, 64, device="cuda", dtype=torch.float32)
+    L.check(lib.ard_window_attention(L.ptr(qd), L.ptr(out), L.ptr(table.cuda().contiguous()), L.ptr(cap), 1.0, 0, B, R, R, Cdim, nH, shift,
+                                     L.stream_ptr()))
+    torch.cuda.synchronize()
+    return rel(out.float().cpu(), ref_out), rel(cap.cpu(), attn)
+
+
+def make_encoder(model="tiny", seed=0, fusion=False, residual=False):
+    from audio_residual_b200.clap import build_clap_module
+    from audio_residual_b200.residual import inject_residuals
+    sd = W.make_state_dict(model, seed=seed)
+    clap = build_clap_module(model, sd, device="cuda:0", enable_fusion=fusion)
+    ores = None
+    if residual:
+        pca, lam = W.make_pca(model, seed=seed)
+        inject_residuals(clap.model.audio_branch, pca, lam)
+        ores = {l: (torch.tensor(pca[l]["mean"], dtype=torch.float32), torch.tensor(pca[l]["components"], dtype=torch.float32),
+                    torch.from_numpy(lam[l])) for l in pca}
+    return clap, sd, ores
+
+
+def check_logmel(B=2):
+    """ard_logmel (FFT + banded mel) vs the oracle's conv-DFT + dense mel matmul, before and after bn0."""
+    clap, sd, _ = make_encoder("tiny")
+    enc = clap.model.audio_branch
+    h = enc._handle()
+    wave = W.make_clips(B, seed=1234)
+    out = torch.empty(B, 1001, 64, device="cuda")
+    out_bn = torch.empty_like(out)
+    lib = L.load()
+    wd = wave.cuda()
+    L.check(lib.ard_logmel(h, L.ptr(wd), B, 480000, 0, 0, L.ptr(out), L.stream_ptr()))
+    L.check(lib.ard_logmel(h, L.ptr(wd), B, 480000, 1, 0, L.ptr(out_bn), L.stream_ptr()))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = O.logmel(O.stft_power(wave, sd), sd)[:, 0]
+        ref_bn = O.bn0_eval(ref, sd)
+    return {"logmel": rel(out.cpu(), ref), "logmel_maxabs_dB": (out.cpu() - ref).abs().max().item(), "logmel_bn": rel(out_bn.cpu(), ref_bn)}
+
+
+def encoder_outputs(clap, wave=None, mel_fusion=None):
+    enc = clap.model.audio_branch
+    if mel_fusion is not None:
+        out = enc.encode(mel_fusion=mel_fusion.cuda(), want_dict=True, want_audio_embed=True)
+    else:
+        out = enc.encode(waveform=wave.cuda(), want_dict=True, want_audio_embed=True)
+    torch.cuda.synchronize()
+    return out
+
+
+def compare_output_dicts(got, ref, ref_emb=None):
+    m = {}
+    for k in ("embedding", "clipwise_output", "framewise_output", "fine_grained_embedding"):
+        m[k] = rel(got[k], ref[k])
+    for l in range(4):
+        m[f"res{l}"] = rel(got["layers_residuals"][l], ref["layers_residuals"][l])
+        m[f"attn{l}"] = rel(got["layers_attention"][l], ref["layers_attention"][l])
+    if ref_emb is not None:
+        m["audio_embed"] = rel(got["audio_embed"], ref_emb)
+    return m
+
+
+def check_encoder_vs_oracle(model="tiny", B=2, residual=False, seed=0):
+    clap, sd, ores = make_encoder(model, seed=seed, residual=residual)
+    wave = W.make_clips(B, seed=1234)
+    got = encoder_outputs(clap, wave)
+    with torch.no_grad():
+        ref = O.htsat_forward({"waveform": wave}, sd, O.CONFIGS[model], ores)
+        ref_emb = O.audio_projection(ref["embedding"], sd)
+    return compare_output_dicts(got, ref, ref_emb)
+
+
+def check_encoder_vs_golden(fname="htsat_tiny_b2.npz"):
+    g = np.load(os.path.join(GOLDEN, fname))
+    model, seed, B, fusion = str(g["meta_model"]), int(g["meta_seed"]), int(g["meta_B"]), bool(int(g["meta_fusion"]))
+    m = {}
+    for tag, residual in (("plain", False), ("residual", True)):
+        clap, sd, ores = make_encoder(model, seed=seed, fusion=fusion, residual=residual)
+        wave = W.make_clips(B, seed=1234)
+        if fusion:
+            # the golden mel_fusion came from the reference's torchaudio featuriser; regenerate it with the oracle port
+            fb = torch.from_numpy(W.mel_filterbank(htk=True, slaney_norm=False)).float()
+            win = torch.from_numpy(W.hann_periodic(1024)).float()
+            mel = torch.stack([O.fusion_mel(w, fb, win) for w in wave])
+            m[f"{tag}_mel_fusion_input"] = rel(golden_sample(torch.stack([mel] * 4, dim=1)), torch.from_numpy(g["mel_fusion_sample"]))
+            got = encoder_outputs(clap, mel_fusion=torch.stack([mel] * 4, dim=1))
+        else:
+            got = encoder_outputs(clap, wave)
+        m[f"{tag}_embedding"] = rel(got["embedding"], torch.from_numpy(g[f"{tag}_embedding"]))
+        m[f"{tag}_audio_embed"] = rel(got["audio_embed"], torch.from_numpy(g[f"{tag}_audio_embed"]))
+        m[f"{tag}_clipwise"] = rel(got["clipwise_output"], torch.from_numpy(g[f"{tag}_clipwise_output"]))
+        m[f"{tag}_framewise"] = rel(golden_sample(got["framewise_output"]), torch.from_numpy(g[f"{tag}_framewise_sample"]))
+        m[f"{tag}_fine"] = rel(golden_sample(got["fine_grained_embedding"]), torch.from_numpy(g[f"{tag}_fine_sample"]))
+        for l in range(4):
+            m[f"{tag}_res{l}"] = rel(golden_sample(got["layers_residuals"][l]), torch.from_numpy(g[f"{tag}_res{l}_sample"]))
+            m[f"{tag}_attn{l}"] = rel(golden_sample(got["layers_attention"][l]), torch.from_numpy(g[f"{tag}_attn{l}_sample"]))
+    return m

@@ -1,0 +1,27 @@
+"""-m gpu: whole-encoder parity (waveform -> output_dict / audio embedding) vs the oracle and the golden fixtures."""
+import pytest
+
+import gpu_checks as G
+
+pytestmark = pytest.mark.gpu
+
+# Per-key tolerances. bf16 tensor-core path: rel err <= 1e-2 (north_star). Attention maps of deeper layers inherit
+# the accumulated bf16 error of the residual stream through a softmax, hence the same 1e-2 bound.
+def _assert_all(m, tol=G.TOL_BF16):
+    bad = {k: v for k, v in m.items() if not (v < tol)}
+    assert not bad, (bad, m)
+
+
+@pytest.mark.parametrize("residual", [False, True])
+def test_tiny_vs_oracle(residual):
+    _assert_all(G.check_encoder_vs_oracle("tiny", 2, residual))
+
+
+def test_tiny_vs_golden():
+    _assert_all(G.check_encoder_vs_golden("htsat_tiny_b2.npz"))
+
+
+def test_base_fusion_vs_golden():
+    m = G.check_encoder_vs_golden("htsat_base_fusion_b2.npz")
+    assert m.pop("plain_mel_fusion_input") < 1e-4 and m.pop("residual_mel_fusion_input") < 1e-4
+    _assert_all(m)

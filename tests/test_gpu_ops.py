@@ -1,0 +1,40 @@
+"""-m gpu: op-level parity of the CUDA kernels (through the C ABI) against torch fp32 / the oracle."""
+import pytest
+
+import gpu_checks as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 96, 96), (1000, 288, 96), (4096, 384, 96), (512, 96, 384), (300, 768, 768),
+                                   (2048, 2304, 768), (640, 527, 4608), (4096, 256, 1024)])
+@pytest.mark.parametrize("out_bf16", [False, True])
+def test_gemm(M, N, K, out_bf16):
+    # operands are bf16-rounded on both sides; fp32 accumulation => only summation-order noise (+ bf16 output rounding)
+    r, _ = G.check_gemm(M, N, K, out_bf16)
+    assert r < (4e-3 if out_bf16 else 2e-5), r
+
+
+def test_gemm_epilogues():
+    assert G.check_gemm(4096, 384, 96, True, act=1)[0] < 4e-3      # exact-erf GELU
+    assert G.check_gemm(512, 512, 768, False, act=2)[0] < 2e-5     # ReLU
+    assert G.check_gemm(4096, 96, 384, False, nres=2)[0] < 2e-5    # two residual adds (patched block, src/residual.py:95)
+    assert G.check_gemm(1024, 192, 384, False, bias=False, nres=1)[0] < 2e-5
+
+
+@pytest.mark.parametrize("C", [96, 128, 192, 256, 384, 512, 768, 1024, 1536, 2048])
+def test_layernorm(C):
+    r_bf16, r_f32 = G.check_layernorm(777, C)
+    assert r_bf16 < 1e-3 and r_f32 < 4e-3, (r_bf16, r_f32)
+
+
+@pytest.mark.parametrize("B,R,C,nH,shift", [(2, 64, 96, 4, 0), (2, 64, 96, 4, 4), (2, 32, 192, 8, 4), (3, 16, 384, 16, 4),
+                                            (2, 8, 768, 32, 4), (2, 64, 128, 4, 4), (2, 16, 512, 16, 0), (1, 32, 256, 8, 4)])
+def test_window_attention(B, R, C, nH, shift):
+    r_out, r_attn = G.check_window_attention(B, R, C, nH, shift)
+    assert r_out < G.TOL_BF16 and r_attn < 1e-3, (r_out, r_attn)    # probabilities are fp32 softmax of bf16-exact logits
+
+
+def test_logmel():
+    m = G.check_logmel()
+    assert m["logmel"] < G.TOL_FP32 and m["logmel_bn"] < 2e-4 and m["logmel_maxabs_dB"] < 5e-3, m

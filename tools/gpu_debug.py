@@ -1,0 +1,58 @@
+"""Run every GPU parity check and print all metrics (does not stop at the first failure). Usage on the GPU box:
+    python tools/gpu_debug.py [ops|encoder|all]
+"""
+import os
+import sys
+import time
+import traceback
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+import gpu_checks as G  # noqa: E402
+
+
+def run(name, fn, *a, **k):
+    t0 = time.time()
+    try:
+        r = fn(*a, **k)
+        torch.cuda.synchronize()
+        print(f"[ok ] {name}: {r}  ({time.time() - t0:.2f}s)", flush=True)
+    except Exception as e:
+        print(f"[ERR] {name}: {type(e).__name__}: {e}", flush=True)
+        traceback.print_exc()
+        try:
+            torch.cuda.synchronize()
+        except Exception as e2:
+            print("CUDA context is broken:", e2, flush=True)
+            sys.exit(3)
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    print(torch.cuda.get_device_name(0), torch.version.cuda, flush=True)
+    if what in ("ops", "all"):
+        for (M, N, K) in [(128, 96, 64), (128, 96, 96), (256, 128, 128), (1000, 288, 96), (4096, 384, 96), (512, 96, 384),
+                          (300, 768, 768), (2048, 2304, 768), (640, 527, 4608), (8192, 192, 384), (4096, 256, 1024)]:
+            run(f"gemm f32 M{M} N{N} K{K}", G.check_gemm, M, N, K, False)
+            run(f"gemm bf16 M{M} N{N} K{K}", G.check_gemm, M, N, K, True)
+        run("gemm gelu bf16", G.check_gemm, 4096, 384, 96, True, act=1)
+        run("gemm relu f32", G.check_gemm, 512, 512, 768, False, act=2)
+        run("gemm 2 resid f32", G.check_gemm, 4096, 96, 384, False, nres=2)
+        run("gemm 1 resid nobias f32", G.check_gemm, 1024, 192, 384, False, bias=False, nres=1)
+        for Cd in (96, 128, 192, 384, 768, 1536):
+            run(f"layernorm C{Cd}", G.check_layernorm, 1000, Cd)
+        for (B, R, Cd, nH, sh) in [(2, 64, 96, 4, 0), (2, 64, 96, 4, 4), (2, 32, 192, 8, 4), (3, 16, 384, 16, 4), (2, 8, 768, 32, 4),
+                                   (2, 64, 128, 4, 4), (2, 16, 512, 16, 0)]:
+            run(f"window_attention B{B} R{R} C{Cd} nH{nH} shift{sh}", G.check_window_attention, B, R, Cd, nH, sh)
+        run("logmel", G.check_logmel)
+    if what in ("encoder", "all"):
+        run("encoder tiny plain vs oracle", G.check_encoder_vs_oracle, "tiny", 2, False)
+        run("encoder tiny residual vs oracle", G.check_encoder_vs_oracle, "tiny", 2, True)
+        run("encoder tiny vs golden", G.check_encoder_vs_golden, "htsat_tiny_b2.npz")
+        run("encoder base fusion vs golden", G.check_encoder_vs_golden, "htsat_base_fusion_b2.npz")
+
+
+if __name__ == "__main__":
+    main()
