@@ -1,0 +1,122 @@
+"""Mirror of the reference's src/analyze_attention.py on top of libard_b200.so.
+
+extract_attention :133-157, run_PCA :13-59, save_pca_results_on_file :62-99, load_pca_csv_results :102-130.
+
+run_PCA in the reference moves every 64x64 attention map to the host, flattens them in a triple Python loop and feeds
+60 sklearn IncrementalPCA objects (~190 s per 32 clips). Here the maps stay on the GPU and each (layer, head) keeps the
+sufficient statistics {n, sum x, sum x x^T} of its 4096-d samples (ard_stats_accumulate, float64 accumulators); the
+spectrum is one eigendecomposition at the end. The reference's IncrementalPCA is *truncated* there (n_components =
+samples of the first batch < 4096), which makes its output batch-order dependent; the exact-covariance spectrum is what
+it approximates, truncated to the same number of components for schema compatibility.
+"""
+import csv
+import os
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from .clap import batch_features
+from .residual import MomentAccumulator, quantize_tensor, pad_or_truncate  # noqa: F401  (re-exported like the reference)
+
+
+class HeadPCA:
+    """Stands in for a fitted sklearn IncrementalPCA: exposes the attributes the reference reads."""
+
+    def __init__(self, D, device):
+        self.acc = MomentAccumulator(D, device)
+        self.first_batch = None
+
+    def partial_fit(self, X):
+        if self.first_batch is None:
+            self.first_batch = X.shape[0]
+        self.acc.update(X)
+        return self
+
+    def finalize(self, n_components=None):
+        self.acc.allreduce()
+        n = self.acc.n
+        s1 = self.acc.s1.cpu().numpy()
+        s2 = self.acc.s2
+        mean = self.acc.s1 / n
+        cov = (s2 - n * torch.outer(mean, mean)) / (n - 1)
+        cov = 0.5 * (cov + cov.t())
+        w = torch.linalg.eigvalsh(cov).flip(0).clamp_min(0).cpu().numpy()    # float64 on the GPU
+        k = n_components or min(self.first_batch or len(w), len(w))
+        self.mean_ = s1 / n
+        self.explained_variance_ = w[:k]
+        self.explained_variance_ratio_ = w[:k] / w.sum()
+        self.n_components_ = k
+        self.n_samples_seen_ = n
+        return self
+
+
+def extract_attention(clap, X, max_len=480000, data_filling="repeatpad", pad_or_truncate=False):
+    """src/analyze_attention.py:133-157: block-mean attention weights per layer, list of 4 x [B*nW_l, nH_l, 64, 64]."""
+    wave = batch_features(X.squeeze(1), max_len, data_filling, device=clap.device, do_pad_or_truncate=pad_or_truncate)
+    enc = clap.model.audio_branch
+    with torch.no_grad():
+        if enc.enable_fusion:
+            out = enc.encode(mel_fusion=clap.fusion_mel(wave, quantize=True), want_dict=True)
+        else:
+            out = enc.encode(waveform=wave, quantize=True, want_dict=True)
+    return out["layers_attention"]
+
+
+def run_PCA(clap, dataloader, num_layers, num_heads, components=None, data_filling="repeatpad", pad_or_truncate=False):
+    """src/analyze_attention.py:13-59. Returns {layer: {head: fitted HeadPCA}}."""
+    pca_models = defaultdict(dict)
+    dev = clap.device
+    for l in range(num_layers):
+        for h in range(num_heads[l]):
+            pca_models[l][h] = HeadPCA(4096, dev)
+    for batch in dataloader:
+        attn = extract_attention(clap, batch[0], data_filling=data_filling, pad_or_truncate=pad_or_truncate)
+        for l, layer_attn in enumerate(attn):                      # [B*nW, nH, 64, 64]
+            for h in range(layer_attn.shape[1]):
+                pca_models[l][h].partial_fit(layer_attn[:, h].reshape(layer_attn.shape[0], 4096))
+    for l in pca_models:
+        for h in pca_models[l]:
+            pca_models[l][h].finalize(components)
+    return pca_models
+
+
+def save_pca_results_on_file(save_dir, dataset_name, fold, pca_models):
+    """src/analyze_attention.py:62-99 (same CSV schema)."""
+    os.makedirs(save_dir, exist_ok=True)
+    csv_path = os.path.join(save_dir, f"{dataset_name}-fold{fold}.csv")
+    with open(csv_path, mode="w", newline="") as file:
+        writer = csv.writer(file)
+        writer.writerow(["layer", "head", "component_index", "explained_variance", "explained_variance_ratio",
+                         "participation_ratio", "intrinsic_dim"])
+        for layer_idx, layer in pca_models.items():
+            for head_idx, pca in layer.items():
+                if not hasattr(pca, "explained_variance_"):
+                    continue
+                exp_var = pca.explained_variance_
+                ratios = pca.explained_variance_ratio_
+                cumsum = ratios.cumsum()
+                intrinsic_dim = (cumsum < 0.99).sum() + 1
+                pr = (exp_var.sum() ** 2) / np.sum(exp_var ** 2)
+                for i, (ev, ratio) in enumerate(zip(exp_var, ratios)):
+                    writer.writerow([layer_idx, head_idx, i, ev, ratio, pr if i == 0 else "", intrinsic_dim if i == 0 else ""])
+    return csv_path
+
+
+def load_pca_csv_results(path):
+    """src/analyze_attention.py:102-130."""
+    results = defaultdict(lambda: {"explained_variance": [], "explained_variance_ratio": [], "participation_ratio": None,
+                                   "intrinsic_dim": None})
+    with open(path, "r", newline="") as file:
+        reader = csv.DictReader(file)
+        for row in reader:
+            key = (int(row["layer"]), int(row["head"]))
+            results[key]["explained_variance"].append(float(row["explained_variance"]))
+            results[key]["explained_variance_ratio"].append(float(row["explained_variance_ratio"]))
+            pr = row.get("participation_ratio", "")
+            if pr and results[key]["participation_ratio"] is None:
+                results[key]["participation_ratio"] = float(pr)
+            dim = row.get("intrinsic_dim", "")
+            if dim and results[key]["intrinsic_dim"] is None:
+                results[key]["intrinsic_dim"] = float(dim)
+    return results

@@ -33,6 +33,22 @@ int check_cuda(cudaError_t e, const char* what) {
 }
 void count_launch(int n) { g_launches += n; }
 
+// ------------------------------------------------------------------------------------------------ profiling
+struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+ProfScope::ProfScope(int cls, cudaStream_t s, double flops, double bytes) : idx(-1), stream(s) {
+    if (!g_prof_on) return;
+    ProfRec r; r.cls = cls; r.flops = flops; r.bytes = bytes;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+    idx = (int)g_prof.size();
+    g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+    if (idx >= 0) cudaEventRecord(g_prof[idx].b, stream);
+}
+
 // ------------------------------------------------------------------------------------------------ device buffers
 struct DevBuf {
     void* p = nullptr;
@@ -559,6 +575,25 @@ int ard_logmel(ard_handle* h, const float* wave, int B, int n_samples, int apply
 
 int ard_stats_accumulate(const float* x, long long rows, int D, double* sum, double* sumsq, void* stream) {
     return stats_accumulate(x, rows, D, sum, sumsq, (cudaStream_t)stream);
+}
+
+int ard_profile_enable(int on) {
+    g_prof_on = on != 0;
+    return 0;
+}
+
+int ard_profile_read(double* ms, double* flops, double* bytes, int* launches, int nclass) {
+    if (nclass < PROF_NCLASS) return set_error(ARD_ERR_SHAPE, "ard_profile_read: need %d classes", (int)PROF_NCLASS);
+    for (int i = 0; i < nclass; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
+    ARD_CUDA(cudaDeviceSynchronize());
+    for (ProfRec& r : g_prof) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        ms[r.cls] += t; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes; launches[r.cls] += 1;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    return 0;
 }
 
 }  // extern "C"

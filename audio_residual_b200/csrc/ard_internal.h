@@ -101,4 +101,14 @@ int stats_accumulate(const float* x, long long rows, int D, double* sum, double*
 // launch accounting (ard_last_launch_count)
 void count_launch(int n = 1);
 
+// Per-kernel-class device timing (ard_profile_*): when enabled, every host launcher brackets its kernel with CUDA events on
+// the launching stream and records the algorithmic flops / bytes of that launch. Off by default (zero overhead).
+enum ProfClass { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_FRONTEND = 3, PROF_HEAD = 4, PROF_OTHER = 5, PROF_NCLASS = 6 };
+struct ProfScope {
+    ProfScope(int cls, cudaStream_t s, double flops, double bytes);
+    ~ProfScope();
+    int idx;
+    cudaStream_t stream;
+};
+
 }  // namespace ard

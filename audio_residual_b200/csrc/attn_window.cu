@@ -256,6 +256,8 @@ int window_attention(const AttnArgs& a, cudaStream_t s) {
         ARD_CUDA(cudaFuncSetAttribute(window_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
         attr_set = true;
     }
+    const double tokens = (double)a.B * a.H * a.W;
+    ProfScope ps(PROF_ATTN, s, 4.0 * tokens * 64 * a.C, tokens * a.C * 2.0 * 4.0 + (a.attn_mean ? tokens * a.nH * 64 * 4.0 * (a.attn_accumulate ? 2 : 1) : 0.0));
     if (hd == 24)
         window_attention_kernel<24><<<(unsigned)blocks, 128, AT_SMEM_BYTES, s>>>(a.qkv, a.out, a.bias_table, a.attn_mean, a.attn_scale, a.attn_accumulate,
                                                                     a.H, a.W, a.C, a.nH, shift);

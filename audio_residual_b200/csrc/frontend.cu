@@ -129,6 +129,7 @@ int stft_logmel(const float* wave, int B, int n_samples, const float* window, co
     const int frames = n_samples / HOPS + 1;
     const int npairs = (frames + 1) / 2;
     dim3 grid((npairs + PAIRS_PER_CTA - 1) / PAIRS_PER_CTA, B);
+    ProfScope ps(PROF_FRONTEND, s, (double)B * npairs * (5.0 * 1024 * 10 + 2.0 * 2 * 1100), 4.0 * B * n_samples + 4.0 * B * frames * 64);
     stft_logmel_kernel<<<grid, 256, 0, s>>>(wave, n_samples, frames, window, twiddle, mel.w, mel.start, mel.len, mel.band_max, bn_scale,
                                            bn_shift, out, quantize);
     return check_cuda(cudaGetLastError(), "stft_logmel launch");
@@ -218,6 +219,7 @@ int patch_embed_ln(const float* logmel, long long clip_stride, int frames, const
     if (frames > 1024) return set_error(ARD_ERR_SHAPE, "the wav size should less than or equal to the swin input size");  // htsat.py:852
     const long long ntok = (long long)B * 4096;
     const unsigned grid = (unsigned)((ntok + 7) / 8);
+    ProfScope ps(PROF_FRONTEND, s, (double)ntok * (2.0 * 16 * C + 16 * 8 + 8.0 * C), 4.0 * B * frames * 64 + 4.0 * ntok * C);
     if (C == 96)
         patch_embed_ln_kernel<3><<<grid, 256, 0, s>>>(logmel, clip_stride, frames, bn_scale, bn_shift, w, bias, gamma, beta, out, ntok);
     else if (C == 128)

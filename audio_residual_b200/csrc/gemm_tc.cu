@@ -311,8 +311,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     const int grid = tiles < num_sms ? tiles : num_sms;
     kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, kp);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return set_error(ARD_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
-    return 0;
+    return check_cuda(e, "gemm launch");
 }
 
 static int pick_bn(int N) {
@@ -343,6 +342,10 @@ int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     kp.bias = a.bias; kp.act = a.act;
     kp.resid1 = a.resid1; kp.ldr1 = a.ldr1; kp.resid2 = a.resid2; kp.ldr2 = a.ldr2;
     kp.aux = a.aux; kp.ld_aux = a.ld_aux; kp.aux_T = a.aux_T > 0 ? a.aux_T : a.M; kp.aux_bstride = a.aux_bstride;
+    const double osz = a.out_bf16 ? 2.0 : 4.0;
+    ProfScope ps(PROF_GEMM, stream, 2.0 * a.M * a.N * a.K,
+                 2.0 * a.M * a.K + 2.0 * a.N * a.K + osz * a.M * a.N + (a.resid1 ? 4.0 * a.M * a.N : 0.0) + (a.resid2 ? 4.0 * a.M * a.N : 0.0) +
+                     (a.aux ? 4.0 * a.M * a.N : 0.0));
 #define ARD_GEMM_CASE(bn)                                                                                          \
     case bn:                                                                                                       \
         return a.out_bf16 ? launch_gemm<bn, true>(ta, tb, tc, kp, num_sms, stream) : launch_gemm<bn, false>(ta, tb, tc, kp, num_sms, stream);

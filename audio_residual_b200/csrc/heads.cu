@@ -56,6 +56,7 @@ int linear_small(const float* x, int ldx, const float* W, const float* bias, flo
     if (smem > 48 * 1024) return set_error(ARD_ERR_SHAPE, "linear_small: K=%d too large", K);
     const int n_per_cta = 64;
     dim3 grid((N + n_per_cta - 1) / n_per_cta, (B + LS_CL - 1) / LS_CL);
+    ProfScope ps(PROF_HEAD, s, 2.0 * B * N * K, 4.0 * ((double)N * K + (double)B * K + (double)B * N));
     linear_small_kernel<<<grid, 256, smem, s>>>(x, ldx, W, bias, y, ldy, B, N, K, act, n_per_cta);
     return check_cuda(cudaGetLastError(), "linear_small launch");
 }
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__
 static int sgemm_tn(const float* a, int lda, const float* b, int ldb, const float* scale, void* out, int ldo, bool out_bf16, int Ma, int Nb,
                     int K, cudaStream_t s) {
     dim3 grid((Nb + 63) / 64, (Ma + 63) / 64);
+    ProfScope ps(PROF_OTHER, s, 2.0 * Ma * Nb * K, 4.0 * ((double)Ma * K + (double)Nb * K + (double)Ma * Nb));
     if (out_bf16)
         sgemm_tn_kernel<true><<<grid, 256, 0, s>>>(a, lda, b, ldb, scale, out, ldo, Ma, Nb, K);
     else

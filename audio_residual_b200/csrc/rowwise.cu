@@ -102,6 +102,7 @@ template <class Rows>
 static int launch_ln(Rows rows, const float* gamma, const float* beta, __nv_bfloat16* out, long long nrows, int C, cudaStream_t s) {
     const int wpb = 8;
     const unsigned grid = (unsigned)((nrows + wpb - 1) / wpb);
+    ProfScope ps(PROF_LN, s, 8.0 * nrows * C, 6.0 * nrows * C);
 #define ARD_LN_CASE(c, vec, nv) \
     case c: layernorm_rows_kernel<vec, nv, Rows><<<grid, wpb * 32, 0, s>>>(rows, gamma, beta, out, nrows); break;
     switch (C) {
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(256) final_norm_mean_kernel(const float* __res
 
 int final_norm_mean(const float* x, const float* gamma, const float* beta, float* emb, float* normed, int B, int T, int C, cudaStream_t s) {
     if (B <= 0) return 0;
+    ProfScope ps(PROF_HEAD, s, 8.0 * B * T * C, 4.0 * B * T * C * (normed ? 2 : 1));
     switch (C) {
         case 768: final_norm_mean_kernel<4, 6><<<B, 256, 0, s>>>(x, gamma, beta, emb, normed, T); break;
         case 1024: final_norm_mean_kernel<4, 8><<<B, 256, 0, s>>>(x, gamma, beta, emb, normed, T); break;

@@ -69,6 +69,8 @@ def load(check_symbols=False):
         lib.ard_quantize_waveform.argtypes = [vp, vp, ll, vp]
         lib.ard_logmel.argtypes = [vp, vp, i, i, i, i, vp, vp]
         lib.ard_stats_accumulate.argtypes = [vp, ll, i, vp, vp, vp]
+        lib.ard_profile_enable.argtypes = [i]
+        lib.ard_profile_read.argtypes = [c_double_p, c_double_p, c_double_p, C.POINTER(C.c_int), i]
         _lib = lib
     if check_symbols:
         missing = [s for s in declared_symbols() if not hasattr(_lib, s)]
@@ -101,3 +103,18 @@ def ptr(t):
         return None
     assert t.is_contiguous(), "tensor handed to the C ABI must be contiguous"
     return C.c_void_p(t.data_ptr())
+
+
+PROF_CLASSES = ("gemm_tc", "window_attention", "layernorm", "frontend", "heads", "other")
+
+
+def profile_enable(on=True):
+    check(load().ard_profile_enable(int(on)))
+
+
+def profile_read():
+    """{class: {"ms", "flops", "bytes", "launches"}} accumulated since the last read (synchronises the device)."""
+    n = len(PROF_CLASSES)
+    ms, fl, by, ln = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)(), (C.c_int * n)()
+    check(load().ard_profile_read(ms, fl, by, ln, n))
+    return {PROF_CLASSES[i]: {"ms": ms[i], "flops": fl[i], "bytes": by[i], "launches": ln[i]} for i in range(n)}

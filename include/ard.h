@@ -136,6 +136,15 @@ int ard_logmel(ard_handle* h, const float* wave, int B, int n_samples, int apply
  * ------------------------------------------------------------------------------------------------------------------ */
 int ard_stats_accumulate(const float* x, long long rows, int D, double* sum, double* sumsq, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Measurement support (bench.py): per-kernel-class device time. Classes: 0 tcgen05 GEMM, 1 window attention,
+ * 2 LayerNorm/merge, 3 front end (STFT/log-mel/patch-embed), 4 heads, 5 other. While enabled every launch is bracketed
+ * by CUDA events on its stream; ard_profile_read synchronises, sums elapsed ms / algorithmic flops / algorithmic bytes /
+ * launch counts per class since the last read, and clears the records.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int ard_profile_enable(int on);
+int ard_profile_read(double* ms, double* flops, double* bytes, int* launches, int nclass);
+
 #ifdef __cplusplus
 }
 #endif

@@ -228,8 +228,24 @@ def run_pca_case(fname="pca_moments.npz"):
     print(f"wrote {path}")
 
 
+def run_keys_case(fname="reference_state_dict.json"):
+    """Key names + shapes of the reference's audio_branch / audio_projection state_dict (drop-in contract for the
+    product's module tree and for ard_set_weight)."""
+    import json
+    out = {}
+    for name, fusion in (("tiny", False), ("base", True)):
+        clap, _ = refimport.build_clap(name, enable_fusion=fusion, fusion_type="aff_2d" if fusion else "None")
+        d = {k: list(v.shape) for k, v in clap.audio_branch.state_dict().items()}
+        d.update({"audio_projection." + k: list(v.shape) for k, v in clap.audio_projection.state_dict().items()})
+        out[f"{name}{'_fusion' if fusion else ''}"] = d
+    path = os.path.join(GOLDEN, fname)
+    json.dump(out, open(path, "w"), indent=0, sort_keys=True)
+    print(f"wrote {path}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
+    run_keys_case()
     run_pca_case()
     run_case("tiny", False, 2, 0, "htsat_tiny_b2.npz")
     run_case("base", True, 2, 1, "htsat_base_fusion_b2.npz")

@@ -85,7 +85,8 @@ def check_layernorm(rows, Cdim, seed=0):
     bt = 0.1 * torch.randn(Cdim, generator=g)
     ref = torch.nn.functional.layer_norm(x, (Cdim,), gm, bt, 1e-5)
     out = torch.empty(rows, Cdim, device="cuda", dtype=torch.bfloat16)
-    L.check(lib.ard_layernorm_bf16(L.ptr(x.cuda()), L.ptr(gm.cuda()), L.ptr(bt.cuda()), L.ptr(out), rows, Cdim, L.stream_ptr()))
+    xd, gd, bd = x.cuda(), gm.cuda(), bt.cuda()   # keep the device copies alive across the async launch
+    L.check(lib.ard_layernorm_bf16(L.ptr(xd), L.ptr(gd), L.ptr(bd), L.ptr(out), rows, Cdim, L.stream_ptr()))
     torch.cuda.synchronize()
     return rel(out.float().cpu(), bf16r(ref)), rel(out.float().cpu(), ref)
 
@@ -126,8 +127,8 @@ def check_window_attention(B, R, Cdim, nH, shift, seed=0):
     qd = qkv.to("cuda", torch.bfloat16).contiguous()
     out = torch.zeros(B * T, Cdim, device="cuda", dtype=torch.bfloat16)
     cap = torch.zeros(B_, nH, 64, 64, device="cuda", dtype=torch.float32)
-    L.check(lib.ard_window_attention(L.ptr(qd), L.ptr(out), L.ptr(table.cuda().contiguous()), L.ptr(cap), 1.0, 0, B, R, R, Cdim, nH, shift,
-                                     L.stream_ptr()))
+    td = table.cuda().contiguous()
+    L.check(lib.ard_window_attention(L.ptr(qd), L.ptr(out), L.ptr(td), L.ptr(cap), 1.0, 0, B, R, R, Cdim, nH, shift, L.stream_ptr()))
     torch.cuda.synchronize()
     return rel(out.float().cpu(), ref_out), rel(cap.cpu(), attn)
 

@@ -1,0 +1,71 @@
+"""`not gpu`: world_size-2 gloo tests of the multi-GPU host logic: clips are batch-sharded with no
+data-path collective; the only collectives are the sum-allreduce of the PCA sufficient statistics and of the flat
+lambda/classifier gradient buffer."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from audio_residual_b200.parallel import allreduce_moments, flat_grad_allreduce, shard_range
+from audio_residual_b200.residual import pca_from_moments
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((1000, 24)) @ rng.standard_normal((24, 24)) + 3.0
+    lo, hi = shard_range(1000, rank, world)
+    Xs = torch.from_numpy(X[lo:hi])
+    n, s1, s2 = allreduce_moments(hi - lo, Xs.sum(0), Xs.T @ Xs)
+    pca = pca_from_moments(n, s1.numpy(), s2.numpy())
+    # gradient buffer: per-rank mean-loss grads over the local shard, combined as the global-batch mean
+    g_l = torch.full((5,), float(rank + 1))
+    g_w = torch.full((3, 2), float(10 * (rank + 1)))
+    flat_grad_allreduce([g_l, g_w], world)
+    if rank == 0:
+        out.put((n, pca["explained_variance"], pca["components"], g_l.clone(), g_w.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_statistics_and_grad_allreduce_match_single_process():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    n, ev, comps, g_l, g_w = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((1000, 24)) @ rng.standard_normal((24, 24)) + 3.0
+    ref = pca_from_moments(1000, X.sum(0), X.T @ X)
+    assert n == 1000
+    assert np.allclose(ev, ref["explained_variance"], rtol=1e-10) and np.allclose(comps, ref["components"], atol=1e-8)
+    assert torch.allclose(g_l, torch.full((5,), 1.5)) and torch.allclose(g_w, torch.full((3, 2), 15.0))
+
+
+def test_shard_range_covers_everything():
+    for n in (0, 1, 7, 250, 2000):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,206 @@
+"""`not gpu`: host-side logic of the drop-in (module tree / state_dict parity, ResiDual injection semantics, featuriser,
+PCA artefact schema, CSV schema) and the C-ABI library's exported surface. No compute calls: there is no GPU here."""
+import copy
+import ctypes
+import json
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from audio_residual_b200 import lib as L
+from audio_residual_b200 import weights as W
+from audio_residual_b200.analyze_attention import load_pca_csv_results, save_pca_results_on_file
+from audio_residual_b200.clap import CLAP_Module, batch_features, float32_to_int16, get_audio_features, int16_to_float32
+from audio_residual_b200.residual import (ResiDual, load_residual, patch_block_with_residual, pca_from_moments, quantize_tensor,
+                                          setup_residual_htsat)
+from oracle import htsat_oracle as O
+
+from gpu_checks import GOLDEN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------------------------------------------- C ABI surface
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    if not os.path.exists(L.LIB_PATH):
+        ge.build()
+    lib = L.load(check_symbols=True)
+    names = L.declared_symbols()
+    assert len(names) >= 20 and "ard_encoder_forward" in names and "ard_gemm_bf16" in names
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.ard_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device ard_create must fail loudly (ARD_ERR_CUDA -> RuntimeError), never fall back."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = L.load()
+    cfg = L.ArdConfig(96, (ctypes.c_int * 4)(2, 2, 6, 2), (ctypes.c_int * 4)(4, 8, 16, 32), 512, 0)
+    h = ctypes.c_void_p()
+    rc = lib.ard_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc == L.ARD_ERR_CUDA
+    with pytest.raises(RuntimeError):
+        L.check(rc)
+    assert b"no CPU fallback" in lib.ard_last_error()
+    m = CLAP_Module(device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.get_audio_embedding_from_data(torch.zeros(1, 480000), use_tensor=True)
+
+
+def test_create_rejects_unknown_model():
+    lib = L.load()
+    cfg = L.ArdConfig(100, (ctypes.c_int * 4)(2, 2, 6, 2), (ctypes.c_int * 4)(4, 8, 16, 32), 512, 0)
+    h = ctypes.c_void_p()
+    assert lib.ard_create(ctypes.byref(cfg), ctypes.byref(h)) == L.ARD_ERR_SHAPE    # htsat.py:1044-1045 RuntimeError in the shim
+    assert lib.ard_set_weight(None, b"x", None, 0) == L.ARD_ERR_SHAPE
+
+
+# ---------------------------------------------------------------------------------------------------- module tree
+@pytest.mark.parametrize("name,fusion", [("tiny", False), ("base", True)])
+def test_state_dict_matches_reference_keys(name, fusion):
+    ref = json.load(open(os.path.join(GOLDEN, "reference_state_dict.json")))[f"{name}{'_fusion' if fusion else ''}"]
+    m = CLAP_Module(enable_fusion=fusion, device="cpu", amodel=f"HTSAT-{name}")
+    own = {k: list(v.shape) for k, v in m.model.audio_branch.state_dict().items()}
+    own.update({"audio_projection." + k: list(v.shape) for k, v in m.model.audio_projection.state_dict().items()})
+    # the aff_2d fusion branch (mel_conv2d + AFF) is unreachable in the reference and not instantiated
+    ref = {k: v for k, v in ref.items() if "mel_conv2d" not in k and "fusion_model" not in k}
+    assert set(own) == set(ref), (set(own) ^ set(ref))
+    assert all(own[k] == ref[k] for k in ref)
+    sd = W.make_state_dict(name, seed=0)
+    for k, v in sd.items():
+        assert list(v.shape) == ref[k], k
+
+
+def test_blocks_addressable_and_deepcopy_relinks():
+    m = CLAP_Module(device="cpu")
+    enc = m.model.audio_branch
+    assert len(enc.layers) == 4 and [len(l.blocks) for l in enc.layers] == [2, 2, 6, 2]
+    assert enc.layers[0].blocks[1].shift_size == 4 and enc.layers[3].blocks[1].shift_size == 0     # htsat.py:393-396
+    assert enc.layers[0].blocks[1].attn_mask.shape == (64, 64, 64) and enc.layers[3].blocks[1].attn_mask is None
+    c = copy.deepcopy(enc)
+    assert c.layers[2].blocks[3]._encoder() is c and enc.layers[2].blocks[3]._encoder() is enc
+    assert c._hb is not enc._hb
+
+
+# ---------------------------------------------------------------------------------------------------- ResiDual API
+def _pca_files(tmp_path, layers=(0, 1, 2, 3)):
+    pca, _ = W.make_pca("tiny", seed=0, layers=layers)
+    files = {}
+    for l, d in pca.items():
+        files[l] = str(tmp_path / f"layer_{l}")
+        with open(files[l], "wb") as f:
+            pickle.dump({"components": d["components"], "mean": d["mean"]}, f)
+    return files, pca
+
+
+def test_setup_residual_htsat_semantics(tmp_path):
+    files, pca = _pca_files(tmp_path)
+    m = CLAP_Module(device="cpu")
+    enc = m.model.audio_branch
+    new, residuals = setup_residual_htsat(enc, files, [0, 2])
+    assert new is not enc and set(residuals) == {0, 2}
+    assert all(b._residual is None for l in enc.layers for b in l.blocks)                # original untouched (deepcopy)
+    assert all(b._residual is residuals[0] for b in new.layers[0].blocks)                # one ResiDual per layer, shared (Q3)
+    assert all(b._residual is residuals[2] for b in new.layers[2].blocks)
+    assert all(b._residual is None for b in new.layers[1].blocks)
+    assert not any(p.requires_grad for p in new.parameters())                            # encoder frozen
+    assert not any("learnable" in n for n, _ in new.named_parameters())                  # not registered (Q4)
+    r = residuals[0]
+    assert r.learnable.requires_grad and torch.equal(r.learnable.data, torch.ones(96))
+    assert r.basis.shape == (96, 96) and r.mean.shape == (96,) and r.basis.dtype == torch.float32
+    assert np.allclose(r.basis.numpy(), pca[0]["components"].astype(np.float32))
+    with pytest.raises(ValueError, match="out of range"):
+        setup_residual_htsat(enc, files, [4])
+    m.model.audio_branch = new                                                           # src/training.py:103
+    assert new._projection is m.model.audio_projection
+
+
+def test_residual_module_surface():
+    basis = torch.linalg.qr(torch.randn(32, 32))[0].T.contiguous()
+    r = ResiDual(basis, torch.zeros(32), n_components=8)
+    assert r.n_components == 8 and r.basis.shape == (8, 32) and r.learnable.shape == (8,)     # rows are sliced (Q11)
+    assert set(dict(r.named_buffers())) == {"mean", "basis"}
+    with pytest.raises(RuntimeError, match="CUDA"):
+        r(torch.zeros(1, 2, 32))
+    blk = CLAP_Module(device="cpu").model.audio_branch.layers[0].blocks[0]
+    patch_block_with_residual(blk, r)
+    assert blk._residual is r and "_residual" not in dict(blk.named_modules())
+
+
+def test_load_residual_reads_reference_fixture_schema(tmp_path):
+    files, pca = _pca_files(tmp_path, layers=(1,))
+    r = load_residual(files[1])
+    assert r.basis.shape == (192, 192) and torch.allclose(r.basis @ r.basis.T, torch.eye(192), atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------- featuriser
+def test_featuriser_matches_oracle():
+    rng = np.random.default_rng(0)
+    clips = [torch.from_numpy(rng.standard_normal(n).astype(np.float32)) for n in (1000, 4800, 12000)]
+    for mode in ("repeatpad", "pad", "repeat"):
+        got = batch_features(clips, 12000, mode)
+        for i, c in enumerate(clips):
+            assert torch.equal(got[i], O.pad_clip(c, 12000, mode))
+        s = get_audio_features({}, clips[0], 12000, "rand_trunc", mode, {})
+        assert torch.equal(s["waveform"], got[0]) and s["longer"].tolist() == [False]
+    with pytest.raises(NotImplementedError):
+        batch_features(clips, 12000, "bogus")
+    with pytest.raises(NotImplementedError):
+        get_audio_features({}, clips[0], 12000, "bogus", "pad", {})
+    with pytest.raises(AttributeError):                                    # reference crashes for > max_len (Q9)
+        get_audio_features({}, torch.zeros(13000), 12000, "rand_trunc", "pad", {})
+    x = rng.uniform(-1.2, 1.2, 100).astype(np.float32)
+    assert np.array_equal(int16_to_float32(float32_to_int16(x)), O.int16_roundtrip_np(x))
+    assert torch.equal(quantize_tensor(torch.from_numpy(x)), O.quantize_tensor(torch.from_numpy(x)))
+
+
+# ---------------------------------------------------------------------------------------------------- PCA artefacts
+def test_pca_from_moments_matches_oracle_and_schema():
+    g = np.load(os.path.join(GOLDEN, "pca_moments.npz"))
+    got = pca_from_moments(int(g["n"]), g["s1"], g["s2"])
+    ref = O.pca_from_moments(int(g["n"]), g["s1"], g["s2"])
+    assert set(got) == {"components", "mean", "explained_variance", "explained_variance_ratio", "n_components", "input_dim",
+                        "num_samples"}                                    # src/residual.py:143-150
+    for k in ("components", "mean", "explained_variance", "explained_variance_ratio"):
+        assert np.allclose(got[k], ref[k])
+    assert np.allclose(got["components"], g["components"], atol=5e-6)       # == sklearn IncrementalPCA incl. sign rule
+    trunc = pca_from_moments(int(g["n"]), g["s1"], g["s2"], n_components=10)
+    assert trunc["components"].shape == (10, 96) and trunc["n_components"] == 10
+
+
+def test_csv_schema_roundtrip(tmp_path):
+    class P:
+        pass
+    models = {0: {}, 1: {}}
+    rng = np.random.default_rng(1)
+    for l in models:
+        for h in range(2):
+            p = P()
+            v = np.sort(rng.uniform(0.1, 2, 16))[::-1]
+            p.explained_variance_, p.explained_variance_ratio_ = v, v / v.sum()
+            models[l][h] = p
+    path = save_pca_results_on_file(str(tmp_path), "ESC50", 0, models)
+    header = open(path).readline().strip().split(",")
+    assert header == ["layer", "head", "component_index", "explained_variance", "explained_variance_ratio", "participation_ratio",
+                      "intrinsic_dim"]                                     # src/analyze_attention.py:70-76
+    back = load_pca_csv_results(path)
+    v = models[1][1].explained_variance_
+    assert np.allclose(back[(1, 1)]["explained_variance"], v)
+    pr, idim = O.spectrum_summaries(v, v / v.sum())
+    assert abs(back[(1, 1)]["participation_ratio"] - pr) < 1e-9 and back[(1, 1)]["intrinsic_dim"] == idim
+
+
+def test_real_reference_pca_fixture_schema():
+    """The reference ships real PCA pickles (residual_pca/ESC50/layer_*_evalfold_*); when mounted, they must load."""
+    p = "/root/reference/residual_pca/ESC50/layer_0_evalfold_0"
+    if not os.path.exists(p):
+        pytest.skip("reference fixtures not mounted")
+    r = load_residual(p)
+    assert r.basis.shape == (96, 96) and r.mean.shape == (96,)
+    assert torch.allclose(r.basis @ r.basis.T, torch.eye(96), atol=1e-4)
