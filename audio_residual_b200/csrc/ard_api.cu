@@ -2,6 +2,7 @@
 // the encoder forward schedule, and the op-level entry points.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <cmath>
@@ -98,6 +99,7 @@ struct ard_handle {
     // workspace
     DevBuf ws_logmel, ws_x, ws_y, ws_xn, ws_ao, ws_qkv, ws_h, ws_normed, ws_emb, ws_hid, ws_proj, ws_tscam_a, ws_tscam_y, ws_wave;
     int last_launches = 0;
+    bool use_fused_ffn = true;   // ARD_FUSED_FFN=0 disables the fused 96-channel FFN kernel (A/B measurements)
 };
 
 namespace ard {
@@ -309,6 +311,9 @@ static int run_block(ard_handle* h, int l, int b, int B, float* X, float* Y, flo
     ARD_TRY(gemm_bf16(g, h->num_sms, s));
     // FFN: (Y) -> LN2 -> fc1+GELU -> fc2
     auto ffn = [&](const float* in, float* out, const float* r1, const float* r2) -> int {
+        if (C == 96 && h->use_fused_ffn && r1 == in)   // whole FFN in one kernel, hidden activation never leaves the SM
+            return ffn_fused_96(in, r2, out, M, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), bw.fc1_w.as<__nv_bfloat16>(), bw.fc1_b.as<float>(),
+                                bw.fc2_w.as<__nv_bfloat16>(), bw.fc2_b.as<float>(), h->num_sms, s);
         ARD_TRY(layernorm_bf16(in, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), XN, M, C, s));
         GemmArgs f;
         f.A = XN; f.lda = C; f.W = bw.fc1_w.as<__nv_bfloat16>(); f.ldw = C; f.out = Hb; f.ldo = 4 * C; f.out_bf16 = 1;
@@ -432,6 +437,7 @@ int ard_create(const ard_config* cfg, ard_handle** out) {
         return set_error(ARD_ERR_CUDA, "no CUDA device: libard_b200 has no CPU fallback");
     }
     h->num_sms = sms;
+    if (const char* e = getenv("ARD_FUSED_FFN")) h->use_fused_ffn = atoi(e) != 0;
     *out = h;
     return 0;
 }
@@ -545,6 +551,15 @@ int ard_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, vo
     g.A = (const __nv_bfloat16*)A; g.lda = lda; g.W = (const __nv_bfloat16*)W; g.ldw = ldw; g.out = out; g.ldo = ldo; g.out_bf16 = out_is_bf16;
     g.M = M; g.N = N; g.K = K; g.bias = bias; g.act = act; g.resid1 = resid1; g.ldr1 = ldr1; g.resid2 = resid2; g.ldr2 = ldr2;
     return gemm_bf16(g, sms, (cudaStream_t)stream);
+}
+
+int ard_ffn_fused_96(const float* x, const float* resid2, float* out, long long M, const float* gamma, const float* beta, const void* w1_bf16,
+                     const float* b1, const void* w2_bf16, const float* b2, void* stream) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return set_error(ARD_ERR_CUDA, "no CUDA device");
+    return ffn_fused_96(x, resid2, out, M, gamma, beta, (const __nv_bfloat16*)w1_bf16, b1, (const __nv_bfloat16*)w2_bf16, b2, sms,
+                        (cudaStream_t)stream);
 }
 
 int ard_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int C, void* stream) {

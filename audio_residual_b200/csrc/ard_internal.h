@@ -51,6 +51,11 @@ int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream);
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                  uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
 
+// ---------------------------------------------------------------- fused FFN, 96-channel stage (ffn_fused.cu)
+// out = x + fc2(gelu(fc1(LayerNorm(x)))) (+ resid2); out may alias x.
+int ffn_fused_96(const float* x, const float* resid2, float* out, long long M, const float* gamma, const float* beta,
+                 const __nv_bfloat16* w1, const float* b1, const __nv_bfloat16* w2, const float* b2, int num_sms, cudaStream_t stream);
+
 // ---------------------------------------------------------------- row-wise kernels (rowwise.cu)
 // LayerNorm over the last dim C of x[rows, C] (fp32) -> bf16; two-pass variance like at::native layer_norm.
 int layernorm_bf16(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, long long rows, int C, cudaStream_t s);
@@ -103,7 +108,7 @@ void count_launch(int n = 1);
 
 // Per-kernel-class device timing (ard_profile_*): when enabled, every host launcher brackets its kernel with CUDA events on
 // the launching stream and records the algorithmic flops / bytes of that launch. Off by default (zero overhead).
-enum ProfClass { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_FRONTEND = 3, PROF_HEAD = 4, PROF_OTHER = 5, PROF_NCLASS = 6 };
+enum ProfClass { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_FRONTEND = 3, PROF_HEAD = 4, PROF_OTHER = 5, PROF_FFN = 6, PROF_NCLASS = 7 };
 struct ProfScope {
     ProfScope(int cls, cudaStream_t s, double flops, double bytes);
     ~ProfScope();

@@ -64,6 +64,7 @@ def load(check_symbols=False):
         lib.ard_last_launch_count.argtypes = [vp]
         lib.ard_gemm_bf16.argtypes = [vp, ll, vp, ll, vp, ll, i, i, i, i, vp, i, vp, ll, vp, ll, vp]
         lib.ard_layernorm_bf16.argtypes = [vp, vp, vp, vp, ll, i, vp]
+        lib.ard_ffn_fused_96.argtypes = [vp, vp, vp, ll, vp, vp, vp, vp, vp, vp, vp]
         lib.ard_window_attention.argtypes = [vp, vp, vp, vp, f, i, i, i, i, i, i, i, vp]
         lib.ard_f32_to_bf16.argtypes = [vp, vp, ll, f, vp]
         lib.ard_quantize_waveform.argtypes = [vp, vp, ll, vp]
@@ -105,7 +106,7 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
-PROF_CLASSES = ("gemm_tc", "window_attention", "layernorm", "frontend", "heads", "other")
+PROF_CLASSES = ("gemm_tc", "window_attention", "layernorm", "frontend", "heads", "other", "ffn_fused")
 
 
 def profile_enable(on=True):

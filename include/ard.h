@@ -114,6 +114,11 @@ int ard_last_launch_count(const ard_handle* h);
 int ard_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int out_is_bf16, int M, int N,
                   int K, const float* bias, int act, const float* resid1, long long ldr1, const float* resid2, long long ldr2,
                   void* stream);
+/* Whole FFN of a 96-channel Swin block in one kernel (htsat.py:479-480; src/residual.py:93-96):
+ * out[M,96] = x + fc2(gelu(fc1(LayerNorm(x; gamma, beta)))) (+ resid2). x, out, resid2 fp32 device (out may alias x);
+ * w1 [384,96], w2 [96,384] bf16 device; b1 [384], b2 [96] fp32 device. */
+int ard_ffn_fused_96(const float* x, const float* resid2, float* out, long long M, const float* gamma, const float* beta, const void* w1_bf16,
+                     const float* b1, const void* w2_bf16, const float* b2, void* stream);
 /* nn.LayerNorm(C, eps=1e-5) over x[rows, C] fp32 -> bf16 (htsat.py:449,479 norm1/norm2). */
 int ard_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int C, void* stream);
 /* Shifted-window attention core of WindowAttention.forward (htsat.py:326-352) incl. roll/partition/reverse addressing
@@ -138,7 +143,7 @@ int ard_stats_accumulate(const float* x, long long rows, int D, double* sum, dou
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Measurement support (bench.py): per-kernel-class device time. Classes: 0 tcgen05 GEMM, 1 window attention,
- * 2 LayerNorm/merge, 3 front end (STFT/log-mel/patch-embed), 4 heads, 5 other. While enabled every launch is bracketed
+ * 2 LayerNorm/merge, 3 front end (STFT/log-mel/patch-embed), 4 heads, 5 other, 6 fused FFN. While enabled every launch is bracketed
  * by CUDA events on its stream; ard_profile_read synchronises, sums elapsed ms / algorithmic flops / algorithmic bytes /
  * launch counts per class since the last read, and clears the records.
  * ------------------------------------------------------------------------------------------------------------------ */
