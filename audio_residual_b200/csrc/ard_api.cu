@@ -113,6 +113,11 @@ static int upload(DevBuf& b, const void* src, size_t bytes) {
     return 0;
 }
 static int upload_f32(DevBuf& b, const std::vector<float>& v) { return upload(b, v.data(), v.size() * 4); }
+static int upload_f16(DevBuf& b, const std::vector<float>& v) {
+    std::vector<__half> t(v.size());
+    for (size_t i = 0; i < v.size(); ++i) t[i] = __float2half_rn(v[i]);
+    return upload(b, t.data(), t.size() * 2);
+}
 static int upload_bf16(DevBuf& b, const std::vector<float>& v) {
     std::vector<__nv_bfloat16> t(v.size());
     for (size_t i = 0; i < v.size(); ++i) t[i] = __float2bfloat16_rn(v[i]);
@@ -214,7 +219,7 @@ static int finalize(ard_handle* h, cudaStream_t) {
             ARD_TRY(get(h, p + "attn.proj.bias", C, &v)); ARD_TRY(upload_f32(bw.proj_b, *v));
             ARD_TRY(get(h, p + "mlp.fc1.weight", (size_t)4 * C * C, &v)); ARD_TRY(upload_bf16(bw.fc1_w, *v));
             ARD_TRY(get(h, p + "mlp.fc1.bias", (size_t)4 * C, &v)); ARD_TRY(upload_f32(bw.fc1_b, *v));
-            ARD_TRY(get(h, p + "mlp.fc2.weight", (size_t)4 * C * C, &v)); ARD_TRY(upload_bf16(bw.fc2_w, *v));
+            ARD_TRY(get(h, p + "mlp.fc2.weight", (size_t)4 * C * C, &v)); ARD_TRY(upload_f16(bw.fc2_w, *v));   // hidden activations are fp16
             ARD_TRY(get(h, p + "mlp.fc2.bias", C, &v)); ARD_TRY(upload_f32(bw.fc2_b, *v));
             ARD_TRY(get(h, p + "attn.relative_position_bias_table", (size_t)225 * nH, &v)); ARD_TRY(upload_f32(bw.rpb, *v));
             if (bw.has_res) {   // proj bias may have changed: refresh (b_proj - mean) and force a re-fold
@@ -313,14 +318,14 @@ static int run_block(ard_handle* h, int l, int b, int B, float* X, float* Y, flo
     auto ffn = [&](const float* in, float* out, const float* r1, const float* r2) -> int {
         if (C == 96 && h->use_fused_ffn && r1 == in)   // whole FFN in one kernel, hidden activation never leaves the SM
             return ffn_fused_96(in, r2, out, M, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), bw.fc1_w.as<__nv_bfloat16>(), bw.fc1_b.as<float>(),
-                                bw.fc2_w.as<__nv_bfloat16>(), bw.fc2_b.as<float>(), h->num_sms, s);
+                                bw.fc2_w.as<__half>(), bw.fc2_b.as<float>(), h->num_sms, s);
         ARD_TRY(layernorm_bf16(in, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), XN, M, C, s));
         GemmArgs f;
         f.A = XN; f.lda = C; f.W = bw.fc1_w.as<__nv_bfloat16>(); f.ldw = C; f.out = Hb; f.ldo = 4 * C; f.out_bf16 = 1;
-        f.M = (int)M; f.N = 4 * C; f.K = C; f.bias = bw.fc1_b.as<float>(); f.act = ARD_ACT_GELU;
+        f.M = (int)M; f.N = 4 * C; f.K = C; f.bias = bw.fc1_b.as<float>(); f.act = ARD_ACT_GELU; f.out_f16 = 1;
         ARD_TRY(gemm_bf16(f, h->num_sms, s));
         f = GemmArgs();
-        f.A = Hb; f.lda = 4 * C; f.W = bw.fc2_w.as<__nv_bfloat16>(); f.ldw = 4 * C; f.out = out; f.ldo = C;
+        f.A = Hb; f.lda = 4 * C; f.W = bw.fc2_w.as<__nv_bfloat16>(); f.ldw = 4 * C; f.out = out; f.ldo = C; f.ab_f16 = 1;
         f.M = (int)M; f.N = C; f.K = 4 * C; f.bias = bw.fc2_b.as<float>();
         f.resid1 = r1; f.ldr1 = C; f.resid2 = r2; f.ldr2 = C;
         return gemm_bf16(f, h->num_sms, s);
@@ -550,15 +555,29 @@ int ard_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, vo
     GemmArgs g;
     g.A = (const __nv_bfloat16*)A; g.lda = lda; g.W = (const __nv_bfloat16*)W; g.ldw = ldw; g.out = out; g.ldo = ldo; g.out_bf16 = out_is_bf16;
     g.M = M; g.N = N; g.K = K; g.bias = bias; g.act = act; g.resid1 = resid1; g.ldr1 = ldr1; g.resid2 = resid2; g.ldr2 = ldr2;
+    if (act == ARD_ACT_GELU_F16) { g.act = ARD_ACT_GELU; g.out_f16 = 1; }
+    return gemm_bf16(g, sms, (cudaStream_t)stream);
+}
+
+int ard_gemm_f16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int out_is_bf16, int M, int N,
+                 int K, const float* bias, int act, const float* resid1, long long ldr1, const float* resid2, long long ldr2,
+                 void* stream) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return set_error(ARD_ERR_CUDA, "no CUDA device");
+    GemmArgs g;
+    g.A = (const __nv_bfloat16*)A; g.lda = lda; g.W = (const __nv_bfloat16*)W; g.ldw = ldw; g.out = out; g.ldo = ldo; g.out_bf16 = out_is_bf16;
+    g.M = M; g.N = N; g.K = K; g.bias = bias; g.act = act; g.resid1 = resid1; g.ldr1 = ldr1; g.resid2 = resid2; g.ldr2 = ldr2;
+    g.ab_f16 = 1;
     return gemm_bf16(g, sms, (cudaStream_t)stream);
 }
 
 int ard_ffn_fused_96(const float* x, const float* resid2, float* out, long long M, const float* gamma, const float* beta, const void* w1_bf16,
-                     const float* b1, const void* w2_bf16, const float* b2, void* stream) {
+                     const float* b1, const void* w2_f16, const float* b2, void* stream) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return set_error(ARD_ERR_CUDA, "no CUDA device");
-    return ffn_fused_96(x, resid2, out, M, gamma, beta, (const __nv_bfloat16*)w1_bf16, b1, (const __nv_bfloat16*)w2_bf16, b2, sms,
+    return ffn_fused_96(x, resid2, out, M, gamma, beta, (const __nv_bfloat16*)w1_bf16, b1, (const __half*)w2_f16, b2, sms,
                         (cudaStream_t)stream);
 }
 

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "../../include/ard.h"
@@ -46,15 +47,17 @@ struct GemmArgs {
     int aux_T = 0;
     long long aux_bstride = 0;
     int force_bn = 0;
+    int ab_f16 = 0;                    // A and W are fp16 instead of bf16 (the fc2 GEMM: hidden activations are fp16)
+    int out_f16 = 0;                   // with out_bf16=1 and act=GELU: GELU in packed fp16, fp16 output
 };
 int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream);
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                  uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
 
 // ---------------------------------------------------------------- fused FFN, 96-channel stage (ffn_fused.cu)
-// out = x + fc2(gelu(fc1(LayerNorm(x)))) (+ resid2); out may alias x.
+// out = x + fc2(gelu(fc1(LayerNorm(x)))) (+ resid2); out may alias x. fc1 weights bf16, fc2 weights fp16 (hidden is fp16).
 int ffn_fused_96(const float* x, const float* resid2, float* out, long long M, const float* gamma, const float* beta,
-                 const __nv_bfloat16* w1, const float* b1, const __nv_bfloat16* w2, const float* b2, int num_sms, cudaStream_t stream);
+                 const __nv_bfloat16* w1, const float* b1, const __half* w2_f16, const float* b2, int num_sms, cudaStream_t stream);
 
 // ---------------------------------------------------------------- row-wise kernels (rowwise.cu)
 // LayerNorm over the last dim C of x[rows, C] (fp32) -> bf16; two-pass variance like at::native layer_norm.

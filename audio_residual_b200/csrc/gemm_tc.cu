@@ -48,6 +48,8 @@ struct GemmKernelParams {
     long long ld_aux;
     int aux_T;
     long long aux_bstride;
+    int ab_f16;          // A and W hold fp16 (else bf16)
+    int out_f16;         // 16-bit output holds fp16 (GELU evaluated in packed fp16), else bf16
 };
 
 template <int BN, bool OUT_BF16>
@@ -114,7 +116,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         // ===================================================== MMA issuer (one thread)
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+            const uint32_t idesc = p.ab_f16 ? umma_idesc_f16(GEMM_BM, BN) : umma_idesc_bf16(GEMM_BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -184,7 +186,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
                     f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
                 }
-                if (p.act == 1) {
+                const bool gelu_half = OUT_BF16 && p.act == 1 && p.out_f16;   // GELU done below in packed fp16
+                if (p.act == 1 && !gelu_half) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
                 } else if (p.act == 2) {
@@ -230,10 +233,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         uint4 u;
-                        u.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
-                        u.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
-                        u.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
-                        u.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+                        if (gelu_half) {
+                            u.x = gelu_erf_f16x2(f[q * 8 + 0], f[q * 8 + 1]);
+                            u.y = gelu_erf_f16x2(f[q * 8 + 2], f[q * 8 + 3]);
+                            u.z = gelu_erf_f16x2(f[q * 8 + 4], f[q * 8 + 5]);
+                            u.w = gelu_erf_f16x2(f[q * 8 + 6], f[q * 8 + 7]);
+                        } else {
+                            u.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+                            u.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+                            u.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+                            u.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+                        }
                         *reinterpret_cast<uint4*>(rowp + ((q ^ sw) << 4)) = u;
                     }
                 } else {
@@ -328,6 +338,7 @@ int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream) {
         return set_error(ARD_ERR_SHAPE, "gemm: bad shape M=%d N=%d K=%d lda=%lld ldw=%lld", a.M, a.N, a.K, a.lda, a.ldw);
     if ((a.out_bf16 && (a.ldo % 8) != 0) || (!a.out_bf16 && (a.ldo % 4) != 0)) return set_error(ARD_ERR_SHAPE, "gemm: ldo alignment");
     if (a.out_bf16 && (a.resid1 || a.resid2 || a.aux)) return set_error(ARD_ERR_SHAPE, "gemm: residual/aux need fp32 output");
+    if (a.out_f16 && !(a.out_bf16 && a.act == ARD_ACT_GELU)) return set_error(ARD_ERR_SHAPE, "gemm: fp16 output is only produced by the GELU epilogue");
     const int BN = a.force_bn ? a.force_bn : pick_bn(a.N);
     CUtensorMap ta, tb, tc;
     if (int rc = make_tmap_2d(&ta, a.A, 2, a.K, a.M, (uint64_t)a.lda * 2, GEMM_BK, GEMM_BM, 128)) return rc;
@@ -342,6 +353,7 @@ int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     kp.bias = a.bias; kp.act = a.act;
     kp.resid1 = a.resid1; kp.ldr1 = a.ldr1; kp.resid2 = a.resid2; kp.ldr2 = a.ldr2;
     kp.aux = a.aux; kp.ld_aux = a.ld_aux; kp.aux_T = a.aux_T > 0 ? a.aux_T : a.M; kp.aux_bstride = a.aux_bstride;
+    kp.ab_f16 = a.ab_f16; kp.out_f16 = a.out_f16;
     const double osz = a.out_bf16 ? 2.0 : 4.0;
     ProfScope ps(PROF_GEMM, stream, 2.0 * a.M * a.N * a.K,
                  2.0 * a.M * a.K + 2.0 * a.N * a.K + osz * a.M * a.N + (a.resid1 ? 4.0 * a.M * a.N : 0.0) + (a.resid2 ? 4.0 * a.M * a.N : 0.0) +

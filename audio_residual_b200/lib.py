@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libard_b200.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "ard.h")
 
 ARD_OK, ARD_ERR_SHAPE, ARD_ERR_DTYPE, ARD_ERR_CUDA, ARD_ERR_STATE, ARD_ERR_KEY, ARD_ERR_NOTIMPL = 0, -1, -2, -3, -4, -5, -6
-ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_GELU_F16 = 0, 1, 2, 3
 
 c_float_p = C.POINTER(C.c_float)
 c_double_p = C.POINTER(C.c_double)
@@ -63,6 +63,7 @@ def load(check_symbols=False):
         lib.ard_workspace_bytes.argtypes = [vp]
         lib.ard_last_launch_count.argtypes = [vp]
         lib.ard_gemm_bf16.argtypes = [vp, ll, vp, ll, vp, ll, i, i, i, i, vp, i, vp, ll, vp, ll, vp]
+        lib.ard_gemm_f16.argtypes = [vp, ll, vp, ll, vp, ll, i, i, i, i, vp, i, vp, ll, vp, ll, vp]
         lib.ard_layernorm_bf16.argtypes = [vp, vp, vp, vp, ll, i, vp]
         lib.ard_ffn_fused_96.argtypes = [vp, vp, vp, ll, vp, vp, vp, vp, vp, vp, vp]
         lib.ard_window_attention.argtypes = [vp, vp, vp, vp, f, i, i, i, i, i, i, i, vp]

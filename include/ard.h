@@ -32,6 +32,7 @@ extern "C" {
 #define ARD_ACT_NONE 0
 #define ARD_ACT_GELU 1  /* exact-erf GELU, htsat.py:151 */
 #define ARD_ACT_RELU 2  /* model.py:541 */
+#define ARD_ACT_GELU_F16 3 /* same GELU evaluated in packed fp16; the 16-bit output then holds fp16 (feeds ard_gemm_f16) */
 
 #define ARD_MAX_LAYERS 4
 #define ARD_CLIP_SAMPLES 480000
@@ -114,11 +115,15 @@ int ard_last_launch_count(const ard_handle* h);
 int ard_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int out_is_bf16, int M, int N,
                   int K, const float* bias, int act, const float* resid1, long long ldr1, const float* resid2, long long ldr2,
                   void* stream);
+/* Same contraction with fp16 A and W operands (fp32 accumulation): the fc2 GEMM, whose input is the fp16 GELU output. */
+int ard_gemm_f16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int out_is_bf16, int M, int N,
+                 int K, const float* bias, int act, const float* resid1, long long ldr1, const float* resid2, long long ldr2,
+                 void* stream);
 /* Whole FFN of a 96-channel Swin block in one kernel (htsat.py:479-480; src/residual.py:93-96):
  * out[M,96] = x + fc2(gelu(fc1(LayerNorm(x; gamma, beta)))) (+ resid2). x, out, resid2 fp32 device (out may alias x);
- * w1 [384,96], w2 [96,384] bf16 device; b1 [384], b2 [96] fp32 device. */
+ * w1 [384,96] bf16, w2 [96,384] fp16 (the hidden activation is fp16), device; b1 [384], b2 [96] fp32 device. */
 int ard_ffn_fused_96(const float* x, const float* resid2, float* out, long long M, const float* gamma, const float* beta, const void* w1_bf16,
-                     const float* b1, const void* w2_bf16, const float* b2, void* stream);
+                     const float* b1, const void* w2_f16, const float* b2, void* stream);
 /* nn.LayerNorm(C, eps=1e-5) over x[rows, C] fp32 -> bf16 (htsat.py:449,479 norm1/norm2). */
 int ard_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int C, void* stream);
 /* Shifted-window attention core of WindowAttention.forward (htsat.py:326-352) incl. roll/partition/reverse addressing

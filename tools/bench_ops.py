@@ -40,7 +40,7 @@ def bench_gemm():
     st = L.stream_ptr()
     for l, (T, C) in enumerate([(4096, 96), (1024, 192), (256, 384), (64, 768)]):
         M = B * T
-        for name, N, K, obf, act, nres in [("qkv", 3 * C, C, 1, 0, 0), ("proj", C, C, 0, 0, 1), ("fc1+gelu", 4 * C, C, 1, 1, 0),
+        for name, N, K, obf, act, nres in [("qkv", 3 * C, C, 1, 0, 0), ("proj", C, C, 0, 0, 1), ("fc1+gelu", 4 * C, C, 1, 1, 0), ("fc1+geluF16", 4 * C, C, 1, 3, 0),
                                            ("fc2+2res", C, 4 * C, 0, 0, 2), ("fc1 nogelu", 4 * C, C, 1, 0, 0), ("fc2 nores", C, 4 * C, 0, 0, 0)]:
             A = torch.randn(M, K, device=dev).to(torch.bfloat16)
             W = torch.randn(N, K, device=dev).to(torch.bfloat16)
@@ -66,7 +66,7 @@ def bench_ffn():
     out = torch.empty_like(x)
     g, bt = torch.ones(C, device=dev), torch.zeros(C, device=dev)
     w1 = (torch.randn(4 * C, C, device=dev) / C ** 0.5).to(torch.bfloat16)
-    w2 = (torch.randn(C, 4 * C, device=dev) / (4 * C) ** 0.5).to(torch.bfloat16)
+    w2 = (torch.randn(C, 4 * C, device=dev) / (4 * C) ** 0.5).to(torch.float16)
     b1, b2 = torch.randn(4 * C, device=dev), torch.randn(C, device=dev)
     for name, rr in (("ffn_fused_96", None), ("ffn_fused_96 +resid2", r2)):
         def fn():
@@ -78,8 +78,8 @@ def bench_ffn():
 
     def unfused():
         L.check(lib.ard_layernorm_bf16(L.ptr(x), L.ptr(g), L.ptr(bt), L.ptr(xn), M, C, st))
-        L.check(lib.ard_gemm_bf16(L.ptr(xn), C, L.ptr(w1), C, L.ptr(hb), 4 * C, 1, M, 4 * C, C, L.ptr(b1), 1, None, 0, None, 0, st))
-        L.check(lib.ard_gemm_bf16(L.ptr(hb), 4 * C, L.ptr(w2), 4 * C, L.ptr(out), C, 0, M, C, 4 * C, L.ptr(b2), 0, L.ptr(x), C, None, 0, st))
+        L.check(lib.ard_gemm_bf16(L.ptr(xn), C, L.ptr(w1), C, L.ptr(hb), 4 * C, 1, M, 4 * C, C, L.ptr(b1), 3, None, 0, None, 0, st))
+        L.check(lib.ard_gemm_f16(L.ptr(hb), 4 * C, L.ptr(w2), 4 * C, L.ptr(out), C, 0, M, C, 4 * C, L.ptr(b2), 0, L.ptr(x), C, None, 0, st))
     us = timeit(unfused)
     report(f"unfused LN+fc1+fc2 M={M}", us, 2.0 * M * C * 4 * C * 2, 34.0 * M * C)
 
