@@ -174,15 +174,57 @@ class CLAP_Module(nn.Module):
         use_tensor=True: tensor input, no quantisation, returns a tensor."""
         self.model.eval()
         enc = self.model.audio_branch
-        wave = batch_features(x, 480000, data_fil, device=self.device)
-        if enc.enable_fusion:
-            out = enc.encode(mel_fusion=self.fusion_mel(wave, quantize=not use_tensor), want_audio_embed=True)
+        if (not enc.enable_fusion and torch.is_tensor(x) and x.device.type == "cpu" and x.dim() == 2 and x.shape[1] == 480000
+                and x.dtype == torch.float32 and x.shape[0] > self.h2d_chunk):
+            emb = self._embed_host_pipelined(x, quantize=not use_tensor)
         else:
-            out = enc.encode(waveform=wave, quantize=not use_tensor, want_audio_embed=True)
-        emb = out["audio_embed"]
+            wave = batch_features(x, 480000, data_fil, device=self.device)
+            if enc.enable_fusion:
+                out = enc.encode(mel_fusion=self.fusion_mel(wave, quantize=not use_tensor), want_audio_embed=True)
+            else:
+                out = enc.encode(waveform=wave, quantize=not use_tensor, want_audio_embed=True)
+            emb = out["audio_embed"]
         if not use_tensor:
             emb = emb.detach().cpu().numpy()
         return emb
+
+    h2d_chunk = 64   # clips per host->device copy when the input batch lives in host memory
+
+    def _embed_host_pipelined(self, x, quantize):
+        """Full-length host batch [N, 480000] fp32: copy chunk k+1 on a side stream while chunk k is encoded, so the PCIe
+        transfer (1.92 MB per clip) hides behind compute instead of adding to it. Pinned input makes the copies asynchronous."""
+        enc = self.model.audio_branch
+        dev = self.device
+        N, ck = x.shape[0], self.h2d_chunk
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream()
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+                self._stage = [torch.empty((ck, 480000), device=dev, dtype=torch.float32) for _ in range(2)]
+                self._stage_free = [torch.cuda.Event() for _ in range(2)]
+            out = torch.empty((N, enc.joint_dim), device=dev, dtype=torch.float32)
+            copied = [torch.cuda.Event() for _ in range(2)]
+            nchunks = (N + ck - 1) // ck
+
+            def start_copy(k):
+                lo, hi = k * ck, min(N, (k + 1) * ck)
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(self._stage_free[k % 2])    # the encoder finished reading this staging buffer
+                    self._stage[k % 2][:hi - lo].copy_(x[lo:hi], non_blocking=True)
+                    copied[k % 2].record(self._copy_stream)
+
+            for b in range(2):
+                self._stage_free[b].record(main)
+            start_copy(0)
+            for k in range(nchunks):
+                if k + 1 < nchunks:
+                    start_copy(k + 1)
+                lo, hi = k * ck, min(N, (k + 1) * ck)
+                main.wait_event(copied[k % 2])
+                res = enc.encode(waveform=self._stage[k % 2][:hi - lo], quantize=quantize, want_audio_embed=True)
+                out[lo:hi].copy_(res["audio_embed"])
+                self._stage_free[k % 2].record(main)
+        return out
 
 
 def build_clap_module(model="tiny", state_dict=None, device="cuda:0", enable_fusion=False, seed=0):

@@ -315,11 +315,15 @@ static int run_block(ard_handle* h, int l, int b, int B, float* X, float* Y, flo
     if (res_out) { g.aux = res_out; g.ld_aux = C; g.aux_T = T; g.aux_bstride = res_bstride; (void)res_T; }
     ARD_TRY(gemm_bf16(g, h->num_sms, s));
     // FFN: (Y) -> LN2 -> fc1+GELU -> fc2
-    auto ffn = [&](const float* in, float* out, const float* r1, const float* r2) -> int {
-        if (C == 96 && h->use_fused_ffn && r1 == in)   // whole FFN in one kernel, hidden activation never leaves the SM
+    // one FFN: out = in + mlp(norm2(in)) (+ r2 inside the fused kernel). `pre_add`: the LayerNorm input is in + pre_add, written back to `in`.
+    auto ffn = [&](float* in, float* out, const float* r2, const float* pre_add) -> int {
+        if (C == 96 && h->use_fused_ffn && pre_add == nullptr)   // whole FFN in one kernel, hidden activation never leaves the SM
             return ffn_fused_96(in, r2, out, M, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), bw.fc1_w.as<__nv_bfloat16>(), bw.fc1_b.as<float>(),
                                 bw.fc2_w.as<__half>(), bw.fc2_b.as<float>(), h->num_sms, s);
-        ARD_TRY(layernorm_bf16(in, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), XN, M, C, s));
+        if (pre_add)
+            ARD_TRY(add_layernorm_bf16(in, pre_add, in, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), XN, M, C, s));
+        else
+            ARD_TRY(layernorm_bf16(in, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), XN, M, C, s));
         GemmArgs f;
         f.A = XN; f.lda = C; f.W = bw.fc1_w.as<__nv_bfloat16>(); f.ldw = C; f.out = Hb; f.ldo = 4 * C; f.out_bf16 = 1;
         f.M = (int)M; f.N = 4 * C; f.K = C; f.bias = bw.fc1_b.as<float>(); f.act = ARD_ACT_GELU; f.out_f16 = 1;
@@ -327,14 +331,17 @@ static int run_block(ard_handle* h, int l, int b, int B, float* X, float* Y, flo
         f = GemmArgs();
         f.A = Hb; f.lda = 4 * C; f.W = bw.fc2_w.as<__nv_bfloat16>(); f.ldw = 4 * C; f.out = out; f.ldo = C; f.ab_f16 = 1;
         f.M = (int)M; f.N = C; f.K = 4 * C; f.bias = bw.fc2_b.as<float>();
-        f.resid1 = r1; f.ldr1 = C; f.resid2 = r2; f.ldr2 = C;
+        f.resid1 = in; f.ldr1 = C; f.resid2 = r2; f.ldr2 = C;
         return gemm_bf16(f, h->num_sms, s);
     };
     if (!bw.has_res) {
-        ARD_TRY(ffn(Y, X, Y, nullptr));            // x = x1 + mlp(norm2(x1))                       htsat.py:480
+        ARD_TRY(ffn(Y, X, nullptr, nullptr));          // x = x1 + mlp(norm2(x1))                       htsat.py:480
+    } else if (C == 96 && h->use_fused_ffn) {
+        ARD_TRY(ffn(Y, Y, X, nullptr));                // x3 = shortcut + (x1 + mlp(norm2(x1)))         src/residual.py:93,95
+        ARD_TRY(ffn(Y, X, nullptr, nullptr));          // x4 = x3 + mlp(norm2(x3))                      src/residual.py:96
     } else {
-        ARD_TRY(ffn(Y, Y, Y, X));                  // x3 = shortcut + (x1 + mlp(norm2(x1)))         src/residual.py:93,95
-        ARD_TRY(ffn(Y, X, Y, nullptr));            // x4 = x3 + mlp(norm2(x3))                      src/residual.py:96
+        ARD_TRY(ffn(Y, Y, nullptr, nullptr));          // x2 = x1 + mlp(norm2(x1))                      src/residual.py:93
+        ARD_TRY(ffn(Y, X, nullptr, X));                // x3 = shortcut + x2 (fused into the norm2 pass), x4 = x3 + mlp(norm2(x3))   :95-96
     }
     return 0;
 }

@@ -24,16 +24,19 @@ constexpr int GEMM_NEPI = 8;                       // epilogue warps
 constexpr int GEMM_THREADS = 64 + GEMM_NEPI * 32;  // 320
 constexpr int GEMM_CSTAGE_BYTES = 4096;            // one 32x32 fp32 chunk (bf16 uses half)
 
-template <int BN>
+template <int BN, bool OUT_BF16>
 struct GemmCfg {
-    static constexpr int STAGES = (BN >= 256) ? 3 : 4;
+    // fp32-output instantiations keep 3 epilogue staging buffers per warp (the residual tile of the NEXT chunk is TMA-loaded
+    // into one while the current chunk is processed in another and the previous one is still being stored) and 3 operand stages.
+    static constexpr int STAGES = OUT_BF16 ? ((BN >= 256) ? 3 : 4) : 3;
+    static constexpr int NBUF = OUT_BF16 ? 2 : 3;
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int CSTAGE_OFF = STAGES * STAGE_BYTES;
-    static constexpr int BIAS_OFF = CSTAGE_OFF + GEMM_NEPI * 2 * GEMM_CSTAGE_BYTES;
+    static constexpr int BIAS_OFF = CSTAGE_OFF + GEMM_NEPI * NBUF * GEMM_CSTAGE_BYTES;
     static constexpr int BAR_OFF = BIAS_OFF + GEMM_NEPI * 32 * 4;
-    static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;  // + alignment slack
+    static constexpr int SMEM_BYTES = BAR_OFF + 512 + 1024;  // barriers + alignment slack
 };
 
 struct GemmKernelParams {
@@ -55,8 +58,8 @@ struct GemmKernelParams {
 template <int BN, bool OUT_BF16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const GemmKernelParams p) {
-    using Cfg = GemmCfg<BN>;
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmKernelParams p) {
+    using Cfg = GemmCfg<BN, OUT_BF16>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, still a shared-space pointer
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
@@ -64,6 +67,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* resid_bar = tempty_bar + 3;          // [GEMM_NEPI][3]: residual tile landed in staging buffer b
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -84,6 +88,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], GEMM_NEPI);
         }
+        for (int i = 0; i < GEMM_NEPI * 3; ++i) mbar_init(&resid_bar[i], 1);
+        tma_prefetch_desc(&tmR);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -148,121 +154,138 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int grp = ew >> 2;                   // column-chunk interleave group
         constexpr int NGRP = GEMM_NEPI / 4;
         constexpr int NCHUNK = BN / 32;
-        uint8_t* cst = smem + Cfg::CSTAGE_OFF + ew * 2 * GEMM_CSTAGE_BYTES;
+        constexpr int NBUF = Cfg::NBUF;
+        uint8_t* cst = smem + Cfg::CSTAGE_OFF + ew * NBUF * GEMM_CSTAGE_BYTES;
         float* bias_w = reinterpret_cast<float*>(smem + Cfg::BIAS_OFF) + ew * 32;
-        int buf = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        uint64_t* rbar = resid_bar + ew * 3;
+        // The first residual (the shortcut) is fetched by TMA into the staging buffer one chunk ahead: coalesced, asynchronous,
+        // no registers. (Row-per-thread LDG.128 of a residual touches 32 different lines per instruction and made the
+        // residual GEMMs LSU-bound.) The sum is formed in place and the same buffer is handed to the TMA store.
+        const bool tma_resid = !OUT_BF16 && p.resid1 != nullptr;
+        auto issue_resid = [&](int t, int cc, int b) {   // lane 0 only
+            const int mb = t / n_blocks, nb = t % n_blocks;
+            mbar_expect_tx(&rbar[b], GEMM_CSTAGE_BYTES);
+            tma_load_2d(cst + b * GEMM_CSTAGE_BYTES, &tmR, &rbar[b], nb * BN + cc * 32, mb * GEMM_BM + quad * 32);
+        };
+        int tile = blockIdx.x, c = grp, it = 0, i = 0;
+        if (tma_resid && tile < num_tiles && lane == 0) issue_resid(tile, c, 0);
+        while (tile < num_tiles) {
+            int ntile = tile, nc = c + NGRP;
+            if (nc >= NCHUNK) { nc = grp; ntile = tile + gridDim.x; }
+            const int b = i % NBUF;
+            if (tma_resid && lane == 0) {
+                tma_store_wait_read<1>();          // buffer (i+1)%3 was last stored two chunks ago
+                if (ntile < num_tiles) issue_resid(ntile, nc, (i + 1) % NBUF);
+            }
             const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
             const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            mbar_wait(&tfull_bar[as], aphase);
-            tc_fence_after();
+            if (c == grp) {                        // first chunk of this tile for this warp
+                mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+                tc_fence_after();
+            }
             const int row = m_blk * GEMM_BM + quad * 32 + lane;
             const bool row_ok = row < p.M;
-            // last chunk index handled by this group
-            int last_c = -1;
-            for (int c = grp; c < NCHUNK; c += NGRP) last_c = c;
-            for (int c = grp; c < NCHUNK; c += NGRP) {
-                const int col0 = n_blk * BN + c * 32;
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + as * 256 + c * 32 + ((uint32_t)(quad * 32) << 16), v);
-                // stage this chunk's bias while the TMEM load is in flight
+            const int col0 = n_blk * BN + c * 32;
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + as * 256 + c * 32 + ((uint32_t)(quad * 32) << 16), v);
+            // stage this chunk's bias while the TMEM load is in flight
+            __syncwarp();
+            bias_w[lane] = (p.bias != nullptr && col0 + lane < p.N) ? __ldg(p.bias + col0 + lane) : 0.0f;
+            __syncwarp();
+            tmem_ld_wait();
+            if (nc == grp) {                       // last chunk of the tile: all TMEM reads of this tile by this warp are done
+                tc_fence_before();
                 __syncwarp();
-                bias_w[lane] = (p.bias != nullptr && col0 + lane < p.N) ? __ldg(p.bias + col0 + lane) : 0.0f;
-                __syncwarp();
-                tmem_ld_wait();
-                if (c == last_c) {                 // all TMEM reads of this tile by this warp are done
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[as]);
+                if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            }
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_w + j);
+                f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
+                f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+                f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            }
+            const bool gelu_half = OUT_BF16 && p.act == 1 && p.out_f16;   // GELU done below in packed fp16
+            if (p.act == 1 && !gelu_half) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            } else if (p.act == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+            }
+            uint8_t* sbuf = cst + b * GEMM_CSTAGE_BYTES;
+            if constexpr (!OUT_BF16) {
+                if (p.aux != nullptr && row_ok) {
+                    float* ap = p.aux + ((long long)(row / p.aux_T) * p.aux_bstride + (row % p.aux_T)) * p.ld_aux + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (col0 + j < p.N) *reinterpret_cast<float4*>(ap + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
                 }
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(bias_w + j);
-                    f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
-                    f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-                    f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-                    f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
-                }
-                const bool gelu_half = OUT_BF16 && p.act == 1 && p.out_f16;   // GELU done below in packed fp16
-                if (p.act == 1 && !gelu_half) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-                } else if (p.act == 2) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-                }
-                if constexpr (!OUT_BF16) {
-                    if (p.aux != nullptr && row_ok) {
-                        float* ap = p.aux + ((long long)(row / p.aux_T) * p.aux_bstride + (row % p.aux_T)) * p.ld_aux + col0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            if (col0 + j < p.N) *reinterpret_cast<float4*>(ap + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    }
-                    if (p.resid1 != nullptr && row_ok) {
-                        const float* rp = p.resid1 + (long long)row * p.ldr1 + col0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (col0 + j < p.N) {
-                                const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
-                                f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
-                            }
-                        }
-                    }
-                    if (p.resid2 != nullptr && row_ok) {
-                        const float* rp = p.resid2 + (long long)row * p.ldr2 + col0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (col0 + j < p.N) {
-                                const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
-                                f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
-                            }
-                        }
-                    }
-                }
-                // staging buffer `buf` was last handed to TMA two chunks ago: make sure it has been read out
-                if (lane == 0) tma_store_wait_read<1>();
-                __syncwarp();
-                uint8_t* sbuf = cst + buf * GEMM_CSTAGE_BYTES;
-                if constexpr (OUT_BF16) {
-                    // row = 64 B (32 bf16), CU_TENSOR_MAP_SWIZZLE_64B: 16-byte unit index ^= (row >> 1) & 3
-                    uint8_t* rowp = sbuf + lane * 64;
-                    const int sw = (lane >> 1) & 3;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint4 u;
-                        if (gelu_half) {
-                            u.x = gelu_erf_f16x2(f[q * 8 + 0], f[q * 8 + 1]);
-                            u.y = gelu_erf_f16x2(f[q * 8 + 2], f[q * 8 + 3]);
-                            u.z = gelu_erf_f16x2(f[q * 8 + 4], f[q * 8 + 5]);
-                            u.w = gelu_erf_f16x2(f[q * 8 + 6], f[q * 8 + 7]);
-                        } else {
-                            u.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
-                            u.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
-                            u.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
-                            u.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
-                        }
-                        *reinterpret_cast<uint4*>(rowp + ((q ^ sw) << 4)) = u;
-                    }
-                } else {
-                    // row = 128 B (32 fp32), CU_TENSOR_MAP_SWIZZLE_128B: 16-byte unit index ^= row & 7
-                    uint8_t* rowp = sbuf + lane * 128;
+                if (tma_resid) {
+                    mbar_wait(&rbar[b], (i / NBUF) & 1);
+                    const uint8_t* rowp = sbuf + lane * 128;
                     const int sw = lane & 7;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        *reinterpret_cast<float4*>(rowp + ((q ^ sw) << 4)) =
-                            make_float4(f[q * 4 + 0], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 r4 = *reinterpret_cast<const float4*>(rowp + ((q ^ sw) << 4));
+                        f[q * 4] += r4.x; f[q * 4 + 1] += r4.y; f[q * 4 + 2] += r4.z; f[q * 4 + 3] += r4.w;
+                    }
                 }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_2d(&tmC, sbuf, col0, m_blk * GEMM_BM + quad * 32);
-                    tma_store_commit();
+                if (p.resid2 != nullptr && row_ok) {
+                    const float* rp = p.resid2 + (long long)row * p.ldr2 + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (col0 + j < p.N) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+                            f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+                        }
+                    }
                 }
-                buf ^= 1;
             }
+            if (!tma_resid) {                      // buffer b was last handed to TMA NBUF chunks ago: make sure it has been read out
+                if (lane == 0) tma_store_wait_read<NBUF - 1>();
+                __syncwarp();
+            }
+            if constexpr (OUT_BF16) {
+                // row = 64 B (32 x 16-bit), CU_TENSOR_MAP_SWIZZLE_64B: 16-byte unit index ^= (row >> 1) & 3
+                uint8_t* rowp = sbuf + lane * 64;
+                const int sw = (lane >> 1) & 3;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4 u;
+                    if (gelu_half) {
+                        u.x = gelu_erf_f16x2(f[q * 8 + 0], f[q * 8 + 1]);
+                        u.y = gelu_erf_f16x2(f[q * 8 + 2], f[q * 8 + 3]);
+                        u.z = gelu_erf_f16x2(f[q * 8 + 4], f[q * 8 + 5]);
+                        u.w = gelu_erf_f16x2(f[q * 8 + 6], f[q * 8 + 7]);
+                    } else {
+                        u.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+                        u.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+                        u.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+                        u.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+                    }
+                    *reinterpret_cast<uint4*>(rowp + ((q ^ sw) << 4)) = u;
+                }
+            } else {
+                // row = 128 B (32 fp32), CU_TENSOR_MAP_SWIZZLE_128B: 16-byte unit index ^= row & 7
+                uint8_t* rowp = sbuf + lane * 128;
+                const int sw = lane & 7;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4*>(rowp + ((q ^ sw) << 4)) = make_float4(f[q * 4 + 0], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&tmC, sbuf, col0, m_blk * GEMM_BM + quad * 32);
+                tma_store_commit();
+            }
+            ++i;
+            if (nc == grp) ++it;
+            tile = ntile;
+            c = nc;
         }
         if (lane == 0) tma_store_wait_all<0>();
     }
@@ -307,9 +330,9 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t in
 }
 
 template <int BN, bool OUT_BF16>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmKernelParams& kp, int num_sms,
-                       cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr, const GemmKernelParams& kp,
+                       int num_sms, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN, OUT_BF16>;
     auto kern = gemm_tc_kernel<BN, OUT_BF16>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -319,14 +342,15 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     }
     const int tiles = ((kp.M + GEMM_BM - 1) / GEMM_BM) * ((kp.N + BN - 1) / BN);
     const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, kp);
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, tr, kp);
     cudaError_t e = cudaGetLastError();
     return check_cuda(e, "gemm launch");
 }
 
-static int pick_bn(int N) {
+static int pick_bn(int N, bool out16) {
     // widest tile that divides N (fewest re-reads of A); fall back to 128 with a clipped last tile.
-    if (N % 256 == 0) return 256;
+    // fp32-output kernels spend their shared memory on 3 epilogue staging buffers per warp and stop at BN = 192.
+    if (out16 && N % 256 == 0) return 256;
     if (N % 192 == 0) return 192;
     if (N % 128 == 0) return 128;
     if (N % 96 == 0) return 96;
@@ -339,14 +363,20 @@ int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     if ((a.out_bf16 && (a.ldo % 8) != 0) || (!a.out_bf16 && (a.ldo % 4) != 0)) return set_error(ARD_ERR_SHAPE, "gemm: ldo alignment");
     if (a.out_bf16 && (a.resid1 || a.resid2 || a.aux)) return set_error(ARD_ERR_SHAPE, "gemm: residual/aux need fp32 output");
     if (a.out_f16 && !(a.out_bf16 && a.act == ARD_ACT_GELU)) return set_error(ARD_ERR_SHAPE, "gemm: fp16 output is only produced by the GELU epilogue");
-    const int BN = a.force_bn ? a.force_bn : pick_bn(a.N);
-    CUtensorMap ta, tb, tc;
+    const int BN = a.force_bn ? a.force_bn : pick_bn(a.N, a.out_bf16 != 0);
+    if (!a.out_bf16 && BN > 192) return set_error(ARD_ERR_SHAPE, "gemm: fp32 output supports BN <= 192");
+    CUtensorMap ta, tb, tc, tr;
     if (int rc = make_tmap_2d(&ta, a.A, 2, a.K, a.M, (uint64_t)a.lda * 2, GEMM_BK, GEMM_BM, 128)) return rc;
     if (int rc = make_tmap_2d(&tb, a.W, 2, a.K, a.N, (uint64_t)a.ldw * 2, GEMM_BK, BN, 128)) return rc;
     if (a.out_bf16) {
         if (int rc = make_tmap_2d(&tc, a.out, 2, a.N, a.M, (uint64_t)a.ldo * 2, 32, 32, 64)) return rc;
     } else {
         if (int rc = make_tmap_2d(&tc, a.out, 4, a.N, a.M, (uint64_t)a.ldo * 4, 32, 32, 128)) return rc;
+    }
+    tr = tc;
+    if (!a.out_bf16 && a.resid1 != nullptr) {
+        if (a.ldr1 % 4) return set_error(ARD_ERR_SHAPE, "gemm: residual leading dimension must be a multiple of 4");
+        if (int rc = make_tmap_2d(&tr, a.resid1, 4, a.N, a.M, (uint64_t)a.ldr1 * 4, 32, 32, 128)) return rc;
     }
     GemmKernelParams kp;
     kp.M = a.M; kp.N = a.N; kp.K = a.K;
@@ -360,12 +390,14 @@ int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream) {
                      (a.aux ? 4.0 * a.M * a.N : 0.0));
 #define ARD_GEMM_CASE(bn)                                                                                          \
     case bn:                                                                                                       \
-        return a.out_bf16 ? launch_gemm<bn, true>(ta, tb, tc, kp, num_sms, stream) : launch_gemm<bn, false>(ta, tb, tc, kp, num_sms, stream);
+        return a.out_bf16 ? launch_gemm<bn, true>(ta, tb, tc, tr, kp, num_sms, stream) : launch_gemm<bn, false>(ta, tb, tc, tr, kp, num_sms, stream);
     switch (BN) {
         ARD_GEMM_CASE(96)
         ARD_GEMM_CASE(128)
         ARD_GEMM_CASE(192)
-        ARD_GEMM_CASE(256)
+        case 256:
+            if (a.out_bf16) return launch_gemm<256, true>(ta, tb, tc, tr, kp, num_sms, stream);
+            break;
     }
 #undef ARD_GEMM_CASE
     return set_error(ARD_ERR_SHAPE, "gemm: unsupported BN=%d", BN);

@@ -77,6 +77,55 @@ def check_gemm(M, N, K, out_bf16, act=0, bias=True, nres=0, seed=0):
     return rel(got, ref), (got - ref).abs().max().item()
 
 
+def check_ffn_fused(M=5000, resid2=True, seed=0):
+    """ard_ffn_fused_96 (LN + fc1 + GELU + fc2 + residuals in one kernel) vs torch fp32 on bf16/fp16-rounded weights."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(seed)
+    Cd = 96
+    x = torch.randn(M, Cd, generator=g) * 1.5 + 0.3
+    r2 = torch.randn(M, Cd, generator=g) if resid2 else None
+    gm, bt = 1 + 0.1 * torch.randn(Cd, generator=g), 0.1 * torch.randn(Cd, generator=g)
+    w1 = torch.randn(4 * Cd, Cd, generator=g) / Cd ** 0.5
+    w2 = torch.randn(Cd, 4 * Cd, generator=g) / (4 * Cd) ** 0.5
+    b1, b2 = 0.1 * torch.randn(4 * Cd, generator=g), 0.1 * torch.randn(Cd, generator=g)
+    ln = torch.nn.functional.layer_norm(x, (Cd,), gm, bt, 1e-5)
+    hdn = torch.nn.functional.gelu(ln @ bf16r(w1).t() + b1)
+    branch = hdn @ w2.half().float().t() + b2
+    ref = x + branch + (r2 if resid2 else 0)
+    d = lambda t: t.cuda().contiguous()
+    xd, r2d, gd, btd = d(x), (d(r2) if resid2 else None), d(gm), d(bt)
+    w1d, w2d, b1d, b2d = d(w1).to(torch.bfloat16), d(w2).to(torch.float16), d(b1), d(b2)
+    out = torch.empty_like(xd)
+    L.check(lib.ard_ffn_fused_96(L.ptr(xd), L.ptr(r2d), L.ptr(out), M, L.ptr(gd), L.ptr(btd), L.ptr(w1d), L.ptr(b1d), L.ptr(w2d), L.ptr(b2d),
+                                 L.stream_ptr()))
+    torch.cuda.synchronize()
+    got_branch = out.cpu() - x - (r2 if resid2 else 0)
+    return rel(out.cpu(), ref), rel(got_branch, branch)
+
+
+def check_gemm_f16_chain(M=3000, Cd=192, seed=0):
+    """fc1 with the packed-fp16 GELU epilogue (ARD_ACT_GELU_F16) feeding the fp16 fc2 GEMM with a TMA-fetched residual."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(seed)
+    xn = torch.randn(M, Cd, generator=g)
+    w1 = torch.randn(4 * Cd, Cd, generator=g) / Cd ** 0.5
+    w2 = torch.randn(Cd, 4 * Cd, generator=g) / (4 * Cd) ** 0.5
+    b1, b2 = 0.1 * torch.randn(4 * Cd, generator=g), 0.1 * torch.randn(Cd, generator=g)
+    res = torch.randn(M, Cd, generator=g)
+    hdn = torch.nn.functional.gelu(bf16r(xn) @ bf16r(w1).t() + b1)
+    ref = hdn @ w2.half().float().t() + b2 + res
+    d = lambda t: t.cuda().contiguous()
+    xd, w1d, w2d = d(xn).to(torch.bfloat16), d(w1).to(torch.bfloat16), d(w2).to(torch.float16)
+    b1d, b2d, rd = d(b1), d(b2), d(res)
+    hb = torch.empty(M, 4 * Cd, device="cuda", dtype=torch.float16)
+    out = torch.empty(M, Cd, device="cuda", dtype=torch.float32)
+    st = L.stream_ptr()
+    L.check(lib.ard_gemm_bf16(L.ptr(xd), Cd, L.ptr(w1d), Cd, L.ptr(hb), 4 * Cd, 1, M, 4 * Cd, Cd, L.ptr(b1d), L.ACT_GELU_F16, None, 0, None, 0, st))
+    L.check(lib.ard_gemm_f16(L.ptr(hb), 4 * Cd, L.ptr(w2d), 4 * Cd, L.ptr(out), Cd, 0, M, Cd, 4 * Cd, L.ptr(b2d), 0, L.ptr(rd), Cd, None, 0, st))
+    torch.cuda.synchronize()
+    return rel(hb.float().cpu(), hdn), rel(out.cpu(), ref)
+
+
 def check_layernorm(rows, Cdim, seed=0):
     lib = L.load()
     g = torch.Generator().manual_seed(seed)

@@ -22,6 +22,17 @@ def test_gemm_epilogues():
     assert G.check_gemm(1024, 192, 384, False, bias=False, nres=1)[0] < 2e-5
 
 
+@pytest.mark.parametrize("M,resid2", [(128, False), (5000, True), (16384 + 77, True)])
+def test_ffn_fused_96(M, resid2):
+    r_out, r_branch = G.check_ffn_fused(M, resid2)
+    assert r_out < 2e-3 and r_branch < 5e-3, (r_out, r_branch)     # bf16 LN output / fp16 hidden operands, fp32 accumulation
+
+
+def test_gemm_f16_hidden_chain():
+    r_h, r_out = G.check_gemm_f16_chain()
+    assert r_h < 1e-3 and r_out < 2e-3, (r_h, r_out)                # fp16 hidden: 10-bit mantissa
+
+
 @pytest.mark.parametrize("C", [96, 128, 192, 256, 384, 512, 768, 1024, 1536, 2048])
 def test_layernorm(C):
     r_bf16, r_f32 = G.check_layernorm(777, C)
