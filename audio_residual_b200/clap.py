@@ -163,11 +163,7 @@ class CLAP_Module(nn.Module):
 
     def fusion_mel(self, wave, quantize=False):
         """get_mel (data.py:363-399) for a batch on device, stacked 4x as data.py:497-501 does for clips <= 10 s."""
-        import ctypes as C
-        from . import lib as L
-        enc = self.model.audio_branch
-        h = enc._handle()
-        raise NotImplementedError("on-device fusion featuriser: scheduled with SURVEY §8(f) rank 1")
+        return self.model.audio_branch.fusion_mel(wave, quantize=quantize)
 
     def get_audio_embedding_from_data(self, x, use_tensor=False, data_fil="repeatpad"):
         """hook.py:158-192. use_tensor=False: numpy/tensor input, int16 round-trip first, returns numpy.

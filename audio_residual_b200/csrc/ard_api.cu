@@ -93,6 +93,8 @@ struct ard_handle {
     // front end
     DevBuf window, twiddle, melw, mstart, mlen, bn_scale, bn_shift;
     int band_max = 0;
+    DevBuf f_window, f_melw, f_mstart, f_mlen;   // fusion featuriser (get_mel, data.py:363-399): htk filters, periodic hann
+    int f_band_max = 0;
     DevBuf pe_w, pe_b, pe_g, pe_beta;
     std::vector<LayerW> layers;
     DevBuf norm_g, norm_b, tscam_w, tscam_b, p0_w, p0_b, p2_w, p2_b;
@@ -133,6 +135,37 @@ static int get(const ard_handle* h, const std::string& key, size_t numel, const 
     return 0;
 }
 
+static int build_mel_bands(const std::vector<float>& melW, DevBuf& w, DevBuf& st_d, DevBuf& ln_d, int* band_max) {
+    std::vector<int> st(64), ln(64);
+    int bmax = 1;
+    for (int m = 0; m < 64; ++m) {
+        int lo = 513, hi = -1;
+        for (int k = 0; k < 513; ++k)
+            if (melW[k * 64 + m] != 0.0f) { lo = k < lo ? k : lo; hi = k; }
+        if (hi < 0) { lo = 0; hi = 0; }
+        st[m] = lo; ln[m] = hi - lo + 1;
+        bmax = ln[m] > bmax ? ln[m] : bmax;
+    }
+    std::vector<float> band((size_t)64 * bmax, 0.f);
+    for (int m = 0; m < 64; ++m)
+        for (int q = 0; q < ln[m]; ++q) band[(size_t)m * bmax + q] = melW[(st[m] + q) * 64 + m];
+    *band_max = bmax;
+    ARD_TRY(upload_f32(w, band));
+    ARD_TRY(upload(st_d, st.data(), 64 * 4));
+    ARD_TRY(upload(ln_d, ln.data(), 64 * 4));
+    return 0;
+}
+
+static int upload_twiddle(ard_handle* h) {
+    std::vector<float> tw(2048);
+    for (int i = 0; i < 1024; ++i) {
+        const double a = -2.0 * M_PI * i / 1024.0;
+        tw[2 * i] = (float)cos(a);
+        tw[2 * i + 1] = (float)sin(a);
+    }
+    return upload_f32(h->twiddle, tw);
+}
+
 static int finalize(ard_handle* h, cudaStream_t) {
     const ard_config& c = h->cfg;
     const std::vector<float>* v = nullptr;
@@ -143,31 +176,16 @@ static int finalize(ard_handle* h, cudaStream_t) {
         ARD_TRY(get(h, "spectrogram_extractor.stft.conv_real.weight", 513 * 1024, &v));
         std::vector<float> win(v->begin(), v->begin() + 1024);
         ARD_TRY(upload_f32(h->window, win));
-        std::vector<float> tw(2048);
-        for (int i = 0; i < 1024; ++i) {
-            const double a = -2.0 * M_PI * i / 1024.0;
-            tw[2 * i] = (float)cos(a);
-            tw[2 * i + 1] = (float)sin(a);
-        }
-        ARD_TRY(upload_f32(h->twiddle, tw));
+        ARD_TRY(upload_twiddle(h));
         ARD_TRY(get(h, "logmel_extractor.melW", 513 * 64, &v));
-        std::vector<int> st(64), ln(64);
-        int bmax = 1;
-        for (int m = 0; m < 64; ++m) {
-            int lo = 513, hi = -1;
-            for (int k = 0; k < 513; ++k)
-                if ((*v)[k * 64 + m] != 0.0f) { lo = k < lo ? k : lo; hi = k; }
-            if (hi < 0) { lo = 0; hi = 0; }
-            st[m] = lo; ln[m] = hi - lo + 1;
-            bmax = ln[m] > bmax ? ln[m] : bmax;
-        }
-        std::vector<float> band((size_t)64 * bmax, 0.f);
-        for (int m = 0; m < 64; ++m)
-            for (int q = 0; q < ln[m]; ++q) band[(size_t)m * bmax + q] = (*v)[(st[m] + q) * 64 + m];
-        h->band_max = bmax;
-        ARD_TRY(upload_f32(h->melw, band));
-        ARD_TRY(upload(h->mstart, st.data(), 64 * 4));
-        ARD_TRY(upload(h->mlen, ln.data(), 64 * 4));
+        ARD_TRY(build_mel_bands(*v, h->melw, h->mstart, h->mlen, &h->band_max));
+    }
+    if (h->host.count("fusion_featuriser.melW")) {   // torchaudio MelSpectrogram(htk, norm=None) filters + window of get_mel
+        ARD_TRY(upload_twiddle(h));
+        ARD_TRY(get(h, "fusion_featuriser.window", 1024, &v));
+        ARD_TRY(upload_f32(h->f_window, *v));
+        ARD_TRY(get(h, "fusion_featuriser.melW", 513 * 64, &v));
+        ARD_TRY(build_mel_bands(*v, h->f_melw, h->f_mstart, h->f_mlen, &h->f_band_max));
     }
     {   // bn0 eval: y = (x - rm) / sqrt(rv + eps) * g + b  ->  scale, shift   (htsat.py:691, :900-902)
         const std::vector<float>*g, *b, *rm, *rv;
@@ -365,7 +383,7 @@ static int encoder_forward(ard_handle* h, const ard_forward_args* a, cudaStream_
         ARD_TRY(h->ws_logmel.ensure((size_t)B * ARD_FRAMES * 64 * 4));
         MelBands mb{h->melw.as<float>(), h->mstart.as<int>(), h->mlen.as<int>(), h->band_max};
         ARD_TRY(stft_logmel(a->waveform, B, ARD_CLIP_SAMPLES, h->window.as<float>(), h->twiddle.as<float2>(), mb, nullptr, nullptr,
-                            h->ws_logmel.as<float>(), a->quantize, s));
+                            h->ws_logmel.as<float>(), 0, 1, a->quantize, s));
         ARD_TRY(patch_embed_ln(h->ws_logmel.as<float>(), (long long)ARD_FRAMES * 64, ARD_FRAMES, h->bn_scale.as<float>(),
                                h->bn_shift.as<float>(), h->pe_w.as<float>(), h->pe_b.as<float>(), h->pe_g.as<float>(), h->pe_beta.as<float>(),
                                X, B, C0, s));
@@ -611,7 +629,16 @@ int ard_logmel(ard_handle* h, const float* wave, int B, int n_samples, int apply
     if (!h->window.p) return set_error(ARD_ERR_STATE, "front-end weights (spectrogram_extractor / logmel_extractor) were never set");
     MelBands mb{h->melw.as<float>(), h->mstart.as<int>(), h->mlen.as<int>(), h->band_max};
     return stft_logmel(wave, B, n_samples, h->window.as<float>(), h->twiddle.as<float2>(), mb, apply_bn ? h->bn_scale.as<float>() : nullptr,
-                       apply_bn ? h->bn_shift.as<float>() : nullptr, out, quantize, (cudaStream_t)stream);
+                       apply_bn ? h->bn_shift.as<float>() : nullptr, out, 0, 1, quantize, (cudaStream_t)stream);
+}
+
+int ard_fusion_mel(ard_handle* h, const float* wave, int B, int n_samples, int quantize, float* out, void* stream) {
+    if (!h || !h->finalized) return set_error(ARD_ERR_STATE, "handle not finalised");
+    if (!h->f_window.p) return set_error(ARD_ERR_STATE, "fusion featuriser tensors (fusion_featuriser.melW / .window) were never set");
+    MelBands mb{h->f_melw.as<float>(), h->f_mstart.as<int>(), h->f_mlen.as<int>(), h->f_band_max};
+    const int frames = n_samples / 480 + 1;
+    return stft_logmel(wave, B, n_samples, h->f_window.as<float>(), h->twiddle.as<float2>(), mb, nullptr, nullptr, out,
+                       4LL * frames * 64, 4, quantize, (cudaStream_t)stream);
 }
 
 int ard_stats_accumulate(const float* x, long long rows, int D, double* sum, double* sumsq, void* stream) {

@@ -93,7 +93,8 @@ struct MelBands {            // banded view of logmel_extractor.melW [513,64]
     int band_max = 0;
 };
 int stft_logmel(const float* wave, int B, int n_samples, const float* window, const float2* twiddle, const MelBands& mel,
-                const float* bn_scale, const float* bn_shift, float* out /*[B,frames,64]*/, int quantize, cudaStream_t s);
+                const float* bn_scale, const float* bn_shift, float* out /*[B,(replicate,)frames,64]*/, long long out_clip_stride, int replicate,
+                int quantize, cudaStream_t s);
 int patch_embed_ln(const float* logmel /*[B,frames,64]*/, long long clip_stride, int frames, const float* bn_scale, const float* bn_shift,
                    const float* w /*[C,16]*/, const float* bias, const float* gamma, const float* beta, float* out /*[B,4096,C]*/, int B,
                    int C, cudaStream_t s);

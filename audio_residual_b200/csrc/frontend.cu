@@ -22,14 +22,20 @@ constexpr int PAIRS_PER_CTA = 8;
 
 ARD_DEVINL float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
+// FFT buffers are indexed through PADI: one float2 of padding after every 4 elements. The radix-4 Stockham passes store with
+// element strides of 4/16/64: unpadded that is an 8-way bank conflict on the first passes (ncu: 56% of all shared wavefronts
+// of this kernel were conflict replays), padded the stride-4 pattern is conflict-free and the others at most 2-way.
+#define PADI(i) ((i) + ((i) >> 2))
+constexpr int NFFT_PAD = NFFT + NFFT / 4;
+
 __global__ void __launch_bounds__(256) stft_logmel_kernel(const float* __restrict__ wave, int n_samples, int frames,
                                                          const float* __restrict__ window, const float2* __restrict__ twiddle,
                                                          const float* __restrict__ melw, const int* __restrict__ mstart,
                                                          const int* __restrict__ mlen, int band_max,
                                                          const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
-                                                         float* __restrict__ out, int quantize) {
-    __shared__ float2 bufA[NFFT];
-    __shared__ float2 bufB[NFFT];
+                                                         float* __restrict__ out, long long out_clip_stride, int replicate, int quantize) {
+    __shared__ float2 bufA[NFFT_PAD];
+    __shared__ float2 bufB[NFFT_PAD];
     __shared__ float2 tw[NFFT];
     __shared__ float win[NFFT];
     __shared__ float pw[2][NBINS + 3];
@@ -43,31 +49,48 @@ __global__ void __launch_bounds__(256) stft_logmel_kernel(const float* __restric
     const int npairs = (frames + 1) >> 1;
     const int p_begin = blockIdx.x * PAIRS_PER_CTA;
     const int p_end = min(p_begin + PAIRS_PER_CTA, npairs);
-    for (int pr = p_begin; pr < p_end; ++pr) {
+    // samples of a frame pair: reflect padding (F.pad mode='reflect', n_fft/2 each side) only matters near the clip ends
+    float va[4], vb[4];
+    auto load_pair = [&](int pr) {
         const int fa = 2 * pr, fb = 2 * pr + 1;
-        __syncthreads();
-        // z[n] = w[n] * (xa[n] + i xb[n]);  reflect padding (F.pad mode='reflect', n_fft/2 each side)
+        const int base_a = fa * HOPS - NFFT / 2;
+        const bool interior = base_a >= 0 && base_a + HOPS + NFFT <= n_samples && fb < frames;   // block-uniform
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int n = tid + 256 * r;
-            float va, vb = 0.f;
-            {
-                int idx = fa * HOPS + n - NFFT / 2;
+            vb[r] = 0.f;
+            if (interior) {
+                va[r] = __ldg(x + base_a + n);
+                vb[r] = __ldg(x + base_a + HOPS + n);
+            } else {
+                int idx = base_a + n;
                 idx = idx < 0 ? -idx : (idx >= n_samples ? 2 * (n_samples - 1) - idx : idx);
-                va = __ldg(x + idx);
+                va[r] = __ldg(x + idx);
+                if (fb < frames) {
+                    idx = base_a + HOPS + n;
+                    idx = idx < 0 ? -idx : (idx >= n_samples ? 2 * (n_samples - 1) - idx : idx);
+                    vb[r] = __ldg(x + idx);
+                }
             }
-            if (fb < frames) {
-                int idx = fb * HOPS + n - NFFT / 2;
-                idx = idx < 0 ? -idx : (idx >= n_samples ? 2 * (n_samples - 1) - idx : idx);
-                vb = __ldg(x + idx);
-            }
+        }
+    };
+    if (p_begin < p_end) load_pair(p_begin);
+    for (int pr = p_begin; pr < p_end; ++pr) {
+        const int fa = 2 * pr;
+        __syncthreads();
+        // z[n] = w[n] * (xa[n] + i xb[n])
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int n = tid + 256 * r;
+            float a0 = va[r], b0 = vb[r];
             if (quantize) {   // quantize_tensor, src/residual.py:210-212
-                va = truncf(fminf(fmaxf(va, -1.f), 1.f) * 32767.0f) / 32767.0f;
-                vb = truncf(fminf(fmaxf(vb, -1.f), 1.f) * 32767.0f) / 32767.0f;
+                a0 = truncf(fminf(fmaxf(a0, -1.f), 1.f) * 32767.0f) / 32767.0f;
+                b0 = truncf(fminf(fmaxf(b0, -1.f), 1.f) * 32767.0f) / 32767.0f;
             }
             const float w = win[n];
-            bufA[n] = make_float2(va * w, vb * w);
+            bufA[PADI(n)] = make_float2(a0 * w, b0 * w);
         }
+        if (pr + 1 < p_end) load_pair(pr + 1);       // next pair's samples are in flight during this pair's FFT
         __syncthreads();
         // radix-4 Stockham autosort FFT, 5 passes (p = 1,4,16,64,256), natural-order output
         float2* src = bufA;
@@ -78,7 +101,7 @@ __global__ void __launch_bounds__(256) stft_logmel_kernel(const float* __restric
             const int k = tid & (p - 1);
             const int j = ((tid - k) << 2) + k;
             const int tstep = (NFFT / 4) / p * k;   // twiddle index for exp(-2 pi i k / (4p))
-            float2 u0 = src[tid], u1 = src[tid + 256], u2 = src[tid + 512], u3 = src[tid + 768];
+            float2 u0 = src[PADI(tid)], u1 = src[PADI(tid + 256)], u2 = src[PADI(tid + 512)], u3 = src[PADI(tid + 768)];
             if (pass > 0) {
                 u1 = cmul(u1, tw[tstep]);
                 u2 = cmul(u2, tw[2 * tstep]);
@@ -89,17 +112,18 @@ __global__ void __launch_bounds__(256) stft_logmel_kernel(const float* __restric
             const float2 v2 = make_float2(u1.x + u3.x, u1.y + u3.y);
             const float2 d = make_float2(u1.x - u3.x, u1.y - u3.y);
             const float2 v3 = make_float2(d.y, -d.x);   // (u1 - u3) * (-i)
-            dst[j] = make_float2(v0.x + v2.x, v0.y + v2.y);
-            dst[j + p] = make_float2(v1.x + v3.x, v1.y + v3.y);
-            dst[j + 2 * p] = make_float2(v0.x - v2.x, v0.y - v2.y);
-            dst[j + 3 * p] = make_float2(v1.x - v3.x, v1.y - v3.y);
+            dst[PADI(j)] = make_float2(v0.x + v2.x, v0.y + v2.y);
+            dst[PADI(j + p)] = make_float2(v1.x + v3.x, v1.y + v3.y);
+            dst[PADI(j + 2 * p)] = make_float2(v0.x - v2.x, v0.y - v2.y);
+            dst[PADI(j + 3 * p)] = make_float2(v1.x - v3.x, v1.y - v3.y);
             __syncthreads();
             float2* t = src; src = dst; dst = t;
         }
         // split the two real spectra and take powers: Xa = (Z[k] + conj Z[N-k]) / 2, Xb = (Z[k] - conj Z[N-k]) / (2i)
         for (int k = tid; k < NBINS; k += 256) {
-            const float2 z = src[k];
-            const float2 zc = src[(NFFT - k) & (NFFT - 1)];
+            const float2 z = src[PADI(k)];
+            const int kc = (NFFT - k) & (NFFT - 1);
+            const float2 zc = src[PADI(kc)];
             const float ar = 0.5f * (z.x + zc.x), ai = 0.5f * (z.y - zc.y);
             const float br = 0.5f * (z.y + zc.y), bi = 0.5f * (zc.x - z.x);
             pw[0][k] = ar * ar + ai * ai;
@@ -116,22 +140,26 @@ __global__ void __launch_bounds__(256) stft_logmel_kernel(const float* __restric
                 for (int q = 0; q < ln; ++q) acc = fmaf(pw[f][st + q], __ldg(wrow + q), acc);
                 float v = 10.0f * log10f(fmaxf(acc, 1e-10f));   // ref=1.0 -> "- 10*log10(max(amin, ref))" is exactly 0
                 if (bn_scale != nullptr) v = fmaf(v, bn_scale[m], bn_shift[m]);
-                out[(b * frames + frame) * NMEL + m] = v;
+                float* o = out + b * out_clip_stride + (long long)frame * NMEL + m;
+                for (int rpl = 0; rpl < replicate; ++rpl) o[(long long)rpl * frames * NMEL] = v;
             }
         }
     }
 }
 
 int stft_logmel(const float* wave, int B, int n_samples, const float* window, const float2* twiddle, const MelBands& mel,
-                const float* bn_scale, const float* bn_shift, float* out, int quantize, cudaStream_t s) {
+                const float* bn_scale, const float* bn_shift, float* out, long long out_clip_stride, int replicate, int quantize,
+                cudaStream_t s) {
     if (B <= 0) return 0;
     if (n_samples <= NFFT / 2) return set_error(ARD_ERR_SHAPE, "stft: clip too short for reflect padding (%d samples)", n_samples);
     const int frames = n_samples / HOPS + 1;
     const int npairs = (frames + 1) / 2;
+    if (out_clip_stride <= 0) out_clip_stride = (long long)frames * NMEL;
+    if (replicate < 1) replicate = 1;
     dim3 grid((npairs + PAIRS_PER_CTA - 1) / PAIRS_PER_CTA, B);
-    ProfScope ps(PROF_FRONTEND, s, (double)B * npairs * (5.0 * 1024 * 10 + 2.0 * 2 * 1100), 4.0 * B * n_samples + 4.0 * B * frames * 64);
+    ProfScope ps(PROF_FRONTEND, s, (double)B * npairs * (5.0 * 1024 * 10 + 2.0 * 2 * 1100), 4.0 * B * n_samples + 4.0 * B * frames * 64 * replicate);
     stft_logmel_kernel<<<grid, 256, 0, s>>>(wave, n_samples, frames, window, twiddle, mel.w, mel.start, mel.len, mel.band_max, bn_scale,
-                                           bn_shift, out, quantize);
+                                           bn_shift, out, out_clip_stride, replicate, quantize);
     return check_cuda(cudaGetLastError(), "stft_logmel launch");
 }
 

@@ -268,6 +268,12 @@ class HTSAT_Swin_Transformer(nn.Module):
                 items = list(self._audio_keys())
                 if self._projection is not None:
                     items += [("audio_projection." + k, v) for k, v in self._projection.state_dict().items()]
+                if self.enable_fusion:
+                    # constants of the fusion featuriser get_mel (data.py:365-378): torchaudio's htk filterbank (norm=None)
+                    # and torch.hann_window(1024) (periodic); they are not checkpoint tensors
+                    from . import weights as W
+                    items += [("fusion_featuriser.melW", torch.from_numpy(W.mel_filterbank(htk=True, slaney_norm=False))),
+                              ("fusion_featuriser.window", torch.from_numpy(W.hann_periodic(1024)))]
                 for k, v in items:
                     t = v.detach().to("cpu", torch.float32).contiguous()
                     L.check(lib.ard_set_weight(hb.h, k.encode(), L.ptr(t), t.numel()))
@@ -370,6 +376,16 @@ class HTSAT_Swin_Transformer(nn.Module):
         with torch.cuda.device(dev):
             L.check(lib.ard_encoder_forward(h, C.byref(a), L.stream_ptr()))
         out["_keepalive"] = src
+        return out
+
+    def fusion_mel(self, wave, quantize=False):
+        """Batched get_mel + 4x stack (data.py:363-399, :497-501) on device: wave [B, 480000] -> mel_fusion [B, 4, 1001, 64]."""
+        h = self._handle()
+        wave = wave.detach().to(self._device(), torch.float32).contiguous()
+        B, n = wave.shape
+        out = torch.empty((B, 4, n // 480 + 1, 64), device=wave.device, dtype=torch.float32)
+        with torch.cuda.device(wave.device):
+            L.check(L.load().ard_fusion_mel(h, L.ptr(wave), B, n, int(bool(quantize)), L.ptr(out), L.stream_ptr()))
         return out
 
     def forward(self, x, mixup_lambda=None, infer_mode=False, device=None):

@@ -70,6 +70,7 @@ def load(check_symbols=False):
         lib.ard_f32_to_bf16.argtypes = [vp, vp, ll, f, vp]
         lib.ard_quantize_waveform.argtypes = [vp, vp, ll, vp]
         lib.ard_logmel.argtypes = [vp, vp, i, i, i, i, vp, vp]
+        lib.ard_fusion_mel.argtypes = [vp, vp, i, i, i, vp, vp]
         lib.ard_stats_accumulate.argtypes = [vp, ll, i, vp, vp, vp]
         lib.ard_profile_enable.argtypes = [i]
         lib.ard_profile_read.argtypes = [c_double_p, c_double_p, c_double_p, C.POINTER(C.c_int), i]

@@ -140,6 +140,12 @@ int ard_quantize_waveform(const float* in, float* out, long long n, void* stream
  * (bn0 applied iff apply_bn). Uses the handle's window / mel filters / BN statistics. */
 int ard_logmel(ard_handle* h, const float* wave, int B, int n_samples, int apply_bn, int quantize, float* out, void* stream);
 
+/* Fusion featuriser: get_mel (training/data.py:363-399: torchaudio MelSpectrogram n_fft 1024 / hop 480 / htk / norm=None +
+ * AmplitudeToDB(top_db=None)) for a batch, stacked 4x as get_audio_features does for clips <= 10 s (data.py:497-501):
+ * wave [B, n_samples] -> out [B, 4, n_samples/480+1, 64]. Needs "fusion_featuriser.melW" [513,64] and
+ * "fusion_featuriser.window" [1024] to have been set with ard_set_weight. */
+int ard_fusion_mel(ard_handle* h, const float* wave, int B, int n_samples, int quantize, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * PCA sufficient statistics (replaces IncrementalPCA.partial_fit in compute_pca_components, src/residual.py:137-138):
  * accumulates n += rows, sum[D] += sum_r x[r], sumsq[D,D] += x^T x in float64 on device. x fp32 [rows, D] device.

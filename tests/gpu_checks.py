@@ -215,6 +215,21 @@ def check_logmel(B=2):
     return {"logmel": rel(out.cpu(), ref), "logmel_maxabs_dB": (out.cpu() - ref).abs().max().item(), "logmel_bn": rel(out_bn.cpu(), ref_bn)}
 
 
+def check_fusion_featuriser(B=2):
+    """ard_fusion_mel (device get_mel, data.py:363-399) vs the golden mel_fusion the reference's torchaudio featuriser produced,
+    and the base+fusion encoder driven from the WAVEFORM through the public API vs the golden audio embedding."""
+    g = np.load(os.path.join(GOLDEN, "htsat_base_fusion_b2.npz"))
+    clap, sd, _ = make_encoder("base", seed=int(g["meta_seed"]), fusion=True)
+    wave = W.make_clips(B, seed=1234)
+    mf = clap.fusion_mel(wave.cuda())
+    torch.cuda.synchronize()
+    m = {"mel_fusion": rel(golden_sample(mf), torch.from_numpy(g["mel_fusion_sample"])),
+         "channels_equal": float((mf[:, 0] - mf[:, 3]).abs().max().item())}
+    emb = clap.get_audio_embedding_from_data(wave, use_tensor=True)
+    m["audio_embed_from_waveform"] = rel(emb, torch.from_numpy(g["plain_audio_embed"]))
+    return m
+
+
 def encoder_outputs(clap, wave=None, mel_fusion=None):
     enc = clap.model.audio_branch
     if mel_fusion is not None:

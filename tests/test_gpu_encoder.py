@@ -25,3 +25,9 @@ def test_base_fusion_vs_golden():
     m = G.check_encoder_vs_golden("htsat_base_fusion_b2.npz")
     assert m.pop("plain_mel_fusion_input") < 1e-4 and m.pop("residual_mel_fusion_input") < 1e-4
     _assert_all(m)
+
+
+def test_fusion_featuriser_and_base_from_waveform():
+    m = G.check_fusion_featuriser()
+    assert m["mel_fusion"] < 1e-4 and m["channels_equal"] == 0.0, m
+    assert m["audio_embed_from_waveform"] < G.TOL_BF16, m

@@ -52,6 +52,7 @@ def main():
         run("encoder tiny residual vs oracle", G.check_encoder_vs_oracle, "tiny", 2, True)
         run("encoder tiny vs golden", G.check_encoder_vs_golden, "htsat_tiny_b2.npz")
         run("encoder base fusion vs golden", G.check_encoder_vs_golden, "htsat_base_fusion_b2.npz")
+        run("fusion featuriser + base from waveform", G.check_fusion_featuriser)
 
 
 if __name__ == "__main__":
