@@ -170,8 +170,9 @@ class CLAP_Module(nn.Module):
         use_tensor=True: tensor input, no quantisation, returns a tensor."""
         self.model.eval()
         enc = self.model.audio_branch
+        training_step = torch.is_grad_enabled() and any(p is not None and p.requires_grad for p in enc._lambda_params())
         if (not enc.enable_fusion and torch.is_tensor(x) and x.device.type == "cpu" and x.dim() == 2 and x.shape[1] == 480000
-                and x.dtype == torch.float32 and x.shape[0] > self.h2d_chunk):
+                and x.dtype == torch.float32 and x.shape[0] > self.h2d_chunk and not training_step):
             emb = self._embed_host_pipelined(x, quantize=not use_tensor)
         else:
             wave = batch_features(x, 480000, data_fil, device=self.device)

@@ -10,7 +10,7 @@
 #include <string>
 #include <vector>
 
-#include "ard_internal.h"
+#include "ard_handle.h"
 
 namespace ard {
 
@@ -50,83 +50,30 @@ ProfScope::~ProfScope() {
     if (idx >= 0) cudaEventRecord(g_prof[idx].b, stream);
 }
 
-// ------------------------------------------------------------------------------------------------ device buffers
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int ensure(size_t n) {
-        if (n <= bytes) return 0;
-        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
-        cudaError_t e = cudaMalloc(&p, n);
-        if (e != cudaSuccess) { p = nullptr; return set_error(ARD_ERR_CUDA, "cudaMalloc(%zu): %s", n, cudaGetErrorString(e)); }
-        bytes = n;
-        return 0;
-    }
-    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-struct BlockW {
-    DevBuf ln1_g, ln1_b, ln2_g, ln2_b;
-    DevBuf qkv_w, qkv_b, proj_w, proj_b, proj_w_f32, fc1_w, fc1_b, fc2_w, fc2_b, rpb;
-    // ResiDual (src/residual.py:14-42) injected after this block's attention
-    bool has_res = false, lambda_set = false;
-    int K = 0;
-    std::vector<float> h_mean;
-    DevBuf res_basis, res_dmean, res_M, proj_w_fold, proj_b_fold, lam_ones;
-};
-struct LayerW {
-    std::vector<BlockW> blocks;
-    DevBuf mg_g, mg_b, mg_w;
-};
-
 }  // namespace ard
 
 using namespace ard;
 
-struct ard_handle {
-    ard_config cfg;
-    int nlayers = 4;
-    int num_sms = 148;
-    bool finalized = false;
-    std::map<std::string, std::vector<float>> host;   // raw state_dict tensors (fp32)
-    // front end
-    DevBuf window, twiddle, melw, mstart, mlen, bn_scale, bn_shift;
-    int band_max = 0;
-    DevBuf f_window, f_melw, f_mstart, f_mlen;   // fusion featuriser (get_mel, data.py:363-399): htk filters, periodic hann
-    int f_band_max = 0;
-    DevBuf pe_w, pe_b, pe_g, pe_beta;
-    std::vector<LayerW> layers;
-    DevBuf norm_g, norm_b, tscam_w, tscam_b, p0_w, p0_b, p2_w, p2_b;
-    // workspace
-    DevBuf ws_logmel, ws_x, ws_y, ws_xn, ws_ao, ws_qkv, ws_h, ws_normed, ws_emb, ws_hid, ws_proj, ws_tscam_a, ws_tscam_y, ws_wave;
-    int last_launches = 0;
-    bool use_fused_ffn = true;   // ARD_FUSED_FFN=0 disables the fused 96-channel FFN kernel (A/B measurements)
-};
-
 namespace ard {
 
-static int C_of(const ard_handle* h, int l) { return h->cfg.embed_dim << l; }
-static int R_of(int l) { return 64 >> l; }   // tokens per side
-
-static int upload(DevBuf& b, const void* src, size_t bytes) {
+int upload(DevBuf& b, const void* src, size_t bytes) {
     ARD_TRY(b.ensure(bytes));
     ARD_CUDA(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
     return 0;
 }
-static int upload_f32(DevBuf& b, const std::vector<float>& v) { return upload(b, v.data(), v.size() * 4); }
-static int upload_f16(DevBuf& b, const std::vector<float>& v) {
+int upload_f32(DevBuf& b, const std::vector<float>& v) { return upload(b, v.data(), v.size() * 4); }
+int upload_f16(DevBuf& b, const std::vector<float>& v) {
     std::vector<__half> t(v.size());
     for (size_t i = 0; i < v.size(); ++i) t[i] = __float2half_rn(v[i]);
     return upload(b, t.data(), t.size() * 2);
 }
-static int upload_bf16(DevBuf& b, const std::vector<float>& v) {
+int upload_bf16(DevBuf& b, const std::vector<float>& v) {
     std::vector<__nv_bfloat16> t(v.size());
     for (size_t i = 0; i < v.size(); ++i) t[i] = __float2bfloat16_rn(v[i]);
     return upload(b, t.data(), t.size() * 2);
 }
 
-static int get(const ard_handle* h, const std::string& key, size_t numel, const std::vector<float>** out) {
+int get(const ard_handle* h, const std::string& key, size_t numel, const std::vector<float>** out) {
     auto it = h->host.find(key);
     if (it == h->host.end()) return set_error(ARD_ERR_STATE, "weight '%s' was never set", key.c_str());
     if (it->second.size() != numel)
@@ -248,6 +195,7 @@ static int finalize(ard_handle* h, cudaStream_t) {
                 ARD_TRY(upload_f32(bw.res_dmean, dm));
                 bw.lambda_set = false;
             }
+            bw.bwd_ready = false;
         }
         if (l < h->nlayers - 1) {
             char pfx[64];
@@ -277,7 +225,7 @@ static int finalize(ard_handle* h, cudaStream_t) {
 }
 
 // ------------------------------------------------------------------------------------------------ forward schedule
-static int ensure_workspace(ard_handle* h, int B) {
+int ensure_workspace(ard_handle* h, int B) {
     const size_t MC = (size_t)B * 4096 * h->cfg.embed_dim;   // max over stages of tokens*channels
     ARD_TRY(h->ws_x.ensure(MC * 4));
     ARD_TRY(h->ws_y.ensure(MC * 4));
@@ -288,12 +236,13 @@ static int ensure_workspace(ard_handle* h, int B) {
     return 0;
 }
 
-static int ensure_fold(ard_handle* h, int l, int b, cudaStream_t s) {
+int ensure_fold(ard_handle* h, int l, int b, cudaStream_t s) {
     BlockW& bw = h->layers[l].blocks[b];
     if (!bw.has_res || bw.lambda_set) return 0;
     // learnable initialises to ones (src/residual.py:27)
     const int C = C_of(h, l);
-    std::vector<float> ones(bw.K, 1.0f);
+    std::vector<float> ones((bw.K + 15) & ~15, 0.0f);   // padded to the backward GEMMs' K granularity
+    for (int i = 0; i < bw.K; ++i) ones[i] = 1.0f;
     ARD_TRY(upload_f32(bw.lam_ones, ones));
     ARD_TRY(residual_fold(bw.proj_w_f32.as<float>(), bw.res_dmean.as<float>(), bw.res_basis.as<float>(), bw.lam_ones.as<float>(), C, bw.K,
                           bw.res_M.as<float>(), bw.proj_w_fold.as<__nv_bfloat16>(), bw.proj_b_fold.as<float>(), s));
@@ -373,6 +322,12 @@ static int encoder_forward(ard_handle* h, const ard_forward_args* a, cudaStream_
     ARD_TRY(ensure_workspace(h, B));
     float* X = h->ws_x.as<float>();
     float* Y = h->ws_y.as<float>();
+    const bool train = a->save_for_backward != 0;
+    h->tape_B = train ? h->tape_B : 0;   // an inference forward overwrites the head activations the backward would read
+    if (train) {
+        ARD_TRY(ensure_tape(h, B));
+        X = h->layers[0].blocks[0].t_s;
+    }
     // ---- front end
     if (h->cfg.enable_fusion) {
         if (!a->mel_fusion) return set_error(ARD_ERR_SHAPE, "fusion model expects mel_fusion input");
@@ -394,16 +349,23 @@ static int encoder_forward(ard_handle* h, const ard_forward_args* a, cudaStream_
         for (int b = 0; b < depth; ++b) {
             float* res = a->layers_residuals[l] ? a->layers_residuals[l] + (long long)b * T * C : nullptr;
             // BasicLayer.forward (htsat.py:589-596): mean of the blocks' maps; residuals concatenated along tokens
-            ARD_TRY(run_block(h, l, b, B, X, Y, a->layers_attention[l], 1.0f / depth, b > 0, res, (long long)depth * T, T, s));
+            if (train) {
+                ARD_TRY(run_block_train(h, l, b, B, a->layers_attention[l], 1.0f / depth, b > 0, res, (long long)depth * T, s));
+                X = h->layers[l].blocks[b].t_out;
+            } else {
+                ARD_TRY(run_block(h, l, b, B, X, Y, a->layers_attention[l], 1.0f / depth, b > 0, res, (long long)depth * T, T, s));
+            }
         }
         if (l < h->nlayers - 1) {   // PatchMerging (htsat.py:505-526)
             __nv_bfloat16* Hb = h->ws_h.as<__nv_bfloat16>();
             ARD_TRY(merge_layernorm_bf16(X, h->layers[l].mg_g.as<float>(), h->layers[l].mg_b.as<float>(), Hb, B, R, R, C, s));
             GemmArgs g;
-            g.A = Hb; g.lda = 4 * C; g.W = h->layers[l].mg_w.as<__nv_bfloat16>(); g.ldw = 4 * C; g.out = Y; g.ldo = 2 * C;
+            float* mout = train ? h->layers[l + 1].blocks[0].t_s : Y;
+            g.A = Hb; g.lda = 4 * C; g.W = h->layers[l].mg_w.as<__nv_bfloat16>(); g.ldw = 4 * C; g.out = mout; g.ldo = 2 * C;
             g.M = B * (T / 4); g.N = 2 * C; g.K = 4 * C;
             ARD_TRY(gemm_bf16(g, h->num_sms, s));
-            float* t = X; X = Y; Y = t;
+            if (train) X = mout;
+            else { float* t = X; X = Y; Y = t; }
         }
     }
     // ---- tail
@@ -498,6 +460,8 @@ int ard_set_block_residual(ard_handle* h, int layer, int block, const float* mea
     BlockW& bw = h->layers[layer].blocks[block];
     bw.K = K;
     bw.h_mean.assign(mean, mean + D);
+    bw.h_basis.assign(basis, basis + (size_t)K * D);
+    bw.bwd_ready = false;
     ARD_TRY(upload(bw.res_basis, basis, (size_t)K * D * 4));
     ARD_TRY(bw.res_M.ensure((size_t)C * C * 4));
     ARD_TRY(bw.proj_w_fold.ensure((size_t)C * C * 2));
@@ -511,6 +475,7 @@ int ard_set_block_residual(ard_handle* h, int layer, int block, const float* mea
     ARD_TRY(upload_f32(bw.res_dmean, dm));
     bw.has_res = true;
     bw.lambda_set = false;
+    if (bw.lam.p) { cudaFree(bw.lam.p); bw.lam.p = nullptr; bw.lam.bytes = 0; }
     return 0;
 }
 
@@ -529,6 +494,11 @@ int ard_set_block_lambda(ard_handle* h, int layer, int block, const float* lambd
     g_launches = 0;
     ARD_TRY(residual_fold(bw.proj_w_f32.as<float>(), bw.res_dmean.as<float>(), bw.res_basis.as<float>(), lambda_dev, C, bw.K,
                           bw.res_M.as<float>(), bw.proj_w_fold.as<__nv_bfloat16>(), bw.proj_b_fold.as<float>(), (cudaStream_t)stream));
+    // keep a (zero-padded) copy of lambda for the backward: gsc = gcoef * lambda
+    const int Kp = (bw.K + 15) & ~15;
+    ARD_TRY(bw.lam.ensure((size_t)Kp * 4));
+    ARD_CUDA(cudaMemsetAsync(bw.lam.p, 0, (size_t)Kp * 4, (cudaStream_t)stream));
+    ARD_CUDA(cudaMemcpyAsync(bw.lam.p, lambda_dev, (size_t)bw.K * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     bw.lambda_set = true;
     return 0;
 }
@@ -560,10 +530,20 @@ int ard_block_forward(ard_handle* h, int layer, int block, const float* x_in, in
     return 0;
 }
 
+int ard_encoder_backward(ard_handle* h, const ard_backward_args* args, void* stream) {
+    if (!h || !args) return set_error(ARD_ERR_SHAPE, "null argument");
+    if (!h->finalized) return set_error(ARD_ERR_STATE, "ard_finalize_weights has not been called");
+    g_launches = 0;
+    const int rc = encoder_backward(h, args, (cudaStream_t)stream);
+    h->last_launches = g_launches;
+    return rc;
+}
+
 long long ard_workspace_bytes(const ard_handle* h) {
     if (!h) return 0;
     const DevBuf* bufs[] = {&h->ws_logmel, &h->ws_x, &h->ws_y, &h->ws_xn, &h->ws_ao, &h->ws_qkv, &h->ws_h, &h->ws_normed,
-                            &h->ws_emb, &h->ws_hid, &h->ws_proj, &h->ws_tscam_a, &h->ws_tscam_y, &h->ws_wave};
+                            &h->ws_emb, &h->ws_hid, &h->ws_proj, &h->ws_tscam_a, &h->ws_tscam_y, &h->ws_wave, &h->tape, &h->bw_g,
+                            &h->bw_gs, &h->bw_t, &h->bw_dh, &h->bw_gb, &h->bw_coef, &h->bw_gcoef, &h->bw_gsc, &h->bw_small};
     long long t = 0;
     for (const DevBuf* b : bufs) t += (long long)b->bytes;
     return t;
@@ -616,6 +596,18 @@ int ard_window_attention(const void* qkv_bf16, void* out_bf16, const float* bias
     a.qkv = (const __nv_bfloat16*)qkv_bf16; a.out = (__nv_bfloat16*)out_bf16; a.bias_table = bias_table; a.attn_mean = attn;
     a.attn_scale = attn_scale; a.attn_accumulate = accumulate; a.B = B; a.H = H; a.W = W; a.C = C; a.nH = nH; a.shift = shift;
     return window_attention(a, (cudaStream_t)stream);
+}
+
+int ard_window_attention_bwd(const void* qkv_bf16, const void* dout_bf16, void* dqkv_bf16, const float* bias_table, int B, int H, int W, int C,
+                             int nH, int shift, void* stream) {
+    AttnArgs a;
+    a.qkv = (const __nv_bfloat16*)qkv_bf16; a.bias_table = bias_table; a.B = B; a.H = H; a.W = W; a.C = C; a.nH = nH; a.shift = shift;
+    return window_attention_bwd(a, (const __nv_bfloat16*)dout_bf16, (__nv_bfloat16*)dqkv_bf16, (cudaStream_t)stream);
+}
+
+int ard_layernorm_bwd(const float* x, const float* grad_out, const float* gamma, const float* add, float* grad_in, long long rows, int C,
+                      void* stream) {
+    return layernorm_bwd(x, grad_out, gamma, add, grad_in, rows, C, (cudaStream_t)stream);
 }
 
 int ard_f32_to_bf16(const float* in, void* out_bf16, long long n, float scale, void* stream) {

@@ -1,0 +1,92 @@
+// Handle layout shared by ard_api.cu (forward schedule, C ABI) and ard_train.cu (saved activations + backward schedule).
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ard_internal.h"
+
+namespace ard {
+
+// ------------------------------------------------------------------------------------------------ device buffers
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int ensure(size_t n) {
+        if (n <= bytes) return 0;
+        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) { p = nullptr; return set_error(ARD_ERR_CUDA, "cudaMalloc(%zu): %s", n, cudaGetErrorString(e)); }
+        bytes = n;
+        return 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct BlockW {
+    DevBuf ln1_g, ln1_b, ln2_g, ln2_b;
+    DevBuf qkv_w, qkv_b, proj_w, proj_b, proj_w_f32, fc1_w, fc1_b, fc2_w, fc2_b, rpb;
+    // ResiDual (src/residual.py:14-42) injected after this block's attention
+    bool has_res = false, lambda_set = false;
+    int K = 0;
+    std::vector<float> h_mean, h_basis;
+    DevBuf res_basis, res_dmean, res_M, proj_w_fold, proj_b_fold, lam_ones;
+    // training (ard_train.cu): current lambda (padded to Kp), transposed / folded weights for the dgrad GEMMs, built lazily
+    int Kp = 0;
+    bool bwd_ready = false;
+    DevBuf lam, fc1_wT, fc2_wT, qkv_wT, proj_wT, res_wc, res_wcT, res_basis_bf16, res_c0;
+    // activations saved by a save_for_backward forward (views into ard_handle::tape)
+    float *t_s = nullptr, *t_x1 = nullptr, *t_x3 = nullptr, *t_out = nullptr;
+    __nv_bfloat16 *t_qkv = nullptr, *t_ao = nullptr;
+};
+struct LayerW {
+    std::vector<BlockW> blocks;
+    DevBuf mg_g, mg_b, mg_w, mg_wT;
+};
+
+}  // namespace ard
+
+struct ard_handle {
+    using DevBuf = ard::DevBuf;
+    using LayerW = ard::LayerW;
+    ard_config cfg;
+    int nlayers = 4;
+    int num_sms = 148;
+    bool finalized = false;
+    std::map<std::string, std::vector<float>> host;   // raw state_dict tensors (fp32)
+    // front end
+    DevBuf window, twiddle, melw, mstart, mlen, bn_scale, bn_shift;
+    int band_max = 0;
+    DevBuf f_window, f_melw, f_mstart, f_mlen;   // fusion featuriser (get_mel, data.py:363-399): htk filters, periodic hann
+    int f_band_max = 0;
+    DevBuf pe_w, pe_b, pe_g, pe_beta;
+    std::vector<LayerW> layers;
+    DevBuf norm_g, norm_b, tscam_w, tscam_b, p0_w, p0_b, p2_w, p2_b;
+    // workspace
+    DevBuf ws_logmel, ws_x, ws_y, ws_xn, ws_ao, ws_qkv, ws_h, ws_normed, ws_emb, ws_hid, ws_proj, ws_tscam_a, ws_tscam_y, ws_wave;
+    int last_launches = 0;
+    bool use_fused_ffn = true;   // ARD_FUSED_FFN=0 disables the fused 96-channel FFN kernel (A/B measurements)
+    // training state
+    DevBuf tape, p0_wT, p2_wT, t_emb, t_hid, t_proj;
+    DevBuf bw_g, bw_gs, bw_t, bw_hpre, bw_dh, bw_gqkv, bw_gb, bw_coef, bw_gcoef, bw_gsc, bw_small;
+    int tape_B = 0;          // batch of the forward whose activations the tape holds (0: none)
+};
+
+
+namespace ard {
+inline int C_of(const ard_handle* h, int l) { return h->cfg.embed_dim << l; }
+inline int R_of(int l) { return 64 >> l; }   // tokens per side
+int upload(DevBuf& b, const void* src, size_t bytes);
+int upload_f32(DevBuf& b, const std::vector<float>& v);
+int upload_f16(DevBuf& b, const std::vector<float>& v);
+int upload_bf16(DevBuf& b, const std::vector<float>& v);
+int get(const ard_handle* h, const std::string& key, size_t numel, const std::vector<float>** out);
+int ensure_workspace(ard_handle* h, int B);
+int ensure_fold(ard_handle* h, int l, int b, cudaStream_t s);
+// training (ard_train.cu)
+int ensure_tape(ard_handle* h, int B);
+int run_block_train(ard_handle* h, int l, int b, int B, float* attn_out, float attn_scale, int attn_acc, float* res_out,
+                    long long res_bstride, cudaStream_t s);
+int encoder_backward(ard_handle* h, const ard_backward_args* a, cudaStream_t s);
+}  // namespace ard

@@ -72,6 +72,8 @@ int merge_layernorm_bf16(const float* x, const float* gamma, const float* beta, 
 int final_norm_mean(const float* x, const float* gamma, const float* beta, float* emb, float* normed, int B, int T, int C, cudaStream_t s);
 int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, float scale, cudaStream_t s);
 int fill_f32(float* p, long long n, float v, cudaStream_t s);
+// backward kernels (training path)
+int layernorm_bwd(const float* x, const float* g, const float* gamma, const float* add, float* out, long long rows, int C, cudaStream_t s);
 
 // ---------------------------------------------------------------- window attention (attn_window.cu)
 struct AttnArgs {
@@ -84,6 +86,7 @@ struct AttnArgs {
     int B = 0, H = 0, W = 0, C = 0, nH = 0, shift = 0;
 };
 int window_attention(const AttnArgs& a, cudaStream_t s);
+int window_attention_bwd(const AttnArgs& a, const __nv_bfloat16* dout, __nv_bfloat16* dqkv, cudaStream_t s);
 
 // ---------------------------------------------------------------- front end (frontend.cu)
 struct MelBands {            // banded view of logmel_extractor.melW [513,64]

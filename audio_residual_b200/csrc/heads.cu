@@ -83,6 +83,48 @@ int l2_normalize(const float* x, float* y, int B, int N, cudaStream_t s) {
     return check_cuda(cudaGetLastError(), "l2_normalize launch");
 }
 
+// backward of F.normalize: y = p / n, n = max(||p||, 1e-12):  dp = (g - y (y . g)) / n
+__global__ void l2_normalize_bwd_kernel(const float* __restrict__ p, const float* __restrict__ g, float* __restrict__ out, int B, int N) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= B) return;
+    float s = 0.f, d = 0.f;
+    for (int k = lane; k < N; k += 32) {
+        const float v = p[(long long)row * N + k];
+        s = fmaf(v, v, s);
+        d = fmaf(v, g[(long long)row * N + k], d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+    const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+    const float yg = d * inv;   // y . g
+    for (int k = lane; k < N; k += 32) {
+        const long long i = (long long)row * N + k;
+        out[i] = (g[i] - p[i] * inv * yg) * inv;
+    }
+}
+int l2_normalize_bwd(const float* p, const float* g, float* out, int B, int N, cudaStream_t s) {
+    if (B <= 0) return 0;
+    l2_normalize_bwd_kernel<<<(B + 7) / 8, 256, 0, s>>>(p, g, out, B, N);
+    return check_cuda(cudaGetLastError(), "l2_normalize_bwd launch");
+}
+
+// g *= (act > 0)   (ReLU backward from the saved post-activation)
+__global__ void relu_bwd_mul_kernel(float* __restrict__ g, const float* __restrict__ act, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        if (!(act[i] > 0.f)) g[i] = 0.f;
+}
+int relu_bwd_mul(float* g, const float* act, long long n, cudaStream_t s) {
+    if (n <= 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    relu_bwd_mul_kernel<<<(unsigned)blocks, 256, 0, s>>>(g, act, n);
+    return check_cuda(cudaGetLastError(), "relu_bwd_mul launch");
+}
+
 // ------------------------------------------------------------------------------------------------ fp32 "TN" GEMM
 // out[i][j] = sum_k a[k*lda + i] * (scale ? scale[k] : 1) * b[k*ldb + j];  i < Ma, j < Nb. 64x64 tile, 4x4 per thread.
 // Only used to re-derive the folded ResiDual projection when lambda changes (C^3 flops, off the per-clip path).

@@ -331,3 +331,220 @@ int quantize_waveform(const float* in, float* out, long long n, cudaStream_t s) 
 }
 
 }  // namespace ard
+
+// ================================================================================================ backward row-wise kernels
+// (ResiDual training step, reference: loss.backward() in src/training.py:30-32 through the frozen encoder)
+namespace ard {
+
+// LayerNorm backward: y = (x - mean) * rstd * gamma + beta over the last dim C.
+//   dx = rstd * (gg - mean(gg) - xhat * mean(gg * xhat)),  gg = g * gamma;   out = (add ? add : 0) + dx   (fp32)
+// Rows may be the PatchMerging gather (MergeRows): x is read and dx written through the same row map.
+template <int VEC, int NV, class Rows>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(Rows xrows, Rows orows, float* __restrict__ out_base,
+                                                           const float* __restrict__ g, const float* __restrict__ gamma,
+                                                           const float* __restrict__ add, long long nrows) {
+    constexpr int C = 32 * VEC * NV;
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    float v[NV][VEC], gg[NV][VEC];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int e = (i * 32 + lane) * VEC;
+        float gm[VEC];
+        load_vec<VEC>(xrows.at(row, e), v[i]);
+        load_vec<VEC>(g + row * C + e, gg[i]);
+        load_vec<VEC>(gamma + e, gm);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) gg[i][k] *= gm[k];
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) s += v[i][k];
+    const float mean = warp_sum(s) * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            v[i][k] -= mean;
+            q = fmaf(v[i][k], v[i][k], q);
+        }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + LN_EPS);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            v[i][k] *= rstd;                 // xhat
+            m1 += gg[i][k];
+            m2 = fmaf(gg[i][k], v[i][k], m2);
+        }
+    m1 = warp_sum(m1) * (1.0f / C);
+    m2 = warp_sum(m2) * (1.0f / C);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int e = (i * 32 + lane) * VEC;
+        float* op = out_base + (orows.at(row, e) - orows.x);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            float d = rstd * (gg[i][k] - m1 - v[i][k] * m2);
+            if (add != nullptr) d += add[op - out_base + k];
+            op[k] = d;
+        }
+    }
+}
+
+template <class Rows>
+static int launch_ln_bwd(Rows xr, Rows orr, float* out, const float* g, const float* gamma, const float* add, long long nrows, int C,
+                         cudaStream_t s) {
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((nrows + wpb - 1) / wpb);
+    ProfScope ps(PROF_LN, s, 16.0 * nrows * C, (add ? 16.0 : 12.0) * nrows * C);
+#define ARD_LNB_CASE(c, vec, nv) \
+    case c: layernorm_bwd_kernel<vec, nv, Rows><<<grid, wpb * 32, 0, s>>>(xr, orr, out, g, gamma, add, nrows); break;
+    switch (C) {
+        ARD_LNB_CASE(96, 1, 3)
+        ARD_LNB_CASE(128, 4, 1)
+        ARD_LNB_CASE(192, 2, 3)
+        ARD_LNB_CASE(256, 4, 2)
+        ARD_LNB_CASE(384, 4, 3)
+        ARD_LNB_CASE(512, 4, 4)
+        ARD_LNB_CASE(768, 4, 6)
+        ARD_LNB_CASE(1024, 4, 8)
+        ARD_LNB_CASE(1536, 4, 12)
+        ARD_LNB_CASE(2048, 4, 16)
+        default: return set_error(ARD_ERR_SHAPE, "layernorm_bwd: unsupported width C=%d", C);
+    }
+#undef ARD_LNB_CASE
+    return check_cuda(cudaGetLastError(), "layernorm_bwd launch");
+}
+
+int layernorm_bwd(const float* x, const float* g, const float* gamma, const float* add, float* out, long long rows, int C, cudaStream_t s) {
+    if (rows <= 0) return 0;
+    return launch_ln_bwd(PlainRows{x, C}, PlainRows{out, C}, out, g, gamma, add, rows, C, s);
+}
+
+// PatchMerging backward of the gather + LayerNorm(4C): g [B*(H/2)*(W/2), 4C] -> dx [B, H*W, C] (every source element appears once)
+int merge_layernorm_bwd(const float* x, const float* g, const float* gamma, float* dx, int B, int H, int W, int C, cudaStream_t s) {
+    const long long rows = (long long)B * (H / 2) * (W / 2);
+    return launch_ln_bwd(MergeRows{x, H, W, C}, MergeRows{dx, H, W, C}, dx, g, gamma, nullptr, rows, 4 * C, s);
+}
+
+// dh <- dh * gelu'(hpre)   (both bf16 [n]); gelu'(x) = Phi(x) + x * phi(x)
+__global__ void gelu_bwd_mul_kernel(__nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ hpre, long long n) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const long long stride = (long long)gridDim.x * blockDim.x * 8;
+    for (; i + 7 < n; i += stride) {
+        uint4 a = *reinterpret_cast<const uint4*>(dh + i);
+        const uint4 b = *reinterpret_cast<const uint4*>(hpre + i);
+        __nv_bfloat162* ap = reinterpret_cast<__nv_bfloat162*>(&a);
+        const __nv_bfloat162* bp = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float2 d = __bfloat1622float2(ap[k]);
+            const float2 x = __bfloat1622float2(bp[k]);
+            const float p0 = 0.5f * (1.0f + erf_fast(x.x * 0.70710678118654752f)) + x.x * 0.3989422804014327f * __expf(-0.5f * x.x * x.x);
+            const float p1 = 0.5f * (1.0f + erf_fast(x.y * 0.70710678118654752f)) + x.y * 0.3989422804014327f * __expf(-0.5f * x.y * x.y);
+            d.x *= p0; d.y *= p1;
+            ap[k] = __floats2bfloat162_rn(d.x, d.y);
+        }
+        *reinterpret_cast<uint4*>(dh + i) = a;
+    }
+}
+int gelu_bwd_mul(__nv_bfloat16* dh, const __nv_bfloat16* hpre, long long n, cudaStream_t s) {
+    if (n <= 0) return 0;
+    if (n % 8) return set_error(ARD_ERR_SHAPE, "gelu_bwd_mul: n must be a multiple of 8");
+    long long blocks = (n / 8 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ProfScope ps(PROF_OTHER, s, 30.0 * n, 6.0 * n);
+    gelu_bwd_mul_kernel<<<(unsigned)blocks, 256, 0, s>>>(dh, hpre, n);
+    return check_cuda(cudaGetLastError(), "gelu_bwd_mul launch");
+}
+
+// Lambda gradient, reduced in-kernel (src/residual.py:39: x_scaled = x_proj * learnable):
+//   dlam[k] += sum_t coef[t,k] * gcoef[t,k];   gsc[t,k] = bf16(gcoef[t,k] * lam[k])   (the gradient flowing on to x_proj)
+// coef, gcoef fp32 [M, K]. Each CTA reduces a slab of rows for 32 columns in registers/smem, one atomicAdd per column per CTA.
+__global__ void __launch_bounds__(256) lambda_grad_kernel(const float* __restrict__ coef, const float* __restrict__ gcoef,
+                                                         const float* __restrict__ lam, float* __restrict__ dlam,
+                                                         __nv_bfloat16* __restrict__ gsc, long long M, int K, long long rows_per_cta) {
+    __shared__ float part[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + tx;
+    const long long r0 = (long long)blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, M);
+    float acc = 0.f;
+    if (col < K) {
+        const float l = lam[col];
+        for (long long r = r0 + ty; r < r1; r += 8) {
+            const float c = coef[r * K + col], gc = gcoef[r * K + col];
+            acc = fmaf(c, gc, acc);
+            gsc[r * K + col] = __float2bfloat16_rn(gc * l);
+        }
+    }
+    part[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && col < K) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += part[w][tx];
+        atomicAdd(dlam + col, t);
+    }
+}
+int lambda_grad(const float* coef, const float* gcoef, const float* lam, float* dlam, __nv_bfloat16* gsc, long long M, int K, cudaStream_t s) {
+    if (M <= 0) return 0;
+    const int cb = (K + 31) / 32;
+    long long ysplit = (148 * 8) / cb + 1;
+    long long rows_per_cta = (M + ysplit - 1) / ysplit;
+    rows_per_cta = ((rows_per_cta + 7) / 8) * 8;
+    ysplit = (M + rows_per_cta - 1) / rows_per_cta;
+    ProfScope ps(PROF_OTHER, s, 3.0 * M * K, 10.0 * M * K);
+    lambda_grad_kernel<<<dim3(cb, (unsigned)ysplit), 256, 0, s>>>(coef, gcoef, lam, dlam, gsc, M, K, rows_per_cta);
+    return check_cuda(cudaGetLastError(), "lambda_grad launch");
+}
+
+// out[b*T + t, c] = g[b, c] * scale   (token-mean backward, htsat.py:810-811)
+__global__ void bcast_rows_kernel(const float* __restrict__ g, float* __restrict__ out, int B, int T, int C, float scale) {
+    const long long total = (long long)B * T * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long long b = i / ((long long)T * C);
+        out[i] = g[b * C + c] * scale;
+    }
+}
+int bcast_rows(const float* g, float* out, int B, int T, int C, float scale, cudaStream_t s) {
+    bcast_rows_kernel<<<148 * 4, 256, 0, s>>>(g, out, B, T, C, scale);
+    return check_cuda(cudaGetLastError(), "bcast_rows launch");
+}
+
+// y = a + b (fp32), optionally also a bf16 copy of the sum
+__global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, __nv_bfloat16* __restrict__ ybf,
+                               long long n) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (; i + 3 < n; i += stride) {
+        float4 u = *reinterpret_cast<const float4*>(a + i);
+        if (b != nullptr) {
+            const float4 w = *reinterpret_cast<const float4*>(b + i);
+            u.x += w.x; u.y += w.y; u.z += w.z; u.w += w.w;
+        }
+        if (y != nullptr) *reinterpret_cast<float4*>(y + i) = u;
+        if (ybf != nullptr) {
+            uint2 p;
+            p.x = pack_bf16x2(u.x, u.y);
+            p.y = pack_bf16x2(u.z, u.w);
+            *reinterpret_cast<uint2*>(ybf + i) = p;
+        }
+    }
+}
+int add_f32(const float* a, const float* b, float* y, __nv_bfloat16* ybf, long long n, cudaStream_t s) {
+    if (n <= 0) return 0;
+    if (n % 4) return set_error(ARD_ERR_SHAPE, "add_f32: n must be a multiple of 4");
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    add_f32_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, b, y, ybf, n);
+    return check_cuda(cudaGetLastError(), "add_f32 launch");
+}
+
+}  // namespace ard

@@ -326,9 +326,25 @@ class HTSAT_Swin_Transformer(nn.Module):
             L.check(lib.ard_block_forward(h, l, b, L.ptr(x), B, L.ptr(out), L.ptr(attn), L.ptr(res), L.stream_ptr()))
         return out, attn, res
 
+    def _lambda_params(self):
+        """Per layer: the ResiDual `learnable` parameter shared by that layer's patched blocks (src/residual.py:186-197), or None."""
+        out = []
+        for layer in self.layers:
+            res = {id(b._residual): b._residual for b in layer.blocks if b._residual is not None}
+            if len(res) > 1:
+                raise NotImplementedError("blocks of one layer must share a single ResiDual module (setup_residual_htsat does)")
+            out.append(next(iter(res.values())).learnable if res else None)
+        return out
+
     def encode(self, waveform=None, mel_fusion=None, quantize=False, want_dict=False, want_audio_embed=False,
-               want_capture=True):
-        """Single entry to ard_encoder_forward. Returns a dict of freshly allocated CUDA tensors."""
+               want_capture=True, save_for_backward=False):
+        """Single entry to ard_encoder_forward. Returns a dict of freshly allocated CUDA tensors.
+        With grad enabled and trainable ResiDual lambdas, `embedding` / `audio_embed` come back attached to the autograd graph
+        (backward = ard_encoder_backward, filling `learnable.grad` as loss.backward() does in src/training.py:30-32)."""
+        if not save_for_backward and torch.is_grad_enabled():
+            lams = self._lambda_params()
+            if any(p is not None and p.requires_grad for p in lams):
+                return _encode_with_grad(self, lams, waveform, mel_fusion, quantize, want_dict, want_audio_embed, want_capture)
         h = self._handle()
         lib = L.load()
         dev = self._device()
@@ -348,6 +364,7 @@ class HTSAT_Swin_Transformer(nn.Module):
         out = {"embedding": torch.empty((B, self.num_features), **f32)}
         a = L.ArdForwardArgs()
         a.B, a.quantize = B, int(bool(quantize))
+        a.save_for_backward = int(bool(save_for_backward))
         if self.enable_fusion:
             a.mel_fusion = src.data_ptr()
         else:
@@ -404,6 +421,60 @@ class HTSAT_Swin_Transformer(nn.Module):
 
     def last_launch_count(self):
         return L.load().ard_last_launch_count(self._hb.h) if self._hb.h is not None else 0
+
+
+class _EncodeFn(torch.autograd.Function):
+    """autograd node around ard_encoder_forward(save_for_backward=1) / ard_encoder_backward. Inputs: the per-layer lambda
+    parameters (only to receive gradients; their values reach the library through _sync_residuals)."""
+
+    @staticmethod
+    def forward(ctx, enc, kw, holder, *lams):
+        out = enc.encode(save_for_backward=True, **kw)
+        holder.update(out)
+        ctx.enc, ctx.B = enc, out["embedding"].shape[0]
+        ctx.layers = [i for i, p in enumerate(enc._lambda_params()) if p is not None]
+        ctx.ks = [p.shape[0] for p in enc._lambda_params() if p is not None]
+        ctx.has_audio = "audio_embed" in out
+        ctx.devs = [p.device for p in enc._lambda_params() if p is not None]
+        return (out["embedding"], out["audio_embed"]) if ctx.has_audio else (out["embedding"],)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        enc = ctx.enc
+        dev = enc._device()
+        lib = L.load()
+        a = L.ArdBackwardArgs()
+        a.B = ctx.B
+        keep = []
+        g_emb = grads[0]
+        g_ae = grads[1] if ctx.has_audio else None
+        if g_emb is not None:
+            g_emb = g_emb.detach().to(dev, torch.float32).contiguous()
+            a.grad_embedding = g_emb.data_ptr()
+        if g_ae is not None:
+            g_ae = g_ae.detach().to(dev, torch.float32).contiguous()
+            a.grad_audio_embed = g_ae.data_ptr()
+        outs = {}
+        for l, k in zip(ctx.layers, ctx.ks):
+            outs[l] = torch.empty(k, device=dev, dtype=torch.float32)
+            a.grad_lambda[l] = outs[l].data_ptr()
+        with torch.cuda.device(dev):
+            L.check(lib.ard_encoder_backward(enc._hb.h, C.byref(a), L.stream_ptr()))
+        keep.extend([g_emb, g_ae])
+        return (None, None, None) + tuple(outs[l].to(d) for l, d in zip(ctx.layers, ctx.devs))
+
+
+def _encode_with_grad(enc, lams, waveform, mel_fusion, quantize, want_dict, want_audio_embed, want_capture):
+    kw = dict(waveform=waveform, mel_fusion=mel_fusion, quantize=quantize, want_dict=want_dict, want_audio_embed=want_audio_embed,
+              want_capture=want_capture)
+    holder = {}
+    live = [p for p in lams if p is not None]
+    res = _EncodeFn.apply(enc, kw, holder, *live)
+    out = dict(holder)
+    out["embedding"] = res[0]
+    if want_audio_embed:
+        out["audio_embed"] = res[1]
+    return out
 
 
 def create_htsat_model(audio_cfg, enable_fusion=False, fusion_type="None"):

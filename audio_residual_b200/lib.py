@@ -28,7 +28,12 @@ class ArdForwardArgs(C.Structure):
     _fields_ = [("waveform", C.c_void_p), ("mel_fusion", C.c_void_p), ("B", C.c_int), ("quantize", C.c_int),
                 ("embedding", C.c_void_p), ("audio_embed", C.c_void_p),
                 ("layers_residuals", C.c_void_p * 4), ("layers_attention", C.c_void_p * 4),
-                ("framewise_output", C.c_void_p), ("clipwise_output", C.c_void_p), ("fine_grained_embedding", C.c_void_p)]
+                ("framewise_output", C.c_void_p), ("clipwise_output", C.c_void_p), ("fine_grained_embedding", C.c_void_p),
+                ("save_for_backward", C.c_int)]
+
+
+class ArdBackwardArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("grad_audio_embed", C.c_void_p), ("grad_embedding", C.c_void_p), ("grad_lambda", C.c_void_p * 4)]
 
 
 _lib = None
@@ -59,6 +64,7 @@ def load(check_symbols=False):
         lib.ard_clear_block_residual.argtypes = [vp, i, i]
         lib.ard_set_block_lambda.argtypes = [vp, i, i, vp, vp]
         lib.ard_encoder_forward.argtypes = [vp, C.POINTER(ArdForwardArgs), vp]
+        lib.ard_encoder_backward.argtypes = [vp, C.POINTER(ArdBackwardArgs), vp]
         lib.ard_block_forward.argtypes = [vp, i, i, vp, i, vp, vp, vp, vp]
         lib.ard_workspace_bytes.argtypes = [vp]
         lib.ard_last_launch_count.argtypes = [vp]
@@ -67,6 +73,8 @@ def load(check_symbols=False):
         lib.ard_layernorm_bf16.argtypes = [vp, vp, vp, vp, ll, i, vp]
         lib.ard_ffn_fused_96.argtypes = [vp, vp, vp, ll, vp, vp, vp, vp, vp, vp, vp]
         lib.ard_window_attention.argtypes = [vp, vp, vp, vp, f, i, i, i, i, i, i, i, vp]
+        lib.ard_window_attention_bwd.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, vp]
+        lib.ard_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, ll, i, vp]
         lib.ard_f32_to_bf16.argtypes = [vp, vp, ll, f, vp]
         lib.ard_quantize_waveform.argtypes = [vp, vp, ll, vp]
         lib.ard_logmel.argtypes = [vp, vp, i, i, i, i, vp, vp]

@@ -92,10 +92,25 @@ typedef struct ard_forward_args {
     float* framewise_output; /* device [B, 1024, 527] or NULL (htsat.py:818,826) */
     float* clipwise_output;  /* device [B, 527] or NULL (htsat.py:820-821,827) */
     float* fine_grained_embedding; /* device [B, 1024, 8*embed_dim] or NULL (htsat.py:807-808,828) */
+    int save_for_backward;   /* 1: keep the activations ard_encoder_backward needs (training step, src/training.py:24-32) */
 } ard_forward_args;
 
 /* HTSAT_Swin_Transformer.forward (htsat.py:881-994) in eval mode + optional audio_projection/normalize. */
 int ard_encoder_forward(ard_handle* h, const ard_forward_args* args, void* stream);
+
+/* Backward of the last ard_encoder_forward(save_for_backward=1) on this handle: what loss.backward() (src/training.py:30-32)
+ * computes for the only trainable tensors of setup_residual_htsat (src/residual.py:199-201): the ResiDual `learnable`
+ * vectors. The encoder is frozen and in eval mode (src/training.py:105-108), so no weight gradients exist.
+ * Inputs are dL/d(audio_embed) and/or dL/d(embedding); grad_lambda[l] (device [K_l] fp32, required for every layer that
+ * carries a ResiDual) is OVERWRITTEN with the gradient summed over the layer's patched blocks, which share one
+ * ResiDual module in the reference (src/residual.py:186-197). */
+typedef struct ard_backward_args {
+    int B;
+    const float* grad_audio_embed;           /* device [B, joint_dim] or NULL */
+    const float* grad_embedding;             /* device [B, 8*embed_dim] or NULL */
+    float* grad_lambda[ARD_MAX_LAYERS];      /* device [K_l] fp32 or NULL */
+} ard_backward_args;
+int ard_encoder_backward(ard_handle* h, const ard_backward_args* args, void* stream);
 
 /* SwinTransformerBlock.forward (htsat.py:439-482) or the ResiDual-patched forward (src/residual.py:58-98) of block
  * (layer, block) on x[B, T_l, C_l] fp32 device. Outputs (device, fp32): x_out [B,T,C]; attn [B*nW,nH,64,64] or NULL;
@@ -132,6 +147,14 @@ int ard_layernorm_bf16(const float* x, const float* gamma, const float* beta, vo
 int ard_window_attention(const void* qkv_bf16, void* out_bf16, const float* bias_table, float* attn, float attn_scale, int accumulate,
                          int B, int H, int W, int C, int nH, int shift, void* stream);
 /* fp32 -> bf16 conversion with scale (device). */
+/* Backward of ard_window_attention w.r.t. qkv (autograd of htsat.py:326-352): dqkv [B*H*W, 3C] bf16 token order from
+ * dout [B*H*W, C] bf16; the probabilities are recomputed from qkv. */
+int ard_window_attention_bwd(const void* qkv_bf16, const void* dout_bf16, void* dqkv_bf16, const float* bias_table, int B, int H, int W, int C,
+                             int nH, int shift, void* stream);
+/* Backward of nn.LayerNorm over the last dim: grad_in = (add ? add : 0) + dLN(x)^T grad_out; all fp32 [rows, C]. */
+int ard_layernorm_bwd(const float* x, const float* grad_out, const float* gamma, const float* add, float* grad_in, long long rows, int C,
+                      void* stream);
+
 int ard_f32_to_bf16(const float* in, void* out_bf16, long long n, float scale, void* stream);
 /* quantize_tensor (src/residual.py:210-212): clamp, *32767, truncate to int16, /32767; in place allowed. */
 int ard_quantize_waveform(const float* in, float* out, long long n, void* stream);

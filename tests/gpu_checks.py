@@ -140,17 +140,10 @@ def check_layernorm(rows, Cdim, seed=0):
     return rel(out.float().cpu(), bf16r(ref)), rel(out.float().cpu(), ref)
 
 
-def check_window_attention(B, R, Cdim, nH, shift, seed=0):
-    """ard_window_attention vs the oracle's attention core on identical (bf16-rounded) qkv."""
-    lib = L.load()
-    g = torch.Generator().manual_seed(seed)
+def _ref_window_attention(qkv, table, B, R, Cdim, nH, shift):
+    """Oracle attention core on token-order qkv [B*T, 3C]: roll -> partition -> attention -> reverse -> roll (htsat.py:452-474, :326-352)."""
     hd = Cdim // nH
     T = R * R
-    qkv = torch.randn(B * T, 3 * Cdim, generator=g)
-    qkv[:, :Cdim] *= hd ** -0.5           # q pre-scaled (the C path folds the scale into the qkv weights)
-    qkv = bf16r(qkv)
-    table = 0.5 * torch.randn(225, nH, generator=g)
-    # oracle: roll -> partition -> attention core -> reverse -> roll   (htsat.py:452-474, :326-352)
     x = qkv.view(B, R, R, 3 * Cdim)
     sh = shift if R > 8 else 0
     if sh > 0:
@@ -172,14 +165,65 @@ def check_window_attention(B, R, Cdim, nH, shift, seed=0):
     o = O.window_reverse(o.view(-1, 8, 8, Cdim), 8, R, R)
     if sh > 0:
         o = torch.roll(o, shifts=(sh, sh), dims=(1, 2))
-    ref_out = o.reshape(B * T, Cdim)
+    return o.reshape(B * T, Cdim), attn
+
+
+def _rand_qkv(B, R, Cdim, nH, seed):
+    g = torch.Generator().manual_seed(seed)
+    hd = Cdim // nH
+    qkv = torch.randn(B * R * R, 3 * Cdim, generator=g)
+    qkv[:, :Cdim] *= hd ** -0.5           # q pre-scaled (the C path folds the scale into the qkv weights)
+    return bf16r(qkv), 0.5 * torch.randn(225, nH, generator=g), g
+
+
+def check_window_attention(B, R, Cdim, nH, shift, seed=0):
+    """ard_window_attention vs the oracle's attention core on identical (bf16-rounded) qkv."""
+    lib = L.load()
+    T = R * R
+    qkv, table, _ = _rand_qkv(B, R, Cdim, nH, seed)
+    ref_out, attn = _ref_window_attention(qkv, table, B, R, Cdim, nH, shift)
     qd = qkv.to("cuda", torch.bfloat16).contiguous()
     out = torch.zeros(B * T, Cdim, device="cuda", dtype=torch.bfloat16)
-    cap = torch.zeros(B_, nH, 64, 64, device="cuda", dtype=torch.float32)
+    cap = torch.zeros(attn.shape[0], nH, 64, 64, device="cuda", dtype=torch.float32)
     td = table.cuda().contiguous()
     L.check(lib.ard_window_attention(L.ptr(qd), L.ptr(out), L.ptr(td), L.ptr(cap), 1.0, 0, B, R, R, Cdim, nH, shift, L.stream_ptr()))
     torch.cuda.synchronize()
     return rel(out.float().cpu(), ref_out), rel(cap.cpu(), attn)
+
+
+def check_window_attention_bwd(B, R, Cdim, nH, shift, seed=0):
+    """ard_window_attention_bwd vs autograd through the oracle's attention core (same bf16-rounded qkv and dout)."""
+    lib = L.load()
+    T = R * R
+    qkv, table, g = _rand_qkv(B, R, Cdim, nH, seed)
+    dout = bf16r(torch.randn(B * T, Cdim, generator=g))
+    qr = qkv.clone().requires_grad_(True)
+    out, _ = _ref_window_attention(qr, table, B, R, Cdim, nH, shift)
+    out.backward(dout)
+    qd = qkv.to("cuda", torch.bfloat16).contiguous()
+    dd = dout.to("cuda", torch.bfloat16).contiguous()
+    dq = torch.zeros(B * T, 3 * Cdim, device="cuda", dtype=torch.bfloat16)
+    td = table.cuda().contiguous()
+    L.check(lib.ard_window_attention_bwd(L.ptr(qd), L.ptr(dd), L.ptr(dq), L.ptr(td), B, R, R, Cdim, nH, shift, L.stream_ptr()))
+    torch.cuda.synchronize()
+    got, ref = dq.float().cpu(), qr.grad
+    return tuple(rel(got[:, i * Cdim:(i + 1) * Cdim], ref[:, i * Cdim:(i + 1) * Cdim]) for i in range(3))
+
+
+def check_layernorm_bwd(rows, Cdim, seed=0, with_add=True):
+    """ard_layernorm_bwd vs autograd of F.layer_norm."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.randn(rows, Cdim, generator=g) * 2 + 0.5).requires_grad_(True)
+    gamma, beta = 1 + 0.2 * torch.randn(Cdim, generator=g), 0.1 * torch.randn(Cdim, generator=g)
+    go, add = torch.randn(rows, Cdim, generator=g), torch.randn(rows, Cdim, generator=g)
+    torch.nn.functional.layer_norm(x, (Cdim,), gamma, beta, 1e-5).backward(go)
+    ref = x.grad + (add if with_add else 0)
+    xd, gd, gm, ad = x.detach().cuda(), go.cuda(), gamma.cuda(), add.cuda()
+    out = torch.empty(rows, Cdim, device="cuda")
+    L.check(lib.ard_layernorm_bwd(L.ptr(xd), L.ptr(gd), L.ptr(gm), L.ptr(ad) if with_add else None, L.ptr(out), rows, Cdim, L.stream_ptr()))
+    torch.cuda.synchronize()
+    return rel(out.cpu(), ref)
 
 
 def make_encoder(model="tiny", seed=0, fusion=False, residual=False):
@@ -190,7 +234,9 @@ def make_encoder(model="tiny", seed=0, fusion=False, residual=False):
     ores = None
     if residual:
         pca, lam = W.make_pca(model, seed=seed)
-        inject_residuals(clap.model.audio_branch, pca, lam)
+        if residual is not True:   # an iterable of layer indices
+            pca = {l: pca[l] for l in residual}
+        clap._residuals = inject_residuals(clap.model.audio_branch, pca, lam)
         ores = {l: (torch.tensor(pca[l]["mean"], dtype=torch.float32), torch.tensor(pca[l]["components"], dtype=torch.float32),
                     torch.from_numpy(lam[l])) for l in pca}
     return clap, sd, ores
@@ -286,4 +332,80 @@ def check_encoder_vs_golden(fname="htsat_tiny_b2.npz"):
         for l in range(4):
             m[f"{tag}_res{l}"] = rel(golden_sample(got["layers_residuals"][l]), torch.from_numpy(g[f"{tag}_res{l}_sample"]))
             m[f"{tag}_attn{l}"] = rel(golden_sample(got["layers_attention"][l]), torch.from_numpy(g[f"{tag}_attn{l}_sample"]))
+    return m
+
+
+def _train_step(clap, wave, text, labels, zero=True):
+    """src/training.py:21-32 on the mirror API: returns (loss, sims); lambda gradients land in res.learnable.grad."""
+    for r in clap._residuals.values():
+        if zero:
+            r.learnable.grad = None
+    emb = clap.get_audio_embedding_from_data(wave.cuda(), use_tensor=True).float()
+    sims = emb @ text.T.cuda()
+    loss = torch.nn.CrossEntropyLoss()(sims, labels.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss.item(), sims.detach().cpu()
+
+
+def check_training_step_vs_golden(fname="htsat_tiny_b2.npz"):
+    """One zero-shot training step (config c3): loss, similarities and d loss / d lambda of every layer vs what the
+    reference's loss.backward() produced (tests/golden, generated by oracle/make_golden.py)."""
+    g = np.load(os.path.join(GOLDEN, fname))
+    model, seed, B = str(g["meta_model"]), int(g["meta_seed"]), int(g["meta_B"])
+    clap, sd, _ = make_encoder(model, seed=seed, residual=True)
+    wave = W.make_clips(B, seed=1234)
+    text = W.make_text_embeds(50, 512, seed=7)
+    labels = torch.from_numpy(g["labels"])
+    loss, sims = _train_step(clap, wave, text, labels)
+    m = {"loss_abs": abs(loss - float(g["train_loss"])), "sims": rel(sims, torch.from_numpy(g["train_sims"]))}
+    for l, r in clap._residuals.items():
+        m[f"lambda_grad{l}"] = rel(r.learnable.grad.cpu(), torch.from_numpy(g[f"lambda_grad{l}"]))
+    return m
+
+
+def check_training_step_vs_oracle(model="tiny", B=2, layers=(1,), seed=0, cosine=False):
+    """ResiDual on a subset of layers (plain blocks above the patched ones exercise the un-patched block backward):
+    lambda gradients vs autograd through the oracle."""
+    clap, sd, ores = make_encoder(model, seed=seed, residual=tuple(layers))
+    wave = W.make_clips(B, seed=99)
+    text = W.make_text_embeds(50, 512, seed=7)
+    labels = torch.from_numpy(np.random.default_rng(5).integers(0, 50, size=B))
+    loss, sims = _train_step(clap, wave, text, labels)
+    ores = {l: (mu, comp, lam.clone().requires_grad_(True)) for l, (mu, comp, lam) in ores.items()}
+    oloss, osims = O.zero_shot_loss(wave, labels, text, sd, W.CONFIGS[model], ores)
+    oloss.backward()
+    m = {"loss_abs": abs(loss - oloss.item()), "sims": rel(sims, osims.detach())}
+    for l, r in clap._residuals.items():
+        a, b = r.learnable.grad.cpu().double(), ores[l][2].grad.double()
+        m[f"lambda_grad{l}"] = rel(a, b)
+        if cosine:
+            m[f"lambda_cos{l}"] = (a @ b / (a.norm() * b.norm())).item()
+            m[f"lambda_norm_ratio{l}"] = (a.norm() / b.norm()).item()
+    return m
+
+
+def check_embedding_grad_vs_oracle(model="tiny", B=2, layers=(0, 1, 2, 3), seed=0, wseed=99):
+    """d loss / d lambda for a loss on output_dict['embedding'] (a linear probe on the 768-d embedding, no ReLU between the
+    encoder and the loss, so the comparison is not perturbed by ReLU gates flipping under bf16 forward error)."""
+    clap, sd, ores = make_encoder(model, seed=seed, residual=tuple(layers))
+    enc = clap.model.audio_branch
+    wave = W.make_clips(B, seed=wseed)
+    NF = enc.num_features
+    g = torch.Generator().manual_seed(3)
+    Wc = torch.randn(50, NF, generator=g) / NF ** 0.5
+    labels = torch.from_numpy(np.random.default_rng(5).integers(0, 50, size=B))
+    for r in clap._residuals.values():
+        r.learnable.grad = None
+    emb = enc.encode(waveform=wave.cuda())["embedding"]
+    loss = torch.nn.functional.cross_entropy(emb @ Wc.T.cuda(), labels.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    ores = {l: (mu, comp, lam.clone().requires_grad_(True)) for l, (mu, comp, lam) in ores.items()}
+    oemb = O.htsat_forward({"waveform": wave}, sd, W.CONFIGS[model], ores)["embedding"]
+    oloss = torch.nn.functional.cross_entropy(oemb @ Wc.T, labels)
+    oloss.backward()
+    m = {"loss_abs": abs(loss.item() - oloss.item()), "embedding": rel(emb.detach().cpu(), oemb.detach())}
+    for l, r in clap._residuals.items():
+        m[f"lambda_grad{l}"] = rel(r.learnable.grad.cpu(), ores[l][2].grad)
     return m

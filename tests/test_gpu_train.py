@@ -1,0 +1,85 @@
+"""-m gpu: the ResiDual training step (config c3): backward kernels vs autograd, lambda gradients vs the reference's
+loss.backward() (golden) and vs autograd through the oracle.
+
+Tolerances. The backward runs on the same bf16 tensor-core GEMMs as the forward, so gradients carry the forward's bf16
+error (<= 1e-2, north_star) plus their own. For a loss on `embedding` (GELU/LayerNorm/softmax only: smooth) the lambda
+gradients agree with the fp32 oracle to <= 1e-2. For the zero-shot loss on `audio_embed` the path crosses the ReLU of
+audio_projection (model.py:539-543): a bf16-sized perturbation of the 768-d embedding flips the gate of the few hidden
+units that sit within that perturbation of zero, and each flipped gate changes the gradient discontinuously, so the
+element-wise bound there is looser (2e-2 on the committed golden case, where it was measured at 9.8e-3) and the
+oracle comparison on other seeds asserts direction (cosine) and norm instead.
+"""
+import pytest
+import torch
+
+import gpu_checks as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("C", [96, 128, 192, 384, 768, 1536])
+def test_layernorm_bwd(C):
+    assert G.check_layernorm_bwd(1000, C) < 1e-5
+    assert G.check_layernorm_bwd(333, C, with_add=False) < 1e-5
+
+
+@pytest.mark.parametrize("B,R,C,nH,shift", [(2, 64, 96, 4, 0), (2, 64, 96, 4, 4), (2, 32, 192, 8, 4), (3, 16, 384, 16, 4),
+                                            (2, 8, 768, 32, 4), (2, 64, 128, 4, 4), (2, 16, 512, 16, 0)])
+def test_window_attention_bwd(B, R, C, nH, shift):
+    dq, dk, dv = G.check_window_attention_bwd(B, R, C, nH, shift)
+    assert max(dq, dk, dv) < 5e-3, (dq, dk, dv)     # bf16 outputs: 2^-9 rounding + bf16 P/dS operands
+
+
+def test_training_step_vs_golden():
+    m = G.check_training_step_vs_golden("htsat_tiny_b2.npz")
+    assert m["loss_abs"] < 2e-3 and m["sims"] < G.TOL_BF16, m
+    for l in range(4):
+        assert m[f"lambda_grad{l}"] < 2e-2, m
+
+
+@pytest.mark.parametrize("layers,B,wseed", [((0, 1, 2, 3), 3, 99), ((2, 3), 2, 1234), ((1,), 2, 7)])
+def test_embedding_loss_lambda_grads_vs_oracle(layers, B, wseed):
+    m = G.check_embedding_grad_vs_oracle("tiny", B, layers, 0, wseed)
+    assert m["embedding"] < G.TOL_BF16, m
+    for l in layers:
+        assert m[f"lambda_grad{l}"] < 1.5e-2, m
+
+
+def test_zero_shot_step_subset_of_layers_vs_oracle():
+    m = G.check_training_step_vs_oracle("tiny", 2, (1,), cosine=True)
+    assert m["loss_abs"] < 2e-3 and m["sims"] < G.TOL_BF16, m
+    assert m["lambda_cos1"] > 0.98 and abs(m["lambda_norm_ratio1"] - 1) < 0.05, m
+
+
+def test_backward_requires_saved_forward():
+    clap, sd, _ = G.make_encoder("tiny", residual=True)
+    enc = clap.model.audio_branch
+    wave = G.W.make_clips(1, seed=3).cuda()
+    with torch.no_grad():
+        enc.encode(waveform=wave)                      # inference forward: nothing saved
+    from audio_residual_b200 import lib as L
+    import ctypes as C
+    a = L.ArdBackwardArgs()
+    a.B = 1
+    g = torch.zeros(1, enc.num_features, device="cuda")
+    a.grad_embedding = g.data_ptr()
+    rc = L.load().ard_encoder_backward(enc._hb.h, C.byref(a), L.stream_ptr())
+    assert rc == L.ARD_ERR_STATE
+    with pytest.raises(RuntimeError):
+        L.check(rc)
+
+
+def test_optimizer_step_changes_output():
+    """Adam over the lambdas (src/training.py:106) through the mirror API: the loss decreases over a few steps."""
+    clap, sd, _ = G.make_encoder("tiny", residual=True)
+    wave = G.W.make_clips(4, seed=21)
+    text = G.W.make_text_embeds(50, 512, seed=7)
+    labels = torch.tensor([3, 17, 3, 41])
+    opt = torch.optim.Adam([r.learnable for r in clap._residuals.values()], lr=0.05)
+    losses = []
+    for _ in range(4):
+        opt.zero_grad()
+        loss, _ = G._train_step(clap, wave, text, labels, zero=False)
+        opt.step()
+        losses.append(loss)
+    assert losses[-1] < losses[0], losses

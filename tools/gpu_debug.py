@@ -47,6 +47,16 @@ def main():
                                    (2, 64, 128, 4, 4), (2, 16, 512, 16, 0)]:
             run(f"window_attention B{B} R{R} C{Cd} nH{nH} shift{sh}", G.check_window_attention, B, R, Cd, nH, sh)
         run("logmel", G.check_logmel)
+    if what in ("bwd", "all"):
+        for Cd in (96, 128, 192, 384, 768, 1536):
+            run(f"layernorm_bwd C{Cd}", G.check_layernorm_bwd, 1000, Cd)
+        run("layernorm_bwd no add", G.check_layernorm_bwd, 777, 384, with_add=False)
+        for (B, R, Cd, nH, sh) in [(2, 64, 96, 4, 0), (2, 64, 96, 4, 4), (2, 32, 192, 8, 4), (3, 16, 384, 16, 4), (2, 8, 768, 32, 4),
+                                   (2, 64, 128, 4, 4), (2, 16, 512, 16, 0)]:
+            run(f"window_attention_bwd B{B} R{R} C{Cd} nH{nH} shift{sh}", G.check_window_attention_bwd, B, R, Cd, nH, sh)
+        run("training step tiny vs golden (reference loss.backward)", G.check_training_step_vs_golden)
+        run("training step tiny layers (1,) vs oracle", G.check_training_step_vs_oracle, "tiny", 2, (1,))
+        run("training step tiny layers (2,3) vs oracle", G.check_training_step_vs_oracle, "tiny", 3, (2, 3))
     if what in ("encoder", "all"):
         run("encoder tiny plain vs oracle", G.check_encoder_vs_oracle, "tiny", 2, False)
         run("encoder tiny residual vs oracle", G.check_encoder_vs_oracle, "tiny", 2, True)
