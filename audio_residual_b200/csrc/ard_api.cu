@@ -17,6 +17,7 @@ namespace ard {
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[1024] = "";
 static thread_local int g_launches = 0;
+static long long g_launch_total = 0;   // process-wide, ard_launch_counter_*
 
 int set_error(int code, const char* fmt, ...) {
     va_list ap;
@@ -27,12 +28,12 @@ int set_error(int code, const char* fmt, ...) {
 }
 int check_cuda(cudaError_t e, const char* what) {
     if (e == cudaSuccess) {
-        if (strstr(what, "launch") != nullptr) ++g_launches;
+        if (strstr(what, "launch") != nullptr) { ++g_launches; ++g_launch_total; }
         return 0;
     }
     return set_error(ARD_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
-void count_launch(int n) { g_launches += n; }
+void count_launch(int n) { g_launches += n; g_launch_total += n; }
 
 // ------------------------------------------------------------------------------------------------ profiling
 struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; };
@@ -549,6 +550,8 @@ long long ard_workspace_bytes(const ard_handle* h) {
     return t;
 }
 int ard_last_launch_count(const ard_handle* h) { return h ? h->last_launches : 0; }
+int ard_launch_counter_reset(void) { g_launch_total = 0; return 0; }
+long long ard_launch_counter_read(void) { return g_launch_total; }
 
 // ---------------------------------------------------------------- op-level entry points
 int ard_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int out_is_bf16, int M, int N,
@@ -634,7 +637,11 @@ int ard_fusion_mel(ard_handle* h, const float* wave, int B, int n_samples, int q
 }
 
 int ard_stats_accumulate(const float* x, long long rows, int D, double* sum, double* sumsq, void* stream) {
-    return stats_accumulate(x, rows, D, sum, sumsq, (cudaStream_t)stream);
+    return stats_accumulate(x, rows, D, D, sum, sumsq, (cudaStream_t)stream);
+}
+
+int ard_stats_accumulate_strided(const float* x, long long rows, long long ldx, int D, double* sum, double* sumsq, void* stream) {
+    return stats_accumulate(x, rows, ldx, D, sum, sumsq, (cudaStream_t)stream);
 }
 
 int ard_profile_enable(int on) {

@@ -111,7 +111,7 @@ int residual_fold(const float* proj_w, const float* dmean, const float* basis, c
 int tscam_im2col(const float* normed, __nv_bfloat16* A, int B, int C, cudaStream_t s);
 int tscam_finish(const float* y, int ldy, float* framewise, float* clipwise, int B, int NC, cudaStream_t s);
 int fine_grained(const float* normed, float* fine, int B, int C, cudaStream_t s);
-int stats_accumulate(const float* x, long long rows, int D, double* sum, double* sumsq, cudaStream_t s);
+int stats_accumulate(const float* x, long long rows, long long ldx, int D, double* sum, double* sumsq, cudaStream_t s);   // stats.cu
 
 // launch accounting (ard_last_launch_count)
 void count_launch(int n = 1);

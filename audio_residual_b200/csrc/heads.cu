@@ -272,64 +272,4 @@ int fine_grained(const float* normed, float* fine, int B, int C, cudaStream_t s)
     return check_cuda(cudaGetLastError(), "fine_grained launch");
 }
 
-// ------------------------------------------------------------------------------------------------ PCA moments
-// sum[D] += sum_r x[r,:],  sumsq[D,D] += x^T x   (float64 accumulators; fp32 products are exact in fp64).
-// Grid: (D/32, D/32, row-splits). Each CTA reduces a slice of rows for a 32x32 block of the covariance.
-__global__ void __launch_bounds__(256) stats_kernel(const float* __restrict__ x, long long rows, int D, double* __restrict__ sum,
-                                                   double* __restrict__ sumsq, long long rows_per_cta) {
-    __shared__ float xi[64][33];
-    __shared__ float xj[64][33];
-    const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
-    if (bj < bi) return;   // upper triangle only; mirrored on write
-    const long long r_begin = (long long)blockIdx.z * rows_per_cta;
-    const long long r_end = min(r_begin + rows_per_cta, rows);
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-    double acc[4] = {0, 0, 0, 0};
-    double colsum = 0.0;
-    for (long long r0 = r_begin; r0 < r_end; r0 += 64) {
-        for (int t = threadIdx.x; t < 64 * 32; t += 256) {
-            const int rr = t >> 5, c = t & 31;
-            const long long r = r0 + rr;
-            const bool ok = r < r_end;
-            xi[rr][c] = (ok && bi + c < D) ? x[r * D + bi + c] : 0.f;
-            xj[rr][c] = (ok && bj + c < D) ? x[r * D + bj + c] : 0.f;
-        }
-        __syncthreads();
-        float part[4] = {0, 0, 0, 0};
-        float cs = 0.f;
-#pragma unroll 8
-        for (int rr = 0; rr < 64; ++rr) {
-            const float bjv = xj[rr][tx];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) part[q] = fmaf(xi[rr][ty * 4 + q], bjv, part[q]);
-            cs += bjv;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[q] += (double)part[q];
-        colsum += (double)cs;
-        __syncthreads();
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int i = bi + ty * 4 + q, j = bj + tx;
-        if (i < D && j < D) {
-            atomicAdd(&sumsq[(long long)i * D + j], acc[q]);
-            if (bi != bj) atomicAdd(&sumsq[(long long)j * D + i], acc[q]);
-        }
-    }
-    if (blockIdx.y == 0 && ty == 0 && bj + tx < D) atomicAdd(&sum[bj + tx], colsum);
-}
-
-int stats_accumulate(const float* x, long long rows, int D, double* sum, double* sumsq, cudaStream_t s) {
-    if (rows <= 0) return 0;
-    const int nb = (D + 31) / 32;
-    long long splits = (148 * 8) / ((long long)nb * (nb + 1) / 2) + 1;
-    long long rows_per_cta = (rows + splits - 1) / splits;
-    rows_per_cta = ((rows_per_cta + 63) / 64) * 64;
-    splits = (rows + rows_per_cta - 1) / rows_per_cta;
-    dim3 grid(nb, nb, (unsigned)splits);
-    stats_kernel<<<grid, 256, 0, s>>>(x, rows, D, sum, sumsq, rows_per_cta);
-    return check_cuda(cudaGetLastError(), "stats launch");
-}
-
 }  // namespace ard

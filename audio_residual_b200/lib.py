@@ -55,6 +55,7 @@ def load(check_symbols=False):
         lib = C.CDLL(LIB_PATH)
         lib.ard_last_error.restype = C.c_char_p
         lib.ard_workspace_bytes.restype = C.c_longlong
+        lib.ard_launch_counter_read.restype = C.c_longlong
         vp, ll, i, f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
         lib.ard_create.argtypes = [C.POINTER(ArdConfig), C.POINTER(vp)]
         lib.ard_destroy.argtypes = [vp]
@@ -80,6 +81,7 @@ def load(check_symbols=False):
         lib.ard_logmel.argtypes = [vp, vp, i, i, i, i, vp, vp]
         lib.ard_fusion_mel.argtypes = [vp, vp, i, i, i, vp, vp]
         lib.ard_stats_accumulate.argtypes = [vp, ll, i, vp, vp, vp]
+        lib.ard_stats_accumulate_strided.argtypes = [vp, ll, ll, i, vp, vp, vp]
         lib.ard_profile_enable.argtypes = [i]
         lib.ard_profile_read.argtypes = [c_double_p, c_double_p, c_double_p, C.POINTER(C.c_int), i]
         _lib = lib

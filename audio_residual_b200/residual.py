@@ -137,9 +137,15 @@ class MomentAccumulator:
         self.s2 = torch.zeros(D, D, device=device, dtype=torch.float64)
 
     def update(self, x):
-        x2 = x.detach().to(torch.float32).contiguous().view(-1, self.D)
+        x = x.detach()
+        if x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1 and x.shape[1] == self.D and x.stride(0) >= self.D:
+            x2, ldx = x, x.stride(0)          # a strided row view (one head's maps) is read in place
+        else:
+            x2 = x.to(torch.float32).contiguous().view(-1, self.D)
+            ldx = self.D
         with torch.cuda.device(x2.device):
-            L.check(L.load().ard_stats_accumulate(L.ptr(x2), x2.shape[0], self.D, L.ptr(self.s1), L.ptr(self.s2), L.stream_ptr()))
+            L.check(L.load().ard_stats_accumulate_strided(C.c_void_p(x2.data_ptr()), x2.shape[0], ldx, self.D, L.ptr(self.s1), L.ptr(self.s2),
+                                                          L.stream_ptr()))
         self.n += x2.shape[0]
 
     def allreduce(self):

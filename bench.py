@@ -150,30 +150,61 @@ def run_reference(args):
     O, sd, ores = oracle_setup()
     g = torch.Generator().manual_seed(99)
     wave = (0.1 * torch.randn(B, 480000, generator=g)).clamp_(-1, 1)
-    with torch.no_grad():
-        for _ in range(max(1, min(args.warmup, 2))):
-            O.get_audio_embedding(wave, sd, O.CONFIGS["tiny"], ores)
-        t0 = time.perf_counter()
-        steps = max(1, min(args.steps, 12))
-        for _ in range(steps):
-            O.get_audio_embedding(wave, sd, O.CONFIGS["tiny"], ores)
-        dt = time.perf_counter() - t0
+    wl = getattr(args, "workload", "infer")
+    if wl == "train":   # src/training.py:21-32 with a Linear(512,50) probe: forward + autograd backward to lambda and the classifier
+        ores = {l: (mu, comp, lam.clone().requires_grad_(True)) for l, (mu, comp, lam) in ores.items()}
+        torch.manual_seed(0)
+        Wc, bc = (0.02 * torch.randn(50, 512)).requires_grad_(True), torch.zeros(50, requires_grad=True)
+        labels = torch.randint(0, 50, (B,))
+
+        def one():
+            loss, _ = O.linear_probe_loss(wave, labels, Wc, bc, sd, O.CONFIGS["tiny"], ores)
+            loss.backward()
+    elif wl == "infer":
+        def one():
+            with torch.no_grad():
+                O.get_audio_embedding(wave, sd, O.CONFIGS["tiny"], ores)
+    else:
+        print(json.dumps({"impl": "reference", "unavailable": f"no CPU reference arm for --workload {wl} (only infer and train are timed)"}), flush=True)
+        return
+    for _ in range(max(1, min(args.warmup, 2))):
+        one()
+    t0 = time.perf_counter()
+    steps = max(1, min(args.steps, 12))
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
     v = B * steps / dt
     sample = f"{steps} steps x {B} clips (bounded sample of the batch-256 workload), torch {torch.__version__} CPU fp32, {torch.get_num_threads()} threads"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": config_dict(256),
+            "data": "synthetic", "config": config_dict(256, wl),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def config_dict(B):
-    return {"workload": "HTSAT-tiny + ResiDual injected in all attention blocks of layers 0-3 (reference-faithful doubled FFN), "
-                        f"inference, batch {B} clips per GPU, 10 s 48 kHz synthetic waveform -> 512-d L2-normalised embedding (BASELINE configs[1])",
-            "batch_per_gpu": B, "clip_samples": 480000, "parallelism": "batch-sharded replicas, no collective",
-            "l2_policy": "per-step inputs (492 MB waveform at B=256) and activations (>2 GB) exceed the 126 MB L2",
-            "weights": "random-init (seeded), random orthonormal PCA basis, lambda = 1 + 0.1 randn"}
+def config_dict(B, workload="infer"):
+    common = {"batch_per_gpu": B, "clip_samples": 480000,
+              "l2_policy": "per-step inputs (492 MB waveform at B=256) and activations (>2 GB) exceed the 126 MB L2",
+              "weights": "random-init (seeded), random orthonormal PCA basis, lambda = 1 + 0.1 randn"}
+    if workload == "train":
+        return dict(common, workload="ResiDual training step (BASELINE configs[2]): HTSAT-tiny frozen, ResiDual on all layers, forward + "
+                                     "backward to every lambda + 50-class Linear(512,50) probe on audio_embed, CE loss, one flat gradient "
+                                     f"allreduce (27,090 floats), Adam step; batch {B} clips per GPU",
+                    parallelism="batch-sharded replicas; one NCCL allreduce of the flat lambda+classifier gradient per step")
+    if workload == "pca":
+        return dict(common, workload="Head-representation PCA statistics (BASELINE configs[3]): HTSAT-tiny forward with capture, per-layer residual "
+                                     "moments (D = 96..768) and per-(layer, head) 4096-d attention-map moments (60 heads) accumulated on the "
+                                     f"tensor cores; batch {B} clips per GPU per step",
+                    parallelism="clip-sharded; moments summed over ranks once at the end (outside the per-step timing)")
+    if workload == "base_fusion":
+        return dict(common, workload="HTSAT-base + feature fusion (aff_2d) + ResiDual on all layers, embedding throughput (BASELINE configs[4]): "
+                                     f"waveform -> device get_mel x4 -> encoder -> 512-d embedding; batch {B} clips per GPU",
+                    parallelism="batch-sharded replicas, no collective")
+    return dict(common, workload="HTSAT-tiny + ResiDual injected in all attention blocks of layers 0-3 (reference-faithful doubled FFN), "
+                                 f"inference, batch {B} clips per GPU, 10 s 48 kHz synthetic waveform -> 512-d L2-normalised embedding (BASELINE configs[1])",
+                parallelism="batch-sharded replicas, no collective")
 
 
 # ------------------------------------------------------------------------------------------------- our arm
@@ -196,14 +227,78 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     B, K, Wm = args.batch, args.steps, max(3, args.warmup)
 
-    clap = build_clap_module("tiny", W.make_state_dict("tiny", seed=0), device=dev)
-    pca, lam = W.make_pca("tiny", seed=0)
-    inject_residuals(clap.model.audio_branch, pca, lam)
+    wl = args.workload
+    model = "base" if wl == "base_fusion" else "tiny"
+    clap = build_clap_module(model, W.make_state_dict(model, seed=0), device=dev, enable_fusion=(wl == "base_fusion"))
+    pca, lam = W.make_pca(model, seed=0)
     enc = clap.model.audio_branch
     wave = synth_clips_device(B, 1234 + rank, dev)
+    launch_box = [0]
+    if wl != "pca":
+        residuals = inject_residuals(enc, pca, lam)
 
-    def step():
-        return enc.encode(waveform=wave, want_audio_embed=True)["audio_embed"]
+    if wl == "infer":
+        def step():
+            return enc.encode(waveform=wave, want_audio_embed=True)["audio_embed"]
+
+        def e2e_step(host):
+            return clap.get_audio_embedding_from_data(host, use_tensor=True).cpu()
+        e2e_api = "CLAP_Module.get_audio_embedding_from_data(x_pinned_host, use_tensor=True).cpu()"
+    elif wl == "base_fusion":
+        def step():
+            return enc.encode(mel_fusion=clap.fusion_mel(wave), want_audio_embed=True)["audio_embed"]
+
+        def e2e_step(host):
+            return clap.get_audio_embedding_from_data(host, use_tensor=True).cpu()
+        e2e_api = "CLAP_Module(enable_fusion=True).get_audio_embedding_from_data(x_pinned_host, use_tensor=True).cpu()"
+    elif wl == "train":
+        from audio_residual_b200.parallel import flat_grad_allreduce
+        for r in residuals.values():
+            r.to(dev)
+        torch.manual_seed(0)
+        cls = torch.nn.Linear(512, 50).to(dev)
+        params = [r.learnable for r in residuals.values()] + list(cls.parameters())
+        opt = torch.optim.Adam(params, lr=1e-3)
+        labels = torch.randint(0, 50, (B,), device=dev, generator=torch.Generator(device=dev).manual_seed(5 + rank))
+
+        def train_step(x):
+            opt.zero_grad(set_to_none=False)
+            emb = clap.get_audio_embedding_from_data(x, use_tensor=True)
+            loss = torch.nn.functional.cross_entropy(cls(emb), labels)
+            loss.backward()
+            flat_grad_allreduce([p.grad for p in params])
+            opt.step()
+            return loss.detach()
+
+        def step():
+            return train_step(wave)
+
+        def e2e_step(host):
+            return train_step(host.to(dev, non_blocking=True)).cpu()
+        e2e_api = "CLAP_Module.get_audio_embedding_from_data(x.to(device), use_tensor=True) -> CE(Linear(512,50)) -> loss.backward() -> allreduce -> Adam.step(); loss.cpu()"
+    else:   # pca
+        from audio_residual_b200.residual import MomentAccumulator
+        res_acc = [MomentAccumulator(96 << l, dev) for l in range(4)]
+        heads = [4, 8, 16, 32]
+        attn_acc = [[MomentAccumulator(4096, dev) for _ in range(heads[l])] for l in range(4)]
+
+        def pca_step(x):
+            out = enc.encode(waveform=x, quantize=True, want_dict=True)
+            for l in range(4):
+                r = out["layers_residuals"][l]
+                res_acc[l].update(r.view(-1, r.shape[-1]))
+                a = out["layers_attention"][l]
+                a3 = a.view(a.shape[0], a.shape[1], 4096)
+                for hd in range(a.shape[1]):
+                    attn_acc[l][hd].update(a3[:, hd])
+            return res_acc[3].s1
+
+        def step():
+            return pca_step(wave)
+
+        def e2e_step(host):
+            return pca_step(host.to(dev, non_blocking=True)).cpu()
+        e2e_api = "encode(want_dict=True) + MomentAccumulator.update per layer and per (layer, head); mean vector .cpu()"
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -211,7 +306,10 @@ def run_ours(args):
     for _ in range(Wm):
         out = step()
     torch.cuda.synchronize()
-    launches_per_step = enc.last_launch_count()
+    L.load().ard_launch_counter_reset()
+    step()
+    torch.cuda.synchronize()
+    launches_per_step = L.load().ard_launch_counter_read()
 
     def barrier():
         torch.cuda.synchronize()
@@ -239,18 +337,18 @@ def run_ours(args):
     host = torch.empty((B, 480000), dtype=torch.float32).pin_memory()
     host.copy_(wave)
     for _ in range(2):
-        clap.get_audio_embedding_from_data(host, use_tensor=True).cpu()
+        e2e_step(host)
     barrier()
     t0 = time.perf_counter()
     Ke = max(2, min(K, 10))
     for _ in range(Ke):
-        emb_host = clap.get_audio_embedding_from_data(host, use_tensor=True).cpu()
+        emb_host = e2e_step(host)
     torch.cuda.synchronize()
     te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = {"value": world * B * Ke / te.item(), "unit": UNIT, "h2d_bytes_per_step": B * 480000 * 4, "d2h_bytes_per_step": int(emb_host.numel() * 4),
-           "api": "CLAP_Module.get_audio_embedding_from_data(x_pinned_host, use_tensor=True).cpu()", "steps": Ke}
+           "api": e2e_api, "steps": Ke}
 
     if rank != 0:
         if world > 1:
@@ -281,7 +379,7 @@ def run_ours(args):
                                         "frac": tc_flops / (tc_ms * 1e-3) / 1e12 / peak,
                                         "ffn_fused_ms_per_step": ff["ms"] / 2, "ffn_fused_launches_per_step": ff["launches"] // 2},
                 "share_of_step_by_class": shares,
-                "whole_step_tensor_frac": (B * GF_PER_CLIP_TINY_FAITHFUL * 1e9) / ((ms_total / K) * 1e-3) / 1e12 / peak}
+                "whole_step_tensor_frac": ((B * GF_PER_CLIP_TINY_FAITHFUL * 1e9) / ((ms_total / K) * 1e-3) / 1e12 / peak) if wl == "infer" else None}
     traffic_file = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(traffic_file):
         roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
@@ -295,7 +393,7 @@ def run_ours(args):
                "sample": f"2 batches x 8 clips of the same workload ({sec:.2f} s/batch), oracle port of the reference's PyTorch CPU path, fp32"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_total / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config_dict(B),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config_dict(B, wl),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu,
             "embedding_checksum": float(out.double().abs().sum().item())}
     print(json.dumps(line), flush=True)
@@ -310,6 +408,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="infer", choices=["infer", "train", "pca", "base_fusion"],
+                    help="infer = the headline (BASELINE configs[1]); the others measure configs[2..4] with the same JSON contract")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -122,6 +122,9 @@ int ard_block_forward(ard_handle* h, int layer, int block, const float* x_in, in
 long long ard_workspace_bytes(const ard_handle* h);
 /* Number of kernels launched by the last ard_encoder_forward / ard_block_forward on this handle. */
 int ard_last_launch_count(const ard_handle* h);
+/* Process-wide count of kernels this library launched since the last reset (forward, backward, folds, statistics). */
+int ard_launch_counter_reset(void);
+long long ard_launch_counter_read(void);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Op-level entry points (the kernels behind the handle; also what the parity tests drive directly)
@@ -171,9 +174,14 @@ int ard_fusion_mel(ard_handle* h, const float* wave, int B, int n_samples, int q
 
 /* ------------------------------------------------------------------------------------------------------------------
  * PCA sufficient statistics (replaces IncrementalPCA.partial_fit in compute_pca_components, src/residual.py:137-138):
- * accumulates n += rows, sum[D] += sum_r x[r], sumsq[D,D] += x^T x in float64 on device. x fp32 [rows, D] device.
+ * accumulates sum[D] += sum_r x[r], sumsq[D,D] += x^T x in float64 on device (the caller counts n). x fp32 [rows, D]
+ * device, D a multiple of 4. X^T X runs on the tcgen05 GEMM with x split into two bf16 terms (fp32-grade products,
+ * fp32 accumulation per chunk of samples, fp64 across chunks). Uses per-process device scratch: one caller at a time.
+ * The _strided form reads rows `ldx` floats apart (e.g. one head's maps out of layers_attention [B*nW, nH, 64, 64],
+ * src/analyze_attention.py:41-49, without a gather copy).
  * ------------------------------------------------------------------------------------------------------------------ */
 int ard_stats_accumulate(const float* x, long long rows, int D, double* sum, double* sumsq, void* stream);
+int ard_stats_accumulate_strided(const float* x, long long rows, long long ldx, int D, double* sum, double* sumsq, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Measurement support (bench.py): per-kernel-class device time. Classes: 0 tcgen05 GEMM, 1 window attention,

@@ -409,3 +409,44 @@ def check_embedding_grad_vs_oracle(model="tiny", B=2, layers=(0, 1, 2, 3), seed=
     for l, r in clap._residuals.items():
         m[f"lambda_grad{l}"] = rel(r.learnable.grad.cpu(), ores[l][2].grad)
     return m
+
+
+def check_stats(rows, D, strided=False, seed=0, calls=1):
+    """ard_stats_accumulate(_strided) vs float64 X^T X / column sums (fp32-grade products are expected: split-bf16 GEMM)."""
+    from audio_residual_b200.residual import MomentAccumulator
+    g = torch.Generator().manual_seed(seed)
+    nh = 3 if strided else 1
+    full = torch.randn(rows, nh, D, generator=g) * 0.7 + 0.3
+    xd = full.cuda()
+    acc = MomentAccumulator(D, xd.device)
+    view = xd[:, 1] if strided else xd[:, 0]
+    per = (rows + calls - 1) // calls
+    for c in range(calls):
+        acc.update(view[c * per:(c + 1) * per])
+    torch.cuda.synchronize()
+    x64 = (full[:, 1] if strided else full[:, 0]).double()
+    return {"n": acc.n - rows, "sum": rel(acc.s1.cpu(), x64.sum(0)), "sumsq": rel(acc.s2.cpu(), x64.t() @ x64)}
+
+
+def check_pca_moments_vs_oracle(layer=2, B=2):
+    """compute_pca_components' statistics of one layer's residuals (a19): GPU forward + tensor-core moments vs the oracle's
+    residuals in float64; the eigen-spectrum of the two covariances is compared as well."""
+    from audio_residual_b200.residual import MomentAccumulator
+    clap, sd, _ = make_encoder("tiny")
+    enc = clap.model.audio_branch
+    wave = W.make_clips(B, seed=77)
+    out = enc.encode(waveform=wave.cuda(), quantize=True, want_dict=True)
+    res = out["layers_residuals"][layer]
+    acc = MomentAccumulator(res.shape[-1], res.device)
+    acc.update(res)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = O.htsat_forward({"waveform": O.quantize_tensor(wave)}, sd, W.CONFIGS["tiny"])["layers_residuals"][layer]
+    X = ref.reshape(-1, ref.shape[-1]).double()
+    n = X.shape[0]
+    mean_ref, mean = X.mean(0), acc.s1.cpu() / n
+    cov_ref = (X - mean_ref).t() @ (X - mean_ref) / (n - 1)
+    cov = (acc.s2.cpu() - n * torch.outer(mean, mean)) / (n - 1)
+    ev_ref, ev = torch.linalg.eigvalsh(cov_ref).flip(0), torch.linalg.eigvalsh(cov).flip(0)
+    k = min(32, ev.numel())
+    return {"n": acc.n - n, "mean": rel(mean, mean_ref), "cov": rel(cov, cov_ref), "top_eigenvalues": rel(ev[:k], ev_ref[:k])}

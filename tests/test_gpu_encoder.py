@@ -31,3 +31,9 @@ def test_fusion_featuriser_and_base_from_waveform():
     m = G.check_fusion_featuriser()
     assert m["mel_fusion"] < 1e-4 and m["channels_equal"] == 0.0, m
     assert m["audio_embed_from_waveform"] < G.TOL_BF16, m
+
+
+@pytest.mark.parametrize("layer", [0, 3])
+def test_pca_moments_vs_oracle(layer):
+    m = G.check_pca_moments_vs_oracle(layer, 2)
+    assert m["n"] == 0 and m["mean"] < G.TOL_BF16 and m["cov"] < 2 * G.TOL_BF16 and m["top_eigenvalues"] < 2 * G.TOL_BF16, m

@@ -49,3 +49,10 @@ def test_window_attention(B, R, C, nH, shift):
 def test_logmel():
     m = G.check_logmel()
     assert m["logmel"] < G.TOL_FP32 and m["logmel_bn"] < 2e-4 and m["logmel_maxabs_dB"] < 5e-3, m
+
+
+@pytest.mark.parametrize("rows,D,strided,calls", [(1000, 96, False, 1), (5000, 192, False, 2), (777, 768, False, 1), (3000, 4096, True, 2),
+                                                  (130, 384, True, 1)])
+def test_stats_accumulate(rows, D, strided, calls):
+    m = G.check_stats(rows, D, strided, calls=calls)
+    assert m["n"] == 0 and m["sum"] < 1e-6 and m["sumsq"] < 1e-5, m

@@ -47,6 +47,11 @@ def main():
                                    (2, 64, 128, 4, 4), (2, 16, 512, 16, 0)]:
             run(f"window_attention B{B} R{R} C{Cd} nH{nH} shift{sh}", G.check_window_attention, B, R, Cd, nH, sh)
         run("logmel", G.check_logmel)
+    if what in ("stats", "all"):
+        for (rows, D, st, calls) in [(1000, 96, False, 1), (5000, 192, False, 2), (777, 768, False, 1), (3000, 4096, True, 2), (130, 384, True, 1)]:
+            run(f"stats rows{rows} D{D} strided={st}", G.check_stats, rows, D, st, calls=calls)
+        run("pca moments layer 0 vs oracle", G.check_pca_moments_vs_oracle, 0, 2)
+        run("pca moments layer 3 vs oracle", G.check_pca_moments_vs_oracle, 3, 2)
     if what in ("bwd", "all"):
         for Cd in (96, 128, 192, 384, 768, 1536):
             run(f"layernorm_bwd C{Cd}", G.check_layernorm_bwd, 1000, Cd)
