@@ -350,18 +350,23 @@ def run_ours(args):
     e2e = {"value": world * B * Ke / te.item(), "unit": UNIT, "h2d_bytes_per_step": B * 480000 * 4, "d2h_bytes_per_step": int(emb_host.numel() * 4),
            "api": e2e_api, "steps": Ke}
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant kernel class, measured live with CUDA events around every launch
-    peaks = read_peaks()
-    L.profile_enable(True)
+    # ---- roofline of the dominant kernel class, measured live with CUDA events around every launch.
+    # Every rank runs the two profiled steps (the training step holds a collective); only rank 0 records and reports.
+    if rank == 0:
+        L.profile_enable(True)
     for _ in range(2):
         step()
+    torch.cuda.synchronize()
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    peaks = read_peaks()
     prof = L.profile_read()
     L.profile_enable(False)
+    if world > 1:
+        dist.barrier()
     tot_ms = sum(v["ms"] for v in prof.values())
     shares = {k: round(v["ms"] / tot_ms, 4) for k, v in prof.items() if v["launches"]}
     gm = prof["gemm_tc"]
