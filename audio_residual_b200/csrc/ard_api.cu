@@ -610,7 +610,7 @@ int ard_window_attention_bwd(const void* qkv_bf16, const void* dout_bf16, void* 
 
 int ard_layernorm_bwd(const float* x, const float* grad_out, const float* gamma, const float* add, float* grad_in, long long rows, int C,
                       void* stream) {
-    return layernorm_bwd(x, grad_out, gamma, add, grad_in, rows, C, (cudaStream_t)stream);
+    return layernorm_bwd(x, grad_out, gamma, add, grad_in, rows, C, (cudaStream_t)stream, 1.0f, nullptr);
 }
 
 int ard_f32_to_bf16(const float* in, void* out_bf16, long long n, float scale, void* stream) {

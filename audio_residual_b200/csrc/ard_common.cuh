@@ -188,6 +188,12 @@ ARD_DEVINL float erf_fast(float x) {
     float r = 1.0f - exp2f(-q * t);
     return copysignf(r, x);
 }
+// d/dx gelu(x) = Phi(x) + x phi(x) = 0.5 (1 + erf(x / sqrt 2)) + x exp(-x^2 / 2) / sqrt(2 pi)
+ARD_DEVINL float gelu_erf_grad(float x) {
+    const float cdf = fmaf(0.5f, erf_fast(x * 0.70710678118654752f), 0.5f);
+    const float pdf = 0.3989422804014327f * exp2f(-0.72134752044448170f * x * x);
+    return fmaf(x, pdf, cdf);
+}
 // Exact-erf GELU of two values in packed fp16 arithmetic (same erf formula as erf_fast): the fp32 pre-activations are
 // rounded to half2 once and the result stays fp16 - it is the A operand of the fp16 fc2 GEMM. ~15 instructions per PAIR
 // instead of ~18 per element, and (10-bit mantissa) 5x closer to the exact GELU than the fp32-GELU -> bf16 operand path

@@ -49,6 +49,8 @@ struct GemmArgs {
     int force_bn = 0;
     int ab_f16 = 0;                    // A and W are fp16 instead of bf16 (the fc2 GEMM: hidden activations are fp16)
     int out_f16 = 0;                   // with out_bf16=1 and act=GELU: GELU in packed fp16, fp16 output
+    const __nv_bfloat16* mul_gelu_bwd = nullptr;   // bf16 [M, ld_mul]: out = acc * gelu'(this), bf16 output only (FFN backward)
+    long long ld_mul = 0;
 };
 int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream);
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
@@ -73,7 +75,9 @@ int final_norm_mean(const float* x, const float* gamma, const float* beta, float
 int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, float scale, cudaStream_t s);
 int fill_f32(float* p, long long n, float v, cudaStream_t s);
 // backward kernels (training path)
-int layernorm_bwd(const float* x, const float* g, const float* gamma, const float* add, float* out, long long rows, int C, cudaStream_t s);
+// out = add_scale*add + dLN(x)^T g (fp32); optional out_bf = bf16(add + dLN(x)^T g)
+int layernorm_bwd(const float* x, const float* g, const float* gamma, const float* add, float* out, long long rows, int C, cudaStream_t s,
+                  float add_scale = 1.0f, __nv_bfloat16* out_bf = nullptr);
 
 // ---------------------------------------------------------------- window attention (attn_window.cu)
 struct AttnArgs {

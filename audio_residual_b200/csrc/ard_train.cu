@@ -22,8 +22,8 @@ namespace ard {
 int l2_normalize_bwd(const float* p, const float* g, float* out, int B, int N, cudaStream_t s);
 int relu_bwd_mul(float* g, const float* act, long long n, cudaStream_t s);
 // rowwise.cu
-int layernorm_bwd(const float* x, const float* g, const float* gamma, const float* add, float* out, long long rows, int C, cudaStream_t s);
-int merge_layernorm_bwd(const float* x, const float* g, const float* gamma, float* dx, int B, int H, int W, int C, cudaStream_t s);
+int merge_layernorm_bwd(const float* x, const float* g, const float* gamma, float* dx, __nv_bfloat16* dx_bf, int B, int H, int W, int C,
+                        cudaStream_t s);
 int gelu_bwd_mul(__nv_bfloat16* dh, const __nv_bfloat16* hpre, long long n, cudaStream_t s);
 int lambda_grad(const float* coef, const float* gcoef, const float* lam, float* dlam, __nv_bfloat16* gsc, long long M, int K, cudaStream_t s);
 int bcast_rows(const float* g, float* out, int B, int T, int C, float scale, cudaStream_t s);
@@ -176,29 +176,28 @@ int run_block_train(ard_handle* h, int l, int b, int B, float* attn_out, float a
 
 // ------------------------------------------------------------------------------------------------ backward schedule
 struct BwdBufs {
-    float *G, *GS, *T, *coef, *gcoef;
+    float *G, *T, *coef, *gcoef;
     __nv_bfloat16 *XN, *HPRE, *DH, *GB, *GQKV, *GAO, *gsc;
 };
 
-// gout = gin + d/dx [ mlp(norm2(x)) ]^T gin      (one FFN residual branch; gout may alias gin)
-static int ffn_backward(ard_handle* h, BlockW& bw, int C, long long M, const float* x, const float* gin, float* gout, const BwdBufs& w,
-                        cudaStream_t s) {
+// gout = out_scale * gin + d/dx [ mlp(norm2(x)) ]^T gin   (one FFN residual branch; gout may alias gin).
+// w.GB must hold bf16(gin) on entry; on exit it holds bf16(gin + branch gradient), the bf16 copy of the un-scaled result.
+static int ffn_backward(ard_handle* h, BlockW& bw, int C, long long M, const float* x, const float* gin, float* gout, float out_scale,
+                        const BwdBufs& w, cudaStream_t s) {
     ARD_TRY(layernorm_bf16(x, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), w.XN, M, C, s));
     GemmArgs f;
     f.A = w.XN; f.lda = C; f.W = bw.fc1_w.as<__nv_bfloat16>(); f.ldw = C; f.out = w.HPRE; f.ldo = 4 * C; f.out_bf16 = 1;
     f.M = (int)M; f.N = 4 * C; f.K = C; f.bias = bw.fc1_b.as<float>();
     ARD_TRY(gemm_bf16(f, h->num_sms, s));                                       // hpre = fc1(norm2(x)), recomputed
-    ARD_TRY(add_f32(gin, nullptr, nullptr, w.GB, M * C, s));
     f = GemmArgs();
     f.A = w.GB; f.lda = C; f.W = bw.fc2_wT.as<__nv_bfloat16>(); f.ldw = C; f.out = w.DH; f.ldo = 4 * C; f.out_bf16 = 1;
-    f.M = (int)M; f.N = 4 * C; f.K = C;
-    ARD_TRY(gemm_bf16(f, h->num_sms, s));                                       // dh = g W2
-    ARD_TRY(gelu_bwd_mul(w.DH, w.HPRE, M * 4 * C, s));                          // dh *= gelu'(hpre)
+    f.M = (int)M; f.N = 4 * C; f.K = C; f.mul_gelu_bwd = w.HPRE; f.ld_mul = 4 * C;
+    ARD_TRY(gemm_bf16(f, h->num_sms, s));                                       // dh = (g W2) * gelu'(hpre), multiplied in the epilogue
     f = GemmArgs();
     f.A = w.DH; f.lda = 4 * C; f.W = bw.fc1_wT.as<__nv_bfloat16>(); f.ldw = 4 * C; f.out = w.T; f.ldo = C;
     f.M = (int)M; f.N = C; f.K = 4 * C;
     ARD_TRY(gemm_bf16(f, h->num_sms, s));                                       // dn2 = dh W1
-    return layernorm_bwd(x, w.T, bw.ln2_g.as<float>(), gin, gout, M, C, s);     // gout = gin + LN2'(dn2)
+    return layernorm_bwd(x, w.T, bw.ln2_g.as<float>(), gin, gout, M, C, s, out_scale, w.GB);   // + LN2'(dn2), and its bf16 copy
 }
 
 // G holds dL/d(block output) on entry and dL/d(block input) on exit. `stop_after_lambda`: nothing below this block needs
@@ -210,10 +209,10 @@ static int block_backward(ard_handle* h, int l, int b, int B, float* dlam, bool 
     ARD_TRY(ensure_backward_weights(h, l, b));
     GemmArgs g;
     if (bw.has_res) {
-        ARD_TRY(ffn_backward(h, bw, C, M, bw.t_x3, w.G, w.G, w, s));             // G  = dL/dx3
-        ARD_TRY(ffn_backward(h, bw, C, M, bw.t_x1, w.G, w.GS, w, s));            // GS = dL/dx1 = dL/dr   (x3 = s + x2, x2 = x1 + mlp)
-        ARD_TRY(add_f32(w.GS, nullptr, nullptr, w.GB, M * C, s));                // bf16(dL/dr)
-        ARD_TRY(add_f32(w.G, w.GS, w.G, nullptr, M * C, s));                     // shortcut: dL/ds so far = dL/dx3 + dL/dx1
+        ARD_TRY(ffn_backward(h, bw, C, M, bw.t_x3, w.G, w.G, 1.0f, w, s));       // G  = dL/dx3, GB = bf16(G)
+        // dL/dx1 = dL/dr = G + FFN'(G)   (x3 = s + x2, x2 = x1 + mlp): only its bf16 copy (GB) is needed below, and the
+        // shortcut sum dL/ds so far = dL/dx3 + dL/dx1 = 2 G + FFN'(G) is written straight into G
+        ARD_TRY(ffn_backward(h, bw, C, M, bw.t_x1, w.G, w.G, 2.0f, w, s));
         const int Kp = bw.Kp;
         g.A = bw.t_ao; g.lda = C; g.W = bw.res_wc.as<__nv_bfloat16>(); g.ldw = C; g.out = w.coef; g.ldo = Kp;
         g.M = (int)M; g.N = Kp; g.K = C; g.bias = bw.res_c0.as<float>();
@@ -230,9 +229,8 @@ static int block_backward(ard_handle* h, int l, int b, int B, float* dlam, bool 
         g.M = (int)M; g.N = C; g.K = Kp;
         ARD_TRY(gemm_bf16(g, h->num_sms, s));                                    // d ao = gsc Wc
     } else {
-        ARD_TRY(ffn_backward(h, bw, C, M, bw.t_x1, w.G, w.G, w, s));             // G = dL/dx1 = dL/ds (shortcut) = dL/dr
+        ARD_TRY(ffn_backward(h, bw, C, M, bw.t_x1, w.G, w.G, 1.0f, w, s));       // G = dL/dx1 = dL/ds (shortcut) = dL/dr, GB = bf16(G)
         if (stop_after_lambda) return 0;
-        ARD_TRY(add_f32(w.G, nullptr, nullptr, w.GB, M * C, s));
         g.A = w.GB; g.lda = C; g.W = bw.proj_wT.as<__nv_bfloat16>(); g.ldw = C; g.out = w.GAO; g.ldo = C; g.out_bf16 = 1;
         g.M = (int)M; g.N = C; g.K = C;
         ARD_TRY(gemm_bf16(g, h->num_sms, s));                                    // d ao = dL/dr Wp
@@ -244,7 +242,7 @@ static int block_backward(ard_handle* h, int l, int b, int B, float* dlam, bool 
     g.A = w.GQKV; g.lda = 3 * C; g.W = bw.qkv_wT.as<__nv_bfloat16>(); g.ldw = 3 * C; g.out = w.T; g.ldo = C;
     g.M = (int)M; g.N = C; g.K = 3 * C;
     ARD_TRY(gemm_bf16(g, h->num_sms, s));                                        // dn1 = dqkv Wqkv
-    return layernorm_bwd(bw.t_s, w.T, bw.ln1_g.as<float>(), w.G, w.G, M, C, s);  // G += LN1'(dn1)
+    return layernorm_bwd(bw.t_s, w.T, bw.ln1_g.as<float>(), w.G, w.G, M, C, s, 1.0f, w.GB);  // G += LN1'(dn1), GB = bf16(G)
 }
 
 int encoder_backward(ard_handle* h, const ard_backward_args* a, cudaStream_t s) {
@@ -271,7 +269,6 @@ int encoder_backward(ard_handle* h, const ard_backward_args* a, cudaStream_t s) 
     if (stop_l < 0) return 0;
     const size_t MC = (size_t)B * 4096 * h->cfg.embed_dim;
     ARD_TRY(h->bw_g.ensure(MC * 4));
-    ARD_TRY(h->bw_gs.ensure(MC * 4));
     ARD_TRY(h->bw_t.ensure(MC * 4));
     ARD_TRY(h->bw_dh.ensure(MC * 4 * 2));
     ARD_TRY(h->bw_gb.ensure(MC * 2));
@@ -280,7 +277,7 @@ int encoder_backward(ard_handle* h, const ard_backward_args* a, cudaStream_t s) 
     ARD_TRY(h->bw_gsc.ensure(MC * 2));
     ARD_TRY(h->bw_small.ensure((size_t)B * (2 * J + NF) * 4 + 1024));
     BwdBufs w;
-    w.G = h->bw_g.as<float>(); w.GS = h->bw_gs.as<float>(); w.T = h->bw_t.as<float>();
+    w.G = h->bw_g.as<float>(); w.T = h->bw_t.as<float>();
     w.coef = h->bw_coef.as<float>(); w.gcoef = h->bw_gcoef.as<float>(); w.gsc = h->bw_gsc.as<__nv_bfloat16>();
     w.XN = h->ws_xn.as<__nv_bfloat16>(); w.HPRE = h->ws_h.as<__nv_bfloat16>(); w.DH = h->bw_dh.as<__nv_bfloat16>();
     w.GB = h->bw_gb.as<__nv_bfloat16>(); w.GQKV = h->ws_qkv.as<__nv_bfloat16>(); w.GAO = h->ws_ao.as<__nv_bfloat16>();
@@ -315,7 +312,7 @@ int encoder_backward(ard_handle* h, const ard_backward_args* a, cudaStream_t s) 
     // ---- token mean + final norm (htsat.py:797, :810-811)
     const LayerW& last = h->layers[h->nlayers - 1];
     ARD_TRY(bcast_rows(g_emb, w.T, B, 64, NF, 1.0f / 64.0f, s));
-    ARD_TRY(layernorm_bwd(last.blocks.back().t_out, w.T, h->norm_g.as<float>(), nullptr, w.G, (long long)B * 64, NF, s));
+    ARD_TRY(layernorm_bwd(last.blocks.back().t_out, w.T, h->norm_g.as<float>(), nullptr, w.G, (long long)B * 64, NF, s, 1.0f, w.GB));
     // ---- swin stages, top down
     for (int l = h->nlayers - 1; l >= stop_l; --l) {
         const int C = C_of(h, l), R = R_of(l);
@@ -335,12 +332,11 @@ int encoder_backward(ard_handle* h, const ard_backward_args* a, cudaStream_t s) 
                 ARD_TRY(get(h, key, (size_t)8 * Cp * Cp, &v));
                 ARD_TRY(transpose_upload_bf16(lw.mg_wT, v->data(), 2 * Cp, 4 * Cp));   // [4Cp, 2Cp]
             }
-            ARD_TRY(add_f32(w.G, nullptr, nullptr, w.GB, Mm * C, s));
-            GemmArgs g;
+            GemmArgs g;   // GB = bf16(G) was written by the last block's norm1 backward
             g.A = w.GB; g.lda = C; g.W = lw.mg_wT.as<__nv_bfloat16>(); g.ldw = C; g.out = w.T; g.ldo = 4 * Cp;
             g.M = (int)Mm; g.N = 4 * Cp; g.K = C;
             ARD_TRY(gemm_bf16(g, h->num_sms, s));
-            ARD_TRY(merge_layernorm_bwd(lw.blocks.back().t_out, w.T, lw.mg_g.as<float>(), w.G, B, Rp, Rp, Cp, s));
+            ARD_TRY(merge_layernorm_bwd(lw.blocks.back().t_out, w.T, lw.mg_g.as<float>(), w.G, w.GB, B, Rp, Rp, Cp, s));
         }
     }
     return 0;

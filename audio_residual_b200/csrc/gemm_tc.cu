@@ -53,6 +53,7 @@ struct GemmKernelParams {
     long long aux_bstride;
     int ab_f16;          // A and W hold fp16 (else bf16)
     int out_f16;         // 16-bit output holds fp16 (GELU evaluated in packed fp16), else bf16
+    int mul_gelu_bwd;    // 16-bit output only: out = acc * gelu'(h), h = the bf16 [M,N] tensor behind tmR (FFN backward: dh = (g W2) * gelu'(hpre))
 };
 
 template <int BN, bool OUT_BF16>
@@ -167,8 +168,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_expect_tx(&rbar[b], GEMM_CSTAGE_BYTES);
             tma_load_2d(cst + b * GEMM_CSTAGE_BYTES, &tmR, &rbar[b], nb * BN + cc * 32, mb * GEMM_BM + quad * 32);
         };
+        // 16-bit output with a multiplicand (gelu' of the recomputed pre-activation): its 32x32 bf16 tile is TMA-prefetched one
+        // chunk ahead into the UPPER half of the staging buffer (the result tile only uses the lower 2 KB), so it never
+        // collides with an outstanding TMA store.
+        const bool tma_mul = OUT_BF16 && p.mul_gelu_bwd != 0;
+        auto issue_mul = [&](int t, int cc, int b) {     // lane 0 only
+            const int mb = t / n_blocks, nb = t % n_blocks;
+            fence_proxy_async_smem();                    // order the warp's earlier generic reads of this half before the async write
+            mbar_expect_tx(&rbar[b], GEMM_CSTAGE_BYTES / 2);
+            tma_load_2d(cst + b * GEMM_CSTAGE_BYTES + GEMM_CSTAGE_BYTES / 2, &tmR, &rbar[b], nb * BN + cc * 32, mb * GEMM_BM + quad * 32);
+        };
         int tile = blockIdx.x, c = grp, it = 0, i = 0;
         if (tma_resid && tile < num_tiles && lane == 0) issue_resid(tile, c, 0);
+        if (tma_mul && tile < num_tiles && lane == 0) issue_mul(tile, c, 0);
         while (tile < num_tiles) {
             int ntile = tile, nc = c + NGRP;
             if (nc >= NCHUNK) { nc = grp; ntile = tile + gridDim.x; }
@@ -176,6 +188,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (tma_resid && lane == 0) {
                 tma_store_wait_read<1>();          // buffer (i+1)%3 was last stored two chunks ago
                 if (ntile < num_tiles) issue_resid(ntile, nc, (i + 1) % NBUF);
+            }
+            if (tma_mul) {
+                __syncwarp();                      // every lane finished reading the other buffer's upper half (chunk i-1)
+                if (lane == 0 && ntile < num_tiles) issue_mul(ntile, nc, (i + 1) % NBUF);
             }
             const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
             const int as = it & 1;
@@ -216,6 +232,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
             }
             uint8_t* sbuf = cst + b * GEMM_CSTAGE_BYTES;
+            if constexpr (OUT_BF16) {
+                if (tma_mul) {
+                    mbar_wait(&rbar[b], (i / NBUF) & 1);
+                    const uint8_t* rowp = sbuf + GEMM_CSTAGE_BYTES / 2 + lane * 64;
+                    const int sw = (lane >> 1) & 3;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 u = *reinterpret_cast<const uint4*>(rowp + ((q ^ sw) << 4));
+                        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float h0 = __uint_as_float(w4[k] << 16), h1 = __uint_as_float(w4[k] & 0xffff0000u);
+                            f[q * 8 + 2 * k] *= gelu_erf_grad(h0);
+                            f[q * 8 + 2 * k + 1] *= gelu_erf_grad(h1);
+                        }
+                    }
+                }
+            }
             if constexpr (!OUT_BF16) {
                 if (p.aux != nullptr && row_ok) {
                     float* ap = p.aux + ((long long)(row / p.aux_T) * p.aux_bstride + (row % p.aux_T)) * p.ld_aux + col0;
@@ -378,12 +412,17 @@ int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream) {
         if (a.ldr1 % 4) return set_error(ARD_ERR_SHAPE, "gemm: residual leading dimension must be a multiple of 4");
         if (int rc = make_tmap_2d(&tr, a.resid1, 4, a.N, a.M, (uint64_t)a.ldr1 * 4, 32, 32, 128)) return rc;
     }
+    if (a.mul_gelu_bwd != nullptr) {
+        if (!a.out_bf16 || a.out_f16 || a.act != ARD_ACT_NONE || (a.ld_mul % 8))
+            return set_error(ARD_ERR_SHAPE, "gemm: the gelu' multiplicand needs a plain bf16 output and ld_mul %% 8 == 0");
+        if (int rc = make_tmap_2d(&tr, a.mul_gelu_bwd, 2, a.N, a.M, (uint64_t)a.ld_mul * 2, 32, 32, 64)) return rc;
+    }
     GemmKernelParams kp;
     kp.M = a.M; kp.N = a.N; kp.K = a.K;
     kp.bias = a.bias; kp.act = a.act;
     kp.resid1 = a.resid1; kp.ldr1 = a.ldr1; kp.resid2 = a.resid2; kp.ldr2 = a.ldr2;
     kp.aux = a.aux; kp.ld_aux = a.ld_aux; kp.aux_T = a.aux_T > 0 ? a.aux_T : a.M; kp.aux_bstride = a.aux_bstride;
-    kp.ab_f16 = a.ab_f16; kp.out_f16 = a.out_f16;
+    kp.ab_f16 = a.ab_f16; kp.out_f16 = a.out_f16; kp.mul_gelu_bwd = a.mul_gelu_bwd != nullptr;
     const double osz = a.out_bf16 ? 2.0 : 4.0;
     ProfScope ps(PROF_GEMM, stream, 2.0 * a.M * a.N * a.K,
                  2.0 * a.M * a.K + 2.0 * a.N * a.K + osz * a.M * a.N + (a.resid1 ? 4.0 * a.M * a.N : 0.0) + (a.resid2 ? 4.0 * a.M * a.N : 0.0) +

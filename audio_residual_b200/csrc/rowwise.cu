@@ -339,10 +339,12 @@ namespace ard {
 // LayerNorm backward: y = (x - mean) * rstd * gamma + beta over the last dim C.
 //   dx = rstd * (gg - mean(gg) - xhat * mean(gg * xhat)),  gg = g * gamma;   out = (add ? add : 0) + dx   (fp32)
 // Rows may be the PatchMerging gather (MergeRows): x is read and dx written through the same row map.
+//   out = add_scale * add + dx  (fp32);   out_bf = bf16(add + dx)  (optional: the next dgrad GEMM's A operand)
 template <int VEC, int NV, class Rows>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(Rows xrows, Rows orows, float* __restrict__ out_base,
                                                            const float* __restrict__ g, const float* __restrict__ gamma,
-                                                           const float* __restrict__ add, long long nrows) {
+                                                           const float* __restrict__ add, float add_scale,
+                                                           __nv_bfloat16* __restrict__ out_bf, long long nrows) {
     constexpr int C = 32 * VEC * NV;
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -390,21 +392,22 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(Rows xrows, Rows oro
         float* op = out_base + (orows.at(row, e) - orows.x);
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            float d = rstd * (gg[i][k] - m1 - v[i][k] * m2);
-            if (add != nullptr) d += add[op - out_base + k];
-            op[k] = d;
+            const float d = rstd * (gg[i][k] - m1 - v[i][k] * m2);
+            const float a = add != nullptr ? add[op - out_base + k] : 0.f;
+            op[k] = fmaf(add_scale, a, d);
+            if (out_bf != nullptr) out_bf[op - out_base + k] = __float2bfloat16_rn(a + d);
         }
     }
 }
 
 template <class Rows>
-static int launch_ln_bwd(Rows xr, Rows orr, float* out, const float* g, const float* gamma, const float* add, long long nrows, int C,
-                         cudaStream_t s) {
+static int launch_ln_bwd(Rows xr, Rows orr, float* out, const float* g, const float* gamma, const float* add, float add_scale,
+                         __nv_bfloat16* out_bf, long long nrows, int C, cudaStream_t s) {
     const int wpb = 8;
     const unsigned grid = (unsigned)((nrows + wpb - 1) / wpb);
-    ProfScope ps(PROF_LN, s, 16.0 * nrows * C, (add ? 16.0 : 12.0) * nrows * C);
+    ProfScope ps(PROF_LN, s, 16.0 * nrows * C, ((add ? 16.0 : 12.0) + (out_bf ? 2.0 : 0.0)) * nrows * C);
 #define ARD_LNB_CASE(c, vec, nv) \
-    case c: layernorm_bwd_kernel<vec, nv, Rows><<<grid, wpb * 32, 0, s>>>(xr, orr, out, g, gamma, add, nrows); break;
+    case c: layernorm_bwd_kernel<vec, nv, Rows><<<grid, wpb * 32, 0, s>>>(xr, orr, out, g, gamma, add, add_scale, out_bf, nrows); break;
     switch (C) {
         ARD_LNB_CASE(96, 1, 3)
         ARD_LNB_CASE(128, 4, 1)
@@ -422,15 +425,17 @@ static int launch_ln_bwd(Rows xr, Rows orr, float* out, const float* g, const fl
     return check_cuda(cudaGetLastError(), "layernorm_bwd launch");
 }
 
-int layernorm_bwd(const float* x, const float* g, const float* gamma, const float* add, float* out, long long rows, int C, cudaStream_t s) {
+int layernorm_bwd(const float* x, const float* g, const float* gamma, const float* add, float* out, long long rows, int C, cudaStream_t s,
+                  float add_scale, __nv_bfloat16* out_bf) {
     if (rows <= 0) return 0;
-    return launch_ln_bwd(PlainRows{x, C}, PlainRows{out, C}, out, g, gamma, add, rows, C, s);
+    return launch_ln_bwd(PlainRows{x, C}, PlainRows{out, C}, out, g, gamma, add, add_scale, out_bf, rows, C, s);
 }
 
 // PatchMerging backward of the gather + LayerNorm(4C): g [B*(H/2)*(W/2), 4C] -> dx [B, H*W, C] (every source element appears once)
-int merge_layernorm_bwd(const float* x, const float* g, const float* gamma, float* dx, int B, int H, int W, int C, cudaStream_t s) {
+int merge_layernorm_bwd(const float* x, const float* g, const float* gamma, float* dx, __nv_bfloat16* dx_bf, int B, int H, int W, int C,
+                        cudaStream_t s) {
     const long long rows = (long long)B * (H / 2) * (W / 2);
-    return launch_ln_bwd(MergeRows{x, H, W, C}, MergeRows{dx, H, W, C}, dx, g, gamma, nullptr, rows, 4 * C, s);
+    return launch_ln_bwd(MergeRows{x, H, W, C}, MergeRows{dx, H, W, C}, dx, g, gamma, nullptr, 1.0f, dx_bf, rows, 4 * C, s);
 }
 
 // dh <- dh * gelu'(hpre)   (both bf16 [n]); gelu'(x) = Phi(x) + x * phi(x)
@@ -446,8 +451,7 @@ __global__ void gelu_bwd_mul_kernel(__nv_bfloat16* __restrict__ dh, const __nv_b
         for (int k = 0; k < 4; ++k) {
             float2 d = __bfloat1622float2(ap[k]);
             const float2 x = __bfloat1622float2(bp[k]);
-            const float p0 = 0.5f * (1.0f + erf_fast(x.x * 0.70710678118654752f)) + x.x * 0.3989422804014327f * __expf(-0.5f * x.x * x.x);
-            const float p1 = 0.5f * (1.0f + erf_fast(x.y * 0.70710678118654752f)) + x.y * 0.3989422804014327f * __expf(-0.5f * x.y * x.y);
+            const float p0 = gelu_erf_grad(x.x), p1 = gelu_erf_grad(x.y);
             d.x *= p0; d.y *= p1;
             ap[k] = __floats2bfloat162_rn(d.x, d.y);
         }
