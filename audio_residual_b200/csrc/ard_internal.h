@@ -47,6 +47,7 @@ struct GemmArgs {
     int aux_T = 0;
     long long aux_bstride = 0;
     int force_bn = 0;
+    int force_pair = 0;                // >0: CTA-pair (cta_group::2) kernel, <0: single-CTA kernel, 0: heuristic / ARD_GEMM_PAIR
     int ab_f16 = 0;                    // A and W are fp16 instead of bf16 (the fc2 GEMM: hidden activations are fp16)
     int out_f16 = 0;                   // with out_bf16=1 and act=GELU: GELU in packed fp16, fp16 output
     const __nv_bfloat16* mul_gelu_bwd = nullptr;   // bf16 [M, ld_mul]: out = acc * gelu'(this), bf16 output only (FFN backward)

@@ -13,6 +13,8 @@
 //
 // The contraction is tensor-core work; for the small-K layers of stages 0/1 (K = 96/192) the kernel is bound by the
 // epilogue's CUDA-core instructions and by HBM, so the epilogue is kept to a few instructions per element.
+#include <stdlib.h>
+
 #include "ard_common.cuh"
 #include "ard_internal.h"
 
@@ -22,19 +24,29 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_NEPI = 8;                       // epilogue warps
 constexpr int GEMM_THREADS = 64 + GEMM_NEPI * 32;  // 320
-constexpr int GEMM_CSTAGE_BYTES = 4096;            // one 32x32 fp32 chunk (bf16 uses half)
 
-template <int BN, bool OUT_BF16>
+template <int BN, bool OUT_BF16, bool PAIR = false>
 struct GemmCfg {
     // fp32-output instantiations keep 3 epilogue staging buffers per warp (the residual tile of the NEXT chunk is TMA-loaded
     // into one while the current chunk is processed in another and the previous one is still being stored) and 3 operand stages.
-    static constexpr int STAGES = OUT_BF16 ? ((BN >= 256) ? 3 : 4) : 3;
+    // PAIR (cta_group::2): each CTA stages its own 128 rows of A and only HALF of the W tile, so a stage is smaller and the
+    // ring is deeper; the L2 -> SM operand traffic per output element drops by a third (256 x BN tile per pair).
     static constexpr int NBUF = OUT_BF16 ? 2 : 3;
+    // one 32x32 chunk: 4 KB fp32 / 2 KB 16-bit. The 16-bit kernels below BN=256 keep 4 KB so the upper half can receive the
+    // gelu' multiplicand tile (FFN backward); at BN=256 the 2 KB form buys a fourth operand stage instead.
+    static constexpr int CST = (OUT_BF16 && BN >= 256) ? 2048 : 4096;
+    static constexpr bool MUL_OK = OUT_BF16 && CST == 4096;
+    // TMEM: 512 fp32 columns = 2 accumulators of up to 256 columns, or 4 of up to 128 (more tiles in flight between the MMA
+    // issuer and the epilogue warps for the narrow-N kernels)
+    static constexpr int ACC_COLS = BN <= 128 ? 128 : 256;
+    static constexpr int NACC = 512 / ACC_COLS;
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * GEMM_BK * 2;
+    static constexpr int STAGES_FIT = (227 * 1024 - 1536 - GEMM_NEPI * (NBUF * CST + 128)) / (A_BYTES + B_BYTES);
+    static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int CSTAGE_OFF = STAGES * STAGE_BYTES;
-    static constexpr int BIAS_OFF = CSTAGE_OFF + GEMM_NEPI * NBUF * GEMM_CSTAGE_BYTES;
+    static constexpr int BIAS_OFF = CSTAGE_OFF + GEMM_NEPI * NBUF * CST;
     static constexpr int BAR_OFF = BIAS_OFF + GEMM_NEPI * 32 * 4;
     static constexpr int SMEM_BYTES = BAR_OFF + 512 + 1024;  // barriers + alignment slack
 };
@@ -56,23 +68,28 @@ struct GemmKernelParams {
     int mul_gelu_bwd;    // 16-bit output only: out = acc * gelu'(h), h = the bf16 [M,N] tensor behind tmR (FFN backward: dh = (g W2) * gelu'(hpre))
 };
 
-template <int BN, bool OUT_BF16>
+template <int BN, bool OUT_BF16, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmKernelParams p) {
-    using Cfg = GemmCfg<BN, OUT_BF16>;
+    using Cfg = GemmCfg<BN, OUT_BF16, PAIR>;
+    constexpr int TILE_M = PAIR ? 2 * GEMM_BM : GEMM_BM;      // rows of one scheduled tile (per CTA pair in PAIR mode)
+    const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0;  // 0 = leader (issues the MMAs)
+    const int sched_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int sched_n = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, still a shared-space pointer
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
     uint64_t* empty_bar = full_bar + Cfg::STAGES;
     uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
-    uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    uint64_t* resid_bar = tempty_bar + 3;          // [GEMM_NEPI][3]: residual tile landed in staging buffer b
+    constexpr int NACC = Cfg::NACC;
+    uint64_t* tempty_bar = tfull_bar + NACC;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + NACC);
+    uint64_t* resid_bar = tempty_bar + NACC + 1;   // [GEMM_NEPI][3]: residual tile landed in staging buffer b
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int m_blocks = (p.M + GEMM_BM - 1) / GEMM_BM;
+    const int m_blocks = (p.M + TILE_M - 1) / TILE_M;
     const int n_blocks = (p.N + BN - 1) / BN;
     const int num_tiles = m_blocks * n_blocks;
     const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
@@ -85,20 +102,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NACC; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], GEMM_NEPI);
+            mbar_init(&tempty_bar[i], PAIR ? 2 * GEMM_NEPI : GEMM_NEPI);
         }
         for (int i = 0; i < GEMM_NEPI * 3; ++i) mbar_init(&resid_bar[i], 1);
         tma_prefetch_desc(&tmR);
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr_smem, 512);
-        tmem_relinquish();
+        if constexpr (PAIR) {
+            tmem_alloc_pair(tmem_ptr_smem, 512);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_ptr_smem, 512);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / multicast commit
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -107,32 +130,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
                 const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
-                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
-                    tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+                    if constexpr (PAIR) {
+                        // both CTAs load their halves; all bytes are counted on the leader's barrier, armed by the leader
+                        if (pair_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                        tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * TILE_M + (int)pair_rank * GEMM_BM);
+                        tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN + (int)pair_rank * (BN / 2));
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                        tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+                        tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+                    }
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer (one thread)
-        if (lane == 0) {
-            const uint32_t idesc = p.ab_f16 ? umma_idesc_f16(GEMM_BM, BN) : umma_idesc_bf16(GEMM_BM, BN);
+        if (lane == 0 && pair_rank == 0) {
+            const uint32_t idesc = p.ab_f16 ? umma_idesc_f16(TILE_M, BN) : umma_idesc_bf16(TILE_M, BN);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                mbar_wait(&tempty_bar[as], aphase ^ 1);
+            for (int tile = sched_id; tile < num_tiles; tile += sched_n, ++it) {
+                const int as = it % NACC;
+                const uint32_t aphase = (it / NACC) & 1;
+                if constexpr (PAIR) mbar_wait_cluster(&tempty_bar[as], aphase ^ 1);
+                else mbar_wait(&tempty_bar[as], aphase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * 256;
+                const uint32_t d_tmem = tmem_base + as * Cfg::ACC_COLS;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -140,12 +171,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint64_t da = umma_desc_sw128(sa);
                     const uint64_t db = umma_desc_sw128(sa + Cfg::A_BYTES);
                     const int ksteps = min(GEMM_BK, p.K - kb * GEMM_BK) >> 4;
-                    for (int k = 0; k < ksteps; ++k)
-                        umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+                    for (int k = 0; k < ksteps; ++k) {
+                        if constexpr (PAIR) umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+                    if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
+                    else umma_commit(&empty_bar[stage]);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[as]);          // accumulator ready
+                // accumulator ready (each CTA's epilogue reads its own 128 rows out of its own TMEM)
+                if constexpr (PAIR) umma_commit_pair(&tfull_bar[as]);
+                else umma_commit(&tfull_bar[as]);
             }
         }
     } else {
@@ -156,7 +193,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int NGRP = GEMM_NEPI / 4;
         constexpr int NCHUNK = BN / 32;
         constexpr int NBUF = Cfg::NBUF;
-        uint8_t* cst = smem + Cfg::CSTAGE_OFF + ew * NBUF * GEMM_CSTAGE_BYTES;
+        uint8_t* cst = smem + Cfg::CSTAGE_OFF + ew * NBUF * Cfg::CST;
         float* bias_w = reinterpret_cast<float*>(smem + Cfg::BIAS_OFF) + ew * 32;
         uint64_t* rbar = resid_bar + ew * 3;
         // The first residual (the shortcut) is fetched by TMA into the staging buffer one chunk ahead: coalesced, asynchronous,
@@ -165,25 +202,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool tma_resid = !OUT_BF16 && p.resid1 != nullptr;
         auto issue_resid = [&](int t, int cc, int b) {   // lane 0 only
             const int mb = t / n_blocks, nb = t % n_blocks;
-            mbar_expect_tx(&rbar[b], GEMM_CSTAGE_BYTES);
-            tma_load_2d(cst + b * GEMM_CSTAGE_BYTES, &tmR, &rbar[b], nb * BN + cc * 32, mb * GEMM_BM + quad * 32);
+            mbar_expect_tx(&rbar[b], Cfg::CST);
+            tma_load_2d(cst + b * Cfg::CST, &tmR, &rbar[b], nb * BN + cc * 32, mb * TILE_M + (int)pair_rank * GEMM_BM + quad * 32);
         };
         // 16-bit output with a multiplicand (gelu' of the recomputed pre-activation): its 32x32 bf16 tile is TMA-prefetched one
         // chunk ahead into the UPPER half of the staging buffer (the result tile only uses the lower 2 KB), so it never
         // collides with an outstanding TMA store.
-        const bool tma_mul = OUT_BF16 && p.mul_gelu_bwd != 0;
+        const bool tma_mul = Cfg::MUL_OK && p.mul_gelu_bwd != 0;
         auto issue_mul = [&](int t, int cc, int b) {     // lane 0 only
             const int mb = t / n_blocks, nb = t % n_blocks;
             fence_proxy_async_smem();                    // order the warp's earlier generic reads of this half before the async write
-            mbar_expect_tx(&rbar[b], GEMM_CSTAGE_BYTES / 2);
-            tma_load_2d(cst + b * GEMM_CSTAGE_BYTES + GEMM_CSTAGE_BYTES / 2, &tmR, &rbar[b], nb * BN + cc * 32, mb * GEMM_BM + quad * 32);
+            mbar_expect_tx(&rbar[b], Cfg::CST / 2);
+            tma_load_2d(cst + b * Cfg::CST + Cfg::CST / 2, &tmR, &rbar[b], nb * BN + cc * 32,
+                        mb * TILE_M + (int)pair_rank * GEMM_BM + quad * 32);
         };
-        int tile = blockIdx.x, c = grp, it = 0, i = 0;
+        int tile = sched_id, c = grp, it = 0, i = 0;
         if (tma_resid && tile < num_tiles && lane == 0) issue_resid(tile, c, 0);
         if (tma_mul && tile < num_tiles && lane == 0) issue_mul(tile, c, 0);
         while (tile < num_tiles) {
             int ntile = tile, nc = c + NGRP;
-            if (nc >= NCHUNK) { nc = grp; ntile = tile + gridDim.x; }
+            if (nc >= NCHUNK) { nc = grp; ntile = tile + sched_n; }
             const int b = i % NBUF;
             if (tma_resid && lane == 0) {
                 tma_store_wait_read<1>();          // buffer (i+1)%3 was last stored two chunks ago
@@ -194,16 +232,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (lane == 0 && ntile < num_tiles) issue_mul(ntile, nc, (i + 1) % NBUF);
             }
             const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
-            const int as = it & 1;
+            const int as = it % NACC;
             if (c == grp) {                        // first chunk of this tile for this warp
-                mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+                mbar_wait(&tfull_bar[as], (it / NACC) & 1);
                 tc_fence_after();
             }
-            const int row = m_blk * GEMM_BM + quad * 32 + lane;
+            const int row0 = m_blk * TILE_M + (int)pair_rank * GEMM_BM + quad * 32;
+            const int row = row0 + lane;
             const bool row_ok = row < p.M;
             const int col0 = n_blk * BN + c * 32;
             uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_base + as * 256 + c * 32 + ((uint32_t)(quad * 32) << 16), v);
+            tmem_ld_32x32b_x32(tmem_base + as * Cfg::ACC_COLS + c * 32 + ((uint32_t)(quad * 32) << 16), v);
             // stage this chunk's bias while the TMEM load is in flight
             __syncwarp();
             bias_w[lane] = (p.bias != nullptr && col0 + lane < p.N) ? __ldg(p.bias + col0 + lane) : 0.0f;
@@ -212,7 +251,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (nc == grp) {                       // last chunk of the tile: all TMEM reads of this tile by this warp are done
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[as]);
+                if (lane == 0) {
+                    if constexpr (PAIR) mbar_arrive_leader(&tempty_bar[as]);
+                    else mbar_arrive(&tempty_bar[as]);
+                }
             }
             float f[32];
 #pragma unroll
@@ -231,11 +273,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
             }
-            uint8_t* sbuf = cst + b * GEMM_CSTAGE_BYTES;
+            uint8_t* sbuf = cst + b * Cfg::CST;
             if constexpr (OUT_BF16) {
                 if (tma_mul) {
                     mbar_wait(&rbar[b], (i / NBUF) & 1);
-                    const uint8_t* rowp = sbuf + GEMM_CSTAGE_BYTES / 2 + lane * 64;
+                    const uint8_t* rowp = sbuf + Cfg::CST / 2 + lane * 64;
                     const int sw = (lane >> 1) & 3;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -313,7 +355,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                tma_store_2d(&tmC, sbuf, col0, m_blk * GEMM_BM + quad * 32);
+                tma_store_2d(&tmC, sbuf, col0, row0);
                 tma_store_commit();
             }
             ++i;
@@ -325,10 +367,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();   // the leader's MMAs read the peer's shared memory: nobody leaves early
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -363,27 +407,60 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t in
     return 0;
 }
 
-template <int BN, bool OUT_BF16>
+template <int BN, bool OUT_BF16, bool PAIR>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr, const GemmKernelParams& kp,
                        int num_sms, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, OUT_BF16>;
-    auto kern = gemm_tc_kernel<BN, OUT_BF16>;
+    using Cfg = GemmCfg<BN, OUT_BF16, PAIR>;
+    static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "gemm: shared memory budget");
+    auto kern = gemm_tc_kernel<BN, OUT_BF16, PAIR>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return set_error(ARD_ERR_CUDA, "cudaFuncSetAttribute(gemm smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
         attr_set = true;
     }
-    const int tiles = ((kp.M + GEMM_BM - 1) / GEMM_BM) * ((kp.N + BN - 1) / BN);
-    const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, tr, kp);
-    cudaError_t e = cudaGetLastError();
-    return check_cuda(e, "gemm launch");
+    constexpr int TILE_M = PAIR ? 2 * GEMM_BM : GEMM_BM;
+    const int tiles = ((kp.M + TILE_M - 1) / TILE_M) * ((kp.N + BN - 1) / BN);
+    if constexpr (PAIR) {
+        // one CTA pair (cluster of 2, same TPC) per 256 x BN tile
+        const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        return check_cuda(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tr, kp), "gemm pair launch");
+    } else {
+        const int grid = tiles < num_sms ? tiles : num_sms;
+        kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, tr, kp);
+        return check_cuda(cudaGetLastError(), "gemm launch");
+    }
+}
+
+// CTA pairs (cta_group::2) halve the W-tile bytes each SM stages and reads per MMA. Measured on B200 (tools/bench_ops.py,
+// profiles/r1_gemm_pair.md): a gain for the deep-K fp32-output GEMMs (fc2 of stages 2/3, K >= 1536: 103 -> 95 us, 91 -> 84 us),
+// a loss for the K = 384 16-bit-output ones (the two CTAs' epilogues gate one shared accumulator hand-off), so the
+// heuristic only pairs the former. ARD_GEMM_PAIR=0/1 forces never/always (read per call so tests can toggle it).
+static bool pick_pair(const GemmArgs& a, int BN) {
+    const char* e = getenv("ARD_GEMM_PAIR");
+    const int mode = e ? (atoi(e) ? 1 : 0) : 2;
+    if (a.force_pair < 0 || mode == 0 || BN < 128) return false;
+    if (a.force_pair > 0 || mode == 1) return true;
+    return !a.out_bf16 && a.K >= 1536 && a.M >= 2048;
 }
 
 static int pick_bn(int N, bool out16) {
     // widest tile that divides N (fewest re-reads of A); fall back to 128 with a clipped last tile.
     // fp32-output kernels spend their shared memory on 3 epilogue staging buffers per warp and stop at BN = 192.
+    if (const char* e = getenv("ARD_GEMM_BN")) {   // development override of the N tile
+        const int forced = atoi(e);
+        if (forced && (out16 || forced <= 192)) return forced;
+    }
     if (out16 && N % 256 == 0) return 256;
     if (N % 192 == 0) return 192;
     if (N % 128 == 0) return 128;
@@ -397,11 +474,13 @@ int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     if ((a.out_bf16 && (a.ldo % 8) != 0) || (!a.out_bf16 && (a.ldo % 4) != 0)) return set_error(ARD_ERR_SHAPE, "gemm: ldo alignment");
     if (a.out_bf16 && (a.resid1 || a.resid2 || a.aux)) return set_error(ARD_ERR_SHAPE, "gemm: residual/aux need fp32 output");
     if (a.out_f16 && !(a.out_bf16 && a.act == ARD_ACT_GELU)) return set_error(ARD_ERR_SHAPE, "gemm: fp16 output is only produced by the GELU epilogue");
-    const int BN = a.force_bn ? a.force_bn : pick_bn(a.N, a.out_bf16 != 0);
+    int BN = a.force_bn ? a.force_bn : pick_bn(a.N, a.out_bf16 != 0);
+    if (a.mul_gelu_bwd != nullptr && BN >= 256) BN = (a.N % 192 == 0) ? 192 : 128;   // the multiplicand tile needs the 4 KB staging form
     if (!a.out_bf16 && BN > 192) return set_error(ARD_ERR_SHAPE, "gemm: fp32 output supports BN <= 192");
     CUtensorMap ta, tb, tc, tr;
     if (int rc = make_tmap_2d(&ta, a.A, 2, a.K, a.M, (uint64_t)a.lda * 2, GEMM_BK, GEMM_BM, 128)) return rc;
-    if (int rc = make_tmap_2d(&tb, a.W, 2, a.K, a.N, (uint64_t)a.ldw * 2, GEMM_BK, BN, 128)) return rc;
+    const bool pair = pick_pair(a, BN);
+    if (int rc = make_tmap_2d(&tb, a.W, 2, a.K, a.N, (uint64_t)a.ldw * 2, GEMM_BK, pair ? BN / 2 : BN, 128)) return rc;
     if (a.out_bf16) {
         if (int rc = make_tmap_2d(&tc, a.out, 2, a.N, a.M, (uint64_t)a.ldo * 2, 32, 32, 64)) return rc;
     } else {
@@ -429,15 +508,31 @@ int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream) {
                      (a.aux ? 4.0 * a.M * a.N : 0.0));
 #define ARD_GEMM_CASE(bn)                                                                                          \
     case bn:                                                                                                       \
-        return a.out_bf16 ? launch_gemm<bn, true>(ta, tb, tc, tr, kp, num_sms, stream) : launch_gemm<bn, false>(ta, tb, tc, tr, kp, num_sms, stream);
+        return a.out_bf16 ? launch_gemm<bn, true, false>(ta, tb, tc, tr, kp, num_sms, stream)                      \
+                          : launch_gemm<bn, false, false>(ta, tb, tc, tr, kp, num_sms, stream);
+#define ARD_GEMM_PAIR_CASE(bn)                                                                                     \
+    case bn:                                                                                                       \
+        return a.out_bf16 ? launch_gemm<bn, true, true>(ta, tb, tc, tr, kp, num_sms, stream)                       \
+                          : launch_gemm<bn, false, true>(ta, tb, tc, tr, kp, num_sms, stream);
+    if (pair) {
+        switch (BN) {
+            ARD_GEMM_PAIR_CASE(128)
+            ARD_GEMM_PAIR_CASE(192)
+            case 256:
+                if (a.out_bf16) return launch_gemm<256, true, true>(ta, tb, tc, tr, kp, num_sms, stream);
+                break;
+        }
+        return set_error(ARD_ERR_SHAPE, "gemm: unsupported pair BN=%d", BN);
+    }
     switch (BN) {
         ARD_GEMM_CASE(96)
         ARD_GEMM_CASE(128)
         ARD_GEMM_CASE(192)
         case 256:
-            if (a.out_bf16) return launch_gemm<256, true>(ta, tb, tc, tr, kp, num_sms, stream);
+            if (a.out_bf16) return launch_gemm<256, true, false>(ta, tb, tc, tr, kp, num_sms, stream);
             break;
     }
+#undef ARD_GEMM_PAIR_CASE
 #undef ARD_GEMM_CASE
     return set_error(ARD_ERR_SHAPE, "gemm: unsupported BN=%d", BN);
 }

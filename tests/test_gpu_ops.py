@@ -15,6 +15,16 @@ def test_gemm(M, N, K, out_bf16):
     assert r < (4e-3 if out_bf16 else 2e-5), r
 
 
+@pytest.mark.parametrize("M,N,K", [(2048, 2304, 768), (5000, 1536, 384), (65536, 384, 1536), (2304, 128, 384), (4097, 192, 3072),
+                                   (300 * 128, 1152, 384)])
+@pytest.mark.parametrize("out_bf16", [False, True])
+def test_gemm_cta_pair(M, N, K, out_bf16, monkeypatch):
+    """The cta_group::2 (CTA-pair, M=256) kernel, forced for every shape incl. M not a multiple of 256."""
+    monkeypatch.setenv("ARD_GEMM_PAIR", "1")
+    r, _ = G.check_gemm(M, N, K, out_bf16, nres=0 if out_bf16 else 1)
+    assert r < (4e-3 if out_bf16 else 2e-5), r
+
+
 def test_gemm_epilogues():
     assert G.check_gemm(4096, 384, 96, True, act=1)[0] < 4e-3      # exact-erf GELU
     assert G.check_gemm(512, 512, 768, False, act=2)[0] < 2e-5     # ReLU

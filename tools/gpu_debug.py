@@ -32,11 +32,18 @@ def run(name, fn, *a, **k):
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     print(torch.cuda.get_device_name(0), torch.version.cuda, flush=True)
+    if what == "pair":
+        for (M, N, K) in [(2048, 2304, 768), (5000, 1536, 384), (65536, 384, 1536), (2304, 128, 384), (4097, 192, 3072), (300 * 128, 1152, 384)]:
+            run(f"gemm pair f32+res M{M} N{N} K{K}", G.check_gemm, M, N, K, False, nres=1)
+            run(f"gemm pair bf16 M{M} N{N} K{K}", G.check_gemm, M, N, K, True)
     if what in ("ops", "all"):
         for (M, N, K) in [(128, 96, 64), (128, 96, 96), (256, 128, 128), (1000, 288, 96), (4096, 384, 96), (512, 96, 384),
                           (300, 768, 768), (2048, 2304, 768), (640, 527, 4608), (8192, 192, 384), (4096, 256, 1024)]:
             run(f"gemm f32 M{M} N{N} K{K}", G.check_gemm, M, N, K, False)
             run(f"gemm bf16 M{M} N{N} K{K}", G.check_gemm, M, N, K, True)
+        for (M, N, K) in [(2048, 2304, 768), (5000, 1536, 384), (65536, 384, 1536), (2304, 128, 384), (4097, 192, 3072), (300 * 128, 1152, 384)]:
+            run(f"gemm pair f32+res M{M} N{N} K{K}", G.check_gemm, M, N, K, False, nres=1)
+            run(f"gemm pair bf16 M{M} N{N} K{K}", G.check_gemm, M, N, K, True)
         run("gemm gelu bf16", G.check_gemm, 4096, 384, 96, True, act=1)
         run("gemm relu f32", G.check_gemm, 512, 512, 768, False, act=2)
         run("gemm 2 resid f32", G.check_gemm, 4096, 96, 384, False, nres=2)
