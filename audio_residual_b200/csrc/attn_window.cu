@@ -7,7 +7,7 @@
 // pure address arithmetic in this kernel's loads and stores (the proj Linear that follows is per-token, so it commutes
 // with the permutation).
 //
-// One CTA (4 warps) per (clip, window, group of 4 heads). Each warp owns 16 query rows; the 64x64 score tile of one
+// One CTA (4 warps) per (clip, window, group of 2 heads; 2 measured faster than 4 or 1: more resident CTAs hide the gather). Each warp owns 16 query rows; the 64x64 score tile of one
 // head lives entirely in registers (mma.sync m16n8k16 bf16 fragments), bias/mask/softmax are applied in registers and
 // P feeds the second MMA directly from registers - S/P never touch shared or global memory unless the caller asks for
 // the attention maps (`attn`, the block-mean capture of BasicLayer.forward htsat.py:589-595).
@@ -18,7 +18,7 @@
 
 namespace ard {
 
-constexpr int AT_HEADS = 4;  // heads per CTA
+constexpr int AT_HEADS = 2;  // heads per CTA
 constexpr int AT_TILE_BYTES = 3 * AT_HEADS * 64 * 64;
 constexpr int AT_SMEM_BYTES = AT_TILE_BYTES + AT_HEADS * 232 * 4 + 2 * 64 * 4;
 

@@ -4,7 +4,7 @@
 //                        reflect-pad 512, periodic-Hann window, 1024-point DFT every 480 samples, |X|^2, mel projection
 //                        (banded view of melW[513,64]), 10*log10(max(.,1e-10)). The reference runs the DFT as two
 //                        Conv1d(1,513,k=1024) (2.1 GFLOP/clip) and writes the 513-bin spectrum; here two real frames share
-//                        one complex radix-4 Stockham FFT in shared memory (~0.05 GFLOP/clip) and only the 64 mel bins
+//                        one complex 1024-point FFT held in a warp's registers (~0.05 GFLOP/clip) and only the 64 mel bins
 //                        reach HBM. Also serves the fusion featuriser's get_mel (data.py:363-399; same formula, htk filters).
 //   patch_embed_ln_kernel : bn0 (eval) + reshape_wav2img (bicubic 1001->1024 along time, fold into 4 frequency-stacked
 //                        quarters; htsat.py:848-863, :900-902) + PatchEmbed conv 4x4/4 + LayerNorm (htsat.py:136-143) fused:
@@ -18,15 +18,46 @@ constexpr int NFFT = 1024;
 constexpr int HOPS = 480;
 constexpr int NBINS = 513;
 constexpr int NMEL = 64;
-constexpr int PAIRS_PER_CTA = 8;
+constexpr int PAIRS_PER_CTA = 16;   // 8 warps x 2 frame pairs
 
-ARD_DEVINL float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// One warp per complex 1024-point FFT, data in registers (1024 = 32 x 32 Cooley-Tukey):
+//   X[k1 + 32 k2] = sum_t W_1024^{t k1} W_32^{t k2} ( sum_j x[t + 32 j] W_32^{j k1} )
+// lane t runs a 32-point FFT over j on x[t + 32 j], multiplies by W_1024^{t k1}, the warp transposes through a padded
+// 32x33 shared tile (the only shared-memory traffic of the transform: 16 KB per FFT instead of 80 KB for five in-smem radix-4
+// passes, which made the previous kernel shared-wavefront bound), lane k1 runs the second 32-point FFT over t.
+// Two real frames ride in one complex transform (z = a + i b), split afterwards with Z[k] and Z[N-k] (one shuffle per bin).
+__host__ __device__ constexpr int brev5(int x) { return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4); }
+__device__ constexpr float C32[16] = {1.000000000e+00f, 9.807852804e-01f, 9.238795325e-01f, 8.314696123e-01f, 7.071067812e-01f, 5.555702330e-01f, 3.826834324e-01f, 1.950903220e-01f, 6.123233996e-17f, -1.950903220e-01f, -3.826834324e-01f, -5.555702330e-01f, -7.071067812e-01f, -8.314696123e-01f, -9.238795325e-01f, -9.807852804e-01f};
+__device__ constexpr float S32[16] = {0.000000000e+00f, 1.950903220e-01f, 3.826834324e-01f, 5.555702330e-01f, 7.071067812e-01f, 8.314696123e-01f, 9.238795325e-01f, 9.807852804e-01f, 1.000000000e+00f, 9.807852804e-01f, 9.238795325e-01f, 8.314696123e-01f, 7.071067812e-01f, 5.555702330e-01f, 3.826834324e-01f, 1.950903220e-01f};
 
-// FFT buffers are indexed through PADI: one float2 of padding after every 4 elements. The radix-4 Stockham passes store with
-// element strides of 4/16/64: unpadded that is an 8-way bank conflict on the first passes (ncu: 56% of all shared wavefronts
-// of this kernel were conflict replays), padded the stride-4 pattern is conflict-free and the others at most 2-way.
-#define PADI(i) ((i) + ((i) >> 2))
-constexpr int NFFT_PAD = NFFT + NFFT / 4;
+// in-place radix-2 DIF, natural-order input, output X[k] lands in element brev5(k); W = exp(-2 pi i / 32)
+ARD_DEVINL void fft32(float (&re)[32], float (&im)[32]) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+#pragma unroll
+        for (int blk = 0; blk < 32; blk += 2 * half) {
+#pragma unroll
+            for (int k = 0; k < half; ++k) {
+                const int i0 = blk + k, i1 = i0 + half;
+                const int tw = k * (16 / half);
+                const float ar = re[i0], ai = im[i0], br = re[i1], bi = im[i1];
+                re[i0] = ar + br;
+                im[i0] = ai + bi;
+                const float dr = ar - br, di = ai - bi;
+                if (tw == 0) {
+                    re[i1] = dr;
+                    im[i1] = di;
+                } else if (tw == 8) {            // * (-i)
+                    re[i1] = di;
+                    im[i1] = -dr;
+                } else {                         // (dr + i di)(c - i s)
+                    re[i1] = fmaf(dr, C32[tw], di * S32[tw]);
+                    im[i1] = fmaf(di, C32[tw], -dr * S32[tw]);
+                }
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256) stft_logmel_kernel(const float* __restrict__ wave, int n_samples, int frames,
                                                          const float* __restrict__ window, const float2* __restrict__ twiddle,
@@ -34,114 +65,123 @@ __global__ void __launch_bounds__(256) stft_logmel_kernel(const float* __restric
                                                          const int* __restrict__ mlen, int band_max,
                                                          const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
                                                          float* __restrict__ out, long long out_clip_stride, int replicate, int quantize) {
-    __shared__ float2 bufA[NFFT_PAD];
-    __shared__ float2 bufB[NFFT_PAD];
-    __shared__ float2 tw[NFFT];
+    __shared__ float2 tw2[32 * 32];        // tw2[k1][t] = W_1024^{t k1}
     __shared__ float win[NFFT];
-    __shared__ float pw[2][NBINS + 3];
-    const int tid = threadIdx.x;
+    __shared__ float wbuf[8][32 * 33];     // per-warp transpose tile, later the two power spectra
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long b = blockIdx.y;
     const float* x = wave + b * n_samples;
     for (int i = tid; i < NFFT; i += 256) {
-        tw[i] = twiddle[i];
-        win[i] = window[i];
+        tw2[i] = __ldg(twiddle + (((i & 31) * (i >> 5)) & (NFFT - 1)));
+        win[i] = __ldg(window + i);
     }
+    __syncthreads();
+    float* buf = wbuf[warp];
     const int npairs = (frames + 1) >> 1;
-    const int p_begin = blockIdx.x * PAIRS_PER_CTA;
-    const int p_end = min(p_begin + PAIRS_PER_CTA, npairs);
-    // samples of a frame pair: reflect padding (F.pad mode='reflect', n_fft/2 each side) only matters near the clip ends
-    float va[4], vb[4];
-    auto load_pair = [&](int pr) {
-        const int fa = 2 * pr, fb = 2 * pr + 1;
+    const int p_end = min((int)(blockIdx.x + 1) * PAIRS_PER_CTA, npairs);
+    for (int pr = blockIdx.x * PAIRS_PER_CTA + warp; pr < p_end; pr += 8) {
+        const int fa = 2 * pr, fb = fa + 1;
         const int base_a = fa * HOPS - NFFT / 2;
-        const bool interior = base_a >= 0 && base_a + HOPS + NFFT <= n_samples && fb < frames;   // block-uniform
+        float re[32], im[32];
+        // ---- samples: lane t holds n = t + 32 j. Frame b is frame a advanced by 480 = 15 * 32 samples: its j < 17 values are
+        // frame a's j + 15 values of the same lane, only j >= 17 is loaded. Reflect padding (F.pad mode='reflect') at clip ends.
+        const bool interior = base_a >= 0 && base_a + HOPS + NFFT <= n_samples;   // warp-uniform
+        if (interior) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int n = tid + 256 * r;
-            vb[r] = 0.f;
-            if (interior) {
-                va[r] = __ldg(x + base_a + n);
-                vb[r] = __ldg(x + base_a + HOPS + n);
-            } else {
-                int idx = base_a + n;
+            for (int j = 0; j < 32; ++j) re[j] = __ldg(x + base_a + lane + 32 * j);
+#pragma unroll
+            for (int j = 0; j < 17; ++j) im[j] = re[j + 15];
+#pragma unroll
+            for (int j = 17; j < 32; ++j) im[j] = __ldg(x + base_a + HOPS + lane + 32 * j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                int idx = base_a + lane + 32 * j;
                 idx = idx < 0 ? -idx : (idx >= n_samples ? 2 * (n_samples - 1) - idx : idx);
-                va[r] = __ldg(x + idx);
-                if (fb < frames) {
-                    idx = base_a + HOPS + n;
-                    idx = idx < 0 ? -idx : (idx >= n_samples ? 2 * (n_samples - 1) - idx : idx);
-                    vb[r] = __ldg(x + idx);
-                }
+                re[j] = __ldg(x + idx);
+                idx = base_a + HOPS + lane + 32 * j;
+                idx = idx < 0 ? -idx : (idx >= n_samples ? 2 * (n_samples - 1) - idx : idx);
+                im[j] = __ldg(x + idx);
             }
         }
-    };
-    if (p_begin < p_end) load_pair(p_begin);
-    for (int pr = p_begin; pr < p_end; ++pr) {
-        const int fa = 2 * pr;
-        __syncthreads();
-        // z[n] = w[n] * (xa[n] + i xb[n])
+        if (fb >= frames) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int n = tid + 256 * r;
-            float a0 = va[r], b0 = vb[r];
+            for (int j = 0; j < 32; ++j) im[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float a0 = re[j], b0 = im[j];
             if (quantize) {   // quantize_tensor, src/residual.py:210-212
                 a0 = truncf(fminf(fmaxf(a0, -1.f), 1.f) * 32767.0f) / 32767.0f;
                 b0 = truncf(fminf(fmaxf(b0, -1.f), 1.f) * 32767.0f) / 32767.0f;
             }
-            const float w = win[n];
-            bufA[PADI(n)] = make_float2(a0 * w, b0 * w);
+            const float w = win[lane + 32 * j];
+            re[j] = a0 * w;
+            im[j] = b0 * w;
         }
-        if (pr + 1 < p_end) load_pair(pr + 1);       // next pair's samples are in flight during this pair's FFT
-        __syncthreads();
-        // radix-4 Stockham autosort FFT, 5 passes (p = 1,4,16,64,256), natural-order output
-        float2* src = bufA;
-        float2* dst = bufB;
+        fft32(re, im);                                   // element r = Y_t[k1 = brev5(r)]
 #pragma unroll
-        for (int pass = 0; pass < 5; ++pass) {
-            const int p = 1 << (2 * pass);
-            const int k = tid & (p - 1);
-            const int j = ((tid - k) << 2) + k;
-            const int tstep = (NFFT / 4) / p * k;   // twiddle index for exp(-2 pi i k / (4p))
-            float2 u0 = src[PADI(tid)], u1 = src[PADI(tid + 256)], u2 = src[PADI(tid + 512)], u3 = src[PADI(tid + 768)];
-            if (pass > 0) {
-                u1 = cmul(u1, tw[tstep]);
-                u2 = cmul(u2, tw[2 * tstep]);
-                u3 = cmul(u3, tw[3 * tstep]);
+        for (int r = 0; r < 32; ++r) {                   // * W_1024^{t k1}
+            const float2 w = tw2[brev5(r) * 32 + lane];
+            const float yr = re[r] * w.x - im[r] * w.y;
+            im[r] = fmaf(re[r], w.y, im[r] * w.x);
+            re[r] = yr;
+        }
+        __syncwarp();                                    // previous pair's mel stage is done with buf
+#pragma unroll
+        for (int r = 0; r < 32; ++r) buf[brev5(r) * 33 + lane] = re[r];
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) re[t] = buf[lane * 33 + t];
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 32; ++r) buf[brev5(r) * 33 + lane] = im[r];
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) im[t] = buf[lane * 33 + t];
+        __syncwarp();
+        fft32(re, im);                                   // lane = k1, element brev5(k2) = Z[k1 + 32 k2]
+        // ---- split the two real spectra and take powers: Xa = (Z[k] + conj Z[N-k]) / 2, Xb = (Z[k] - conj Z[N-k]) / (2i),
+        // N - k = ((32 - k1) & 31) + 32 (31 - k2) for k1 > 0, and 32 ((32 - k2) & 31) for k1 = 0. Bins 0..512 only.
+        const int plane = (32 - lane) & 31;
+#pragma unroll
+        for (int k2 = 0; k2 <= 16; ++k2) {
+            const float zr = re[brev5(k2)], zi = im[brev5(k2)];
+            float qr = __shfl_sync(0xffffffffu, re[brev5(31 - k2)], plane);
+            float qi = __shfl_sync(0xffffffffu, im[brev5(31 - k2)], plane);
+            if (lane == 0) {
+                qr = re[brev5((32 - k2) & 31)];
+                qi = im[brev5((32 - k2) & 31)];
             }
-            const float2 v0 = make_float2(u0.x + u2.x, u0.y + u2.y);
-            const float2 v1 = make_float2(u0.x - u2.x, u0.y - u2.y);
-            const float2 v2 = make_float2(u1.x + u3.x, u1.y + u3.y);
-            const float2 d = make_float2(u1.x - u3.x, u1.y - u3.y);
-            const float2 v3 = make_float2(d.y, -d.x);   // (u1 - u3) * (-i)
-            dst[PADI(j)] = make_float2(v0.x + v2.x, v0.y + v2.y);
-            dst[PADI(j + p)] = make_float2(v1.x + v3.x, v1.y + v3.y);
-            dst[PADI(j + 2 * p)] = make_float2(v0.x - v2.x, v0.y - v2.y);
-            dst[PADI(j + 3 * p)] = make_float2(v1.x - v3.x, v1.y - v3.y);
-            __syncthreads();
-            float2* t = src; src = dst; dst = t;
+            const float sr = zr + qr, di = zi - qi, si = zi + qi, dr = zr - qr;
+            const int k = lane + 32 * k2;
+            if (k <= NFFT / 2) {
+                buf[k] = 0.25f * fmaf(sr, sr, di * di);
+                buf[520 + k] = 0.25f * fmaf(si, si, dr * dr);
+            }
         }
-        // split the two real spectra and take powers: Xa = (Z[k] + conj Z[N-k]) / 2, Xb = (Z[k] - conj Z[N-k]) / (2i)
-        for (int k = tid; k < NBINS; k += 256) {
-            const float2 z = src[PADI(k)];
-            const int kc = (NFFT - k) & (NFFT - 1);
-            const float2 zc = src[PADI(kc)];
-            const float ar = 0.5f * (z.x + zc.x), ai = 0.5f * (z.y - zc.y);
-            const float br = 0.5f * (z.y + zc.y), bi = 0.5f * (zc.x - z.x);
-            pw[0][k] = ar * ar + ai * ai;
-            pw[1][k] = br * br + bi * bi;
-        }
-        __syncthreads();
-        if (tid < 2 * NMEL) {
-            const int f = tid >> 6, m = tid & 63;
-            const int frame = fa + f;
-            if (frame < frames) {
-                const int st = mstart[m], ln = mlen[m];
-                const float* wrow = melw + m * band_max;
-                float acc = 0.f;
-                for (int q = 0; q < ln; ++q) acc = fmaf(pw[f][st + q], __ldg(wrow + q), acc);
-                float v = 10.0f * log10f(fmaxf(acc, 1e-10f));   // ref=1.0 -> "- 10*log10(max(amin, ref))" is exactly 0
-                if (bn_scale != nullptr) v = fmaf(v, bn_scale[m], bn_shift[m]);
-                float* o = out + b * out_clip_stride + (long long)frame * NMEL + m;
-                for (int rpl = 0; rpl < replicate; ++rpl) o[(long long)rpl * frames * NMEL] = v;
+        __syncwarp();
+        // ---- banded mel projection + log: lane handles mel bins lane and lane + 32 of both frames
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int m = lane + 32 * half;
+            const int st = __ldg(mstart + m), ln = __ldg(mlen + m);
+            const float* wrow = melw + m * band_max;
+            float acc0 = 0.f, acc1 = 0.f;
+            for (int q = 0; q < ln; ++q) {
+                const float w = __ldg(wrow + q);
+                acc0 = fmaf(buf[st + q], w, acc0);
+                acc1 = fmaf(buf[520 + st + q], w, acc1);
+            }
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+                const int frame = fa + f;
+                if (frame < frames) {
+                    float v = 10.0f * log10f(fmaxf(f ? acc1 : acc0, 1e-10f));   // ref=1.0 -> "- 10*log10(max(amin, ref))" is exactly 0
+                    if (bn_scale != nullptr) v = fmaf(v, bn_scale[m], bn_shift[m]);
+                    float* o = out + b * out_clip_stride + (long long)frame * NMEL + m;
+                    for (int rpl = 0; rpl < replicate; ++rpl) o[(long long)rpl * frames * NMEL] = v;
+                }
             }
         }
     }
@@ -168,6 +208,8 @@ int stft_logmel(const float* wave, int B, int n_samples, const float* window, co
 ARD_DEVINL float cc1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
 ARD_DEVINL float cc2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
 
+constexpr int PE_TOK_PER_WARP = 32;   // consecutive tokens (same patch row) handled by one warp
+
 template <int CPL>   // channels per lane: C = 32 * CPL
 __global__ void __launch_bounds__(256) patch_embed_ln_kernel(const float* __restrict__ mel, long long clip_stride, int frames,
                                                             const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
@@ -175,69 +217,95 @@ __global__ void __launch_bounds__(256) patch_embed_ln_kernel(const float* __rest
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ out, long long ntokens) {
     constexpr int C = 32 * CPL;
-    __shared__ float wt[16][C];   // transposed conv weight: wt[kh*4+kw][c]
-    for (int i = threadIdx.x; i < 16 * C; i += blockDim.x) {
-        const int c = i / 16, n = i % 16;
-        wt[n][c] = wconv[i];
-    }
-    __syncthreads();
     const int lane = threadIdx.x & 31;
-    const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (tok >= ntokens) return;
-    const long long b = tok >> 12;
-    const int t = (int)(tok & 4095);
-    const int ph = t >> 6, pwi = t & 63;
-    // lanes 0..15 each produce one pixel of the 4x4 patch: image row 4ph+i -> (quarter r, mel bin f), col 4pw+j -> time
-    float pix = 0.f;
-    {
-        const int i = (lane >> 2) & 3, j = lane & 3;
-        const int r = ph >> 4;
-        const int f = ((ph & 15) << 2) + i;
-        const int tau = r * 256 + pwi * 4 + j;                 // index on the 1024-frame (interpolated) time axis
-        const float scale = (float)(frames - 1) / (float)(1024 - 1);   // align_corners=True
-        const float real = scale * (float)tau;
-        const int x0 = (int)floorf(real);
-        const float tt = real - (float)x0;
-        const float A = -0.75f;
-        const float cw[4] = {cc2(tt + 1.f, A), cc1(tt, A), cc1(1.f - tt, A), cc2(2.f - tt, A)};
-        const float* mp = mel + b * clip_stride + f;
-        const float sc = bn_scale ? bn_scale[f] : 1.f, sh = bn_shift ? bn_shift[f] : 0.f;
+    // each lane keeps the 4x4 conv weights, bias and LayerNorm affine of its CPL channels in registers for the whole run of
+    // tokens (16 * CPL + 3 * CPL values): no shared memory, no per-block weight staging
+    float wr[16][CPL], bq[CPL], gq[CPL], eq[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+        const int c = lane + 32 * q;
+        bq[q] = __ldg(bconv + c);
+        gq[q] = __ldg(gamma + c);
+        eq[q] = __ldg(beta + c);
+#pragma unroll
+        for (int n = 0; n < 16; ++n) wr[n][q] = __ldg(wconv + c * 16 + n);
+    }
+    const long long tok0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PE_TOK_PER_WARP;
+    if (tok0 >= ntokens) return;
+    // The warp's 32 tokens share one patch row (64 tokens per row, runs are 32-aligned): clip, quarter r, mel bins f are fixed.
+    // Two tokens per step: lanes 0..15 produce the 4x4 pixels of the even token, lanes 16..31 those of the odd one
+    // (image row 4ph+i -> (quarter r, mel bin f), col 4pw+j -> time). The next step's mel taps are loaded before this step's
+    // arithmetic so the L2 latency overlaps it.
+    const long long b = tok0 >> 12;
+    const int t0 = (int)(tok0 & 4095);
+    const int ph = t0 >> 6, pw0 = t0 & 63;
+    const int i = (lane >> 2) & 3, j = lane & 3, sub = lane >> 4;
+    const int r = ph >> 4;
+    const int f = ((ph & 15) << 2) + i;
+    const float scale = (float)(frames - 1) / (float)(1024 - 1);   // align_corners=True
+    const float A = -0.75f;
+    const float* mp = mel + b * clip_stride + f;
+    const float sc = bn_scale ? __ldg(bn_scale + f) : 1.f, sh = bn_shift ? __ldg(bn_shift + f) : 0.f;
+    auto taps = [&](int it, float (&v)[4]) {
+        const int tau = r * 256 + (pw0 + it + sub) * 4 + j;        // index on the 1024-frame (interpolated) time axis
+        const int x0 = (int)floorf(scale * (float)tau);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             int xi = x0 - 1 + k;
             xi = xi < 0 ? 0 : (xi > frames - 1 ? frames - 1 : xi);
-            const float v = fmaf(__ldg(mp + (long long)xi * NMEL), sc, sh);     // bn0 before the interpolation (htsat.py:900-902)
-            pix = fmaf(v, cw[k], pix);
+            v[k] = __ldg(mp + (long long)xi * NMEL);
         }
-    }
-    float acc[CPL];
+    };
+    float v[4], vn[4];
+    taps(0, v);
+    for (int it = 0; it < PE_TOK_PER_WARP; it += 2) {
+        if (it + 2 < PE_TOK_PER_WARP) taps(it + 2, vn);
+        float pix;
+        {
+            const int tau = r * 256 + (pw0 + it + sub) * 4 + j;
+            const float real = scale * (float)tau;
+            const float tt = real - floorf(real);
+            pix = fmaf(v[0], sc, sh) * cc2(tt + 1.f, A);                   // bn0 before the interpolation (htsat.py:900-902)
+            pix = fmaf(fmaf(v[1], sc, sh), cc1(tt, A), pix);
+            pix = fmaf(fmaf(v[2], sc, sh), cc1(1.f - tt, A), pix);
+            pix = fmaf(fmaf(v[3], sc, sh), cc2(2.f - tt, A), pix);
+        }
+        float acc[2][CPL];
 #pragma unroll
-    for (int q = 0; q < CPL; ++q) acc[q] = __ldg(bconv + lane + 32 * q);
+        for (int q = 0; q < CPL; ++q) acc[0][q] = acc[1][q] = bq[q];
 #pragma unroll
-    for (int n = 0; n < 16; ++n) {
-        const float pv = __shfl_sync(0xffffffffu, pix, n);
+        for (int n = 0; n < 16; ++n) {
+            const float p0 = __shfl_sync(0xffffffffu, pix, n);
+            const float p1 = __shfl_sync(0xffffffffu, pix, 16 + n);
 #pragma unroll
-        for (int q = 0; q < CPL; ++q) acc[q] = fmaf(pv, wt[n][lane + 32 * q], acc[q]);
-    }
-    float s = 0.f;
+            for (int q = 0; q < CPL; ++q) {
+                acc[0][q] = fmaf(p0, wr[n][q], acc[0][q]);
+                acc[1][q] = fmaf(p1, wr[n][q], acc[1][q]);
+            }
+        }
 #pragma unroll
-    for (int q = 0; q < CPL; ++q) s += acc[q];
+        for (int u = 0; u < 2; ++u) {
+            const long long tok = tok0 + it + u;
+            float s = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s * (1.0f / C);
-    float var = 0.f;
+            for (int q = 0; q < CPL; ++q) s += acc[u][q];
 #pragma unroll
-    for (int q = 0; q < CPL; ++q) {
-        const float d = acc[q] - mean;
-        var = fmaf(d, d, var);
-    }
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mean = s * (1.0f / C);
+            float var = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-    const float rstd = rsqrtf(var * (1.0f / C) + 1e-5f);
+            for (int q = 0; q < CPL; ++q) {
+                const float d = acc[u][q] - mean;
+                var = fmaf(d, d, var);
+            }
 #pragma unroll
-    for (int q = 0; q < CPL; ++q) {
-        const int c = lane + 32 * q;
-        out[tok * C + c] = fmaf((acc[q] - mean) * rstd, __ldg(gamma + c), __ldg(beta + c));
+            for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+            const float rstd = rsqrtf(var * (1.0f / C) + 1e-5f);
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) out[tok * C + lane + 32 * q] = fmaf((acc[u][q] - mean) * rstd, gq[q], eq[q]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = vn[k];
     }
 }
 
@@ -246,7 +314,7 @@ int patch_embed_ln(const float* logmel, long long clip_stride, int frames, const
     if (B <= 0) return 0;
     if (frames > 1024) return set_error(ARD_ERR_SHAPE, "the wav size should less than or equal to the swin input size");  // htsat.py:852
     const long long ntok = (long long)B * 4096;
-    const unsigned grid = (unsigned)((ntok + 7) / 8);
+    const unsigned grid = (unsigned)((ntok + 8 * PE_TOK_PER_WARP - 1) / (8 * PE_TOK_PER_WARP));
     ProfScope ps(PROF_FRONTEND, s, (double)ntok * (2.0 * 16 * C + 16 * 8 + 8.0 * C), 4.0 * B * frames * 64 + 4.0 * ntok * C);
     if (C == 96)
         patch_embed_ln_kernel<3><<<grid, 256, 0, s>>>(logmel, clip_stride, frames, bn_scale, bn_shift, w, bias, gamma, beta, out, ntok);

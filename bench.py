@@ -300,6 +300,8 @@ def run_ours(args):
             return pca_step(host.to(dev, non_blocking=True)).cpu()
         e2e_api = "encode(want_dict=True) + MomentAccumulator.update per layer and per (layer, head); mean vector .cpu()"
 
+    if wl != "train":   # inference workloads run as the reference's evaluate() does (src/training.py:47): no autograd tape
+        torch.set_grad_enabled(False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()          # started before warm-up so nvidia-smi is already streaming when the timed region begins
@@ -347,8 +349,17 @@ def run_ours(args):
     te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    # bare pinned-host -> device copy rate of the same buffer: the floor the e2e step cannot beat (1.92 MB per clip over PCIe)
+    dst = torch.empty_like(wave)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for _ in range(3):
+        dst.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * host.numel() * 4 / (time.perf_counter() - t1) / 1e9
+    del dst
     e2e = {"value": world * B * Ke / te.item(), "unit": UNIT, "h2d_bytes_per_step": B * 480000 * 4, "d2h_bytes_per_step": int(emb_host.numel() * 4),
-           "api": e2e_api, "steps": Ke}
+           "api": e2e_api, "steps": Ke, "h2d_gbs_measured": h2d_gbs, "h2d_bound_clips_per_s": world * h2d_gbs * 1e9 / (480000 * 4)}
 
     # ---- roofline of the dominant kernel class, measured live with CUDA events around every launch.
     # Every rank runs the two profiled steps (the training step holds a collective); only rank 0 records and reports.

@@ -37,3 +37,18 @@ def test_fusion_featuriser_and_base_from_waveform():
 def test_pca_moments_vs_oracle(layer):
     m = G.check_pca_moments_vs_oracle(layer, 2)
     assert m["n"] == 0 and m["mean"] < G.TOL_BF16 and m["cov"] < 2 * G.TOL_BF16 and m["top_eigenvalues"] < 2 * G.TOL_BF16, m
+
+
+def test_host_batch_pipelined_equals_device_batch():
+    """get_audio_embedding_from_data on a pinned host batch (chunked copies overlapped with the encoder) returns exactly what
+    one device-resident call returns, for batch sizes around the chunk boundaries."""
+    import torch
+    clap, sd, _ = G.make_encoder("tiny", residual=True)
+    with torch.no_grad():
+        for n in (65, 100, 137):
+            wave = G.W.make_clips(n, seed=n)
+            ref = clap.model.audio_branch.encode(waveform=wave.cuda(), want_audio_embed=True)["audio_embed"]
+            got = clap.get_audio_embedding_from_data(wave.pin_memory(), use_tensor=True)
+            assert got.shape == ref.shape
+            # per-clip arithmetic is independent of the batch it rides in: bit-identical
+            assert torch.equal(got, ref), (n, (got - ref).abs().max().item())
