@@ -22,32 +22,37 @@ namespace ard {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_NEPI = 8;                       // epilogue warps
-constexpr int GEMM_THREADS = 64 + GEMM_NEPI * 32;  // 320
 
-template <int BN, bool OUT_BF16, bool PAIR = false>
+template <int BN, bool OUT_BF16, bool PAIR = false, bool MUL = false, int NEPI_ = 8>
 struct GemmCfg {
-    // fp32-output instantiations keep 3 epilogue staging buffers per warp (the residual tile of the NEXT chunk is TMA-loaded
-    // into one while the current chunk is processed in another and the previous one is still being stored) and 3 operand stages.
+    // Epilogue warps: 8, or 16 for the 16-bit-output kernels with a transcendental epilogue (GELU, gelu'). ncu on the stage-2
+    // fc1+GELU GEMM with 8 warps: issue slots 52 % busy (two dependent-chain warps per scheduler) while the tensor pipe idled
+    // at 37 % - that work needs more warps in flight (measured 105 -> 94 us, stage 1: 189 -> 143 us). The plain 16-bit
+    // kernels (qkv, dgrads) are faster with 8 warps and the fourth operand stage the saved staging memory buys.
+    static constexpr int NEPI = NEPI_;
+    static constexpr int THREADS = 64 + NEPI * 32;
+    static constexpr int NGRP = NEPI / 4;                       // warps per TMEM lane quadrant = column-chunk interleave groups
+    static constexpr int NCHUNK = BN / 32;
+    static constexpr int ACTIVE_GRP = NGRP < NCHUNK ? NGRP : NCHUNK;
+    // Staging buffers per epilogue warp: 2 when results are only stored; 3 when a tile is TMA-prefetched INTO the staging
+    // buffer one chunk ahead (the fp32 shortcut residual, or the bf16 gelu' multiplicand of the FFN backward, MUL): one
+    // buffer is landing, one is being processed, one is still being stored.
+    static constexpr int NBUF = (OUT_BF16 && !MUL) ? 2 : 3;
+    static constexpr int CST = OUT_BF16 ? 2048 : 4096;          // one 32x32 chunk: 2 KB 16-bit / 4 KB fp32
     // PAIR (cta_group::2): each CTA stages its own 128 rows of A and only HALF of the W tile, so a stage is smaller and the
     // ring is deeper; the L2 -> SM operand traffic per output element drops by a third (256 x BN tile per pair).
-    static constexpr int NBUF = OUT_BF16 ? 2 : 3;
-    // one 32x32 chunk: 4 KB fp32 / 2 KB 16-bit. The 16-bit kernels below BN=256 keep 4 KB so the upper half can receive the
-    // gelu' multiplicand tile (FFN backward); at BN=256 the 2 KB form buys a fourth operand stage instead.
-    static constexpr int CST = (OUT_BF16 && BN >= 256) ? 2048 : 4096;
-    static constexpr bool MUL_OK = OUT_BF16 && CST == 4096;
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * GEMM_BK * 2;
     // TMEM: 512 fp32 columns = 2 accumulators of up to 256 columns, or 4 of up to 128 (more tiles in flight between the MMA
     // issuer and the epilogue warps for the narrow-N kernels)
     static constexpr int ACC_COLS = BN <= 128 ? 128 : 256;
     static constexpr int NACC = 512 / ACC_COLS;
-    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-    static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * GEMM_BK * 2;
-    static constexpr int STAGES_FIT = (227 * 1024 - 1536 - GEMM_NEPI * (NBUF * CST + 128)) / (A_BYTES + B_BYTES);
+    static constexpr int STAGES_FIT = (227 * 1024 - 1536 - NEPI * (NBUF * CST + 128)) / (A_BYTES + B_BYTES);
     static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int CSTAGE_OFF = STAGES * STAGE_BYTES;
-    static constexpr int BIAS_OFF = CSTAGE_OFF + GEMM_NEPI * NBUF * CST;
-    static constexpr int BAR_OFF = BIAS_OFF + GEMM_NEPI * 32 * 4;
+    static constexpr int BIAS_OFF = CSTAGE_OFF + NEPI * NBUF * CST;
+    static constexpr int BAR_OFF = BIAS_OFF + NEPI * 32 * 4;
     static constexpr int SMEM_BYTES = BAR_OFF + 512 + 1024;  // barriers + alignment slack
 };
 
@@ -68,11 +73,12 @@ struct GemmKernelParams {
     int mul_gelu_bwd;    // 16-bit output only: out = acc * gelu'(h), h = the bf16 [M,N] tensor behind tmR (FFN backward: dh = (g W2) * gelu'(hpre))
 };
 
-template <int BN, bool OUT_BF16, bool PAIR>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, bool OUT_BF16, bool PAIR, bool MUL, int NEPI>
+__global__ void __launch_bounds__((GemmCfg<BN, OUT_BF16, PAIR, MUL, NEPI>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmKernelParams p) {
-    using Cfg = GemmCfg<BN, OUT_BF16, PAIR>;
+    using Cfg = GemmCfg<BN, OUT_BF16, PAIR, MUL, NEPI>;
+    constexpr int GEMM_NEPI = Cfg::NEPI;
     constexpr int TILE_M = PAIR ? 2 * GEMM_BM : GEMM_BM;      // rows of one scheduled tile (per CTA pair in PAIR mode)
     const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0;  // 0 = leader (issues the MMAs)
     const int sched_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -85,7 +91,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int NACC = Cfg::NACC;
     uint64_t* tempty_bar = tfull_bar + NACC;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + NACC);
-    uint64_t* resid_bar = tempty_bar + NACC + 1;   // [GEMM_NEPI][3]: residual tile landed in staging buffer b
+    uint64_t* resid_bar = tempty_bar + NACC + 1;   // [NEPI][3]: prefetched tile landed in staging buffer b
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -104,7 +110,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < NACC; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], PAIR ? 2 * GEMM_NEPI : GEMM_NEPI);
+            mbar_init(&tempty_bar[i], (PAIR ? 2 : 1) * 4 * Cfg::ACTIVE_GRP);
         }
         for (int i = 0; i < GEMM_NEPI * 3; ++i) mbar_init(&resid_bar[i], 1);
         tma_prefetch_desc(&tmR);
@@ -190,35 +196,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ew = warp - 2;
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
         const int grp = ew >> 2;                   // column-chunk interleave group
-        constexpr int NGRP = GEMM_NEPI / 4;
-        constexpr int NCHUNK = BN / 32;
+        constexpr int NGRP = Cfg::NGRP;
+        constexpr int NCHUNK = Cfg::NCHUNK;
         constexpr int NBUF = Cfg::NBUF;
         uint8_t* cst = smem + Cfg::CSTAGE_OFF + ew * NBUF * Cfg::CST;
         float* bias_w = reinterpret_cast<float*>(smem + Cfg::BIAS_OFF) + ew * 32;
         uint64_t* rbar = resid_bar + ew * 3;
-        // The first residual (the shortcut) is fetched by TMA into the staging buffer one chunk ahead: coalesced, asynchronous,
-        // no registers. (Row-per-thread LDG.128 of a residual touches 32 different lines per instruction and made the
-        // residual GEMMs LSU-bound.) The sum is formed in place and the same buffer is handed to the TMA store.
-        const bool tma_resid = !OUT_BF16 && p.resid1 != nullptr;
+        // A tile the epilogue combines with the accumulator is fetched by TMA into the staging buffer one chunk ahead:
+        // coalesced, asynchronous, no registers. (Row-per-thread LDG.128 touches 32 different lines per instruction and made
+        // the residual GEMMs LSU-bound.) fp32 output: the shortcut residual, added in place. 16-bit output (MUL): the bf16
+        // pre-activation whose gelu' multiplies the result (FFN backward). The same buffer is then handed to the TMA store.
+        const bool tma_resid = MUL || (!OUT_BF16 && p.resid1 != nullptr);
         auto issue_resid = [&](int t, int cc, int b) {   // lane 0 only
             const int mb = t / n_blocks, nb = t % n_blocks;
             mbar_expect_tx(&rbar[b], Cfg::CST);
             tma_load_2d(cst + b * Cfg::CST, &tmR, &rbar[b], nb * BN + cc * 32, mb * TILE_M + (int)pair_rank * GEMM_BM + quad * 32);
         };
-        // 16-bit output with a multiplicand (gelu' of the recomputed pre-activation): its 32x32 bf16 tile is TMA-prefetched one
-        // chunk ahead into the UPPER half of the staging buffer (the result tile only uses the lower 2 KB), so it never
-        // collides with an outstanding TMA store.
-        const bool tma_mul = Cfg::MUL_OK && p.mul_gelu_bwd != 0;
-        auto issue_mul = [&](int t, int cc, int b) {     // lane 0 only
-            const int mb = t / n_blocks, nb = t % n_blocks;
-            fence_proxy_async_smem();                    // order the warp's earlier generic reads of this half before the async write
-            mbar_expect_tx(&rbar[b], Cfg::CST / 2);
-            tma_load_2d(cst + b * Cfg::CST + Cfg::CST / 2, &tmR, &rbar[b], nb * BN + cc * 32,
-                        mb * TILE_M + (int)pair_rank * GEMM_BM + quad * 32);
-        };
-        int tile = sched_id, c = grp, it = 0, i = 0;
+        int tile = grp < NCHUNK ? sched_id : num_tiles;   // BN = 96 has 3 chunks: the fourth group of a 16-warp epilogue idles
+        int c = grp, it = 0, i = 0;
         if (tma_resid && tile < num_tiles && lane == 0) issue_resid(tile, c, 0);
-        if (tma_mul && tile < num_tiles && lane == 0) issue_mul(tile, c, 0);
         while (tile < num_tiles) {
             int ntile = tile, nc = c + NGRP;
             if (nc >= NCHUNK) { nc = grp; ntile = tile + sched_n; }
@@ -226,10 +222,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (tma_resid && lane == 0) {
                 tma_store_wait_read<1>();          // buffer (i+1)%3 was last stored two chunks ago
                 if (ntile < num_tiles) issue_resid(ntile, nc, (i + 1) % NBUF);
-            }
-            if (tma_mul) {
-                __syncwarp();                      // every lane finished reading the other buffer's upper half (chunk i-1)
-                if (lane == 0 && ntile < num_tiles) issue_mul(ntile, nc, (i + 1) % NBUF);
             }
             const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
             const int as = it % NACC;
@@ -274,10 +266,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
             }
             uint8_t* sbuf = cst + b * Cfg::CST;
-            if constexpr (OUT_BF16) {
-                if (tma_mul) {
+            if constexpr (MUL) {
+                {
                     mbar_wait(&rbar[b], (i / NBUF) & 1);
-                    const uint8_t* rowp = sbuf + Cfg::CST / 2 + lane * 64;
+                    const uint8_t* rowp = sbuf + lane * 64;
                     const int sw = (lane >> 1) & 3;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -299,7 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < 32; j += 4)
                         if (col0 + j < p.N) *reinterpret_cast<float4*>(ap + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
                 }
-                if (tma_resid) {
+                if (tma_resid) {   // (never MUL here: MUL implies a 16-bit output)
                     mbar_wait(&rbar[b], (i / NBUF) & 1);
                     const uint8_t* rowp = sbuf + lane * 128;
                     const int sw = lane & 7;
@@ -407,12 +399,12 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t in
     return 0;
 }
 
-template <int BN, bool OUT_BF16, bool PAIR>
+template <int BN, bool OUT_BF16, bool PAIR, bool MUL = false, int NEPI = 8>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr, const GemmKernelParams& kp,
                        int num_sms, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, OUT_BF16, PAIR>;
-    static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "gemm: shared memory budget");
-    auto kern = gemm_tc_kernel<BN, OUT_BF16, PAIR>;
+    using Cfg = GemmCfg<BN, OUT_BF16, PAIR, MUL, NEPI>;
+    static_assert(Cfg::SMEM_BYTES <= 227 * 1024 && Cfg::STAGES >= 3, "gemm: shared memory budget");
+    auto kern = gemm_tc_kernel<BN, OUT_BF16, PAIR, MUL, NEPI>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -426,7 +418,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
         const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * pairs);
-        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.blockDim = dim3(Cfg::THREADS);
         cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
         cfg.stream = stream;
         cudaLaunchAttribute at[1];
@@ -437,7 +429,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
         return check_cuda(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tr, kp), "gemm pair launch");
     } else {
         const int grid = tiles < num_sms ? tiles : num_sms;
-        kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, tr, kp);
+        kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, tr, kp);
         return check_cuda(cudaGetLastError(), "gemm launch");
     }
 }
@@ -475,11 +467,11 @@ int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     if (a.out_bf16 && (a.resid1 || a.resid2 || a.aux)) return set_error(ARD_ERR_SHAPE, "gemm: residual/aux need fp32 output");
     if (a.out_f16 && !(a.out_bf16 && a.act == ARD_ACT_GELU)) return set_error(ARD_ERR_SHAPE, "gemm: fp16 output is only produced by the GELU epilogue");
     int BN = a.force_bn ? a.force_bn : pick_bn(a.N, a.out_bf16 != 0);
-    if (a.mul_gelu_bwd != nullptr && BN >= 256) BN = (a.N % 192 == 0) ? 192 : 128;   // the multiplicand tile needs the 4 KB staging form
+    if (a.mul_gelu_bwd != nullptr) BN = (a.N % 192 == 0) ? 192 : 128;   // the multiplicand kernels are built for these two tiles
     if (!a.out_bf16 && BN > 192) return set_error(ARD_ERR_SHAPE, "gemm: fp32 output supports BN <= 192");
     CUtensorMap ta, tb, tc, tr;
     if (int rc = make_tmap_2d(&ta, a.A, 2, a.K, a.M, (uint64_t)a.lda * 2, GEMM_BK, GEMM_BM, 128)) return rc;
-    const bool pair = pick_pair(a, BN);
+    const bool pair = a.mul_gelu_bwd == nullptr && pick_pair(a, BN);
     if (int rc = make_tmap_2d(&tb, a.W, 2, a.K, a.N, (uint64_t)a.ldw * 2, GEMM_BK, pair ? BN / 2 : BN, 128)) return rc;
     if (a.out_bf16) {
         if (int rc = make_tmap_2d(&tc, a.out, 2, a.N, a.M, (uint64_t)a.ldo * 2, 32, 32, 64)) return rc;
@@ -514,6 +506,18 @@ int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     case bn:                                                                                                       \
         return a.out_bf16 ? launch_gemm<bn, true, true>(ta, tb, tc, tr, kp, num_sms, stream)                       \
                           : launch_gemm<bn, false, true>(ta, tb, tc, tr, kp, num_sms, stream);
+    if (a.mul_gelu_bwd != nullptr) {
+        if (BN == 192) return launch_gemm<192, true, false, true, 16>(ta, tb, tc, tr, kp, num_sms, stream);
+        return launch_gemm<128, true, false, true, 16>(ta, tb, tc, tr, kp, num_sms, stream);
+    }
+    if (a.out_bf16 && a.act == ARD_ACT_GELU && !pair && a.K <= 384) {   // epilogue-bound (short K loop): 16 epilogue warps
+        switch (BN) {
+            case 96: return launch_gemm<96, true, false, false, 16>(ta, tb, tc, tr, kp, num_sms, stream);
+            case 128: return launch_gemm<128, true, false, false, 16>(ta, tb, tc, tr, kp, num_sms, stream);
+            case 192: return launch_gemm<192, true, false, false, 16>(ta, tb, tc, tr, kp, num_sms, stream);
+            case 256: return launch_gemm<256, true, false, false, 16>(ta, tb, tc, tr, kp, num_sms, stream);
+        }
+    }
     if (pair) {
         switch (BN) {
             ARD_GEMM_PAIR_CASE(128)
