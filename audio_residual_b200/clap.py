@@ -171,7 +171,7 @@ class CLAP_Module(nn.Module):
         self.model.eval()
         enc = self.model.audio_branch
         training_step = torch.is_grad_enabled() and any(p is not None and p.requires_grad for p in enc._lambda_params())
-        if (not enc.enable_fusion and torch.is_tensor(x) and x.device.type == "cpu" and x.dim() == 2 and x.shape[1] == 480000
+        if (torch.is_tensor(x) and x.device.type == "cpu" and x.dim() == 2 and x.shape[1] == 480000
                 and x.dtype == torch.float32 and x.shape[0] > self.h2d_chunk and not training_step):
             emb = self._embed_host_pipelined(x, quantize=not use_tensor)
         else:
@@ -235,7 +235,11 @@ class CLAP_Module(nn.Module):
                 if k + 1 < len(bounds):
                     start_copy(k + 1)
                 main.wait_event(copied[k % 2])
-                res = enc.encode(waveform=self._stage[k % 2][:hi - lo], quantize=quantize, want_audio_embed=True)
+                chunk = self._stage[k % 2][:hi - lo]
+                if enc.enable_fusion:   # get_mel + 4x stack on device (data.py:363-399, :497-501), then the fused encoder
+                    res = enc.encode(mel_fusion=enc.fusion_mel(chunk, quantize=quantize), want_audio_embed=True)
+                else:
+                    res = enc.encode(waveform=chunk, quantize=quantize, want_audio_embed=True)
                 out[lo:hi].copy_(res["audio_embed"])
                 self._stage_free[k % 2].record(main)
         return out
