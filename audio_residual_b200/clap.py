@@ -161,6 +161,36 @@ class CLAP_Module(nn.Module):
         self.model.to(self.device)
         return self
 
+    def load_ckpt(self, ckpt=None, model_id=-1, verbose=True):
+        """hook.py:75-119 + factory.py:53-70 for the audio side. `ckpt` is a path to (or an already loaded) LAION-CLAP
+        checkpoint: optional {"state_dict": ...} wrapper, optional "module." prefix, audio tower under `audio_branch.`, the
+        projection under `audio_projection.`; text tower / logit scales / the unreachable aff_2d fusion branch are ignored.
+        Downloading the paper checkpoints (ckpt=None) needs the network and is not available here."""
+        if ckpt is None:
+            raise RuntimeError("load_ckpt(ckpt=None) would download the LAION-CLAP weights (hook.py:91-112): pass a local checkpoint")
+        sd = torch.load(ckpt, map_location="cpu", weights_only=False) if isinstance(ckpt, (str, bytes)) or hasattr(ckpt, "__fspath__") else ckpt
+        if isinstance(sd, dict) and "state_dict" in sd:
+            sd = sd["state_dict"]
+        if next(iter(sd)).startswith("module"):
+            sd = {k[7:]: v for k, v in sd.items()}
+        ab = self.model.audio_branch
+        own = ab.state_dict()
+        branch = {k[len("audio_branch."):]: v for k, v in sd.items() if k.startswith("audio_branch.")}
+        # index / mask / counter buffers are derived from the architecture: optional in the checkpoint
+        derived = ("relative_position_index", "attn_mask", "num_batches_tracked")
+        missing = [k for k in own if k not in branch and not k.endswith(derived)]
+        if missing:
+            raise RuntimeError(f"Error(s) in loading state_dict for {type(ab).__name__}: Missing key(s): {missing[:8]}"
+                               f"{' ...' if len(missing) > 8 else ''}")
+        ab.load_state_dict({k: branch[k] for k in own if k in branch}, strict=False)
+        proj = {k[len("audio_projection."):]: v for k, v in sd.items() if k.startswith("audio_projection.")}
+        self.model.audio_projection.load_state_dict(proj)
+        self.model.to(self.device)
+        if verbose:
+            skipped = sorted({k.split(".")[0] for k in sd if not k.startswith(("audio_branch.", "audio_projection."))})
+            print(f"Loaded {len(own)} audio_branch and {len(proj)} audio_projection tensors; ignored groups: {skipped}")
+        return self
+
     def fusion_mel(self, wave, quantize=False):
         """get_mel (data.py:363-399) for a batch on device, stacked 4x as data.py:497-501 does for clips <= 10 s."""
         return self.model.audio_branch.fusion_mel(wave, quantize=quantize)

@@ -110,6 +110,24 @@ def inject_residuals(model, pca, lambdas=None):
     return residuals
 
 
+def save_lambdas(residuals, path):
+    """The reference never persists the trained `learnable` vectors (the ResiDual modules are not registered on the model,
+    SURVEY Q4); this writes {layer: lambda[K]} so a trained reweighting can be restored with load_lambdas."""
+    torch.save({int(l): r.learnable.detach().cpu().clone() for l, r in residuals.items()}, path)
+
+
+def load_lambdas(residuals, path):
+    sd = torch.load(path, map_location="cpu")
+    for l, r in residuals.items():
+        if int(l) not in sd:
+            raise KeyError(f"no lambda saved for layer {l}")
+        if sd[int(l)].shape != r.learnable.shape:
+            raise ValueError(f"layer {l}: saved lambda has shape {tuple(sd[int(l)].shape)}, expected {tuple(r.learnable.shape)}")
+        with torch.no_grad():
+            r.learnable.copy_(sd[int(l)].to(r.learnable.device))
+    return residuals
+
+
 def quantize_tensor(audio_tensor: torch.Tensor) -> torch.Tensor:
     """src/residual.py:210-212 (runs on the tensor's device; a fused on-device variant is `quantize=True` on the encoder)."""
     audio_tensor = torch.clamp(audio_tensor, -1.0, 1.0)

@@ -204,3 +204,41 @@ def test_real_reference_pca_fixture_schema():
     r = load_residual(p)
     assert r.basis.shape == (96, 96) and r.mean.shape == (96,)
     assert torch.allclose(r.basis @ r.basis.T, torch.eye(96), atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------- checkpoints
+def test_load_ckpt_reference_layout(tmp_path):
+    """hook.py:75-119: a LAION-CLAP style checkpoint ({"state_dict": {"module.audio_branch....": ...}}) loads into the mirror;
+    text-tower tensors are ignored, a missing audio tensor raises like nn.Module.load_state_dict does."""
+    sd = W.make_state_dict("tiny", seed=3)
+    ck = {}
+    for k, v in sd.items():
+        ck["module." + (k if k.startswith("audio_projection.") else "audio_branch." + k)] = v
+    ck["module.text_branch.embeddings.word_embeddings.weight"] = torch.zeros(4, 4)
+    ck["module.logit_scale_a"] = torch.tensor(1.0)
+    path = tmp_path / "ckpt.pt"
+    torch.save({"state_dict": ck, "epoch": 1}, path)
+    m = CLAP_Module(device="cpu").load_ckpt(str(path), verbose=False)
+    got = m.model.audio_branch.state_dict()
+    for k in ("layers.2.blocks.3.attn.qkv.weight", "bn0.running_var", "patch_embed.proj.weight", "logmel_extractor.melW"):
+        assert torch.equal(got[k], torch.as_tensor(sd[k])), k
+    assert torch.equal(m.model.audio_projection.state_dict()["2.weight"], torch.as_tensor(sd["audio_projection.2.weight"]))
+    del ck["module.audio_branch.layers.0.blocks.0.norm1.weight"]
+    with pytest.raises(RuntimeError, match="Missing key"):
+        CLAP_Module(device="cpu").load_ckpt({"state_dict": ck}, verbose=False)
+    with pytest.raises(RuntimeError, match="download"):
+        CLAP_Module(device="cpu").load_ckpt(None)
+
+
+def test_lambda_save_restore(tmp_path):
+    from audio_residual_b200.residual import inject_residuals, load_lambdas, save_lambdas
+    m = CLAP_Module(device="cpu")
+    pca, lam = W.make_pca("tiny", seed=0)
+    res = inject_residuals(m.model.audio_branch, pca, lam)
+    save_lambdas(res, tmp_path / "lam.pt")
+    for r in res.values():
+        with torch.no_grad():
+            r.learnable.fill_(1.0)
+    load_lambdas(res, tmp_path / "lam.pt")
+    for l, r in res.items():
+        assert torch.allclose(r.learnable.detach(), torch.as_tensor(lam[l]))
