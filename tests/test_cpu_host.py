@@ -214,6 +214,8 @@ def test_load_ckpt_reference_layout(tmp_path):
     ck = {}
     for k, v in sd.items():
         ck["module." + (k if k.startswith("audio_projection.") else "audio_branch." + k)] = v
+    for k, v in CLAP_Module(device="cpu").model.audio_branch.state_dict().items():   # buffers + the unused `head` Linear a real checkpoint carries
+        ck.setdefault("module.audio_branch." + k, v)
     ck["module.text_branch.embeddings.word_embeddings.weight"] = torch.zeros(4, 4)
     ck["module.logit_scale_a"] = torch.tensor(1.0)
     path = tmp_path / "ckpt.pt"
