@@ -41,7 +41,8 @@ def bench_gemm():
     for l, (T, C) in enumerate([(4096, 96), (1024, 192), (256, 384), (64, 768)]):
         M = B * T
         for name, N, K, obf, act, nres in [("qkv", 3 * C, C, 1, 0, 0), ("proj", C, C, 0, 0, 1), ("fc1+gelu", 4 * C, C, 1, 1, 0), ("fc1+geluF16", 4 * C, C, 1, 3, 0),
-                                           ("fc2+2res", C, 4 * C, 0, 0, 2), ("fc1 nogelu", 4 * C, C, 1, 0, 0), ("fc2 nores", C, 4 * C, 0, 0, 0)]:
+                                           ("fc2+2res", C, 4 * C, 0, 0, 2), ("fc1 nogelu", 4 * C, C, 1, 0, 0), ("fc2 nores", C, 4 * C, 0, 0, 0),
+                                           ("fc2 bf16out", C, 4 * C, 1, 0, 0), ("fc2+1res", C, 4 * C, 0, 0, 1)]:
             A = torch.randn(M, K, device=dev).to(torch.bfloat16)
             W = torch.randn(N, K, device=dev).to(torch.bfloat16)
             bias = torch.randn(N, device=dev)
