@@ -450,3 +450,37 @@ def check_pca_moments_vs_oracle(layer=2, B=2):
     ev_ref, ev = torch.linalg.eigvalsh(cov_ref).flip(0), torch.linalg.eigvalsh(cov).flip(0)
     k = min(32, ev.numel())
     return {"n": acc.n - n, "mean": rel(mean, mean_ref), "cov": rel(cov, cov_ref), "top_eigenvalues": rel(ev[:k], ev_ref[:k])}
+
+
+def check_quantize_waveform(n=480000 * 2 + 8, seed=0):
+    """ard_quantize_waveform vs the oracle's quantize_tensor (src/residual.py:210-212): integer arithmetic, bit-exact."""
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.rand(n, generator=g) * 2.4 - 1.2)          # includes values outside [-1, 1]
+    x[:6] = torch.tensor([1.0, -1.0, 0.0, 1.0 / 32767.0, -0.5 / 32767.0, 0.99999])
+    xd = x.cuda()
+    out = torch.empty_like(xd)
+    L.check(L.load().ard_quantize_waveform(L.ptr(xd), L.ptr(out), n, L.stream_ptr()))
+    torch.cuda.synchronize()
+    return int((out.cpu() != O.quantize_tensor(x)).sum().item())
+
+
+def check_argmax_vs_golden(fname="htsat_tiny_b2.npz"):
+    """north_star: argmax class predictions identical to the reference's (zero-shot similarities over 50 classes with the
+    ResiDual-patched model, and the 527-way clipwise output of the plain model)."""
+    g = np.load(os.path.join(GOLDEN, fname))
+    model, seed, B = str(g["meta_model"]), int(g["meta_seed"]), int(g["meta_B"])
+    wave = W.make_clips(B, seed=1234)
+    text = W.make_text_embeds(50, 512, seed=7)
+    clap, _, _ = make_encoder(model, seed=seed, residual=True)
+    with torch.no_grad():
+        emb = clap.get_audio_embedding_from_data(wave.cuda(), use_tensor=True).float().cpu()
+    sims = emb @ text.T
+    ref_sims = torch.from_numpy(g["train_sims"])
+    clap2, _, _ = make_encoder(model, seed=seed)
+    with torch.no_grad():
+        clip = encoder_outputs(clap2, wave)["clipwise_output"]
+    ref_clip = torch.from_numpy(g["plain_clipwise_output"])
+    margin = (ref_sims.topk(2, dim=-1).values[:, 0] - ref_sims.topk(2, dim=-1).values[:, 1]).min().item()
+    return {"zero_shot_argmax_mismatch": int((sims.argmax(-1) != ref_sims.argmax(-1)).sum()),
+            "clipwise_argmax_mismatch": int((clip.argmax(-1).cpu() != ref_clip.argmax(-1)).sum()),
+            "reference_top1_top2_margin": margin, "sims_max_abs_err": (sims - ref_sims).abs().max().item()}

@@ -52,3 +52,9 @@ def test_host_batch_pipelined_equals_device_batch():
             assert got.shape == ref.shape
             # per-clip arithmetic is independent of the batch it rides in: bit-identical
             assert torch.equal(got, ref), (n, (got - ref).abs().max().item())
+
+
+def test_argmax_predictions_identical_to_reference():
+    m = G.check_argmax_vs_golden("htsat_tiny_b2.npz")
+    assert m["zero_shot_argmax_mismatch"] == 0 and m["clipwise_argmax_mismatch"] == 0, m
+    assert m["sims_max_abs_err"] < m["reference_top1_top2_margin"], m   # the agreement is not luck: error below the decision margin

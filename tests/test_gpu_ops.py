@@ -66,3 +66,7 @@ def test_logmel():
 def test_stats_accumulate(rows, D, strided, calls):
     m = G.check_stats(rows, D, strided, calls=calls)
     assert m["n"] == 0 and m["sum"] < 1e-6 and m["sumsq"] < 1e-5, m
+
+
+def test_quantize_waveform_bit_exact():
+    assert G.check_quantize_waveform() == 0
