@@ -254,6 +254,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         const int lw = warp - FF_W_LN;                 // rows [lw*32, +32) of the tile
         uint8_t* a1 = smem + FF_A1_OFF;
         const int l8 = lane & 7, rsub = lane >> 3;     // 8 lanes per row, 4 rows per warp instruction
+        int a1_off[3];                                 // byte offset of this lane's three 8-byte stores for row-group 0
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int c0 = l8 * 12 + q * 4, kb = c0 >> 5, cc = c0 & 31;
+            a1_off[q] = kb * FF_A1_KB + (lw * 32 + rsub) * 64 + (((cc >> 3) ^ (rsub >> 1)) << 4) + (cc & 7) * 2;
+        }
         auto prefetch_tile = [&](int t) {              // pull the tile's x (and second-residual) rows into L2 one tile ahead
             if (t >= num_tiles) return;
             const long long r = (long long)t * FF_BM + lw * 32 + lane;
@@ -273,68 +279,53 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             prefetch_tile(tile + gridDim.x);
-            // 4 batches of 2 row-groups (8 rows), software-pipelined: batch k+1's loads fly while batch k is normalised;
-            // batch 0's latency overlaps the wait for the previous tile's fc1 MMAs (A1 is single-buffered).
+            // 8 row-groups (4 rows per warp instruction), loads issued two groups ahead: group k+2's loads fly while group k is
+            // normalised; group 0/1's latency overlaps the wait for the previous tile's fc1 MMAs (A1 is single-buffered).
+            // Three 12-register buffers instead of two 24-register ones: the 72-register budget of this 26-warp CTA spilled.
             const long long row0 = (long long)tile * FF_BM + lw * 32;
-            float4 v[2][2][3];
-            auto load_batch = [&](int bi, float4 (&dst)[2][3]) {
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const long long row = row0 + (bi * 2 + g) * 4 + rsub;
-                    if (row < p.M) {
-                        const float4* xr = reinterpret_cast<const float4*>(p.x + row * FF_C + l8 * 12);
-                        dst[g][0] = __ldg(xr); dst[g][1] = __ldg(xr + 1); dst[g][2] = __ldg(xr + 2);
-                    } else {
-                        dst[g][0] = dst[g][1] = dst[g][2] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+            float4 v[3][3];
+            auto load_group = [&](int gi, float4 (&dst)[3]) {
+                const long long row = row0 + gi * 4 + rsub;
+                if (row < p.M) {
+                    const float4* xr = reinterpret_cast<const float4*>(p.x + row * FF_C + l8 * 12);
+                    dst[0] = __ldg(xr); dst[1] = __ldg(xr + 1); dst[2] = __ldg(xr + 2);
+                } else {
+                    dst[0] = dst[1] = dst[2] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
-            load_batch(0, v[0]);
+            load_group(0, v[0]);
+            load_group(1, v[1]);
             mbar_wait(a1_free, (it & 1) ^ 1);
 #pragma unroll
-            for (int bi = 0; bi < 4; ++bi) {
-                if (bi + 1 < 4) load_batch(bi + 1, v[(bi + 1) & 1]);
-                float4 (&cur)[2][3] = v[bi & 1];
-                float sm[2], qv[2];
+            for (int gi = 0; gi < 8; ++gi) {
+                if (gi + 2 < 8) load_group(gi + 2, v[(gi + 2) % 3]);
+                float4 (&cur)[3] = v[gi % 3];
+                float sm = 0.f;
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    sm[g] = 0.f;
+                for (int q = 0; q < 3; ++q) sm += (cur[q].x + cur[q].y) + (cur[q].z + cur[q].w);
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) sm[g] += (cur[g][q].x + cur[g][q].y) + (cur[g][q].z + cur[g][q].w);
+                for (int sh = 4; sh > 0; sh >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, sh);
+                const float mean = sm * (1.0f / FF_C);
+                float qv = 0.f;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    cur[q].x -= mean; cur[q].y -= mean; cur[q].z -= mean; cur[q].w -= mean;
+                    qv += (cur[q].x * cur[q].x + cur[q].y * cur[q].y) + (cur[q].z * cur[q].z + cur[q].w * cur[q].w);
                 }
 #pragma unroll
-                for (int sh = 4; sh > 0; sh >>= 1)
+                for (int sh = 4; sh > 0; sh >>= 1) qv += __shfl_xor_sync(0xffffffffu, qv, sh);
+                const float rstd = rsqrtf(qv * (1.0f / FF_C) + 1e-5f);
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) sm[g] += __shfl_xor_sync(0xffffffffu, sm[g], sh);
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const float mean = sm[g] * (1.0f / FF_C);
-                    qv[g] = 0.f;
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        cur[g][q].x -= mean; cur[g][q].y -= mean; cur[g][q].z -= mean; cur[g][q].w -= mean;
-                        qv[g] += (cur[g][q].x * cur[g][q].x + cur[g][q].y * cur[g][q].y) + (cur[g][q].z * cur[g][q].z + cur[g][q].w * cur[g][q].w);
-                    }
-                }
-#pragma unroll
-                for (int sh = 4; sh > 0; sh >>= 1)
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) qv[g] += __shfl_xor_sync(0xffffffffu, qv[g], sh);
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const float rstd = rsqrtf(qv[g] * (1.0f / FF_C) + 1e-5f);
-                    const int rr = lw * 32 + (bi * 2 + g) * 4 + rsub;
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        const int c0 = l8 * 12 + q * 4;                       // 4 channels = 8 bytes of bf16, inside one 16-byte unit
-                        const float4 gm = *reinterpret_cast<const float4*>(gs + c0);
-                        const float4 bt = *reinterpret_cast<const float4*>(bs + c0);
-                        uint2 pk;
-                        pk.x = pack_bf16x2(fmaf(cur[g][q].x * rstd, gm.x, bt.x), fmaf(cur[g][q].y * rstd, gm.y, bt.y));
-                        pk.y = pack_bf16x2(fmaf(cur[g][q].z * rstd, gm.z, bt.z), fmaf(cur[g][q].w * rstd, gm.w, bt.w));
-                        const int kb = c0 >> 5, cc = c0 & 31;
-                        *reinterpret_cast<uint2*>(a1 + kb * FF_A1_KB + rr * 64 + ((((cc >> 3) ^ ((rr >> 1) & 3))) << 4) + (cc & 7) * 2) = pk;
-                    }
+                for (int q = 0; q < 3; ++q) {
+                    const int c0 = l8 * 12 + q * 4;                       // 4 channels = 8 bytes of bf16, inside one 16-byte unit
+                    const float4 gm = *reinterpret_cast<const float4*>(gs + c0);
+                    const float4 bt = *reinterpret_cast<const float4*>(bs + c0);
+                    uint2 pk;
+                    pk.x = pack_bf16x2(fmaf(cur[q].x * rstd, gm.x, bt.x), fmaf(cur[q].y * rstd, gm.y, bt.y));
+                    pk.y = pack_bf16x2(fmaf(cur[q].z * rstd, gm.z, bt.z), fmaf(cur[q].w * rstd, gm.w, bt.w));
+                    // row rr = lw*32 + gi*4 + rsub; SWIZZLE_64B unit index ^= (rr >> 1) & 3 = ((gi & 1) << 1) | (rsub >> 1): the
+                    // gi-dependent part is a compile-time XOR of bit 5 plus a compile-time row offset (3 address registers, not 24)
+                    *reinterpret_cast<uint2*>(a1 + ((a1_off[q] ^ ((gi & 1) << 5)) + gi * 256)) = pk;
                 }
             }
             fence_proxy_async_smem();
