@@ -105,6 +105,38 @@ ARD_DEVINL void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, 
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A run of NK (k-step) MMAs over one swizzled k-block in ONE asm statement: D (+)= A[:, 16k..] * B[:, 16k..], descriptors
+// advance by 2 (32 bytes) per k-step. Issued from divergent code (lane 0 of the issuer warp) every tcgen05.mma costs a dozen
+// SASS instructions when written as separate statements (R2UR of each operand + an ELECT / BRA.U.ANY wrapper per
+// instruction, ~85 cycles per MMA measured in the fused FFN); inside one statement the operands are converted once.
+// `first_acc` = accumulate flag of the first MMA (the rest always accumulate).
+template <int NK>
+ARD_DEVINL void umma_f16_ss_run(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t first_acc) {
+    static_assert(NK == 2 || NK == 4, "k-steps per swizzled k-block: 2 (SWIZZLE_64B) or 4 (SWIZZLE_128B)");
+    if constexpr (NK == 2) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 a1, b1;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, 1;\n\t}\n"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(first_acc)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\t"
+            "add.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\t"
+            "add.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, 1;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, 1;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, 1;\n\t}\n"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(first_acc)
+            : "memory");
+    }
+}
 // Arrives (count 1) on the mbarrier once all previously issued tcgen05.mma of this thread have completed.
 // Implies tcgen05.fence::before_thread_sync.
 ARD_DEVINL void umma_commit(uint64_t* bar) {

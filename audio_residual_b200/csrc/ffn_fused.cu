@@ -29,6 +29,14 @@
 
 namespace ard {
 
+// Development aid (tools/ffn_trace.py builds a separate library with -DARD_FFN_TRACE): per-role clock64() stamps of CTA 0.
+#ifdef ARD_FFN_TRACE
+__device__ long long g_ffn_trace[8][64][8];   // [role][event index][field]
+#define FF_TRACE(role, idx, field) do { if (blockIdx.x == 0 && (idx) < 64) g_ffn_trace[role][idx][field] = clock64(); } while (0)
+#else
+#define FF_TRACE(role, idx, field) do { } while (0)
+#endif
+
 constexpr int FF_C = 96;
 constexpr int FF_HD = 4 * FF_C;         // 384
 constexpr int FF_NCH = FF_HD / 64;      // 6 hidden chunks of 64
@@ -151,7 +159,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                 }
             };
             load_resid(0);                                   // in flight while fc2 of this tile finishes
+            if (warp == 0 && lane == 0) FF_TRACE(0, it, 0);
             mbar_wait(&y_full[yb], (it >> 1) & 1);
+            if (warp == 0 && lane == 0) FF_TRACE(0, it, 1);
             tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < 6; ++c) {                    // 16-column chunks
@@ -188,65 +198,81 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                 }
                 cbuf ^= 1;
             }
+            if (warp == 0 && lane == 0) FF_TRACE(0, it, 2);
         }
         if (lane == 0) tma_store_wait_all<0>();
     } else if (warp == FF_W_MMA) {
-        // ============================================================ weight load + MMA issue (one thread)
-        if (lane == 0) {
+        // ============================================================ weight load + fc1 MMA issue
+        // The whole warp runs the loop (all lanes wait on the barriers) and one elected lane issues: in warp-convergent code
+        // ptxas keeps descriptors / TMEM addresses / loop state on the uniform datapath and emits the chunk's UTCHMMAs back to
+        // back. Issued from a lane-0 branch each MMA cost ~12 SASS instructions (R2UR per operand + an ELECT / BRA.U.ANY
+        // wrapper) = ~85 cycles, so the 36 fc1 MMAs of a tile took 5 k cycles - as long as the tile's whole GELU phase -
+        // and delayed a1_free, i.e. the next tile's LayerNorm (tools/ffn_trace.py timeline, profiles/r1_ffn_fused.md).
+        if (elect_one_sync()) {
             mbar_expect_tx(w_full, FF_W1_BYTES + FF_W2_BYTES);
             for (int kb = 0; kb < 3; ++kb)
                 for (int hf = 0; hf < 2; ++hf)
                     tma_load_2d(smem + FF_W1_OFF + kb * FF_W1_KB + hf * 192 * 64, &tmW1, w_full, kb * 32, hf * 192);
             for (int j = 0; j < FF_NCH; ++j) tma_load_2d(smem + FF_W2_OFF + j * FF_W2_KB, &tmW2, w_full, j * 64, 0);
-            mbar_wait(w_full, 0);
-            constexpr uint32_t idesc1 = umma_idesc_bf16(FF_BM, 64);
-            constexpr uint32_t idesc2 = umma_idesc_f16(FF_BM, FF_C);   // A2 (GELU output) and W2 are fp16
-            const uint32_t sW1 = smem_u32(smem + FF_W1_OFF), sW2 = smem_u32(smem + FF_W2_OFF);
-            const uint32_t sA1 = smem_u32(smem + FF_A1_OFF), sA2 = smem_u32(smem + FF_A2_OFF);
-            // fc1 issuer: runs over the CTA's GLOBAL chunk sequence g = 6*tile_iter + j, up to FF_NHB chunks ahead of the GELU
-            // warps (bounded by h_free) and across tile boundaries (bounded by a1_full). H buffer = g & 3 (n-th use g >> 2).
-            // fc2 is issued by a second thread (warp FF_W_MMA2) so neither issuer waits on the other's barriers.
-            const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-            const int total = my_tiles * FF_NCH;
-            for (int g = 0; g < total; ++g) {
-                const int t = g / FF_NCH, j = g - t * FF_NCH;
-                if (j == 0) mbar_wait(a1_full, t & 1);       // this tile's LayerNorm output is in A1
+        }
+        __syncwarp();
+        mbar_wait(w_full, 0);
+        constexpr uint32_t idesc1 = umma_idesc_bf16(FF_BM, 64);
+        const uint64_t dA1 = umma_desc_sw64(smem_u32(smem + FF_A1_OFF)), dW1 = umma_desc_sw64(smem_u32(smem + FF_W1_OFF));
+        // fc1 issuer: runs over the CTA's GLOBAL chunk sequence g = 6*tile_iter + j, up to FF_NHB chunks ahead of the GELU
+        // warps (bounded by h_free) and across tile boundaries (bounded by a1_full). H buffer = g & 3 (n-th use g >> 2).
+        // fc2 is issued by a second warp (FF_W_MMA2) so neither issuer waits on the other's barriers.
+        const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        int g = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            if (lane == 0) FF_TRACE(1, g, 0);
+            mbar_wait(a1_full, t & 1);                       // this tile's LayerNorm output is in A1
+#pragma unroll 1
+            for (int j = 0; j < FF_NCH; ++j, ++g) {
                 const int hb = g & (FF_NHB - 1);
+                if (lane == 0) FF_TRACE(1, g, 1);
                 mbar_wait(&h_free[hb], ((g >> 2) & 1) ^ 1);
+                if (lane == 0) FF_TRACE(1, g, 2);
                 tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t d = tmem_base + FF_TM_H + hb * 64;
+                    const uint64_t db = dW1 + (uint64_t)(j * ((64 * 64) >> 4));
 #pragma unroll
-                for (int kb = 0; kb < 3; ++kb) {
-                    const uint64_t da = umma_desc_sw64(sA1 + kb * FF_A1_KB);
-                    const uint64_t db = umma_desc_sw64(sW1 + kb * FF_W1_KB + j * 64 * 64);
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
-                        umma_bf16_ss(tmem_base + FF_TM_H + hb * 64, da + 2 * ks, db + 2 * ks, idesc1, (kb | ks) != 0);
+                    for (int kb = 0; kb < 3; ++kb)          // descriptor start-address field is in 16-byte units
+                        umma_f16_ss_run<2>(d, dA1 + (uint64_t)(kb * (FF_A1_KB >> 4)), db + (uint64_t)(kb * (FF_W1_KB >> 4)), idesc1, kb != 0);
+                    umma_commit(&h_full[hb]);
+                    if (j == FF_NCH - 1) umma_commit(a1_free);
                 }
-                umma_commit(&h_full[hb]);
-                if (j == FF_NCH - 1) umma_commit(a1_free);
+                __syncwarp();
+                if (lane == 0) FF_TRACE(1, g, 3);
             }
         }
     } else if (warp == FF_W_MMA2) {
-        // ============================================================ fc2 issuer (one thread): Y += A2_g W2[:, j]^T
-        if (lane == 0) {
-            mbar_wait(w_full, 0);
-            constexpr uint32_t idesc2 = umma_idesc_f16(FF_BM, FF_C);   // A2 (GELU output) and W2 are fp16
-            const uint32_t sW2 = smem_u32(smem + FF_W2_OFF), sA2 = smem_u32(smem + FF_A2_OFF);
-            const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-            const int total = my_tiles * FF_NCH;
-            for (int g = 0; g < total; ++g) {
-                const int t = g / FF_NCH, j = g - t * FF_NCH;
-                const int b = g & 1, yb = t & 1;
+        // ============================================================ fc2 issuer: Y += A2_g W2[:, j]^T (same convergent pattern)
+        mbar_wait(w_full, 0);
+        constexpr uint32_t idesc2 = umma_idesc_f16(FF_BM, FF_C);   // A2 (GELU output) and W2 are fp16
+        const uint64_t dW2 = umma_desc_sw128(smem_u32(smem + FF_W2_OFF)), dA2 = umma_desc_sw128(smem_u32(smem + FF_A2_OFF));
+        const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        int g = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int yb = t & 1;
+#pragma unroll 1
+            for (int j = 0; j < FF_NCH; ++j, ++g) {
+                const int b = g & 1;
+                if (lane == 0) FF_TRACE(2, g, 0);
                 mbar_wait(&a2_full[b], (g >> 1) & 1);
+                if (lane == 0) FF_TRACE(2, g, 1);
                 if (j == 0) mbar_wait(&y_free[yb], ((t >> 1) & 1) ^ 1);
+                if (lane == 0) FF_TRACE(2, g, 2);
                 tc_fence_after();
-                const uint64_t da = umma_desc_sw128(sA2 + b * FF_A2_BYTES);
-                const uint64_t db = umma_desc_sw128(sW2 + j * FF_W2_KB);
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    umma_bf16_ss(tmem_base + FF_TM_Y + yb * 128, da + 2 * ks, db + 2 * ks, idesc2, (j | ks) != 0);
-                umma_commit(&a2_free[b]);
-                if (j == FF_NCH - 1) umma_commit(&y_full[yb]);
+                if (elect_one_sync()) {
+                    umma_f16_ss_run<4>(tmem_base + FF_TM_Y + yb * 128, dA2 + (uint64_t)(b * (FF_A2_BYTES >> 4)),
+                                       dW2 + (uint64_t)(j * (FF_W2_KB >> 4)), idesc2, j != 0);
+                    umma_commit(&a2_free[b]);
+                    if (j == FF_NCH - 1) umma_commit(&y_full[yb]);
+                }
+                __syncwarp();
+                if (lane == 0) FF_TRACE(2, g, 3);
             }
         }
     } else if (warp < FF_W_GELU) {
@@ -295,7 +321,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
             };
             load_group(0, v[0]);
             load_group(1, v[1]);
+            if (lw == 0 && lane == 0) FF_TRACE(3, it, 0);
             mbar_wait(a1_free, (it & 1) ^ 1);
+            if (lw == 0 && lane == 0) FF_TRACE(3, it, 1);
 #pragma unroll
             for (int gi = 0; gi < 8; ++gi) {
                 if (gi + 2 < 8) load_group(gi + 2, v[(gi + 2) % 3]);
@@ -331,6 +359,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(a1_full);
+            if (lw == 0 && lane == 0) FF_TRACE(3, it, 2);
         }
     } else if (warp < FF_W_MMA2) {
         // ============================================================ GELU warps: H_j (TMEM) -> bf16 A2 operand tile
@@ -349,7 +378,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                 const int j = 2 * jj + grp;
                 const int g = it * FF_NCH + j;              // global chunk index of this CTA
                 const int hb = g & (FF_NHB - 1);
+                if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 0);
                 mbar_wait(&h_full[hb], (g >> 2) & 1);
+                if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 1);
                 tc_fence_after();
                 uint32_t pk[16];
 #pragma unroll
@@ -370,7 +401,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                         pk[s * 8 + i / 2 + 1] = gelu_erf_f16x2(__uint_as_float(v[i + 2]) + b4.z, __uint_as_float(v[i + 3]) + b4.w);
                     }
                 }
+                if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 2);
                 mbar_wait(&a2_free[grp], ((g >> 1) & 1) ^ 1);   // fc2 MMAs that read the previous contents have retired
+                if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 3);
                 uint8_t* rowp = smem + FF_A2_OFF + grp * FF_A2_BYTES + row * 128;
                 const int sw = row & 7;
 #pragma unroll
@@ -379,6 +412,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a2_full[grp]);
+                if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 4);
             }
         }
     }
@@ -416,3 +450,9 @@ int ffn_fused_96(const float* x, const float* resid2, float* out, long long M, c
 }
 
 }  // namespace ard
+
+#ifdef ARD_FFN_TRACE
+extern "C" int ard_debug_ffn_trace(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, ard::g_ffn_trace, sizeof(long long) * 8 * 64 * 8);
+}
+#endif
