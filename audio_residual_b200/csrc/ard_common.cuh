@@ -58,6 +58,22 @@ ARD_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// Wait for roles that expect to idle for thousands of cycles (epilogue / issuer warps of the fused kernels). A bare
+// try_wait returns after ~20 cycles, so every idle warp keeps issuing a TRYWAIT + BRA pair: in the fused FFN half of all
+// issued instructions were such polls, taken from the schedulers the GELU / LayerNorm warps were running on. The suspend-time
+// hint lets the hardware park the warp until the phase completes (or the hint expires) instead.
+ARD_DEVINL void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+            : "memory");
+    }
+}
 
 // ------------------------------------------------------------------------------------------------ TMA
 ARD_DEVINL void tma_prefetch_desc(const CUtensorMap* m) {
@@ -110,31 +126,35 @@ ARD_DEVINL void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, 
 // SASS instructions when written as separate statements (R2UR of each operand + an ELECT / BRA.U.ANY wrapper per
 // instruction, ~85 cycles per MMA measured in the fused FFN); inside one statement the operands are converted once.
 // `first_acc` = accumulate flag of the first MMA (the rest always accumulate).
-template <int NK>
+#define ARD_UMMA_RUN2(CG)                                                                      \
+    asm volatile(                                                                              \
+        "{\n\t.reg .pred p;\n\t.reg .b64 a1, b1;\n\t"                                         \
+        "setp.ne.b32 p, %4, 0;\n\t"                                                            \
+        "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\t"                                         \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], %1, %2, %3, p;\n\t"                      \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], a1, b1, %3, 1;\n\t}\n"                   \
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(first_acc)                    \
+        : "memory")
+#define ARD_UMMA_RUN4(CG)                                                                      \
+    asm volatile(                                                                              \
+        "{\n\t.reg .pred p;\n\t.reg .b64 a1, b1, a2, b2, a3, b3;\n\t"                         \
+        "setp.ne.b32 p, %4, 0;\n\t"                                                            \
+        "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\t"                                         \
+        "add.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\t"                                         \
+        "add.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"                                         \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], %1, %2, %3, p;\n\t"                      \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], a1, b1, %3, 1;\n\t"                      \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], a2, b2, %3, 1;\n\t"                      \
+        "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], a3, b3, %3, 1;\n\t}\n"                   \
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(first_acc)                    \
+        : "memory")
+template <int NK, bool PAIR = false>
 ARD_DEVINL void umma_f16_ss_run(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t first_acc) {
-    static_assert(NK == 2 || NK == 4, "k-steps per swizzled k-block: 2 (SWIZZLE_64B) or 4 (SWIZZLE_128B)");
+    static_assert(NK == 2 || NK == 4, "k-steps per run: 2 (SWIZZLE_64B k-block / half of a 128B one) or 4 (SWIZZLE_128B)");
     if constexpr (NK == 2) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t.reg .b64 a1, b1;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, 1;\n\t}\n"
-            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(first_acc)
-            : "memory");
+        if constexpr (PAIR) ARD_UMMA_RUN2("2"); else ARD_UMMA_RUN2("1");
     } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t.reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\t"
-            "add.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\t"
-            "add.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, 1;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, 1;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, 1;\n\t}\n"
-            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(first_acc)
-            : "memory");
+        if constexpr (PAIR) ARD_UMMA_RUN4("2"); else ARD_UMMA_RUN4("1");
     }
 }
 // Arrives (count 1) on the mbarrier once all previously issued tcgen05.mma of this thread have completed.
@@ -290,20 +310,22 @@ ARD_DEVINL float gelu_erf_grad(float x) {
 // to the exact GELU than the fp32-GELU -> bf16 operand path (rel. l2 error 3.2e-4 vs 1.7e-3 on N(0,1.5) inputs,
 // emulated in tools/fit_erf.py --f16).
 //
-// Formula: erf(x / sqrt 2) = tanh(x P(min(x^2, 16))), P = degree-2 fit of atanh(erf(x / sqrt 2)) / x (tools/fit_erf.py --tanh):
-// max |erf error| 1.1e-4, max |GELU error| 2.9e-5 in exact arithmetic, i.e. below fp16 resolution; evaluated in fp16 the
-// rel. l2 error against the float64 erf GELU is 3.2e-4 (same as the 1 - 2^(-tQ(t)) form it replaces). 10 instructions per
-// pair: the previous form's h2exp2 expanded to 2 cvt + 2 MUFU.EX2 + 2 FFMA + pack; tanh.approx.f16x2 is 2 MUFU.TANH.F16 + PRMT.
-ARD_DEVINL uint32_t gelu_erf_f16x2(float a, float b) {
-    const __half2 x = __floats2half2_rn(a, b);
-    const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(16.0f));      // clamp: tanh has saturated to +-1 in fp16 by |x| = 4
-    __half2 p = __hfma2(__float2half2_rn(-3.57353399e-04f), x2, __float2half2_rn(3.70422079e-02f));
-    p = __hfma2(p, x2, __float2half2_rn(7.97467283e-01f));
-    const __half2 u = __hmul2(x, p);
+// Formula: erf(x / sqrt 2) = tanh(x (c0 + c1 x^2)), the classic tanh form with c0, c1 re-fitted to the ERF GELU (minimax on
+// the absolute GELU error, tools/fit_erf.py --tanh): max |GELU error| 2.7e-4, below fp16 resolution of the values that matter;
+// evaluated in fp16 the rel. l2 error against the float64 erf GELU is 3.7e-4 on N(0,1.5) inputs (3.2e-4 for the
+// 1 - 2^(-tQ(t)) form it replaces). The argument is y = x / 2 (the caller folds the halving into its fp32 bias add:
+// y = 0.5 acc + 0.5 b): gelu(x) = y + y tanh(y (2 c0 + 8 c1 y^2)), 4 packed ops + 2 MUFU.TANH.F16 + PRMT per pair. Measured
+// on B200 (tools/micro/mufu_rate.cu): HFMA2 issues at 64 lanes/clk/SM - half the FFMA rate - and MUFU at 16 elements/clk/SM
+// whatever the format, so the cost of a packed GELU is its op count: the previous form's h2exp2 expanded to 2 cvt + 2 MUFU.EX2
+// + 2 FFMA + pack and its polynomial was 6 HFMA2 (25 instructions per pair; now 9). No clamp is needed: y^2 -> inf gives
+// p = +inf, u = +-inf, tanh = +-1.
+ARD_DEVINL uint32_t gelu_erf_f16x2_halved(float ya, float yb) {
+    const __half2 y = __floats2half2_rn(ya, yb);
+    const __half2 p = __hfma2(__float2half2_rn(8.0f * 3.470089e-02f), __hmul2(y, y), __float2half2_rn(2.0f * 8.0015708e-01f));
+    const __half2 u = __hmul2(y, p);
     uint32_t tb;
     asm("tanh.approx.f16x2 %0, %1;" : "=r"(tb) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
-    const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
-    const __half2 g = __hfma2(hx, *reinterpret_cast<const __half2*>(&tb), hx);
+    const __half2 g = __hfma2(y, *reinterpret_cast<const __half2*>(&tb), y);
     return *reinterpret_cast<const uint32_t*>(&g);
 }
 ARD_DEVINL float gelu_erf(float x) {

@@ -40,9 +40,11 @@ __device__ long long g_ffn_trace[8][64][8];   // [role][event index][field]
 constexpr int FF_C = 96;
 constexpr int FF_HD = 4 * FF_C;         // 384
 constexpr int FF_NCH = FF_HD / 64;      // 6 hidden chunks of 64
+constexpr int FF_NPAIR = FF_NCH / 2;    // fc1 is issued per PAIR of chunks (N = 128 per MMA)
 constexpr int FF_BM = 128;
+constexpr int FF_EPI_WARPS = 8;
 constexpr int FF_GELU_WARPS = 16;
-constexpr int FF_W_MMA = 4, FF_W_LN = 5, FF_W_GELU = 9, FF_W_MMA2 = FF_W_GELU + FF_GELU_WARPS;   // fc1 issuer, LN, GELU, fc2 issuer
+constexpr int FF_W_MMA = FF_EPI_WARPS, FF_W_GELU = FF_W_MMA + 1, FF_W_MMA2 = FF_W_GELU + FF_GELU_WARPS;   // fc1 issuer, GELU+LN, fc2 issuer
 constexpr int FF_THREADS = (FF_W_MMA2 + 1) * 32;   // 832
 
 constexpr int FF_W1_KB = FF_HD * 64;            // bytes per 32-wide k-block of W1 (384 rows x 64 B)
@@ -56,12 +58,12 @@ constexpr int FF_A1_OFF = FF_W2_OFF + FF_W2_BYTES;
 constexpr int FF_A1_BYTES = 3 * FF_A1_KB;       // 24576
 constexpr int FF_A2_OFF = FF_A1_OFF + FF_A1_BYTES;
 constexpr int FF_A2_BYTES = FF_BM * 128;        // 16384 per buffer
-constexpr int FF_CST_OFF = FF_A2_OFF + 2 * FF_A2_BYTES;    // 4 warps x 2 buffers x (32 rows x 64 B)
-constexpr int FF_VEC_OFF = FF_CST_OFF + 4 * 4096;          // b1[384] b2[96] gamma[96] beta[96]
+constexpr int FF_CST_OFF = FF_A2_OFF + 2 * FF_A2_BYTES;    // 8 warps x (32 rows x 64 B)
+constexpr int FF_VEC_OFF = FF_CST_OFF + FF_EPI_WARPS * 2048;   // b1[384] b2[96] gamma[96] beta[96]
 constexpr int FF_BAR_OFF = FF_VEC_OFF + (FF_HD + 3 * FF_C) * 4;
 constexpr int FF_SMEM_BYTES = FF_BAR_OFF + 256 + 1024;
 
-constexpr int FF_NHB = 4;       // H accumulators in flight
+constexpr int FF_NHB = 4;       // H accumulators in flight (two pairs)
 constexpr int FF_TM_H = 0;      // TMEM columns: H0..H3 @0/64/128/192, Y0 @256, Y1 @384
 constexpr int FF_TM_Y = 256;
 
@@ -98,8 +100,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = (p.M + FF_BM - 1) / FF_BM;
+    const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-    for (int i = threadIdx.x; i < FF_HD; i += FF_THREADS) b1s[i] = p.b1[i];
+    for (int i = threadIdx.x; i < FF_HD; i += FF_THREADS) b1s[i] = 0.5f * p.b1[i];   // the GELU takes x / 2 (gelu_erf_f16x2_halved)
     for (int i = threadIdx.x; i < FF_C; i += FF_THREADS) {
         b2s[i] = p.b2[i];
         gs[i] = p.gamma[i];
@@ -110,7 +113,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         tma_prefetch_desc(&tmW2);
         tma_prefetch_desc(&tmOut);
         mbar_init(w_full, 1);
-        mbar_init(a1_full, 4);
+        mbar_init(a1_full, FF_GELU_WARPS);
         mbar_init(a1_free, 1);
         for (int i = 0; i < FF_NHB; ++i) {
             mbar_init(&h_full[i], 1);
@@ -120,7 +123,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
             mbar_init(&a2_full[i], FF_GELU_WARPS / 2);
             mbar_init(&a2_free[i], 1);
             mbar_init(&y_full[i], 1);
-            mbar_init(&y_free[i], 4);
+            mbar_init(&y_free[i], FF_EPI_WARPS);
         }
         fence_barrier_init();
     }
@@ -133,15 +136,16 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp < FF_W_MMA) {
+    if (warp < FF_EPI_WARPS) {
         // ============================================================ output epilogue warps
-        uint8_t* cst = smem + FF_CST_OFF + warp * 4096;
+        // warp w: TMEM lane quadrant w & 3 (rows 32(w&3)..), column half w >> 2 (three 16-column chunks)
+        const int quad = warp & 3, c_begin = (warp >> 2) * 3;
+        uint8_t* sbuf = smem + FF_CST_OFF + warp * 2048;
         const bool has_r2 = p.resid2 != nullptr;
-        int cbuf = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int yb = it & 1;
-            const long long row = (long long)tile * FF_BM + warp * 32 + lane;
+            const long long row = (long long)tile * FF_BM + quad * 32 + lane;
             const bool row_ok = row < p.M;
             float4 r1[4], r2[4];
             auto load_resid = [&](int c) {
@@ -158,17 +162,18 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                     }
                 }
             };
-            load_resid(0);                                   // in flight while fc2 of this tile finishes
+            load_resid(c_begin);                             // in flight while fc2 of this tile finishes
             if (warp == 0 && lane == 0) FF_TRACE(0, it, 0);
-            mbar_wait(&y_full[yb], (it >> 1) & 1);
+            mbar_wait_parked(&y_full[yb], (it >> 1) & 1);
             if (warp == 0 && lane == 0) FF_TRACE(0, it, 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < 6; ++c) {                    // 16-column chunks
+            for (int cc = 0; cc < 3; ++cc) {                 // 16-column chunks
+                const int c = c_begin + cc;
                 uint32_t v[16];
-                tmem_ld_32x32b_x16(tmem_base + FF_TM_Y + yb * 128 + c * 16 + ((uint32_t)(warp * 32) << 16), v);
+                tmem_ld_32x32b_x16(tmem_base + FF_TM_Y + yb * 128 + c * 16 + ((uint32_t)(quad * 32) << 16), v);
                 tmem_ld_wait();
-                if (c == 5) {
+                if (cc == 2) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&y_free[yb]);
@@ -182,10 +187,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                     o[j].z = __uint_as_float(v[j * 4 + 2]) + b4.z + r1[j].z + r2[j].z;
                     o[j].w = __uint_as_float(v[j * 4 + 3]) + b4.w + r1[j].w + r2[j].w;
                 }
-                if (c + 1 < 6) load_resid(c + 1);            // next chunk's residuals fly during the staging / TMA store below
-                if (lane == 0) tma_store_wait_read<1>();
+                if (cc + 1 < 3) load_resid(c + 1);           // next chunk's residuals fly during the staging / TMA store below
+                if (lane == 0) tma_store_wait_read<0>();     // the previous chunk's store has read the (single) staging buffer
                 __syncwarp();
-                uint8_t* sbuf = cst + cbuf * 2048;
                 uint8_t* rowp = sbuf + lane * 64;
                 const int sw = (lane >> 1) & 3;              // SWIZZLE_64B: 16-byte unit index ^= (row >> 1) & 3
 #pragma unroll
@@ -193,10 +197,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_2d(&tmOut, sbuf, c * 16, tile * FF_BM + warp * 32);
+                    tma_store_2d(&tmOut, sbuf, c * 16, tile * FF_BM + quad * 32);
                     tma_store_commit();
                 }
-                cbuf ^= 1;
             }
             if (warp == 0 && lane == 0) FF_TRACE(0, it, 2);
         }
@@ -204,10 +207,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     } else if (warp == FF_W_MMA) {
         // ============================================================ weight load + fc1 MMA issue
         // The whole warp runs the loop (all lanes wait on the barriers) and one elected lane issues: in warp-convergent code
-        // ptxas keeps descriptors / TMEM addresses / loop state on the uniform datapath and emits the chunk's UTCHMMAs back to
-        // back. Issued from a lane-0 branch each MMA cost ~12 SASS instructions (R2UR per operand + an ELECT / BRA.U.ANY
-        // wrapper) = ~85 cycles, so the 36 fc1 MMAs of a tile took 5 k cycles - as long as the tile's whole GELU phase -
-        // and delayed a1_free, i.e. the next tile's LayerNorm (tools/ffn_trace.py timeline, profiles/r1_ffn_fused.md).
+        // ptxas keeps descriptors / TMEM addresses / loop state on the uniform datapath and emits the UTCHMMAs back to back
+        // (issued from a lane-0 branch each MMA cost ~12 SASS instructions: R2UR per operand + an ELECT / BRA.U.ANY wrapper).
         if (elect_one_sync()) {
             mbar_expect_tx(w_full, FF_W1_BYTES + FF_W2_BYTES);
             for (int kb = 0; kb < 3; ++kb)
@@ -216,43 +217,45 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
             for (int j = 0; j < FF_NCH; ++j) tma_load_2d(smem + FF_W2_OFF + j * FF_W2_KB, &tmW2, w_full, j * 64, 0);
         }
         __syncwarp();
-        mbar_wait(w_full, 0);
-        constexpr uint32_t idesc1 = umma_idesc_bf16(FF_BM, 64);
+        mbar_wait_parked(w_full, 0);
+        // fc1 per PAIR of hidden chunks: H[:, 128 jp ..] = A1 W1[128 jp .., :]^T as M128 N128 K16 MMAs (N = 64 MMAs read 6 KB of
+        // operands per 32 tensor-cycles and ran at half rate on shared-memory bandwidth; N = 128 reads 8 KB per 64). Pair
+        // P = 3 t + jp lands in H buffers 2 (P & 1), 2 (P & 1) + 1; the issuer runs up to two pairs ahead of the GELU warps
+        // (bounded by h_free) and across tile boundaries (bounded by a1_full). fc2 is issued by a second warp (FF_W_MMA2).
+        constexpr uint32_t idesc1 = umma_idesc_bf16(FF_BM, 128);
         const uint64_t dA1 = umma_desc_sw64(smem_u32(smem + FF_A1_OFF)), dW1 = umma_desc_sw64(smem_u32(smem + FF_W1_OFF));
-        // fc1 issuer: runs over the CTA's GLOBAL chunk sequence g = 6*tile_iter + j, up to FF_NHB chunks ahead of the GELU
-        // warps (bounded by h_free) and across tile boundaries (bounded by a1_full). H buffer = g & 3 (n-th use g >> 2).
-        // fc2 is issued by a second warp (FF_W_MMA2) so neither issuer waits on the other's barriers.
-        const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-        int g = 0;
+        int P = 0;
         for (int t = 0; t < my_tiles; ++t) {
-            if (lane == 0) FF_TRACE(1, g, 0);
-            mbar_wait(a1_full, t & 1);                       // this tile's LayerNorm output is in A1
+            if (lane == 0) FF_TRACE(1, P, 0);
+            mbar_wait_parked(a1_full, t & 1);                       // this tile's LayerNorm output is in A1
 #pragma unroll 1
-            for (int j = 0; j < FF_NCH; ++j, ++g) {
-                const int hb = g & (FF_NHB - 1);
-                if (lane == 0) FF_TRACE(1, g, 1);
-                mbar_wait(&h_free[hb], ((g >> 2) & 1) ^ 1);
-                if (lane == 0) FF_TRACE(1, g, 2);
+            for (int jp = 0; jp < FF_NPAIR; ++jp, ++P) {
+                const int hb = (P & 1) * 2;
+                const uint32_t par = ((P >> 1) & 1) ^ 1;     // buffers hb, hb+1 are on their (P >> 1)-th use
+                if (lane == 0) FF_TRACE(1, P, 1);
+                mbar_wait_parked(&h_free[hb], par);
+                mbar_wait_parked(&h_free[hb + 1], par);
+                if (lane == 0) FF_TRACE(1, P, 2);
                 tc_fence_after();
                 if (elect_one_sync()) {
                     const uint32_t d = tmem_base + FF_TM_H + hb * 64;
-                    const uint64_t db = dW1 + (uint64_t)(j * ((64 * 64) >> 4));
+                    const uint64_t db = dW1 + (uint64_t)(jp * ((128 * 64) >> 4));   // descriptor start address is in 16-byte units
 #pragma unroll
-                    for (int kb = 0; kb < 3; ++kb)          // descriptor start-address field is in 16-byte units
+                    for (int kb = 0; kb < 3; ++kb)
                         umma_f16_ss_run<2>(d, dA1 + (uint64_t)(kb * (FF_A1_KB >> 4)), db + (uint64_t)(kb * (FF_W1_KB >> 4)), idesc1, kb != 0);
                     umma_commit(&h_full[hb]);
-                    if (j == FF_NCH - 1) umma_commit(a1_free);
+                    umma_commit(&h_full[hb + 1]);
+                    if (jp == FF_NPAIR - 1) umma_commit(a1_free);
                 }
                 __syncwarp();
-                if (lane == 0) FF_TRACE(1, g, 3);
+                if (lane == 0) FF_TRACE(1, P, 3);
             }
         }
     } else if (warp == FF_W_MMA2) {
         // ============================================================ fc2 issuer: Y += A2_g W2[:, j]^T (same convergent pattern)
-        mbar_wait(w_full, 0);
+        mbar_wait_parked(w_full, 0);
         constexpr uint32_t idesc2 = umma_idesc_f16(FF_BM, FF_C);   // A2 (GELU output) and W2 are fp16
         const uint64_t dW2 = umma_desc_sw128(smem_u32(smem + FF_W2_OFF)), dA2 = umma_desc_sw128(smem_u32(smem + FF_A2_OFF));
-        const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         int g = 0;
         for (int t = 0; t < my_tiles; ++t) {
             const int yb = t & 1;
@@ -260,9 +263,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
             for (int j = 0; j < FF_NCH; ++j, ++g) {
                 const int b = g & 1;
                 if (lane == 0) FF_TRACE(2, g, 0);
-                mbar_wait(&a2_full[b], (g >> 1) & 1);
+                mbar_wait_parked(&a2_full[b], (g >> 1) & 1);
                 if (lane == 0) FF_TRACE(2, g, 1);
-                if (j == 0) mbar_wait(&y_free[yb], ((t >> 1) & 1) ^ 1);
+                if (j == 0) mbar_wait_parked(&y_free[yb], ((t >> 1) & 1) ^ 1);
                 if (lane == 0) FF_TRACE(2, g, 2);
                 tc_fence_after();
                 if (elect_one_sync()) {
@@ -275,102 +278,107 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                 if (lane == 0) FF_TRACE(2, g, 3);
             }
         }
-    } else if (warp < FF_W_GELU) {
-        // ============================================================ LayerNorm producers
-        const int lw = warp - FF_W_LN;                 // rows [lw*32, +32) of the tile
+    } else {
+        // ============================================================ GELU + LayerNorm warps
+        // 16 warps in two groups: group g turns the hidden chunks j = g, g+2, g+4 of every tile (TMEM, fp32) into the fp16 A2
+        // operand of fc2 (+ b1, erf GELU in packed fp16 math, SWIZZLE_128B tile in shared memory), so that while one group sits
+        // in the latency part of a chunk (barrier, TMEM load, async-proxy fence) the other is issuing math.
+        // The same warps also produce the NEXT tile's LayerNorm operand A1: 8 rows per warp (8 lanes per row, 12 contiguous
+        // channels each, 3-step butterflies, bf16 rows written straight into the SWIZZLE_64B K-major layout), group 0 after its
+        // first chunk of the current tile and group 1 after its second. With four dedicated LayerNorm warps (32 rows each, one
+        // latency-bound chain of ~1200 instructions) LN took 8.4 k cycles per tile and, A1 being single-buffered, serialised with
+        // the 4 k-cycle fc1 issue train: 12.3 k cycles per tile while the GELU warps idled 42 % (tools/ffn_trace.py). Spread
+        // over 16 warps it is ~1 k cycles in the shadow of the other group's GELU chunk, and A1 is free by then because fc1 of
+        // the current tile is issued (pairwise) as soon as the first pair has been read out of TMEM.
+        const int ew = warp - FF_W_GELU;
+        const int quad = warp & 3;
+        const int grp = ew >> 3;          // chunk parity this warp works on == A2 buffer it fills
+        const int half = (ew >> 2) & 1;   // which 32 of the chunk's 64 hidden columns
+        const int row = quad * 32 + lane; // row inside the tile == TMEM lane
+        const int l8 = lane & 7, rsub = lane >> 3;     // LayerNorm mapping: 8 lanes per row, 4 rows per warp instruction
         uint8_t* a1 = smem + FF_A1_OFF;
-        const int l8 = lane & 7, rsub = lane >> 3;     // 8 lanes per row, 4 rows per warp instruction
         int a1_off[3];                                 // byte offset of this lane's three 8-byte stores for row-group 0
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
             const int c0 = l8 * 12 + q * 4, kb = c0 >> 5, cc = c0 & 31;
-            a1_off[q] = kb * FF_A1_KB + (lw * 32 + rsub) * 64 + (((cc >> 3) ^ (rsub >> 1)) << 4) + (cc & 7) * 2;
+            a1_off[q] = kb * FF_A1_KB + (ew * 8 + rsub) * 64 + (((cc >> 3) ^ (rsub >> 1)) << 4) + (cc & 7) * 2;
         }
-        auto prefetch_tile = [&](int t) {              // pull the tile's x (and second-residual) rows into L2 one tile ahead
-            if (t >= num_tiles) return;
-            const long long r = (long long)t * FF_BM + lw * 32 + lane;
-            if (r >= p.M) return;
-            const char* a = reinterpret_cast<const char*>(p.x + r * FF_C);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 256));
-            if (p.resid2 != nullptr) {
-                const char* c = reinterpret_cast<const char*>(p.resid2 + r * FF_C);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(c));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(c + 128));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(c + 256));
-            }
+        // pull a tile's x (and second-residual) rows of this warp into L2: 8 rows x 384 B = 24 lines of 128 B
+        auto prefetch_tile = [&](int tile) {
+            if (tile >= num_tiles || lane >= 24) return;
+            const long long r0 = (long long)tile * FF_BM + ew * 8;
+            if (r0 * FF_C * 4 + (lane + 1) * 128 > (long long)p.M * FF_C * 4) return;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.x + r0 * FF_C) + lane * 128));
+            if (p.resid2 != nullptr)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.resid2 + r0 * FF_C) + lane * 128));
         };
-        prefetch_tile(blockIdx.x);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            prefetch_tile(tile + gridDim.x);
-            // 8 row-groups (4 rows per warp instruction), loads issued two groups ahead: group k+2's loads fly while group k is
-            // normalised; group 0/1's latency overlaps the wait for the previous tile's fc1 MMAs (A1 is single-buffered).
-            // Three 12-register buffers instead of two 24-register ones: the 72-register budget of this 26-warp CTA spilled.
-            const long long row0 = (long long)tile * FF_BM + lw * 32;
-            float4 v[3][3];
-            auto load_group = [&](int gi, float4 (&dst)[3]) {
-                const long long row = row0 + gi * 4 + rsub;
-                if (row < p.M) {
-                    const float4* xr = reinterpret_cast<const float4*>(p.x + row * FF_C + l8 * 12);
-                    dst[0] = __ldg(xr); dst[1] = __ldg(xr + 1); dst[2] = __ldg(xr + 2);
+        // LayerNorm of rows [ew*8, ew*8+8) of `tile` into A1; `lt` = this CTA's tile counter of `tile`
+        auto layernorm_tile = [&](int tile, int lt) {
+            const long long row0 = (long long)tile * FF_BM + ew * 8;
+            float4 v[2][3];
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+                const long long r = row0 + gi * 4 + rsub;
+                if (r < p.M) {
+                    const float4* xr = reinterpret_cast<const float4*>(p.x + r * FF_C + l8 * 12);
+                    v[gi][0] = __ldg(xr); v[gi][1] = __ldg(xr + 1); v[gi][2] = __ldg(xr + 2);
                 } else {
-                    dst[0] = dst[1] = dst[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[gi][0] = v[gi][1] = v[gi][2] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-            };
-            load_group(0, v[0]);
-            load_group(1, v[1]);
-            if (lw == 0 && lane == 0) FF_TRACE(3, it, 0);
-            mbar_wait(a1_free, (it & 1) ^ 1);
-            if (lw == 0 && lane == 0) FF_TRACE(3, it, 1);
+            }
+            prefetch_tile(tile + gridDim.x);
+            if (ew == 0 && lane == 0) FF_TRACE(3, lt, 0);
+            mbar_wait_parked(a1_free, (lt & 1) ^ 1);                // fc1 MMAs of the previous tile have read A1
+            if (ew == 0 && lane == 0) FF_TRACE(3, lt, 1);
+            float sm[2], qv[2];
 #pragma unroll
-            for (int gi = 0; gi < 8; ++gi) {
-                if (gi + 2 < 8) load_group(gi + 2, v[(gi + 2) % 3]);
-                float4 (&cur)[3] = v[gi % 3];
-                float sm = 0.f;
+            for (int gi = 0; gi < 2; ++gi) {
+                sm[gi] = 0.f;
 #pragma unroll
-                for (int q = 0; q < 3; ++q) sm += (cur[q].x + cur[q].y) + (cur[q].z + cur[q].w);
+                for (int q = 0; q < 3; ++q) sm[gi] += (v[gi][q].x + v[gi][q].y) + (v[gi][q].z + v[gi][q].w);
+            }
 #pragma unroll
-                for (int sh = 4; sh > 0; sh >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, sh);
-                const float mean = sm * (1.0f / FF_C);
-                float qv = 0.f;
+            for (int sh = 4; sh > 0; sh >>= 1)
+#pragma unroll
+                for (int gi = 0; gi < 2; ++gi) sm[gi] += __shfl_xor_sync(0xffffffffu, sm[gi], sh);
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+                const float mean = sm[gi] * (1.0f / FF_C);
+                qv[gi] = 0.f;
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
-                    cur[q].x -= mean; cur[q].y -= mean; cur[q].z -= mean; cur[q].w -= mean;
-                    qv += (cur[q].x * cur[q].x + cur[q].y * cur[q].y) + (cur[q].z * cur[q].z + cur[q].w * cur[q].w);
+                    v[gi][q].x -= mean; v[gi][q].y -= mean; v[gi][q].z -= mean; v[gi][q].w -= mean;
+                    qv[gi] += (v[gi][q].x * v[gi][q].x + v[gi][q].y * v[gi][q].y) + (v[gi][q].z * v[gi][q].z + v[gi][q].w * v[gi][q].w);
                 }
+            }
 #pragma unroll
-                for (int sh = 4; sh > 0; sh >>= 1) qv += __shfl_xor_sync(0xffffffffu, qv, sh);
-                const float rstd = rsqrtf(qv * (1.0f / FF_C) + 1e-5f);
+            for (int sh = 4; sh > 0; sh >>= 1)
+#pragma unroll
+                for (int gi = 0; gi < 2; ++gi) qv[gi] += __shfl_xor_sync(0xffffffffu, qv[gi], sh);
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+                const float rstd = rsqrtf(qv[gi] * (1.0f / FF_C) + 1e-5f);
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                     const int c0 = l8 * 12 + q * 4;                       // 4 channels = 8 bytes of bf16, inside one 16-byte unit
                     const float4 gm = *reinterpret_cast<const float4*>(gs + c0);
                     const float4 bt = *reinterpret_cast<const float4*>(bs + c0);
                     uint2 pk;
-                    pk.x = pack_bf16x2(fmaf(cur[q].x * rstd, gm.x, bt.x), fmaf(cur[q].y * rstd, gm.y, bt.y));
-                    pk.y = pack_bf16x2(fmaf(cur[q].z * rstd, gm.z, bt.z), fmaf(cur[q].w * rstd, gm.w, bt.w));
-                    // row rr = lw*32 + gi*4 + rsub; SWIZZLE_64B unit index ^= (rr >> 1) & 3 = ((gi & 1) << 1) | (rsub >> 1): the
-                    // gi-dependent part is a compile-time XOR of bit 5 plus a compile-time row offset (3 address registers, not 24)
+                    pk.x = pack_bf16x2(fmaf(v[gi][q].x * rstd, gm.x, bt.x), fmaf(v[gi][q].y * rstd, gm.y, bt.y));
+                    pk.y = pack_bf16x2(fmaf(v[gi][q].z * rstd, gm.z, bt.z), fmaf(v[gi][q].w * rstd, gm.w, bt.w));
+                    // row rr = ew*8 + gi*4 + rsub; SWIZZLE_64B unit index ^= (rr >> 1) & 3 = ((gi & 1) << 1) | (rsub >> 1): the
+                    // gi-dependent part is a compile-time XOR of bit 5 plus a compile-time row offset
                     *reinterpret_cast<uint2*>(a1 + ((a1_off[q] ^ ((gi & 1) << 5)) + gi * 256)) = pk;
                 }
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(a1_full);
-            if (lw == 0 && lane == 0) FF_TRACE(3, it, 2);
-        }
-    } else if (warp < FF_W_MMA2) {
-        // ============================================================ GELU warps: H_j (TMEM) -> bf16 A2 operand tile
-        // Two groups of 8 warps take alternate hidden chunks (group g: chunks g, g+2, g+4) so that while one group sits in
-        // the latency part of a chunk (barrier wait, TMEM load, async-proxy fence) the other group is issuing GELU math.
-        // With all 16 warps on the same chunk the phases were in lock-step and those latencies added to the math time.
-        const int ew = warp - FF_W_GELU;
-        const int quad = warp & 3;
-        const int grp = ew >> 3;          // chunk parity this warp works on == A2 buffer it fills
-        const int half = (ew >> 2) & 1;   // which 32 of the chunk's 64 hidden columns
-        const int row = quad * 32 + lane; // row inside the tile == TMEM lane
+            if (ew == 0 && lane == 0) FF_TRACE(3, lt, 2);
+        };
+
+        prefetch_tile(blockIdx.x);
+        if (my_tiles > 0) layernorm_tile(blockIdx.x, 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
 #pragma unroll
@@ -379,7 +387,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                 const int g = it * FF_NCH + j;              // global chunk index of this CTA
                 const int hb = g & (FF_NHB - 1);
                 if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 0);
-                mbar_wait(&h_full[hb], (g >> 2) & 1);
+                mbar_wait_parked(&h_full[hb], (g >> 2) & 1);
                 if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 1);
                 tc_fence_after();
                 uint32_t pk[16];
@@ -397,12 +405,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
                         const float4 b4 = *reinterpret_cast<const float4*>(bb + i);
-                        pk[s * 8 + i / 2] = gelu_erf_f16x2(__uint_as_float(v[i]) + b4.x, __uint_as_float(v[i + 1]) + b4.y);
-                        pk[s * 8 + i / 2 + 1] = gelu_erf_f16x2(__uint_as_float(v[i + 2]) + b4.z, __uint_as_float(v[i + 3]) + b4.w);
+                        pk[s * 8 + i / 2] = gelu_erf_f16x2_halved(fmaf(__uint_as_float(v[i]), 0.5f, b4.x), fmaf(__uint_as_float(v[i + 1]), 0.5f, b4.y));
+                        pk[s * 8 + i / 2 + 1] = gelu_erf_f16x2_halved(fmaf(__uint_as_float(v[i + 2]), 0.5f, b4.z), fmaf(__uint_as_float(v[i + 3]), 0.5f, b4.w));
                     }
                 }
                 if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 2);
-                mbar_wait(&a2_free[grp], ((g >> 1) & 1) ^ 1);   // fc2 MMAs that read the previous contents have retired
+                mbar_wait_parked(&a2_free[grp], ((g >> 1) & 1) ^ 1);   // fc2 MMAs that read the previous contents have retired
                 if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 3);
                 uint8_t* rowp = smem + FF_A2_OFF + grp * FF_A2_BYTES + row * 128;
                 const int sw = row & 7;
@@ -413,6 +421,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a2_full[grp]);
                 if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 4);
+                if (jj == grp && tile + (int)gridDim.x < num_tiles) layernorm_tile(tile + gridDim.x, it + 1);
             }
         }
     }

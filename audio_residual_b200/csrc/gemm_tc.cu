@@ -132,8 +132,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
-        // ===================================================== TMA producer
-        if (lane == 0) {
+        // ===================================================== TMA producer (warp-convergent loop, one elected lane issues)
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
@@ -142,23 +142,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
-                    if constexpr (PAIR) {
-                        // both CTAs load their halves; all bytes are counted on the leader's barrier, armed by the leader
-                        if (pair_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-                        tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * TILE_M + (int)pair_rank * GEMM_BM);
-                        tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN + (int)pair_rank * (BN / 2));
-                    } else {
-                        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                        tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
-                        tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+                    if (elect_one_sync()) {
+                        if constexpr (PAIR) {
+                            // both CTAs load their halves; all bytes are counted on the leader's barrier, armed by the leader
+                            if (pair_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * TILE_M + (int)pair_rank * GEMM_BM);
+                            tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN + (int)pair_rank * (BN / 2));
+                        } else {
+                            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                            tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+                            tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer (one thread)
-        if (lane == 0 && pair_rank == 0) {
+        // ===================================================== MMA issuer
+        // The whole warp runs the loop and one elected lane issues: in warp-convergent code the descriptors, TMEM address and
+        // loop state stay on the uniform datapath and a k-block's UTCHMMAs are emitted back to back. Issued from a lane-0 branch
+        // every MMA cost ~12 SASS instructions (R2UR per operand, ELECT / BRA.U.ANY wrapper), ~85 cycles on a busy scheduler:
+        // more than a BN <= 128 MMA takes to execute.
+        if (pair_rank == 0) {
             const uint32_t idesc = p.ab_f16 ? umma_idesc_f16(TILE_M, BN) : umma_idesc_bf16(TILE_M, BN);
             int stage = 0;
             uint32_t phase = 0;
@@ -176,19 +183,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint64_t da = umma_desc_sw128(sa);
                     const uint64_t db = umma_desc_sw128(sa + Cfg::A_BYTES);
-                    const int ksteps = min(GEMM_BK, p.K - kb * GEMM_BK) >> 4;
-                    for (int k = 0; k < ksteps; ++k) {
-                        if constexpr (PAIR) umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                        else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    const int ksteps = min(GEMM_BK, p.K - kb * GEMM_BK) >> 4;   // 4, or 1..3 in the last k-block (K % 16 == 0)
+                    if (elect_one_sync()) {
+                        if (ksteps == 4) {
+                            umma_f16_ss_run<4, PAIR>(d_tmem, da, db, idesc, kb != 0);
+                        } else {
+                            if (ksteps >= 2) umma_f16_ss_run<2, PAIR>(d_tmem, da, db, idesc, kb != 0);
+                            if (ksteps & 1) {
+                                const int k = ksteps - 1;
+                                if constexpr (PAIR) umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                                else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            }
+                        }
+                        // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+                        if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
+                        else umma_commit(&empty_bar[stage]);
+                        // accumulator ready (each CTA's epilogue reads its own 128 rows out of its own TMEM)
+                        if (kb == num_kb - 1) {
+                            if constexpr (PAIR) umma_commit_pair(&tfull_bar[as]);
+                            else umma_commit(&tfull_bar[as]);
+                        }
                     }
-                    // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-                    if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
-                    else umma_commit(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                // accumulator ready (each CTA's epilogue reads its own 128 rows out of its own TMEM)
-                if constexpr (PAIR) umma_commit_pair(&tfull_bar[as]);
-                else umma_commit(&tfull_bar[as]);
             }
         }
     } else {
@@ -237,7 +255,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld_32x32b_x32(tmem_base + as * Cfg::ACC_COLS + c * 32 + ((uint32_t)(quad * 32) << 16), v);
             // stage this chunk's bias while the TMEM load is in flight
             __syncwarp();
-            bias_w[lane] = (p.bias != nullptr && col0 + lane < p.N) ? __ldg(p.bias + col0 + lane) : 0.0f;
+            const bool gelu_half = OUT_BF16 && p.act == 1 && p.out_f16;   // GELU done below in packed fp16, on x / 2
+            const float pre_scale = gelu_half ? 0.5f : 1.0f;
+            bias_w[lane] = (p.bias != nullptr && col0 + lane < p.N) ? pre_scale * __ldg(p.bias + col0 + lane) : 0.0f;
             __syncwarp();
             tmem_ld_wait();
             if (nc == grp) {                       // last chunk of the tile: all TMEM reads of this tile by this warp are done
@@ -252,12 +272,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(bias_w + j);
-                f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
-                f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-                f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-                f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+                f[j + 0] = fmaf(__uint_as_float(v[j + 0]), pre_scale, b4.x);
+                f[j + 1] = fmaf(__uint_as_float(v[j + 1]), pre_scale, b4.y);
+                f[j + 2] = fmaf(__uint_as_float(v[j + 2]), pre_scale, b4.z);
+                f[j + 3] = fmaf(__uint_as_float(v[j + 3]), pre_scale, b4.w);
             }
-            const bool gelu_half = OUT_BF16 && p.act == 1 && p.out_f16;   // GELU done below in packed fp16
             if (p.act == 1 && !gelu_half) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
@@ -324,10 +343,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int q = 0; q < 4; ++q) {
                     uint4 u;
                     if (gelu_half) {
-                        u.x = gelu_erf_f16x2(f[q * 8 + 0], f[q * 8 + 1]);
-                        u.y = gelu_erf_f16x2(f[q * 8 + 2], f[q * 8 + 3]);
-                        u.z = gelu_erf_f16x2(f[q * 8 + 4], f[q * 8 + 5]);
-                        u.w = gelu_erf_f16x2(f[q * 8 + 6], f[q * 8 + 7]);
+                        u.x = gelu_erf_f16x2_halved(f[q * 8 + 0], f[q * 8 + 1]);
+                        u.y = gelu_erf_f16x2_halved(f[q * 8 + 2], f[q * 8 + 3]);
+                        u.z = gelu_erf_f16x2_halved(f[q * 8 + 4], f[q * 8 + 5]);
+                        u.w = gelu_erf_f16x2_halved(f[q * 8 + 6], f[q * 8 + 7]);
                     } else {
                         u.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
                         u.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
