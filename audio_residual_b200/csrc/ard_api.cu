@@ -185,6 +185,11 @@ static int finalize(ard_handle* h, cudaStream_t) {
             ARD_TRY(get(h, p + "attn.proj.bias", C, &v)); ARD_TRY(upload_f32(bw.proj_b, *v));
             ARD_TRY(get(h, p + "mlp.fc1.weight", (size_t)4 * C * C, &v)); ARD_TRY(upload_bf16(bw.fc1_w, *v));
             ARD_TRY(get(h, p + "mlp.fc1.bias", (size_t)4 * C, &v)); ARD_TRY(upload_f32(bw.fc1_b, *v));
+            {
+                std::vector<float> hb(*v);
+                for (auto& t : hb) t *= 0.5f;
+                ARD_TRY(upload_f32(bw.fc1_b_half, hb));   // ffn_wide's packed GELU takes x / 2
+            }
             ARD_TRY(get(h, p + "mlp.fc2.weight", (size_t)4 * C * C, &v)); ARD_TRY(upload_f16(bw.fc2_w, *v));   // hidden activations are fp16
             ARD_TRY(get(h, p + "mlp.fc2.bias", C, &v)); ARD_TRY(upload_f32(bw.fc2_b, *v));
             ARD_TRY(get(h, p + "attn.relative_position_bias_table", (size_t)225 * nH, &v)); ARD_TRY(upload_f32(bw.rpb, *v));
@@ -284,10 +289,19 @@ static int run_block(ard_handle* h, int l, int b, int B, float* X, float* Y, flo
     ARD_TRY(gemm_bf16(g, h->num_sms, s));
     // FFN: (Y) -> LN2 -> fc1+GELU -> fc2
     // one FFN: out = in + mlp(norm2(in)) (+ r2 inside the fused kernel). `pre_add`: the LayerNorm input is in + pre_add, written back to `in`.
+    // ffn_wide (weights streamed from L2) is used where it measures faster than LayerNorm + two GEMMs: the plain FFN of the
+    // 192-channel stage (249 vs 341 us at B = 256 incl. the shortcut add). With a second residual (344 vs 339 us) and at
+    // C = 384 (254 vs 200 us: three ring slots cannot cover the L2 latency) the unfused chain stays. ARD_FUSED_FFN_WIDE=2 forces
+    // it everywhere (A/B measurements), =0 disables it.
+    const bool wide = (C == 192 || C == 384) && h->use_fused_ffn_wide == 2;
+    const bool wide_plain = C == 192 && h->use_fused_ffn_wide == 1;
     auto ffn = [&](float* in, float* out, const float* r2, const float* pre_add) -> int {
         if (C == 96 && h->use_fused_ffn && pre_add == nullptr)   // whole FFN in one kernel, hidden activation never leaves the SM
             return ffn_fused_96(in, r2, out, M, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), bw.fc1_w.as<__nv_bfloat16>(), bw.fc1_b.as<float>(),
                                 bw.fc2_w.as<__half>(), bw.fc2_b.as<float>(), h->num_sms, s);
+        if ((wide || (wide_plain && r2 == nullptr)) && pre_add == nullptr)   // same, weights streamed from L2
+            return ffn_fused_wide(in, r2, out, M, C, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), bw.fc1_w.as<__nv_bfloat16>(),
+                                  bw.fc1_b_half.as<float>(), bw.fc2_w.as<__half>(), bw.fc2_b.as<float>(), h->num_sms, s);
         if (pre_add)
             ARD_TRY(add_layernorm_bf16(in, pre_add, in, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), XN, M, C, s));
         else
@@ -304,9 +318,12 @@ static int run_block(ard_handle* h, int l, int b, int B, float* X, float* Y, flo
     };
     if (!bw.has_res) {
         ARD_TRY(ffn(Y, X, nullptr, nullptr));          // x = x1 + mlp(norm2(x1))                       htsat.py:480
-    } else if (C == 96 && h->use_fused_ffn) {
+    } else if ((C == 96 && h->use_fused_ffn) || wide) {
         ARD_TRY(ffn(Y, Y, X, nullptr));                // x3 = shortcut + (x1 + mlp(norm2(x1)))         src/residual.py:93,95
         ARD_TRY(ffn(Y, X, nullptr, nullptr));          // x4 = x3 + mlp(norm2(x3))                      src/residual.py:96
+    } else if (wide_plain) {
+        ARD_TRY(ffn(Y, Y, X, nullptr));                // x3 via the fc2 GEMM's two-residual epilogue, then the fused kernel
+        ARD_TRY(ffn(Y, X, nullptr, nullptr));
     } else {
         ARD_TRY(ffn(Y, Y, nullptr, nullptr));          // x2 = x1 + mlp(norm2(x1))                      src/residual.py:93
         ARD_TRY(ffn(Y, X, nullptr, X));                // x3 = shortcut + x2 (fused into the norm2 pass), x4 = x3 + mlp(norm2(x3))   :95-96
@@ -431,6 +448,7 @@ int ard_create(const ard_config* cfg, ard_handle** out) {
     }
     h->num_sms = sms;
     if (const char* e = getenv("ARD_FUSED_FFN")) h->use_fused_ffn = atoi(e) != 0;
+    if (const char* e = getenv("ARD_FUSED_FFN_WIDE")) h->use_fused_ffn_wide = atoi(e);
     *out = h;
     return 0;
 }
@@ -587,6 +605,15 @@ int ard_ffn_fused_96(const float* x, const float* resid2, float* out, long long 
         return set_error(ARD_ERR_CUDA, "no CUDA device");
     return ffn_fused_96(x, resid2, out, M, gamma, beta, (const __nv_bfloat16*)w1_bf16, b1, (const __half*)w2_f16, b2, sms,
                         (cudaStream_t)stream);
+}
+
+int ard_ffn_fused_wide(const float* x, const float* resid2, float* out, long long M, int C, const float* gamma, const float* beta,
+                       const void* w1_bf16, const float* b1_half, const void* w2_f16, const float* b2, void* stream) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return set_error(ARD_ERR_CUDA, "no CUDA device");
+    return ffn_fused_wide(x, resid2, out, M, C, gamma, beta, (const __nv_bfloat16*)w1_bf16, b1_half, (const __half*)w2_f16, b2, sms,
+                          (cudaStream_t)stream);
 }
 
 int ard_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int C, void* stream) {

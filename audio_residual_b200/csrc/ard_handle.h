@@ -26,7 +26,7 @@ struct DevBuf {
 
 struct BlockW {
     DevBuf ln1_g, ln1_b, ln2_g, ln2_b;
-    DevBuf qkv_w, qkv_b, proj_w, proj_b, proj_w_f32, fc1_w, fc1_b, fc2_w, fc2_b, rpb;
+    DevBuf qkv_w, qkv_b, proj_w, proj_b, proj_w_f32, fc1_w, fc1_b, fc1_b_half, fc2_w, fc2_b, rpb;
     // ResiDual (src/residual.py:14-42) injected after this block's attention
     bool has_res = false, lambda_set = false;
     int K = 0;
@@ -67,6 +67,7 @@ struct ard_handle {
     DevBuf ws_logmel, ws_x, ws_y, ws_xn, ws_ao, ws_qkv, ws_h, ws_normed, ws_emb, ws_hid, ws_proj, ws_tscam_a, ws_tscam_y, ws_wave;
     int last_launches = 0;
     bool use_fused_ffn = true;   // ARD_FUSED_FFN=0 disables the fused 96-channel FFN kernel (A/B measurements)
+    int use_fused_ffn_wide = 1;    // ARD_FUSED_FFN_WIDE: 0 never, 1 where it measures faster (default), 2 for every C = 192 / 384 FFN
     // training state
     DevBuf tape, p0_wT, p2_wT, t_emb, t_hid, t_proj;
     DevBuf bw_g, bw_gs, bw_t, bw_hpre, bw_dh, bw_gqkv, bw_gb, bw_coef, bw_gcoef, bw_gsc, bw_small;

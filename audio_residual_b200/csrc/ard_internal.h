@@ -62,6 +62,10 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t in
 int ffn_fused_96(const float* x, const float* resid2, float* out, long long M, const float* gamma, const float* beta,
                  const __nv_bfloat16* w1, const float* b1, const __half* w2_f16, const float* b2, int num_sms, cudaStream_t stream);
 
+// same for the 192- / 384-channel stages, weights streamed from L2 through a TMA ring (ffn_wide.cu). b1_half = 0.5 * fc1 bias.
+int ffn_fused_wide(const float* x, const float* resid2, float* out, long long M, int C, const float* gamma, const float* beta,
+                   const __nv_bfloat16* w1, const float* b1_half, const __half* w2_f16, const float* b2, int num_sms, cudaStream_t stream);
+
 // ---------------------------------------------------------------- row-wise kernels (rowwise.cu)
 // LayerNorm over the last dim C of x[rows, C] (fp32) -> bf16; two-pass variance like at::native layer_norm.
 int layernorm_bf16(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, long long rows, int C, cudaStream_t s);

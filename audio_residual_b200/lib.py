@@ -9,7 +9,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libard_b200.so")
+LIB_PATH = os.environ.get("ARD_LIB_PATH") or os.path.join(_HERE, "libard_b200.so")   # ARD_LIB_PATH: A/B builds of the same ABI (tools/)
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "ard.h")
 
 ARD_OK, ARD_ERR_SHAPE, ARD_ERR_DTYPE, ARD_ERR_CUDA, ARD_ERR_STATE, ARD_ERR_KEY, ARD_ERR_NOTIMPL = 0, -1, -2, -3, -4, -5, -6
@@ -73,6 +73,7 @@ def load(check_symbols=False):
         lib.ard_gemm_f16.argtypes = [vp, ll, vp, ll, vp, ll, i, i, i, i, vp, i, vp, ll, vp, ll, vp]
         lib.ard_layernorm_bf16.argtypes = [vp, vp, vp, vp, ll, i, vp]
         lib.ard_ffn_fused_96.argtypes = [vp, vp, vp, ll, vp, vp, vp, vp, vp, vp, vp]
+        lib.ard_ffn_fused_wide.argtypes = [vp, vp, vp, ll, i, vp, vp, vp, vp, vp, vp, vp]
         lib.ard_window_attention.argtypes = [vp, vp, vp, vp, f, i, i, i, i, i, i, i, vp]
         lib.ard_window_attention_bwd.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, vp]
         lib.ard_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, ll, i, vp]

@@ -142,6 +142,10 @@ int ard_gemm_f16(const void* A, long long lda, const void* W, long long ldw, voi
  * w1 [384,96] bf16, w2 [96,384] fp16 (the hidden activation is fp16), device; b1 [384], b2 [96] fp32 device. */
 int ard_ffn_fused_96(const float* x, const float* resid2, float* out, long long M, const float* gamma, const float* beta, const void* w1_bf16,
                      const float* b1, const void* w2_f16, const float* b2, void* stream);
+/* The same FFN for the 192- and 384-channel stages (C = 192 | 384): w1 [4C,C] bf16, w2 [C,4C] fp16, streamed from L2 per
+ * 128-token tile. b1_half = 0.5 * fc1 bias [4C] (the packed-fp16 GELU is evaluated on x / 2). */
+int ard_ffn_fused_wide(const float* x, const float* resid2, float* out, long long M, int C, const float* gamma, const float* beta,
+                       const void* w1_bf16, const float* b1_half, const void* w2_f16, const float* b2, void* stream);
 /* nn.LayerNorm(C, eps=1e-5) over x[rows, C] fp32 -> bf16 (htsat.py:449,479 norm1/norm2). */
 int ard_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int C, void* stream);
 /* Shifted-window attention core of WindowAttention.forward (htsat.py:326-352) incl. roll/partition/reverse addressing

@@ -77,11 +77,11 @@ def check_gemm(M, N, K, out_bf16, act=0, bias=True, nres=0, seed=0):
     return rel(got, ref), (got - ref).abs().max().item()
 
 
-def check_ffn_fused(M=5000, resid2=True, seed=0):
-    """ard_ffn_fused_96 (LN + fc1 + GELU + fc2 + residuals in one kernel) vs torch fp32 on bf16/fp16-rounded weights."""
+def check_ffn_fused(M=5000, resid2=True, seed=0, Cd=96, alias=False):
+    """ard_ffn_fused_96 / ard_ffn_fused_wide (LN + fc1 + GELU + fc2 + residuals in one kernel) vs torch fp32 on bf16/fp16-rounded
+    weights. `alias`: the output overwrites x (how the forward schedule calls it)."""
     lib = L.load()
     g = torch.Generator().manual_seed(seed)
-    Cd = 96
     x = torch.randn(M, Cd, generator=g) * 1.5 + 0.3
     r2 = torch.randn(M, Cd, generator=g) if resid2 else None
     gm, bt = 1 + 0.1 * torch.randn(Cd, generator=g), 0.1 * torch.randn(Cd, generator=g)
@@ -95,9 +95,14 @@ def check_ffn_fused(M=5000, resid2=True, seed=0):
     d = lambda t: t.cuda().contiguous()
     xd, r2d, gd, btd = d(x), (d(r2) if resid2 else None), d(gm), d(bt)
     w1d, w2d, b1d, b2d = d(w1).to(torch.bfloat16), d(w2).to(torch.float16), d(b1), d(b2)
-    out = torch.empty_like(xd)
-    L.check(lib.ard_ffn_fused_96(L.ptr(xd), L.ptr(r2d), L.ptr(out), M, L.ptr(gd), L.ptr(btd), L.ptr(w1d), L.ptr(b1d), L.ptr(w2d), L.ptr(b2d),
-                                 L.stream_ptr()))
+    out = xd if alias else torch.empty_like(xd)
+    if Cd == 96:
+        L.check(lib.ard_ffn_fused_96(L.ptr(xd), L.ptr(r2d), L.ptr(out), M, L.ptr(gd), L.ptr(btd), L.ptr(w1d), L.ptr(b1d), L.ptr(w2d), L.ptr(b2d),
+                                     L.stream_ptr()))
+    else:
+        b1h = (0.5 * b1d).contiguous()
+        L.check(lib.ard_ffn_fused_wide(L.ptr(xd), L.ptr(r2d), L.ptr(out), M, Cd, L.ptr(gd), L.ptr(btd), L.ptr(w1d), L.ptr(b1h), L.ptr(w2d),
+                                       L.ptr(b2d), L.stream_ptr()))
     torch.cuda.synchronize()
     got_branch = out.cpu() - x - (r2 if resid2 else 0)
     return rel(out.cpu(), ref), rel(got_branch, branch)

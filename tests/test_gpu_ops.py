@@ -38,6 +38,13 @@ def test_ffn_fused_96(M, resid2):
     assert r_out < 2e-3 and r_branch < 5e-3, (r_out, r_branch)     # bf16 LN output / fp16 hidden operands, fp32 accumulation
 
 
+@pytest.mark.parametrize("C,M,resid2,alias", [(192, 128, False, False), (192, 5000, True, True), (192, 148 * 128 * 3 + 77, True, False),
+                                             (384, 100, False, True), (384, 5000, True, False), (384, 148 * 128 * 2 + 300, False, True)])
+def test_ffn_fused_wide(C, M, resid2, alias):
+    r_out, r_branch = G.check_ffn_fused(M, resid2, Cd=C, alias=alias)
+    assert r_out < 2e-3 and r_branch < 5e-3, (C, M, r_out, r_branch)
+
+
 def test_gemm_f16_hidden_chain():
     r_h, r_out = G.check_gemm_f16_chain()
     assert r_h < 1e-3 and r_out < 2e-3, (r_h, r_out)                # fp16 hidden: 10-bit mantissa

@@ -85,6 +85,35 @@ def bench_ffn():
     report(f"unfused LN+fc1+fc2 M={M}", us, 2.0 * M * C * 4 * C * 2, 34.0 * M * C)
 
 
+def bench_ffn_wide():
+    lib = L.load()
+    st = L.stream_ptr()
+    for T, C in ((1024, 192), (256, 384)):
+        M = B * T
+        x = torch.randn(M, C, device=dev)
+        r2 = torch.randn(M, C, device=dev)
+        out = torch.empty_like(x)
+        g, bt = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        w1 = (torch.randn(4 * C, C, device=dev) / C ** 0.5).to(torch.bfloat16)
+        w2 = (torch.randn(C, 4 * C, device=dev) / (4 * C) ** 0.5).to(torch.float16)
+        b1, b2 = torch.randn(4 * C, device=dev), torch.randn(C, device=dev)
+        b1h = 0.5 * b1
+        xn = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
+        hb = torch.empty(M, 4 * C, device=dev, dtype=torch.bfloat16)
+        for name, rr in ((f"ffn_fused_wide C={C}", None), (f"ffn_fused_wide C={C} +resid2", r2)):
+            def fn():
+                L.check(lib.ard_ffn_fused_wide(L.ptr(x), L.ptr(rr), L.ptr(out), M, C, L.ptr(g), L.ptr(bt), L.ptr(w1), L.ptr(b1h), L.ptr(w2), L.ptr(b2), st))
+            us = timeit(fn)
+            report(f"{name} M={M}", us, 2.0 * M * C * 4 * C * 2, 4.0 * M * C * (2 + (rr is not None)))
+
+        def unfused():
+            L.check(lib.ard_layernorm_bf16(L.ptr(x), L.ptr(g), L.ptr(bt), L.ptr(xn), M, C, st))
+            L.check(lib.ard_gemm_bf16(L.ptr(xn), C, L.ptr(w1), C, L.ptr(hb), 4 * C, 1, M, 4 * C, C, L.ptr(b1), 3, None, 0, None, 0, st))
+            L.check(lib.ard_gemm_f16(L.ptr(hb), 4 * C, L.ptr(w2), 4 * C, L.ptr(out), C, 0, M, C, 4 * C, L.ptr(b2), 0, L.ptr(x), C, None, 0, st))
+        us = timeit(unfused)
+        report(f"unfused LN+fc1+fc2 C={C} M={M}", us, 2.0 * M * C * 4 * C * 2, 34.0 * M * C)
+
+
 def bench_attn():
     lib = L.load()
     st = L.stream_ptr()
@@ -133,7 +162,7 @@ def bench_front():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gemm", "ffn", "attn", "ln", "front"]
+    which = sys.argv[1:] or ["gemm", "ffn", "ffnw", "attn", "ln", "front"]
     print(torch.cuda.get_device_name(0), "B =", B, flush=True)
     for w in which:
-        {"gemm": bench_gemm, "ffn": bench_ffn, "attn": bench_attn, "ln": bench_ln, "front": bench_front}[w]()
+        {"gemm": bench_gemm, "ffn": bench_ffn, "ffnw": bench_ffn_wide, "attn": bench_attn, "ln": bench_ln, "front": bench_front}[w]()
