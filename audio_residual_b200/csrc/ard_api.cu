@@ -449,6 +449,7 @@ int ard_create(const ard_config* cfg, ard_handle** out) {
     h->num_sms = sms;
     if (const char* e = getenv("ARD_FUSED_FFN")) h->use_fused_ffn = atoi(e) != 0;
     if (const char* e = getenv("ARD_FUSED_FFN_WIDE")) h->use_fused_ffn_wide = atoi(e);
+    if (const char* e = getenv("ARD_GRAPHS")) h->use_graphs = atoi(e);
     *out = h;
     return 0;
 }
@@ -462,6 +463,7 @@ int ard_set_weight(ard_handle* h, const char* key, const float* data, long long 
     if (!h || !key || !data || numel <= 0) return set_error(ARD_ERR_SHAPE, "ard_set_weight: bad argument");
     h->host[std::string(key)] = std::vector<float>(data, data + numel);
     h->finalized = false;
+    ++h->graph_epoch;
     return 0;
 }
 
@@ -477,6 +479,7 @@ int ard_set_block_residual(ard_handle* h, int layer, int block, const float* mea
     const int C = C_of(h, layer);
     if (D != C || K <= 0 || K > D) return set_error(ARD_ERR_SHAPE, "ResiDual basis [%d,%d] does not match layer width %d", K, D, C);
     BlockW& bw = h->layers[layer].blocks[block];
+    ++h->graph_epoch;
     bw.K = K;
     bw.h_mean.assign(mean, mean + D);
     bw.h_basis.assign(basis, basis + (size_t)K * D);
@@ -501,6 +504,7 @@ int ard_set_block_residual(ard_handle* h, int layer, int block, const float* mea
 int ard_clear_block_residual(ard_handle* h, int layer, int block) {
     if (!h || layer < 0 || layer >= h->nlayers || block < 0 || block >= h->cfg.depths[layer]) return set_error(ARD_ERR_SHAPE, "bad block index");
     h->layers[layer].blocks[block].has_res = false;
+    ++h->graph_epoch;
     return 0;
 }
 
@@ -522,10 +526,90 @@ int ard_set_block_lambda(ard_handle* h, int layer, int block, const float* lambd
     return 0;
 }
 
+// Inference forward with only the pooled outputs requested: replayed from a CUDA graph keyed by (input pointer, batch,
+// quantize, audio_embed wanted). First use runs kernel by kernel (allocates workspaces, folds lambdas), second use captures,
+// later uses replay. The graph writes handle-owned output buffers; two small device copies hand the result to the caller, so
+// freshly allocated output tensors do not defeat the cache. Anything that moves a device buffer or changes the schedule
+// (weights, ResiDual injection, a larger workspace) bumps an epoch and the entry is re-captured.
+static int forward_graphed(ard_handle* h, const ard_forward_args* args, cudaStream_t s, bool* handled) {
+    *handled = false;
+    const bool eligible = h->use_graphs && h->finalized && !g_prof_on && !args->save_for_backward && args->B > 0 && args->embedding &&
+                          !args->framewise_output && !args->clipwise_output && !args->fine_grained_embedding &&
+                          !args->layers_residuals[0] && !args->layers_residuals[1] && !args->layers_residuals[2] && !args->layers_residuals[3] &&
+                          !args->layers_attention[0] && !args->layers_attention[1] && !args->layers_attention[2] && !args->layers_attention[3];
+    if (!eligible) return 0;
+    const void* src = h->cfg.enable_fusion ? (const void*)args->mel_fusion : (const void*)args->waveform;
+    if (!src) return 0;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return 0;   // the caller is capturing: stay out of it
+    const int NF = C_of(h, h->nlayers - 1), J = h->cfg.joint_dim, B = args->B;
+    ard_handle::GraphKey key{src, B, args->quantize, args->audio_embed != nullptr};
+    auto it = h->graphs.find(key);
+    const bool fresh = it != h->graphs.end() && it->second.epoch == h->graph_epoch && it->second.aepoch == alloc_epoch();
+    if (!fresh) {
+        // first sighting (or stale): run eagerly, make sure everything a capture must not allocate exists, remember the key
+        if (it != h->graphs.end() && it->second.exec) { cudaGraphExecDestroy(it->second.exec); it->second.exec = nullptr; }
+        if (h->graphs.size() >= 32 && it == h->graphs.end()) {   // bounded cache: drop the least recently used entry
+            auto lru = h->graphs.begin();
+            for (auto jt = h->graphs.begin(); jt != h->graphs.end(); ++jt)
+                if (jt->second.last_use < lru->second.last_use) lru = jt;
+            if (lru->second.exec) cudaGraphExecDestroy(lru->second.exec);
+            h->graphs.erase(lru);
+        }
+        const int rc = encoder_forward(h, args, s);
+        *handled = true;
+        if (rc) return rc;
+        ARD_TRY(h->g_emb.ensure((size_t)B * NF * 4));
+        ARD_TRY(h->g_ae.ensure((size_t)B * J * 4));
+        ard_handle::GraphEntry e;
+        e.epoch = h->graph_epoch; e.aepoch = alloc_epoch(); e.last_use = ++h->graph_clock;
+        h->graphs[key] = e;
+        return 0;
+    }
+    ard_handle::GraphEntry& e = it->second;
+    e.last_use = ++h->graph_clock;
+    if (!e.exec) {
+        ard_forward_args a2 = *args;
+        a2.embedding = h->g_emb.as<float>();
+        if (args->audio_embed) a2.audio_embed = h->g_ae.as<float>();
+        const int before = g_launches;
+        if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError(); h->cap_stream = nullptr; h->use_graphs = 0; return 0;
+        }
+        if (cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); h->use_graphs = 0; return 0; }
+        const int rc = encoder_forward(h, &a2, h->cap_stream);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+        const int captured = g_launches - before;
+        g_launches = before; g_launch_total -= captured;      // nothing ran yet
+        if (rc || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            h->graphs.erase(it);
+            return 0;                                          // fall back to the eager path
+        }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess || !exec) { cudaGetLastError(); h->graphs.erase(it); return 0; }
+        e.exec = exec;
+        e.launches = captured;
+    }
+    ARD_CUDA(cudaGraphLaunch(e.exec, s));
+    count_launch(e.launches);
+    ARD_CUDA(cudaMemcpyAsync(args->embedding, h->g_emb.p, (size_t)B * NF * 4, cudaMemcpyDeviceToDevice, s));
+    if (args->audio_embed) ARD_CUDA(cudaMemcpyAsync(args->audio_embed, h->g_ae.p, (size_t)B * J * 4, cudaMemcpyDeviceToDevice, s));
+    h->tape_B = 0;
+    *handled = true;
+    return 0;
+}
+
 int ard_encoder_forward(ard_handle* h, const ard_forward_args* args, void* stream) {
     if (!h || !args) return set_error(ARD_ERR_SHAPE, "null argument");
     g_launches = 0;
-    const int rc = encoder_forward(h, args, (cudaStream_t)stream);
+    bool handled = false;
+    int rc = forward_graphed(h, args, (cudaStream_t)stream, &handled);
+    if (!handled && rc == 0) rc = encoder_forward(h, args, (cudaStream_t)stream);
     h->last_launches = g_launches;
     return rc;
 }

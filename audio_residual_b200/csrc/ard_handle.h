@@ -9,12 +9,19 @@
 namespace ard {
 
 // ------------------------------------------------------------------------------------------------ device buffers
+// bumped whenever a device buffer is (re)allocated: captured CUDA graphs hold raw pointers and are stale afterwards
+inline unsigned long long& alloc_epoch() {
+    static unsigned long long e = 0;
+    return e;
+}
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
     ~DevBuf() { if (p) cudaFree(p); }
     int ensure(size_t n) {
         if (n <= bytes) return 0;
+        ++alloc_epoch();
         if (p) { cudaFree(p); p = nullptr; bytes = 0; }
         cudaError_t e = cudaMalloc(&p, n);
         if (e != cudaSuccess) { p = nullptr; return set_error(ARD_ERR_CUDA, "cudaMalloc(%zu): %s", n, cudaGetErrorString(e)); }
@@ -72,6 +79,35 @@ struct ard_handle {
     DevBuf tape, p0_wT, p2_wT, t_emb, t_hid, t_proj;
     DevBuf bw_g, bw_gs, bw_t, bw_hpre, bw_dh, bw_gqkv, bw_gb, bw_coef, bw_gcoef, bw_gsc, bw_small;
     int tape_B = 0;          // batch of the forward whose activations the tape holds (0: none)
+    // CUDA-graph replay of the inference forward (ard_api.cu): the ~110 launches of a forward cost ~1.1 ms of fixed launch /
+    // ramp latency whatever the batch; replaying a captured graph removes the host side of that and most of the device side.
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;   // null: this (input, batch) was seen once and ran eagerly; captured on its next use
+        unsigned long long epoch = 0, aepoch = 0;
+        int launches = 0;
+        unsigned long long last_use = 0;
+    };
+    struct GraphKey {
+        const void* src;
+        int B, quantize, want_ae;
+        bool operator<(const GraphKey& o) const {
+            if (src != o.src) return src < o.src;
+            if (B != o.B) return B < o.B;
+            if (quantize != o.quantize) return quantize < o.quantize;
+            return want_ae < o.want_ae;
+        }
+    };
+    std::map<GraphKey, GraphEntry> graphs;
+    unsigned long long graph_epoch = 0;   // bumped when weights / injected ResiDual modules change
+    unsigned long long graph_clock = 0;
+    int use_graphs = 1;                   // ARD_GRAPHS=0: always launch kernel by kernel
+    DevBuf g_emb, g_ae;                   // outputs of the captured forward, copied to the caller's tensors after each replay
+    cudaStream_t cap_stream = nullptr;    // capture happens on a private stream (the caller's may be the legacy default stream)
+    ~ard_handle() {
+        for (auto& kv : graphs)
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        if (cap_stream) cudaStreamDestroy(cap_stream);
+    }
 };
 
 

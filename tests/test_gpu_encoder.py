@@ -58,3 +58,39 @@ def test_argmax_predictions_identical_to_reference():
     m = G.check_argmax_vs_golden("htsat_tiny_b2.npz")
     assert m["zero_shot_argmax_mismatch"] == 0 and m["clipwise_argmax_mismatch"] == 0, m
     assert m["sims_max_abs_err"] < m["reference_top1_top2_margin"], m   # the agreement is not luck: error below the decision margin
+
+
+def test_graph_replay_is_bit_identical_and_tracks_lambda():
+    """The inference forward is replayed from a CUDA graph from the third call on the same input buffer: results must equal
+    the kernel-by-kernel launches bit for bit, follow in-place changes of the input and of lambda (re-folded weights are read
+    at replay time) and survive a larger batch re-allocating the workspace."""
+    import torch
+    from audio_residual_b200 import lib as L
+    clap, sd, _ = G.make_encoder("tiny", residual=True)
+    enc = clap.model.audio_branch
+    lib = L.load()
+    wave = G.W.make_clips(5, seed=3).cuda()
+    with torch.no_grad():
+        lib.ard_launch_counter_reset()
+        outs = [enc.encode(waveform=wave, want_audio_embed=True) for _ in range(4)]   # eager, capture + replay, replay, replay
+        per_call = lib.ard_launch_counter_read() / 4
+        for o in outs[1:]:
+            assert torch.equal(o["audio_embed"], outs[0]["audio_embed"]) and torch.equal(o["embedding"], outs[0]["embedding"])
+        assert per_call == int(per_call) and per_call > 50, per_call                  # replays are counted launch for launch
+        # new contents in the same buffer
+        wave2 = G.W.make_clips(5, seed=4).cuda()
+        ref2 = enc.encode(waveform=wave2, want_audio_embed=True)["audio_embed"].clone()   # different pointer: eager
+        wave.copy_(wave2)
+        assert torch.equal(enc.encode(waveform=wave, want_audio_embed=True)["audio_embed"], ref2)
+        # lambda changes between replays
+        lam = enc._lambda_params()[2]
+        lam.mul_(1.5)                      # in-place under no_grad: bumps the version the shim watches
+        got = enc.encode(waveform=wave, want_audio_embed=True)["audio_embed"].clone()
+        ref3 = enc.encode(waveform=wave2, want_audio_embed=True)["audio_embed"]          # second sighting of wave2: capture
+        assert torch.equal(got, ref3) and not torch.equal(got, ref2)
+        # a larger batch grows the workspace: stale graphs must be dropped, not replayed into freed memory
+        big = G.W.make_clips(9, seed=5).cuda()
+        enc.encode(waveform=big, want_audio_embed=True)
+        again = enc.encode(waveform=wave, want_audio_embed=True)["audio_embed"]
+        assert torch.equal(again, got)
+        torch.cuda.synchronize()
