@@ -34,6 +34,12 @@ int check_cuda(cudaError_t e, const char* what) {
     return set_error(ARD_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
 void count_launch(int n) { g_launches += n; g_launch_total += n; }
+bool pdl_enabled() {
+    // Off by default: measured on B200 (tools/batch_sweep.py) it does not shorten the forward (B = 1: 1.03 vs 1.01 ms, B = 256:
+    // 11.99 vs 11.57 ms) - successor CTAs that start early compete with the predecessor's tail for the SMs they share.
+    static const bool on = [] { const char* e = getenv("ARD_PDL"); return e != nullptr && atoi(e) != 0; }();
+    return on;
+}
 
 // ------------------------------------------------------------------------------------------------ profiling
 struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; };

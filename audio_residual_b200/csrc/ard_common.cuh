@@ -30,6 +30,15 @@ ARD_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
     return r;
 }
 
+// Programmatic dependent launch (enqueue_pdl in ard_internal.h): a kernel launched with the programmatic-serialization attribute
+// may START while its predecessor in the stream is still running. pdl_launch_dependents() (first statement of every kernel)
+// lets the successor's CTAs be scheduled as soon as SMs free up; pdl_wait() blocks until the predecessor grid has completed
+// and its writes are visible, and must precede the first access to any global buffer (reads AND writes: the predecessor may
+// still be reading what this kernel overwrites). Everything before it - barrier / TMEM / shared-memory set-up, descriptor
+// prefetch - overlaps the predecessor's tail. Both are no-ops in a kernel launched without the attribute.
+ARD_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+ARD_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------ mbarrier
 ARD_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -122,6 +122,21 @@ int tscam_finish(const float* y, int ldy, float* framewise, float* clipwise, int
 int fine_grained(const float* normed, float* fine, int B, int C, cudaStream_t s);
 int stats_accumulate(const float* x, long long rows, long long ldx, int D, double* sum, double* sumsq, cudaStream_t s);   // stats.cu
 
+// Launch with programmatic dependent launch allowed (see pdl_wait in ard_common.cuh). ONLY for kernels that call pdl_wait()
+// before their first global-memory access. ARD_PDL=0 launches them fully serialised (A/B measurements).
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline cudaError_t enqueue_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // launch accounting (ard_last_launch_count)
 void count_launch(int n = 1);
 

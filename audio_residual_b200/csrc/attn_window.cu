@@ -50,6 +50,8 @@ template <int HD>
 __global__ void __launch_bounds__(128) window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                                                                const float* __restrict__ bias_table, float* __restrict__ attn,
                                                                float attn_scale, int attn_acc, int H, int W, int C, int nH, int shift) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int UPH = HD / 8;             // 16-byte units per head row (3 or 4)
     constexpr int UPR = AT_HEADS * UPH;     // units per (row, q|k|v) segment for this CTA's 4 heads
     constexpr int NT_O = HD / 8;            // output n-tiles
@@ -538,11 +540,11 @@ int window_attention(const AttnArgs& a, cudaStream_t s) {
     const double tokens = (double)a.B * a.H * a.W;
     ProfScope ps(PROF_ATTN, s, 4.0 * tokens * 64 * a.C, tokens * a.C * 2.0 * 4.0 + (a.attn_mean ? tokens * a.nH * 64 * 4.0 * (a.attn_accumulate ? 2 : 1) : 0.0));
     if (hd == 24)
-        window_attention_kernel<24><<<(unsigned)blocks, 128, AT_SMEM_BYTES, s>>>(a.qkv, a.out, a.bias_table, a.attn_mean, a.attn_scale, a.attn_accumulate,
-                                                                    a.H, a.W, a.C, a.nH, shift);
+        ARD_CUDA(enqueue_pdl(window_attention_kernel<24>, dim3((unsigned)blocks), dim3(128), AT_SMEM_BYTES, s, a.qkv, a.out, a.bias_table, a.attn_mean,
+                            a.attn_scale, a.attn_accumulate, a.H, a.W, a.C, a.nH, shift));
     else if (hd == 32)
-        window_attention_kernel<32><<<(unsigned)blocks, 128, AT_SMEM_BYTES, s>>>(a.qkv, a.out, a.bias_table, a.attn_mean, a.attn_scale, a.attn_accumulate,
-                                                                    a.H, a.W, a.C, a.nH, shift);
+        ARD_CUDA(enqueue_pdl(window_attention_kernel<32>, dim3((unsigned)blocks), dim3(128), AT_SMEM_BYTES, s, a.qkv, a.out, a.bias_table, a.attn_mean,
+                            a.attn_scale, a.attn_accumulate, a.H, a.W, a.C, a.nH, shift));
     else
         return set_error(ARD_ERR_SHAPE, "window_attention: head_dim %d unsupported (24 or 32)", hd);
     return check_cuda(cudaGetLastError(), "window_attention launch");

@@ -98,10 +98,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     uint64_t* y_free = bars + 17;   // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 19);
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = (p.M + FF_BM - 1) / FF_BM;
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
+    // (biases / LayerNorm affine are weights, never written by a predecessor kernel: safe to read before pdl_wait)
     for (int i = threadIdx.x; i < FF_HD; i += FF_THREADS) b1s[i] = 0.5f * p.b1[i];   // the GELU takes x / 2 (gelu_erf_f16x2_halved)
     for (int i = threadIdx.x; i < FF_C; i += FF_THREADS) {
         b2s[i] = p.b2[i];
@@ -135,6 +137,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();
 
     if (warp < FF_EPI_WARPS) {
         // ============================================================ output epilogue warps
@@ -454,7 +457,7 @@ int ffn_fused_96(const float* x, const float* resid2, float* out, long long M, c
     const int grid = tiles < num_sms ? tiles : num_sms;
     const double MC = (double)M * FF_C;
     ProfScope ps(PROF_FFN, stream, 2.0 * M * FF_C * FF_HD * 2.0, MC * 4.0 * (2.0 + (resid2 ? 1.0 : 0.0)) + 2.0 * 2.0 * FF_C * FF_HD);
-    ffn_fused_kernel<<<grid, FF_THREADS, FF_SMEM_BYTES, stream>>>(t1, t2, to, p);
+    ARD_CUDA(enqueue_pdl(ffn_fused_kernel, dim3(grid), dim3(FF_THREADS), FF_SMEM_BYTES, stream, t1, t2, to, p));
     return check_cuda(cudaGetLastError(), "ffn_fused launch");
 }
 

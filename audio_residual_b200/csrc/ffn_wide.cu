@@ -104,6 +104,7 @@ ffn_wide_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
     uint64_t* y_free = bars + 24;       // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 26);
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = (p.M + FW_BM - 1) / FW_BM;
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -141,6 +142,7 @@ ffn_wide_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();
 
     if (warp < FW_EPI_WARPS) {
         // ============================================================ output epilogue warps
@@ -500,7 +502,7 @@ static int launch_ffn_wide(const float* x, const float* resid2, float* out, long
     const int grid = tiles < num_sms ? tiles : num_sms;
     const double MC = (double)M * C;
     ProfScope ps(PROF_FFN, stream, 2.0 * M * C * Cfg::HD * 2.0, MC * 4.0 * (2.0 + (resid2 ? 1.0 : 0.0)) + 2.0 * 2.0 * C * Cfg::HD);
-    ffn_wide_kernel<C><<<grid, FW_THREADS, Cfg::SMEM_BYTES, stream>>>(t1, t2, to, p);
+    ARD_CUDA(enqueue_pdl(ffn_wide_kernel<C>, dim3(grid), dim3(FW_THREADS), Cfg::SMEM_BYTES, stream, t1, t2, to, p));
     return check_cuda(cudaGetLastError(), "ffn_wide launch");
 }
 

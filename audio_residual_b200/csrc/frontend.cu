@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(256) stft_logmel_kernel(const float* __restric
                                                          const int* __restrict__ mlen, int band_max,
                                                          const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
                                                          float* __restrict__ out, long long out_clip_stride, int replicate, int quantize) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float2 tw2[32 * 32];        // tw2[k1][t] = W_1024^{t k1}
     __shared__ float win[NFFT];
     __shared__ float wbuf[8][32 * 33];     // per-warp transpose tile, later the two power spectra
@@ -198,8 +200,8 @@ int stft_logmel(const float* wave, int B, int n_samples, const float* window, co
     if (replicate < 1) replicate = 1;
     dim3 grid((npairs + PAIRS_PER_CTA - 1) / PAIRS_PER_CTA, B);
     ProfScope ps(PROF_FRONTEND, s, (double)B * npairs * (5.0 * 1024 * 10 + 2.0 * 2 * 1100), 4.0 * B * n_samples + 4.0 * B * frames * 64 * replicate);
-    stft_logmel_kernel<<<grid, 256, 0, s>>>(wave, n_samples, frames, window, twiddle, mel.w, mel.start, mel.len, mel.band_max, bn_scale,
-                                           bn_shift, out, out_clip_stride, replicate, quantize);
+    ARD_CUDA(enqueue_pdl(stft_logmel_kernel, grid, dim3(256), 0, s, wave, n_samples, frames, window, twiddle, mel.w, mel.start, mel.len, mel.band_max,
+                        bn_scale, bn_shift, out, out_clip_stride, replicate, quantize));
     return check_cuda(cudaGetLastError(), "stft_logmel launch");
 }
 
@@ -216,7 +218,10 @@ __global__ void __launch_bounds__(256) patch_embed_ln_kernel(const float* __rest
                                                             const float* __restrict__ wconv, const float* __restrict__ bconv,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ out, long long ntokens) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int C = 32 * CPL;
+    __shared__ __align__(16) float pixbuf[8][2][32];   // per warp, double-buffered (the next step's store must not race this step's reads)
     const int lane = threadIdx.x & 31;
     // each lane keeps the 4x4 conv weights, bias and LayerNorm affine of its CPL channels in registers for the whole run of
     // tokens (16 * CPL + 3 * CPL values): no shared memory, no per-block weight staging
@@ -273,15 +278,23 @@ __global__ void __launch_bounds__(256) patch_embed_ln_kernel(const float* __rest
         float acc[2][CPL];
 #pragma unroll
         for (int q = 0; q < CPL; ++q) acc[0][q] = acc[1][q] = bq[q];
+        // broadcast the 2 x 16 pixels through shared memory: one store + eight broadcast LDS.128 instead of 32 shuffles (the
+        // kernel was bound by the shuffle pipe: 26 SHFL per token at one warp-shuffle per clock per SM)
+        float* pb = pixbuf[threadIdx.x >> 5][(it >> 1) & 1];
+        pb[lane] = pix;
+        __syncwarp();
 #pragma unroll
-        for (int n = 0; n < 16; ++n) {
-            const float p0 = __shfl_sync(0xffffffffu, pix, n);
-            const float p1 = __shfl_sync(0xffffffffu, pix, 16 + n);
+        for (int n4 = 0; n4 < 4; ++n4) {
+            const float4 a4 = *reinterpret_cast<const float4*>(pb + n4 * 4);
+            const float4 b4 = *reinterpret_cast<const float4*>(pb + 16 + n4 * 4);
+            const float pa[4] = {a4.x, a4.y, a4.z, a4.w}, pc[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int q = 0; q < CPL; ++q) {
-                acc[0][q] = fmaf(p0, wr[n][q], acc[0][q]);
-                acc[1][q] = fmaf(p1, wr[n][q], acc[1][q]);
-            }
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    acc[0][q] = fmaf(pa[k], wr[n4 * 4 + k][q], acc[0][q]);
+                    acc[1][q] = fmaf(pc[k], wr[n4 * 4 + k][q], acc[1][q]);
+                }
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -317,9 +330,9 @@ int patch_embed_ln(const float* logmel, long long clip_stride, int frames, const
     const unsigned grid = (unsigned)((ntok + 8 * PE_TOK_PER_WARP - 1) / (8 * PE_TOK_PER_WARP));
     ProfScope ps(PROF_FRONTEND, s, (double)ntok * (2.0 * 16 * C + 16 * 8 + 8.0 * C), 4.0 * B * frames * 64 + 4.0 * ntok * C);
     if (C == 96)
-        patch_embed_ln_kernel<3><<<grid, 256, 0, s>>>(logmel, clip_stride, frames, bn_scale, bn_shift, w, bias, gamma, beta, out, ntok);
+        ARD_CUDA(enqueue_pdl(patch_embed_ln_kernel<3>, dim3(grid), dim3(256), 0, s, logmel, clip_stride, frames, bn_scale, bn_shift, w, bias, gamma, beta, out, ntok));
     else if (C == 128)
-        patch_embed_ln_kernel<4><<<grid, 256, 0, s>>>(logmel, clip_stride, frames, bn_scale, bn_shift, w, bias, gamma, beta, out, ntok);
+        ARD_CUDA(enqueue_pdl(patch_embed_ln_kernel<4>, dim3(grid), dim3(256), 0, s, logmel, clip_stride, frames, bn_scale, bn_shift, w, bias, gamma, beta, out, ntok));
     else
         return set_error(ARD_ERR_SHAPE, "patch_embed: unsupported embed_dim %d", C);
     return check_cuda(cudaGetLastError(), "patch_embed_ln launch");

@@ -93,6 +93,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + NACC);
     uint64_t* resid_bar = tempty_bar + NACC + 1;   // [NEPI][3]: prefetched tile landed in staging buffer b
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int m_blocks = (p.M + TILE_M - 1) / TILE_M;
@@ -130,6 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();   // operands / residuals come from the predecessor kernel; everything above overlapped its tail
 
     if (warp == 0) {
         // ===================================================== TMA producer (warp-convergent loop, one elected lane issues)
@@ -440,15 +442,17 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
         cfg.blockDim = dim3(Cfg::THREADS);
         cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
         cfg.stream = stream;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
         return check_cuda(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tr, kp), "gemm pair launch");
     } else {
         const int grid = tiles < num_sms ? tiles : num_sms;
-        kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, tr, kp);
+        ARD_CUDA(enqueue_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, ta, tb, tc, tr, kp));
         return check_cuda(cudaGetLastError(), "gemm launch");
     }
 }

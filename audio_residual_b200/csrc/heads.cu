@@ -13,6 +13,8 @@ constexpr int LS_CL = 8;
 __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W,
                                                           const float* __restrict__ bias, float* __restrict__ y, int ldy, int B, int N,
                                                           int K, int act, int n_per_cta) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float xs[];   // [LS_CL][K]
     const int b0 = blockIdx.y * LS_CL;
     const int nb = min(LS_CL, B - b0);
@@ -57,12 +59,14 @@ int linear_small(const float* x, int ldx, const float* W, const float* bias, flo
     const int n_per_cta = 64;
     dim3 grid((N + n_per_cta - 1) / n_per_cta, (B + LS_CL - 1) / LS_CL);
     ProfScope ps(PROF_HEAD, s, 2.0 * B * N * K, 4.0 * ((double)N * K + (double)B * K + (double)B * N));
-    linear_small_kernel<<<grid, 256, smem, s>>>(x, ldx, W, bias, y, ldy, B, N, K, act, n_per_cta);
+    ARD_CUDA(enqueue_pdl(linear_small_kernel, grid, dim3(256), smem, s, x, ldx, W, bias, y, ldy, B, N, K, act, n_per_cta));
     return check_cuda(cudaGetLastError(), "linear_small launch");
 }
 
 // F.normalize(x, dim=-1): x / max(||x||_2, 1e-12); one warp per row
 __global__ void l2_normalize_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int N) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B) return;
@@ -79,7 +83,7 @@ __global__ void l2_normalize_kernel(const float* __restrict__ x, float* __restri
 
 int l2_normalize(const float* x, float* y, int B, int N, cudaStream_t s) {
     if (B <= 0) return 0;
-    l2_normalize_kernel<<<(B + 7) / 8, 256, 0, s>>>(x, y, B, N);
+    ARD_CUDA(enqueue_pdl(l2_normalize_kernel, dim3((B + 7) / 8), dim3(256), 0, s, x, y, B, N));
     return check_cuda(cudaGetLastError(), "l2_normalize launch");
 }
 

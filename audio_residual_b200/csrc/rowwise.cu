@@ -64,6 +64,8 @@ struct MergeRows {
 template <int VEC, int NV, class Rows>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(Rows rows, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             __nv_bfloat16* __restrict__ out, long long nrows) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int C = 32 * VEC * NV;
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -105,6 +107,8 @@ __global__ void __launch_bounds__(256) add_layernorm_rows_kernel(const float* __
                                                                 float* __restrict__ sum_out, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                                                 long long nrows) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int C = 32 * VEC * NV;
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -156,7 +160,7 @@ int add_layernorm_bf16(const float* x, const float* add, float* sum_out, const f
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
     ProfScope ps(PROF_LN, s, 9.0 * rows * C, 14.0 * rows * C);
 #define ARD_ALN_CASE(c, vec, nv) \
-    case c: add_layernorm_rows_kernel<vec, nv><<<grid, wpb * 32, 0, s>>>(x, add, sum_out, gamma, beta, out, rows); break;
+    case c: ARD_CUDA(enqueue_pdl(add_layernorm_rows_kernel<vec, nv>, dim3(grid), dim3(wpb * 32), 0, s, x, add, sum_out, gamma, beta, out, rows)); break;
     switch (C) {
         ARD_ALN_CASE(96, 1, 3)
         ARD_ALN_CASE(128, 4, 1)
@@ -178,7 +182,7 @@ static int launch_ln(Rows rows, const float* gamma, const float* beta, __nv_bflo
     const unsigned grid = (unsigned)((nrows + wpb - 1) / wpb);
     ProfScope ps(PROF_LN, s, 8.0 * nrows * C, 6.0 * nrows * C);
 #define ARD_LN_CASE(c, vec, nv) \
-    case c: layernorm_rows_kernel<vec, nv, Rows><<<grid, wpb * 32, 0, s>>>(rows, gamma, beta, out, nrows); break;
+    case c: ARD_CUDA(enqueue_pdl(layernorm_rows_kernel<vec, nv, Rows>, dim3(grid), dim3(wpb * 32), 0, s, rows, gamma, beta, out, nrows)); break;
     switch (C) {
         ARD_LN_CASE(96, 1, 3)
         ARD_LN_CASE(128, 4, 1)
@@ -215,6 +219,8 @@ template <int VEC, int NV>
 __global__ void __launch_bounds__(256) final_norm_mean_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float* __restrict__ emb,
                                                              float* __restrict__ normed, int T) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int C = 32 * VEC * NV;
     __shared__ float part[8][C];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -272,8 +278,8 @@ int final_norm_mean(const float* x, const float* gamma, const float* beta, float
     if (B <= 0) return 0;
     ProfScope ps(PROF_HEAD, s, 8.0 * B * T * C, 4.0 * B * T * C * (normed ? 2 : 1));
     switch (C) {
-        case 768: final_norm_mean_kernel<4, 6><<<B, 256, 0, s>>>(x, gamma, beta, emb, normed, T); break;
-        case 1024: final_norm_mean_kernel<4, 8><<<B, 256, 0, s>>>(x, gamma, beta, emb, normed, T); break;
+        case 768: ARD_CUDA(enqueue_pdl(final_norm_mean_kernel<4, 6>, dim3(B), dim3(256), 0, s, x, gamma, beta, emb, normed, T)); break;
+        case 1024: ARD_CUDA(enqueue_pdl(final_norm_mean_kernel<4, 8>, dim3(B), dim3(256), 0, s, x, gamma, beta, emb, normed, T)); break;
         default: return set_error(ARD_ERR_SHAPE, "final norm: unsupported width C=%d", C);
     }
     return check_cuda(cudaGetLastError(), "final_norm_mean launch");
