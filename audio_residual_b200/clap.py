@@ -216,11 +216,12 @@ class CLAP_Module(nn.Module):
         return emb
 
     h2d_chunk = 64                        # host batches larger than this are copied in chunks overlapped with the encoder
-    h2d_schedule = (16, 40, 80, 136, 216, 256)   # chunk sizes in clips: a small first copy (nothing overlaps it), then growing
+    h2d_schedule = (24, 50, 80, 116, 156, 204, 256)   # chunk sizes in clips: a small first copy (nothing overlaps it), then growing
 
     def _chunk_bounds(self, N):
-        """Each copy fits under the previous chunk's encode (0.035 ms/clip over PCIe gen5 vs ~0.8 ms + 0.05 ms/clip of
-        encoder time on a B200); chunks are capped so the two staging buffers stay small for any N."""
+        """Each copy must fit under the previous chunk's encode: 0.0346 ms/clip over PCIe gen5 (55.5 GB/s measured) against
+        0.79 ms + 0.040 ms/clip of graph-replayed encoder time on a B200 (tools/batch_sweep.py), i.e. the next chunk may hold
+        at most 22.8 + 1.156 x the clips of the current one; chunks are capped so the two staging buffers stay small for any N."""
         bounds, lo, i = [], 0, 0
         while lo < N:
             c = self.h2d_schedule[min(i, len(self.h2d_schedule) - 1)]
