@@ -169,6 +169,31 @@ ARD_DEVINL void umma_f16_ss_run(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_
         if constexpr (PAIR) ARD_UMMA_RUN4("2"); else ARD_UMMA_RUN4("1");
     }
 }
+// Same run with the A operand in TENSOR MEMORY (M = 128: row i in lane i, two 16-bit K elements per 32-bit column, so a
+// K = 16 step is 8 columns): D (+)= A_tmem[:, 16k..] * B[:, 16k..]. Four k-steps = one 64-wide k-block.
+ARD_DEVINL void umma_f16_ts_run4(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t first_acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 b1, b2, b3;\n\t.reg .b32 a1, a2, a3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "add.s64 b1, %2, 2;\n\tadd.s64 b2, %2, 4;\n\tadd.s64 b3, %2, 6;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %3, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %3, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b3, %3, 1;\n\t}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(first_acc)
+        : "memory");
+}
+// registers -> TMEM: this warp's 32 lanes x 16 consecutive 32-bit columns
+ARD_DEVINL void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+ARD_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // Arrives (count 1) on the mbarrier once all previously issued tcgen05.mma of this thread have completed.
 // Implies tcgen05.fence::before_thread_sync.
 ARD_DEVINL void umma_commit(uint64_t* bar) {

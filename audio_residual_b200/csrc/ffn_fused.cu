@@ -57,15 +57,21 @@ constexpr int FF_A1_KB = FF_BM * 64;            // 8192
 constexpr int FF_A1_OFF = FF_W2_OFF + FF_W2_BYTES;
 constexpr int FF_A1_BYTES = 3 * FF_A1_KB;       // 24576
 constexpr int FF_A2_OFF = FF_A1_OFF + FF_A1_BYTES;
-constexpr int FF_A2_BYTES = FF_BM * 128;        // 16384 per buffer
+constexpr int FF_A2_BYTES = FF_BM * 128;        // 16384 per buffer (FF_A2_TMEM = 0); with the A2 tile in tensor memory the same
+                                                // 32 KB hold the TMA-prefetched residual tiles: 8 warps x {x, resid2} x (32 rows x 64 B)
+constexpr int FF_RB_OFF = FF_A2_OFF;
 constexpr int FF_CST_OFF = FF_A2_OFF + 2 * FF_A2_BYTES;    // 8 warps x (32 rows x 64 B)
 constexpr int FF_VEC_OFF = FF_CST_OFF + FF_EPI_WARPS * 2048;   // b1[384] b2[96] gamma[96] beta[96]
 constexpr int FF_BAR_OFF = FF_VEC_OFF + (FF_HD + 3 * FF_C) * 4;
 constexpr int FF_SMEM_BYTES = FF_BAR_OFF + 256 + 1024;
 
 constexpr int FF_NHB = 4;       // H accumulators in flight (two pairs)
-constexpr int FF_TM_H = 0;      // TMEM columns: H0..H3 @0/64/128/192, Y0 @256, Y1 @384
+constexpr int FF_TM_H = 0;      // TMEM columns: H0..H3 @0/64/128/192, Y0 @256 (96 used), Y1 @384
 constexpr int FF_TM_Y = 256;
+#ifndef FF_A2_TMEM
+#define FF_A2_TMEM 1            // 1: the GELU output reaches fc2 through tensor memory (A operand from TMEM); 0: through shared memory (A/B)
+#endif
+constexpr int FF_TM_A2 = 352;   // A2 buffer g: 32 columns (64 fp16 per row) at 352 + 128 g, in the gaps after Y0 / Y1
 
 struct FfnParams {
     const float* x;        // [M, 96] fp32  (LayerNorm input and first residual)
@@ -79,7 +85,8 @@ struct FfnParams {
 
 __global__ void __launch_bounds__(FF_THREADS, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                 const __grid_constant__ CUtensorMap tmOut, const FfnParams p) {
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmX,
+                 const __grid_constant__ CUtensorMap tmR2, const FfnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned, still a shared-space pointer
     float* b1s = reinterpret_cast<float*>(smem + FF_VEC_OFF);
@@ -97,6 +104,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     uint64_t* y_full = bars + 15;   // [2]
     uint64_t* y_free = bars + 17;   // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 19);
+    uint64_t* rbar = bars + 20;     // [8] residual tiles landed (one per epilogue warp)
 
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -127,6 +135,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
             mbar_init(&y_full[i], 1);
             mbar_init(&y_free[i], FF_EPI_WARPS);
         }
+        for (int i = 0; i < FF_EPI_WARPS; ++i) mbar_init(&rbar[i], 1);
         fence_barrier_init();
     }
     if (warp == FF_W_MMA) {
@@ -145,6 +154,74 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         const int quad = warp & 3, c_begin = (warp >> 2) * 3;
         uint8_t* sbuf = smem + FF_CST_OFF + warp * 2048;
         const bool has_r2 = p.resid2 != nullptr;
+#if FF_A2_TMEM
+        // The residual tiles (x, and the second residual) of a chunk are fetched by TMA one chunk ahead into this warp's two
+        // 2 KB buffers: coalesced, asynchronous, no registers held across the wait. (Row-per-thread LDG.128 touches 32 lines
+        // per instruction; with a second residual it cost 160 us per launch.) Chunk sequence number q = 3 * it + cc.
+        uint8_t* rb1 = smem + FF_RB_OFF + warp * 4096;
+        uint8_t* rb2 = rb1 + 2048;
+        auto fetch_resid = [&](int tile, int c) {       // lane 0 only
+            mbar_expect_tx(&rbar[warp], has_r2 ? 4096 : 2048);
+            tma_load_2d(rb1, &tmX, &rbar[warp], c * 16, tile * FF_BM + quad * 32);
+            if (has_r2) tma_load_2d(rb2, &tmR2, &rbar[warp], c * 16, tile * FF_BM + quad * 32);
+        };
+        if (lane == 0 && (int)blockIdx.x < num_tiles) fetch_resid(blockIdx.x, c_begin);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int yb = it & 1;
+            if (warp == 0 && lane == 0) FF_TRACE(0, it, 0);
+            mbar_wait_parked(&y_full[yb], (it >> 1) & 1);
+            if (warp == 0 && lane == 0) FF_TRACE(0, it, 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < 3; ++cc) {                 // 16-column chunks
+                const int c = c_begin + cc;
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(tmem_base + FF_TM_Y + yb * 128 + c * 16 + ((uint32_t)(quad * 32) << 16), v);
+                mbar_wait(&rbar[warp], (uint32_t)((it * 3 + cc) & 1));
+                const int sw = (lane >> 1) & 3;              // SWIZZLE_64B: 16-byte unit index ^= (row >> 1) & 3
+                float4 r1[4], r2[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    r1[j] = *reinterpret_cast<const float4*>(rb1 + lane * 64 + ((j ^ sw) << 4));
+                    r2[j] = has_r2 ? *reinterpret_cast<const float4*>(rb2 + lane * 64 + ((j ^ sw) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                __syncwarp();                                // every lane has read the buffers: the next fetch may overwrite them
+                if (lane == 0) {
+                    if (cc + 1 < 3) fetch_resid(tile, c + 1);
+                    else if (tile + (int)gridDim.x < num_tiles) fetch_resid(tile + gridDim.x, c_begin);
+                }
+                tmem_ld_wait();
+                if (cc == 2) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&y_free[yb]);
+                }
+                float4 o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(b2s + c * 16 + j * 4);
+                    o[j].x = __uint_as_float(v[j * 4 + 0]) + b4.x + r1[j].x + r2[j].x;
+                    o[j].y = __uint_as_float(v[j * 4 + 1]) + b4.y + r1[j].y + r2[j].y;
+                    o[j].z = __uint_as_float(v[j * 4 + 2]) + b4.z + r1[j].z + r2[j].z;
+                    o[j].w = __uint_as_float(v[j * 4 + 3]) + b4.w + r1[j].w + r2[j].w;
+                }
+                if (lane == 0) tma_store_wait_read<0>();     // the previous chunk's store has read the (single) staging buffer
+                __syncwarp();
+                uint8_t* rowp = sbuf + lane * 64;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(rowp + ((j ^ sw) << 4)) = o[j];
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmOut, sbuf, c * 16, tile * FF_BM + quad * 32);
+                    tma_store_commit();
+                }
+            }
+            if (warp == 0 && lane == 0) FF_TRACE(0, it, 2);
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+#else
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int yb = it & 1;
@@ -166,9 +243,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                 }
             };
             load_resid(c_begin);                             // in flight while fc2 of this tile finishes
-            if (warp == 0 && lane == 0) FF_TRACE(0, it, 0);
             mbar_wait_parked(&y_full[yb], (it >> 1) & 1);
-            if (warp == 0 && lane == 0) FF_TRACE(0, it, 1);
             tc_fence_after();
 #pragma unroll 1
             for (int cc = 0; cc < 3; ++cc) {                 // 16-column chunks
@@ -204,9 +279,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                     tma_store_commit();
                 }
             }
-            if (warp == 0 && lane == 0) FF_TRACE(0, it, 2);
         }
         if (lane == 0) tma_store_wait_all<0>();
+#endif
     } else if (warp == FF_W_MMA) {
         // ============================================================ weight load + fc1 MMA issue
         // The whole warp runs the loop (all lanes wait on the barriers) and one elected lane issues: in warp-convergent code
@@ -272,8 +347,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                 if (lane == 0) FF_TRACE(2, g, 2);
                 tc_fence_after();
                 if (elect_one_sync()) {
+#if FF_A2_TMEM
+                    umma_f16_ts_run4(tmem_base + FF_TM_Y + yb * 128, tmem_base + FF_TM_A2 + b * 128, dW2 + (uint64_t)(j * (FF_W2_KB >> 4)), idesc2,
+                                     j != 0);
+#else
                     umma_f16_ss_run<4>(tmem_base + FF_TM_Y + yb * 128, dA2 + (uint64_t)(b * (FF_A2_BYTES >> 4)),
                                        dW2 + (uint64_t)(j * (FF_W2_KB >> 4)), idesc2, j != 0);
+#endif
                     umma_commit(&a2_free[b]);
                     if (j == FF_NCH - 1) umma_commit(&y_full[yb]);
                 }
@@ -415,12 +495,20 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                 if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 2);
                 mbar_wait_parked(&a2_free[grp], ((g >> 1) & 1) ^ 1);   // fc2 MMAs that read the previous contents have retired
                 if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 3);
+#if FF_A2_TMEM
+                // 32 fp16 of this lane's row = 16 packed columns of the A2 tile in tensor memory (K pair 2c, 2c+1 in column c)
+                tmem_st_32x32b_x16(tmem_base + FF_TM_A2 + grp * 128 + half * 16 + ((uint32_t)(quad * 32) << 16), pk);
+                tmem_st_wait();
+                tc_fence_before();
+                (void)row;
+#else
                 uint8_t* rowp = smem + FF_A2_OFF + grp * FF_A2_BYTES + row * 128;
                 const int sw = row & 7;
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     *reinterpret_cast<uint4*>(rowp + (((half * 4 + q) ^ sw) << 4)) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
                 fence_proxy_async_smem();
+#endif
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a2_full[grp]);
                 if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 4);
@@ -446,6 +534,9 @@ int ffn_fused_96(const float* x, const float* resid2, float* out, long long M, c
     ARD_TRY(make_tmap_2d(&t1, w1, 2, FF_C, FF_HD, (uint64_t)FF_C * 2, 32, 192, 64));
     ARD_TRY(make_tmap_2d(&t2, w2_f16, 2, FF_HD, FF_C, (uint64_t)FF_HD * 2, 64, FF_C, 128));
     ARD_TRY(make_tmap_2d(&to, out, 4, FF_C, (uint64_t)M, (uint64_t)FF_C * 4, 16, 32, 64));
+    CUtensorMap tx, tr;
+    ARD_TRY(make_tmap_2d(&tx, x, 4, FF_C, (uint64_t)M, (uint64_t)FF_C * 4, 16, 32, 64));
+    ARD_TRY(make_tmap_2d(&tr, resid2 ? resid2 : x, 4, FF_C, (uint64_t)M, (uint64_t)FF_C * 4, 16, 32, 64));
     static bool attr_set = false;
     if (!attr_set) {
         ARD_CUDA(cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
@@ -457,7 +548,7 @@ int ffn_fused_96(const float* x, const float* resid2, float* out, long long M, c
     const int grid = tiles < num_sms ? tiles : num_sms;
     const double MC = (double)M * FF_C;
     ProfScope ps(PROF_FFN, stream, 2.0 * M * FF_C * FF_HD * 2.0, MC * 4.0 * (2.0 + (resid2 ? 1.0 : 0.0)) + 2.0 * 2.0 * FF_C * FF_HD);
-    ARD_CUDA(enqueue_pdl(ffn_fused_kernel, dim3(grid), dim3(FF_THREADS), FF_SMEM_BYTES, stream, t1, t2, to, p));
+    ARD_CUDA(enqueue_pdl(ffn_fused_kernel, dim3(grid), dim3(FF_THREADS), FF_SMEM_BYTES, stream, t1, t2, to, tx, tr, p));
     return check_cuda(cudaGetLastError(), "ffn_fused launch");
 }
 
