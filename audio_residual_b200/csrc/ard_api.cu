@@ -295,17 +295,16 @@ static int run_block(ard_handle* h, int l, int b, int B, float* X, float* Y, flo
     ARD_TRY(gemm_bf16(g, h->num_sms, s));
     // FFN: (Y) -> LN2 -> fc1+GELU -> fc2
     // one FFN: out = in + mlp(norm2(in)) (+ r2 inside the fused kernel). `pre_add`: the LayerNorm input is in + pre_add, written back to `in`.
-    // ffn_wide (weights streamed from L2) is used where it measures faster than LayerNorm + two GEMMs: the plain FFN of the
-    // 192-channel stage (249 vs 341 us at B = 256 incl. the shortcut add). With a second residual (344 vs 339 us) and at
-    // C = 384 (254 vs 200 us: three ring slots cannot cover the L2 latency) the unfused chain stays. ARD_FUSED_FFN_WIDE=2 forces
-    // it everywhere (A/B measurements), =0 disables it.
-    const bool wide = (C == 192 || C == 384) && h->use_fused_ffn_wide == 2;
-    const bool wide_plain = C == 192 && h->use_fused_ffn_wide == 1;
+    // ffn_wide (weights streamed from L2) is used where it measures faster than LayerNorm + two GEMMs: both FFNs of the
+    // 192-channel stage (217 / 255 us plain / with second residual vs 341 / 339 us at B = 256). At C = 384 (254 vs 200 us: three
+    // ring slots cannot cover the L2 latency) the unfused chain stays. ARD_FUSED_FFN_WIDE=2 forces it for C = 384 too (A/B
+    // measurements), =0 disables it.
+    const bool wide = (C == 192 && h->use_fused_ffn_wide >= 1) || (C == 384 && h->use_fused_ffn_wide == 2);
     auto ffn = [&](float* in, float* out, const float* r2, const float* pre_add) -> int {
         if (C == 96 && h->use_fused_ffn && pre_add == nullptr)   // whole FFN in one kernel, hidden activation never leaves the SM
             return ffn_fused_96(in, r2, out, M, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), bw.fc1_w.as<__nv_bfloat16>(), bw.fc1_b.as<float>(),
                                 bw.fc2_w.as<__half>(), bw.fc2_b.as<float>(), h->num_sms, s);
-        if ((wide || (wide_plain && r2 == nullptr)) && pre_add == nullptr)   // same, weights streamed from L2
+        if (wide && pre_add == nullptr)                          // same, weights streamed from L2
             return ffn_fused_wide(in, r2, out, M, C, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), bw.fc1_w.as<__nv_bfloat16>(),
                                   bw.fc1_b_half.as<float>(), bw.fc2_w.as<__half>(), bw.fc2_b.as<float>(), h->num_sms, s);
         if (pre_add)
@@ -327,9 +326,6 @@ static int run_block(ard_handle* h, int l, int b, int B, float* X, float* Y, flo
     } else if ((C == 96 && h->use_fused_ffn) || wide) {
         ARD_TRY(ffn(Y, Y, X, nullptr));                // x3 = shortcut + (x1 + mlp(norm2(x1)))         src/residual.py:93,95
         ARD_TRY(ffn(Y, X, nullptr, nullptr));          // x4 = x3 + mlp(norm2(x3))                      src/residual.py:96
-    } else if (wide_plain) {
-        ARD_TRY(ffn(Y, Y, X, nullptr));                // x3 via the fc2 GEMM's two-residual epilogue, then the fused kernel
-        ARD_TRY(ffn(Y, X, nullptr, nullptr));
     } else {
         ARD_TRY(ffn(Y, Y, nullptr, nullptr));          // x2 = x1 + mlp(norm2(x1))                      src/residual.py:93
         ARD_TRY(ffn(Y, X, nullptr, X));                // x3 = shortcut + x2 (fused into the norm2 pass), x4 = x3 + mlp(norm2(x3))   :95-96

@@ -186,6 +186,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                     r1[j] = *reinterpret_cast<const float4*>(rb1 + lane * 64 + ((j ^ sw) << 4));
                     r2[j] = has_r2 ? *reinterpret_cast<const float4*>(rb2 + lane * 64 + ((j ^ sw) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+                fence_proxy_async_smem();                    // order this lane's generic-proxy reads before the async-proxy (TMA) overwrite
                 __syncwarp();                                // every lane has read the buffers: the next fetch may overwrite them
                 if (lane == 0) {
                     if (cc + 1 < 3) fetch_resid(tile, c + 1);

@@ -49,7 +49,12 @@ struct FwCfg {
     static constexpr int NCH = HD / 64;              // hidden chunks per tile (12 / 24)
     static constexpr int NS = C / 192;               // slots per ring entry (1 / 2)
     static constexpr int KB1 = C / 64;               // fc1 k-blocks (3 / 6)
-    static constexpr int NYB = C == 192 ? 2 : 1;     // Y accumulators
+    static constexpr int NYB = 1;                    // Y accumulators
+    // C = 192: the GELU output reaches fc2 through TENSOR MEMORY (A operand from TMEM; Y 0-191, A2 192-255, H 384-511) and the
+    // 32 KB of shared memory that held the A2 tiles hold the TMA-prefetched residual tiles of the epilogue instead (see
+    // ffn_fused.cu: 372 -> 251 us there). At C = 384, Y + H fill all 512 TMEM columns: A2 and the residual loads stay as before.
+    static constexpr bool A2T = C == 192;
+    static constexpr int TM_A2 = 192;
     // LayerNorm operand buffers / ring slots. Measured at C = 192 (B = 256, M = 262144): one A1 buffer + 5 slots 249 us, two A1
     // buffers (next tile's LayerNorm overlapped) + 3 slots 277 us: the ring depth is worth more than the overlap.
     static constexpr int NA1 = 1;
@@ -63,7 +68,7 @@ struct FwCfg {
     static constexpr int CST_OFF = RING_OFF + NSLOT * FW_SLOT;   // 8 warps x (32 rows x 64 B)
     static constexpr int VEC_OFF = CST_OFF + FW_EPI_WARPS * 2048;   // b2[C] gamma[C] beta[C]
     static constexpr int BAR_OFF = VEC_OFF + 3 * C * 4;
-    static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+    static constexpr int SMEM_BYTES = BAR_OFF + 320 + 1024;
     static_assert(SMEM_BYTES <= 227 * 1024, "ffn_wide: shared memory budget");
     static constexpr int LN_CH = C / 16;             // channels per lane in the LayerNorm mapping (16 lanes per row)
     static constexpr int LN_V4 = LN_CH / 4;          // float4 per lane per row (3 / 6)
@@ -83,7 +88,8 @@ struct FwParams {
 template <int C>
 __global__ void __launch_bounds__(FW_THREADS, 1)
 ffn_wide_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                const __grid_constant__ CUtensorMap tmOut, const FwParams p) {
+                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmX,
+                const __grid_constant__ CUtensorMap tmR2, const FwParams p) {
     using Cfg = FwCfg<C>;
     constexpr int NCH = Cfg::NCH, NS = Cfg::NS, NSLOT = Cfg::NSLOT, NYB = Cfg::NYB, NA1 = Cfg::NA1;
     extern __shared__ uint8_t smem_raw[];
@@ -103,6 +109,7 @@ ffn_wide_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
     uint64_t* y_full = bars + 22;       // [2]
     uint64_t* y_free = bars + 24;       // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 26);
+    uint64_t* rbar = bars + 28;         // [8] residual tiles landed (one per epilogue warp)
 
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -132,6 +139,7 @@ ffn_wide_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
             mbar_init(&y_full[i], 1);
             mbar_init(&y_free[i], FW_EPI_WARPS);
         }
+        for (int i = 0; i < FW_EPI_WARPS; ++i) mbar_init(&rbar[i], 1);
         fence_barrier_init();
     }
     if (warp == FW_W_MMA) {
@@ -151,6 +159,71 @@ ffn_wide_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
         const int quad = warp & 3, c_begin = (warp >> 2) * NCC;
         uint8_t* sbuf = smem + Cfg::CST_OFF + warp * 2048;
         const bool has_r2 = p.resid2 != nullptr;
+        if constexpr (Cfg::A2T) {
+            // residual tiles fetched by TMA one chunk ahead into this warp's two 2 KB buffers (chunk sequence q = NCC * it + cc)
+            uint8_t* rb1 = smem + Cfg::A2_OFF + warp * 4096;
+            uint8_t* rb2 = rb1 + 2048;
+            auto fetch_resid = [&](int tile, int c) {       // lane 0 only
+                mbar_expect_tx(&rbar[warp], has_r2 ? 4096 : 2048);
+                tma_load_2d(rb1, &tmX, &rbar[warp], c * 16, tile * FW_BM + quad * 32);
+                if (has_r2) tma_load_2d(rb2, &tmR2, &rbar[warp], c * 16, tile * FW_BM + quad * 32);
+            };
+            if (lane == 0) fetch_resid(blockIdx.x, c_begin);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                if (warp == 0 && lane == 0) FW_TRACE(0, it, 0);
+                mbar_wait_parked(&y_full[0], (uint32_t)(it & 1));
+                if (warp == 0 && lane == 0) FW_TRACE(0, it, 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int cc = 0; cc < NCC; ++cc) {           // 16-column chunks
+                    const int c = c_begin + cc;
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(tmem_base + c * 16 + ((uint32_t)(quad * 32) << 16), v);
+                    mbar_wait(&rbar[warp], (uint32_t)((it * NCC + cc) & 1));
+                    const int sw = (lane >> 1) & 3;          // SWIZZLE_64B: 16-byte unit index ^= (row >> 1) & 3
+                    float4 r1[4], r2[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        r1[j] = *reinterpret_cast<const float4*>(rb1 + lane * 64 + ((j ^ sw) << 4));
+                        r2[j] = has_r2 ? *reinterpret_cast<const float4*>(rb2 + lane * 64 + ((j ^ sw) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    fence_proxy_async_smem();                // order this lane's generic-proxy reads before the async-proxy (TMA) overwrite
+                    __syncwarp();                            // every lane has read the buffers: the next fetch may overwrite them
+                    if (lane == 0) {
+                        if (cc + 1 < NCC) fetch_resid(tile, c + 1);
+                        else if (tile + (int)gridDim.x < num_tiles) fetch_resid(tile + gridDim.x, c_begin);
+                    }
+                    tmem_ld_wait();
+                    if (cc == NCC - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&y_free[0]);
+                    }
+                    float4 o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(b2s + c * 16 + j * 4);
+                        o[j].x = __uint_as_float(v[j * 4 + 0]) + b4.x + r1[j].x + r2[j].x;
+                        o[j].y = __uint_as_float(v[j * 4 + 1]) + b4.y + r1[j].y + r2[j].y;
+                        o[j].z = __uint_as_float(v[j * 4 + 2]) + b4.z + r1[j].z + r2[j].z;
+                        o[j].w = __uint_as_float(v[j * 4 + 3]) + b4.w + r1[j].w + r2[j].w;
+                    }
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+                    uint8_t* rowp = sbuf + lane * 64;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(rowp + ((j ^ sw) << 4)) = o[j];
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmOut, sbuf, c * 16, tile * FW_BM + quad * 32);
+                        tma_store_commit();
+                    }
+                }
+                if (warp == 0 && lane == 0) FW_TRACE(0, it, 2);
+            }
+        } else {
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int yb = it % NYB;
@@ -212,6 +285,7 @@ ffn_wide_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
                 }
             }
             if (warp == 0 && lane == 0) FW_TRACE(0, it, 2);
+        }
         }
         if (lane == 0) tma_store_wait_all<0>();
     } else if (warp == FW_W_TMA) {
@@ -312,8 +386,12 @@ ffn_wide_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
                     mbar_wait_parked(&ring_full[slot], (uint32_t)((n / NSLOT) & 1));
                     tc_fence_after();
                     if (elect_one_sync()) {
-                        umma_f16_ss_run<4>(tmem_base + yb * 192 + s * 192, dA2 + (uint64_t)(b * (Cfg::A2_BYTES >> 4)),
-                                           umma_desc_sw128(ring_u32 + slot * FW_SLOT), idesc2, j != 0);
+                        if constexpr (Cfg::A2T)
+                            umma_f16_ts_run4(tmem_base + yb * 192 + s * 192, tmem_base + Cfg::TM_A2 + b * 32,
+                                             umma_desc_sw128(ring_u32 + slot * FW_SLOT), idesc2, j != 0);
+                        else
+                            umma_f16_ss_run<4>(tmem_base + yb * 192 + s * 192, dA2 + (uint64_t)(b * (Cfg::A2_BYTES >> 4)),
+                                               umma_desc_sw128(ring_u32 + slot * FW_SLOT), idesc2, j != 0);
                         umma_commit(&ring_empty[slot]);
                         if (s == NS - 1) {
                             umma_commit(&a2_free[b]);
@@ -456,12 +534,19 @@ ffn_wide_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
                 if ((ew & 7) == 0 && lane == 0) FW_TRACE(4 + grp, (int)g, 2);
                 mbar_wait_parked(&a2_free[grp], (uint32_t)(((g >> 1) & 1) ^ 1));   // fc2 MMAs that read the previous contents have retired
                 if ((ew & 7) == 0 && lane == 0) FW_TRACE(4 + grp, (int)g, 3);
-                uint8_t* rowp = smem + Cfg::A2_OFF + grp * Cfg::A2_BYTES + row * 128;
-                const int sw = row & 7;
+                if constexpr (Cfg::A2T) {
+                    // 32 fp16 of this lane's row = 16 packed columns of the A2 tile in tensor memory (K pair 2c, 2c+1 in column c)
+                    tmem_st_32x32b_x16(tmem_base + Cfg::TM_A2 + grp * 32 + half * 16 + ((uint32_t)(quad * 32) << 16), pk);
+                    tmem_st_wait();
+                    tc_fence_before();
+                } else {
+                    uint8_t* rowp = smem + Cfg::A2_OFF + grp * Cfg::A2_BYTES + row * 128;
+                    const int sw = row & 7;
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<uint4*>(rowp + (((half * 4 + q) ^ sw) << 4)) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-                fence_proxy_async_smem();
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<uint4*>(rowp + (((half * 4 + q) ^ sw) << 4)) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+                    fence_proxy_async_smem();
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a2_full[grp]);
                 if ((ew & 7) == 0 && lane == 0) FW_TRACE(4 + grp, (int)g, 4);
@@ -491,6 +576,9 @@ static int launch_ffn_wide(const float* x, const float* resid2, float* out, long
     ARD_TRY(make_tmap_2d(&t1, w1, 2, C, Cfg::HD, (uint64_t)C * 2, 64, 64, 128));
     ARD_TRY(make_tmap_2d(&t2, w2_f16, 2, Cfg::HD, C, (uint64_t)Cfg::HD * 2, 64, 192, 128));
     ARD_TRY(make_tmap_2d(&to, out, 4, C, (uint64_t)M, (uint64_t)C * 4, 16, 32, 64));
+    CUtensorMap tx, tr;
+    ARD_TRY(make_tmap_2d(&tx, x, 4, C, (uint64_t)M, (uint64_t)C * 4, 16, 32, 64));
+    ARD_TRY(make_tmap_2d(&tr, resid2 ? resid2 : x, 4, C, (uint64_t)M, (uint64_t)C * 4, 16, 32, 64));
     static bool attr_set = false;
     if (!attr_set) {
         ARD_CUDA(cudaFuncSetAttribute(ffn_wide_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -502,7 +590,7 @@ static int launch_ffn_wide(const float* x, const float* resid2, float* out, long
     const int grid = tiles < num_sms ? tiles : num_sms;
     const double MC = (double)M * C;
     ProfScope ps(PROF_FFN, stream, 2.0 * M * C * Cfg::HD * 2.0, MC * 4.0 * (2.0 + (resid2 ? 1.0 : 0.0)) + 2.0 * 2.0 * C * Cfg::HD);
-    ARD_CUDA(enqueue_pdl(ffn_wide_kernel<C>, dim3(grid), dim3(FW_THREADS), Cfg::SMEM_BYTES, stream, t1, t2, to, p));
+    ARD_CUDA(enqueue_pdl(ffn_wide_kernel<C>, dim3(grid), dim3(FW_THREADS), Cfg::SMEM_BYTES, stream, t1, t2, to, tx, tr, p));
     return check_cuda(cudaGetLastError(), "ffn_wide launch");
 }
 

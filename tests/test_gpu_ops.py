@@ -32,7 +32,7 @@ def test_gemm_epilogues():
     assert G.check_gemm(1024, 192, 384, False, bias=False, nres=1)[0] < 2e-5
 
 
-@pytest.mark.parametrize("M,resid2", [(128, False), (5000, True), (16384 + 77, True)])
+@pytest.mark.parametrize("M,resid2", [(128, False), (5000, True), (16384 + 77, True), (148 * 128 * 3 + 77, True), (148 * 128 * 2, False)])
 def test_ffn_fused_96(M, resid2):
     r_out, r_branch = G.check_ffn_fused(M, resid2)
     assert r_out < 2e-3 and r_branch < 5e-3, (r_out, r_branch)     # bf16 LN output / fp16 hidden operands, fp32 accumulation
