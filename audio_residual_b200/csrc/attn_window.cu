@@ -13,6 +13,8 @@
 // the attention maps (`attn`, the block-mean capture of BasicLayer.forward htsat.py:589-595).
 // The per-(window, head) problem is 64x64x24: far too small for a tcgen05 tile, and the kernel is bound by the softmax
 // ALU/MUFU work (4096 exp per head-window vs 0.4 MFLOP of MMA), so the register-resident mma.sync form is the right tool.
+#include <type_traits>
+
 #include "ard_common.cuh"
 #include "ard_internal.h"
 
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const __nv_bfloat
     const int ih0 = r0 >> 3, iw0 = r0 & 7, ih1 = ih0 + 1;
     // shift-mask bitmaps over this thread's 16 key columns
     uint32_t neq0 = 0, neq1 = 0;
-    if (shift > 0) {
+    if (shift > 0 && (wh == (H >> 3) - 1 || ww == nWw - 1)) {
         const int l0 = tok_lab[r0], l1 = tok_lab[r0 + 8];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
@@ -126,6 +128,12 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const __nv_bfloat
     const uint32_t tiles_u32 = smem_u32(tiles);
     constexpr float LOG2E = 1.4426950408889634f;
 
+    // The shift mask is non-zero only in windows that straddle the roll seam (last window row / column of a shifted block): for
+    // all other windows - every window of the unshifted blocks - the per-element mask test (LOP3 + ISETP + predicated FADD, a
+    // quarter of the kernel's instructions, and the kernel is issue-bound at 77 % issue-active) is compiled out.
+    const bool masked = shift > 0 && (wh == (H >> 3) - 1 || ww == nWw - 1);
+    auto head_loop = [&](auto masked_tag) {
+    constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll 1
     for (int hh = 0; hh < AT_HEADS; ++hh) {
         const uint32_t qs = tiles_u32 + (0 * AT_HEADS + hh) * 4096;
@@ -156,8 +164,10 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const __nv_bfloat
                 const int i0 = (ih0 - nt + 7) * 15 + (iw0 - jw + 7);
                 float v0 = s[nt][e] + tb[i0];
                 float v1 = s[nt][2 + e] + tb[i0 + 15];      // row r0+8: ih1 = ih0+1
-                if ((neq0 >> (nt * 2 + e)) & 1) v0 -= 100.0f;
-                if ((neq1 >> (nt * 2 + e)) & 1) v1 -= 100.0f;
+                if constexpr (MASKED) {
+                    if ((neq0 >> (nt * 2 + e)) & 1) v0 -= 100.0f;
+                    if ((neq1 >> (nt * 2 + e)) & 1) v1 -= 100.0f;
+                }
                 s[nt][e] = v0;
                 s[nt][2 + e] = v1;
                 m0 = fmaxf(m0, v0);
@@ -232,6 +242,9 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const __nv_bfloat
             *reinterpret_cast<uint32_t*>(qt + tile_off(r0 + 8, nd) + (lane & 3) * 4) = pack_bf16x2(o[nd][2] * inv1, o[nd][3] * inv1);
         }
     }
+    };
+    if (masked) head_loop(std::true_type{});
+    else head_loop(std::false_type{});
     __syncwarp();
     // ---- scatter this warp's 16 output rows back to token order: (attn @ v).transpose(1,2).reshape(B_, N, C) htsat.py:354
     for (int i = lane; i < 16 * UPR; i += 32) {
