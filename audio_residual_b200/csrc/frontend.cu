@@ -9,6 +9,8 @@
 //   patch_embed_ln_kernel : bn0 (eval) + reshape_wav2img (bicubic 1001->1024 along time, fold into 4 frequency-stacked
 //                        quarters; htsat.py:848-863, :900-902) + PatchEmbed conv 4x4/4 + LayerNorm (htsat.py:136-143) fused:
 //                        the 256x256 image never exists in memory.
+#include <cstdlib>
+
 #include "ard_common.cuh"
 #include "ard_internal.h"
 
@@ -322,6 +324,157 @@ __global__ void __launch_bounds__(256) patch_embed_ln_kernel(const float* __rest
     }
 }
 
+// Tensor-core form of the same op. The 4x4 conv is a [tokens, 16] x [16, C] product: exactly one k-step of mma.sync
+// m16n8k16. To keep fp32-grade accuracy on bf16 tensor cores both operands are split, x = hi + lo with hi = bf16(x),
+// lo = bf16(x - hi), and three products are accumulated (hi*hi + lo*hi + hi*lo: relative error ~2^-16). A warp walks runs of 32
+// consecutive tokens of one patch row: the 32 lanes compute the 2 x 16 pixels of two tokens per step as before (bn0 ->
+// bicubic -> fold), park them as split bf16 in a padded shared tile, then run two 16-token m-tiles: A fragments by
+// ldmatrix, the weight fragments live in registers for the warp's whole life, LayerNorm on the accumulators (a row's 96/128
+// channels sit in the 4 lanes of a quad: two shuffles per reduction instead of five per token), 8-byte stores.
+// The SIMT kernel above spent 26 shuffles and ~140 instructions per token (360 us at B = 256); this one ~45.
+constexpr int PE_RUNS_PER_WARP = 4;     // 128 tokens per warp: amortises the weight-fragment set-up
+constexpr int PE_APITCH = 48;           // bytes per token row of the pixel tile (16 bf16 + pad: conflict-free ldmatrix)
+
+template <int NT>   // n-tiles of 8 channels: C = 8 * NT (12 or 16)
+__global__ void __launch_bounds__(256) patch_embed_ln_mma_kernel(const float* __restrict__ mel, long long clip_stride, int frames,
+                                                                const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
+                                                                const float* __restrict__ wconv, const float* __restrict__ bconv,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float* __restrict__ out, long long ntokens) {
+    pdl_launch_dependents();
+    pdl_wait();
+    constexpr int C = 8 * NT;
+    __shared__ __align__(16) uint8_t atile[8][2][32 * PE_APITCH];   // per warp: hi / lo pixel tiles [32 tokens][16 pixels] bf16
+    __shared__ float2 aff[3][C / 2];                                // conv bias, LayerNorm gamma, beta as channel pairs
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < C / 2; i += blockDim.x) {
+        aff[0][i] = make_float2(__ldg(bconv + 2 * i), __ldg(bconv + 2 * i + 1));
+        aff[1][i] = make_float2(__ldg(gamma + 2 * i), __ldg(gamma + 2 * i + 1));
+        aff[2][i] = make_float2(__ldg(beta + 2 * i), __ldg(beta + 2 * i + 1));
+    }
+    // B fragments of W^T [k = pixel][n = channel] (m16n8k16 col-major B): lane holds k = (lane%4)*2 + {0,1} (+8), n = lane/4
+    uint32_t bh[NT][2], bl[NT][2];
+    {
+        const int k0 = (lane & 3) * 2, n = lane >> 2;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const float* wp = wconv + (nt * 8 + n) * 16;
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                const float w0 = __ldg(wp + k0 + 8 * hlf), w1 = __ldg(wp + k0 + 8 * hlf + 1);
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
+                bh[nt][hlf] = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
+                bl[nt][hlf] = pack_bf16x2(w0 - __bfloat162float(h0), w1 - __bfloat162float(h1));
+            }
+        }
+    }
+    __syncthreads();
+    uint8_t* at_hi = atile[warp][0];
+    uint8_t* at_lo = atile[warp][1];
+    const int i = (lane >> 2) & 3, j = lane & 3, sub = lane >> 4;
+    const float scale = (float)(frames - 1) / (float)(1024 - 1);   // align_corners=True
+    const float A = -0.75f;
+    const long long warp_tok0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * (32 * PE_RUNS_PER_WARP);
+#pragma unroll 1
+    for (int run = 0; run < PE_RUNS_PER_WARP; ++run) {
+        const long long tok0 = warp_tok0 + run * 32;
+        if (tok0 >= ntokens) break;
+        // The run's 32 tokens share one patch row (64 tokens per row, runs are 32-aligned): clip, quarter r, mel bins f are fixed.
+        // (Staging the run's ~128 source frames in shared memory first was measured slower: 0.97 vs 0.79 ms for the front end -
+        // the staging loads are a serial latency per run, while these taps are prefetched one step ahead.)
+        const long long b = tok0 >> 12;
+        const int t0 = (int)(tok0 & 4095);
+        const int ph = t0 >> 6, pw0 = t0 & 63;
+        const int r = ph >> 4;
+        const int f = ((ph & 15) << 2) + i;
+        const float* mp = mel + b * clip_stride + f;
+        const float sc = bn_scale ? __ldg(bn_scale + f) : 1.f, sh = bn_shift ? __ldg(bn_shift + f) : 0.f;
+        auto taps = [&](int it, float (&v)[4]) {
+            const int tau = r * 256 + (pw0 + it + sub) * 4 + j;        // index on the 1024-frame (interpolated) time axis
+            const int x0 = (int)floorf(scale * (float)tau);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int xi = x0 - 1 + k;
+                xi = xi < 0 ? 0 : (xi > frames - 1 ? frames - 1 : xi);
+                v[k] = __ldg(mp + (long long)xi * NMEL);
+            }
+        };
+        float v[4], vn[4];
+        taps(0, v);
+        __syncwarp();                                  // the previous run's ldmatrix reads of the pixel tiles are done
+#pragma unroll 1
+        for (int it = 0; it < 32; it += 2) {
+            if (it + 2 < 32) taps(it + 2, vn);
+            const int tau = r * 256 + (pw0 + it + sub) * 4 + j;
+            const float real = scale * (float)tau;
+            const float tt = real - floorf(real);
+            float pix = fmaf(v[0], sc, sh) * cc2(tt + 1.f, A);             // bn0 before the interpolation (htsat.py:900-902)
+            pix = fmaf(fmaf(v[1], sc, sh), cc1(tt, A), pix);
+            pix = fmaf(fmaf(v[2], sc, sh), cc1(1.f - tt, A), pix);
+            pix = fmaf(fmaf(v[3], sc, sh), cc2(2.f - tt, A), pix);
+            const __nv_bfloat16 hi = __float2bfloat16_rn(pix);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(pix - __bfloat162float(hi));
+            const int off = (it + sub) * PE_APITCH + (lane & 15) * 2;      // token it+sub, pixel n = 4 i + j
+            *reinterpret_cast<__nv_bfloat16*>(at_hi + off) = hi;
+            *reinterpret_cast<__nv_bfloat16*>(at_lo + off) = lo;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = vn[k];
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int mt = 0; mt < 2; ++mt) {
+            // A fragments (16 tokens x 16 pixels): ldmatrix.x4, lane -> row (lane & 15), 16-byte half (lane >> 4)
+            uint32_t ah[4], al[4];
+            const uint32_t aoff = (uint32_t)((mt * 16 + (lane & 15)) * PE_APITCH + (lane >> 4) * 16);
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(ah[0]), "=r"(ah[1]), "=r"(ah[2]), "=r"(ah[3]) : "r"(smem_u32(at_hi) + aoff));
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(al[0]), "=r"(al[1]), "=r"(al[2]), "=r"(al[3]) : "r"(smem_u32(at_lo) + aoff));
+            float acc[NT][4];
+            const int cp = lane & 3;                   // this lane's channel pair inside an n-tile: channels 8 nt + 2 cp, +1
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const float2 bb = aff[0][nt * 4 + cp];
+                acc[nt][0] = bb.x; acc[nt][1] = bb.y; acc[nt][2] = bb.x; acc[nt][3] = bb.y;
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                             : "r"(ah[0]), "r"(ah[1]), "r"(ah[2]), "r"(ah[3]), "r"(bh[nt][0]), "r"(bh[nt][1]));
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                             : "r"(al[0]), "r"(al[1]), "r"(al[2]), "r"(al[3]), "r"(bh[nt][0]), "r"(bh[nt][1]));
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                             : "r"(ah[0]), "r"(ah[1]), "r"(ah[2]), "r"(ah[3]), "r"(bl[nt][0]), "r"(bl[nt][1]));
+            }
+            // LayerNorm over the C channels of rows g = lane / 4 (acc[.][0..1]) and g + 8 (acc[.][2..3]): the row lives in the quad
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) { s0 += acc[nt][0] + acc[nt][1]; s1 += acc[nt][2] + acc[nt][3]; }
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+            const float m0 = s0 * (1.0f / C), m1 = s1 * (1.0f / C);
+            float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                acc[nt][0] -= m0; acc[nt][1] -= m0; acc[nt][2] -= m1; acc[nt][3] -= m1;
+                q0 = fmaf(acc[nt][0], acc[nt][0], fmaf(acc[nt][1], acc[nt][1], q0));
+                q1 = fmaf(acc[nt][2], acc[nt][2], fmaf(acc[nt][3], acc[nt][3], q1));
+            }
+            q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+            q0 += __shfl_xor_sync(0xffffffffu, q0, 2); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+            const float r0 = rsqrtf(q0 * (1.0f / C) + 1e-5f), r1 = rsqrtf(q1 * (1.0f / C) + 1e-5f);
+            float* o0 = out + (tok0 + mt * 16 + (lane >> 2)) * C + cp * 2;
+            float* o1 = o0 + 8 * C;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const float2 gg = aff[1][nt * 4 + cp], be = aff[2][nt * 4 + cp];
+                *reinterpret_cast<float2*>(o0 + nt * 8) = make_float2(fmaf(acc[nt][0] * r0, gg.x, be.x), fmaf(acc[nt][1] * r0, gg.y, be.y));
+                *reinterpret_cast<float2*>(o1 + nt * 8) = make_float2(fmaf(acc[nt][2] * r1, gg.x, be.x), fmaf(acc[nt][3] * r1, gg.y, be.y));
+            }
+        }
+    }
+}
+
 int patch_embed_ln(const float* logmel, long long clip_stride, int frames, const float* bn_scale, const float* bn_shift, const float* w,
                    const float* bias, const float* gamma, const float* beta, float* out, int B, int C, cudaStream_t s) {
     if (B <= 0) return 0;
@@ -329,6 +482,15 @@ int patch_embed_ln(const float* logmel, long long clip_stride, int frames, const
     const long long ntok = (long long)B * 4096;
     const unsigned grid = (unsigned)((ntok + 8 * PE_TOK_PER_WARP - 1) / (8 * PE_TOK_PER_WARP));
     ProfScope ps(PROF_FRONTEND, s, (double)ntok * (2.0 * 16 * C + 16 * 8 + 8.0 * C), 4.0 * B * frames * 64 + 4.0 * ntok * C);
+    static const bool use_mma = [] { const char* e = getenv("ARD_PATCH_EMBED_MMA"); return e == nullptr || atoi(e) != 0; }();
+    if (use_mma && (C == 96 || C == 128)) {
+        const unsigned gm = (unsigned)((ntok + 8 * 32 * PE_RUNS_PER_WARP - 1) / (8 * 32 * PE_RUNS_PER_WARP));
+        if (C == 96)
+            ARD_CUDA(enqueue_pdl(patch_embed_ln_mma_kernel<12>, dim3(gm), dim3(256), 0, s, logmel, clip_stride, frames, bn_scale, bn_shift, w, bias, gamma, beta, out, ntok));
+        else
+            ARD_CUDA(enqueue_pdl(patch_embed_ln_mma_kernel<16>, dim3(gm), dim3(256), 0, s, logmel, clip_stride, frames, bn_scale, bn_shift, w, bias, gamma, beta, out, ntok));
+        return check_cuda(cudaGetLastError(), "patch_embed_ln launch");
+    }
     if (C == 96)
         ARD_CUDA(enqueue_pdl(patch_embed_ln_kernel<3>, dim3(grid), dim3(256), 0, s, logmel, clip_stride, frames, bn_scale, bn_shift, w, bias, gamma, beta, out, ntok));
     else if (C == 128)
