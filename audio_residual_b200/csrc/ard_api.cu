@@ -275,11 +275,15 @@ static int run_block(ard_handle* h, int l, int b, int B, float* X, float* Y, flo
     __nv_bfloat16* Hb = h->ws_h.as<__nv_bfloat16>();
     const int shift = (b % 2 == 0) ? 0 : 4;   // htsat.py:563
 
-    ARD_TRY(layernorm_bf16(X, bw.ln1_g.as<float>(), bw.ln1_b.as<float>(), XN, M, C, s));
     GemmArgs g;
-    g.A = XN; g.lda = C; g.W = bw.qkv_w.as<__nv_bfloat16>(); g.ldw = C; g.out = QKV; g.ldo = 3 * C; g.out_bf16 = 1;
-    g.M = (int)M; g.N = 3 * C; g.K = C; g.bias = bw.qkv_b.as<float>();
-    ARD_TRY(gemm_bf16(g, h->num_sms, s));
+    if (C == 96 && h->use_ln_qkv) {   // norm1 + qkv in one kernel: the bf16 LayerNorm output never reaches HBM
+        ARD_TRY(ln_qkv_96(X, bw.ln1_g.as<float>(), bw.ln1_b.as<float>(), bw.qkv_w.as<__nv_bfloat16>(), bw.qkv_b.as<float>(), QKV, M, h->num_sms, s));
+    } else {
+        ARD_TRY(layernorm_bf16(X, bw.ln1_g.as<float>(), bw.ln1_b.as<float>(), XN, M, C, s));
+        g.A = XN; g.lda = C; g.W = bw.qkv_w.as<__nv_bfloat16>(); g.ldw = C; g.out = QKV; g.ldo = 3 * C; g.out_bf16 = 1;
+        g.M = (int)M; g.N = 3 * C; g.K = C; g.bias = bw.qkv_b.as<float>();
+        ARD_TRY(gemm_bf16(g, h->num_sms, s));
+    }
     AttnArgs a;
     a.qkv = QKV; a.out = AO; a.bias_table = bw.rpb.as<float>(); a.attn_mean = attn_out; a.attn_scale = attn_scale; a.attn_accumulate = attn_acc;
     a.B = B; a.H = R; a.W = R; a.C = C; a.nH = nH; a.shift = shift;
@@ -452,6 +456,7 @@ int ard_create(const ard_config* cfg, ard_handle** out) {
     if (const char* e = getenv("ARD_FUSED_FFN")) h->use_fused_ffn = atoi(e) != 0;
     if (const char* e = getenv("ARD_FUSED_FFN_WIDE")) h->use_fused_ffn_wide = atoi(e);
     if (const char* e = getenv("ARD_GRAPHS")) h->use_graphs = atoi(e);
+    if (const char* e = getenv("ARD_LN_QKV")) h->use_ln_qkv = atoi(e) != 0;
     *out = h;
     return 0;
 }
@@ -700,6 +705,14 @@ int ard_ffn_fused_wide(const float* x, const float* resid2, float* out, long lon
         return set_error(ARD_ERR_CUDA, "no CUDA device");
     return ffn_fused_wide(x, resid2, out, M, C, gamma, beta, (const __nv_bfloat16*)w1_bf16, b1_half, (const __half*)w2_f16, b2, sms,
                           (cudaStream_t)stream);
+}
+
+int ard_ln_qkv_96(const float* x, const float* gamma, const float* beta, const void* w_bf16, const float* bias, void* qkv_bf16, long long M,
+                  void* stream) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return set_error(ARD_ERR_CUDA, "no CUDA device");
+    return ln_qkv_96(x, gamma, beta, (const __nv_bfloat16*)w_bf16, bias, (__nv_bfloat16*)qkv_bf16, M, sms, (cudaStream_t)stream);
 }
 
 int ard_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int C, void* stream) {

@@ -74,6 +74,7 @@ struct ard_handle {
     DevBuf ws_logmel, ws_x, ws_y, ws_xn, ws_ao, ws_qkv, ws_h, ws_normed, ws_emb, ws_hid, ws_proj, ws_tscam_a, ws_tscam_y, ws_wave;
     int last_launches = 0;
     bool use_fused_ffn = true;   // ARD_FUSED_FFN=0 disables the fused 96-channel FFN kernel (A/B measurements)
+    bool use_ln_qkv = true;      // ARD_LN_QKV=0: LayerNorm kernel + qkv GEMM instead of ln_qkv_96 (A/B measurements)
     int use_fused_ffn_wide = 1;    // ARD_FUSED_FFN_WIDE: 0 never, 1 where it measures faster (default), 2 for every C = 192 / 384 FFN
     // training state
     DevBuf tape, p0_wT, p2_wT, t_emb, t_hid, t_proj;

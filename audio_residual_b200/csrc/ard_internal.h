@@ -66,6 +66,11 @@ int ffn_fused_96(const float* x, const float* resid2, float* out, long long M, c
 int ffn_fused_wide(const float* x, const float* resid2, float* out, long long M, int C, const float* gamma, const float* beta,
                    const __nv_bfloat16* w1, const float* b1_half, const __half* w2_f16, const float* b2, int num_sms, cudaStream_t stream);
 
+// ---------------------------------------------------------------- fused norm1 + qkv projection, 96-channel stage (ln_qkv.cu)
+// qkv[M, 288] bf16 = LayerNorm(x[M, 96]; gamma, beta) w^T + bias
+int ln_qkv_96(const float* x, const float* gamma, const float* beta, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* qkv, long long M,
+              int num_sms, cudaStream_t stream);
+
 // ---------------------------------------------------------------- row-wise kernels (rowwise.cu)
 // LayerNorm over the last dim C of x[rows, C] (fp32) -> bf16; two-pass variance like at::native layer_norm.
 int layernorm_bf16(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, long long rows, int C, cudaStream_t s);

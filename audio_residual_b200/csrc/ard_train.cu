@@ -137,11 +137,16 @@ int run_block_train(ard_handle* h, int l, int b, int B, float* attn_out, float a
     const long long M = (long long)B * T;
     __nv_bfloat16* XN = h->ws_xn.as<__nv_bfloat16>();
     __nv_bfloat16* Hb = h->ws_h.as<__nv_bfloat16>();
-    ARD_TRY(layernorm_bf16(bw.t_s, bw.ln1_g.as<float>(), bw.ln1_b.as<float>(), XN, M, C, s));
     GemmArgs g;
-    g.A = XN; g.lda = C; g.W = bw.qkv_w.as<__nv_bfloat16>(); g.ldw = C; g.out = bw.t_qkv; g.ldo = 3 * C; g.out_bf16 = 1;
-    g.M = (int)M; g.N = 3 * C; g.K = C; g.bias = bw.qkv_b.as<float>();
-    ARD_TRY(gemm_bf16(g, h->num_sms, s));
+    if (C == 96 && h->use_ln_qkv) {
+        ARD_TRY(ln_qkv_96(bw.t_s, bw.ln1_g.as<float>(), bw.ln1_b.as<float>(), bw.qkv_w.as<__nv_bfloat16>(), bw.qkv_b.as<float>(), bw.t_qkv, M,
+                          h->num_sms, s));
+    } else {
+        ARD_TRY(layernorm_bf16(bw.t_s, bw.ln1_g.as<float>(), bw.ln1_b.as<float>(), XN, M, C, s));
+        g.A = XN; g.lda = C; g.W = bw.qkv_w.as<__nv_bfloat16>(); g.ldw = C; g.out = bw.t_qkv; g.ldo = 3 * C; g.out_bf16 = 1;
+        g.M = (int)M; g.N = 3 * C; g.K = C; g.bias = bw.qkv_b.as<float>();
+        ARD_TRY(gemm_bf16(g, h->num_sms, s));
+    }
     AttnArgs a;
     a.qkv = bw.t_qkv; a.out = bw.t_ao; a.bias_table = bw.rpb.as<float>(); a.attn_mean = attn_out; a.attn_scale = attn_scale;
     a.attn_accumulate = attn_acc; a.B = B; a.H = R; a.W = R; a.C = C; a.nH = nH; a.shift = (b % 2 == 0) ? 0 : 4;

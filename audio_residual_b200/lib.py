@@ -74,6 +74,7 @@ def load(check_symbols=False):
         lib.ard_layernorm_bf16.argtypes = [vp, vp, vp, vp, ll, i, vp]
         lib.ard_ffn_fused_96.argtypes = [vp, vp, vp, ll, vp, vp, vp, vp, vp, vp, vp]
         lib.ard_ffn_fused_wide.argtypes = [vp, vp, vp, ll, i, vp, vp, vp, vp, vp, vp, vp]
+        lib.ard_ln_qkv_96.argtypes = [vp, vp, vp, vp, vp, vp, ll, vp]
         lib.ard_window_attention.argtypes = [vp, vp, vp, vp, f, i, i, i, i, i, i, i, vp]
         lib.ard_window_attention_bwd.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, vp]
         lib.ard_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, ll, i, vp]

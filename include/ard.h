@@ -146,6 +146,10 @@ int ard_ffn_fused_96(const float* x, const float* resid2, float* out, long long 
  * 128-token tile. b1_half = 0.5 * fc1 bias [4C] (the packed-fp16 GELU is evaluated on x / 2). */
 int ard_ffn_fused_wide(const float* x, const float* resid2, float* out, long long M, int C, const float* gamma, const float* beta,
                        const void* w1_bf16, const float* b1_half, const void* w2_f16, const float* b2, void* stream);
+/* norm1 + qkv projection of a 96-channel Swin block in one kernel (htsat.py:449 + :329): qkv[M,288] bf16 =
+ * LayerNorm(x[M,96]; gamma, beta) w^T + bias, w [288,96] bf16 (q rows pre-scaled by head_dim^-0.5), all device pointers. */
+int ard_ln_qkv_96(const float* x, const float* gamma, const float* beta, const void* w_bf16, const float* bias, void* qkv_bf16, long long M,
+                  void* stream);
 /* nn.LayerNorm(C, eps=1e-5) over x[rows, C] fp32 -> bf16 (htsat.py:449,479 norm1/norm2). */
 int ard_layernorm_bf16(const float* x, const float* gamma, const float* beta, void* out_bf16, long long rows, int C, void* stream);
 /* Shifted-window attention core of WindowAttention.forward (htsat.py:326-352) incl. roll/partition/reverse addressing

@@ -108,6 +108,24 @@ def check_ffn_fused(M=5000, resid2=True, seed=0, Cd=96, alias=False):
     return rel(out.cpu(), ref), rel(got_branch, branch)
 
 
+def check_ln_qkv(M=5000, seed=0):
+    """ard_ln_qkv_96 (norm1 + qkv projection in one kernel) vs torch fp32 LayerNorm + Linear on the bf16-rounded weight."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(seed)
+    Cd = 96
+    x = torch.randn(M, Cd, generator=g) * 1.5 + 0.3
+    gm, bt = 1 + 0.1 * torch.randn(Cd, generator=g), 0.1 * torch.randn(Cd, generator=g)
+    w = torch.randn(3 * Cd, Cd, generator=g) / Cd ** 0.5
+    b = 0.1 * torch.randn(3 * Cd, generator=g)
+    ref = bf16r(torch.nn.functional.layer_norm(x, (Cd,), gm, bt, 1e-5)) @ bf16r(w).t() + b
+    d = lambda t: t.cuda().contiguous()
+    xd, gd, btd, wd, bd = d(x), d(gm), d(bt), d(w).to(torch.bfloat16), d(b)
+    out = torch.empty(M, 3 * Cd, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.ard_ln_qkv_96(L.ptr(xd), L.ptr(gd), L.ptr(btd), L.ptr(wd), L.ptr(bd), L.ptr(out), M, L.stream_ptr()))
+    torch.cuda.synchronize()
+    return rel(out.float().cpu(), ref)
+
+
 def check_gemm_f16_chain(M=3000, Cd=192, seed=0):
     """fc1 with the packed-fp16 GELU epilogue (ARD_ACT_GELU_F16) feeding the fp16 fc2 GEMM with a TMA-fetched residual."""
     lib = L.load()

@@ -45,6 +45,11 @@ def test_ffn_fused_wide(C, M, resid2, alias):
     assert r_out < 2e-3 and r_branch < 5e-3, (C, M, r_out, r_branch)
 
 
+@pytest.mark.parametrize("M", [128, 5000, 148 * 128 * 3 + 77])
+def test_ln_qkv_96(M):
+    assert G.check_ln_qkv(M) < 4e-3, M          # bf16 output rounding (2^-9) on top of bf16 operands
+
+
 def test_gemm_f16_hidden_chain():
     r_h, r_out = G.check_gemm_f16_chain()
     assert r_h < 1e-3 and r_out < 2e-3, (r_h, r_out)                # fp16 hidden: 10-bit mantissa

@@ -114,6 +114,26 @@ def bench_ffn_wide():
         report(f"unfused LN+fc1+fc2 C={C} M={M}", us, 2.0 * M * C * 4 * C * 2, 34.0 * M * C)
 
 
+def bench_lnqkv():
+    lib = L.load()
+    st = L.stream_ptr()
+    M, C = B * 4096, 96
+    x = torch.randn(M, C, device=dev)
+    g, bt = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+    w = (torch.randn(3 * C, C, device=dev) / C ** 0.5).to(torch.bfloat16)
+    b = torch.randn(3 * C, device=dev)
+    out = torch.empty(M, 3 * C, device=dev, dtype=torch.bfloat16)
+    xn = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
+    us = timeit(lambda: L.check(lib.ard_ln_qkv_96(L.ptr(x), L.ptr(g), L.ptr(bt), L.ptr(w), L.ptr(b), L.ptr(out), M, st)))
+    report(f"ln_qkv_96 M={M}", us, 2.0 * M * 3 * C * C, 4.0 * M * C + 2.0 * M * 3 * C)
+
+    def unfused():
+        L.check(lib.ard_layernorm_bf16(L.ptr(x), L.ptr(g), L.ptr(bt), L.ptr(xn), M, C, st))
+        L.check(lib.ard_gemm_bf16(L.ptr(xn), C, L.ptr(w), C, L.ptr(out), 3 * C, 1, M, 3 * C, C, L.ptr(b), 0, None, 0, None, 0, st))
+    us = timeit(unfused)
+    report(f"unfused LN + qkv M={M}", us, 2.0 * M * 3 * C * C, 8.0 * M * C + 2.0 * M * 3 * C)
+
+
 def bench_attn():
     lib = L.load()
     st = L.stream_ptr()
@@ -165,4 +185,4 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "ffn", "ffnw", "attn", "ln", "front"]
     print(torch.cuda.get_device_name(0), "B =", B, flush=True)
     for w in which:
-        {"gemm": bench_gemm, "ffn": bench_ffn, "ffnw": bench_ffn_wide, "attn": bench_attn, "ln": bench_ln, "front": bench_front}[w]()
+        {"gemm": bench_gemm, "ffn": bench_ffn, "ffnw": bench_ffn_wide, "lnqkv": bench_lnqkv, "attn": bench_attn, "ln": bench_ln, "front": bench_front}[w]()
