@@ -81,9 +81,6 @@ ARD_DEVINL void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
             : "memory");
-#ifdef ARD_WAIT_SLEEP
-        if (!ok) __nanosleep(ARD_WAIT_SLEEP);
-#endif
     }
 }
 

@@ -5,25 +5,26 @@
 //
 // Unfused, one FFN at stage 0 moves 34 bytes per token-channel through HBM (LN out, 4C hidden written and re-read) and is
 // ~6x over its HBM floor; here x is read once (+ once more for the residual add, from L2) and the result written once.
-// Both weight matrices (2 x 72 KB bf16) stay resident in shared memory for the life of the persistent CTA; the 4C-wide
-// hidden activation only ever exists as a 128x64 TMEM accumulator and a 16 KB bf16 shared-memory operand tile.
+// Both weight matrices (2 x 72 KB) stay resident in shared memory for the life of the persistent CTA; the 4C-wide hidden
+// activation only ever exists in TENSOR MEMORY: as a 128x64 fp32 accumulator, then as the packed-fp16 A operand of fc2.
 //
-// Persistent CTA (one per SM), 25 warps, every role loops over the CTA's 128-token tiles:
-//   warps 0-3   : output epilogue (warp w owns TMEM lanes 32w..): Y accumulator -> + b2 + x (+ resid2) -> swizzled staging
-//                 -> TMA store; the next chunk's residual loads are in flight while the current chunk is staged/stored
-//   warp 4      : TMEM allocator, one-time TMA load of W1/W2, single-thread tcgen05.mma issue. Per 64-wide hidden chunk j:
-//                 H_j = A1 W1_j^T (M128 N64 K96), then Y += GELU(H_j) W2[:, j]^T (M128 N96 K64); H is triple-buffered in
-//                 TMEM so the tensor core runs up to three chunks ahead of the GELU warps
-//   warps 5-8   : LayerNorm producers: 8 lanes per row (12 contiguous channels each), 4 rows per warp instruction, 3-step
-//                 butterflies; bf16 rows written straight into the SWIZZLE_64B K-major A-operand layout tcgen05 expects;
-//                 rows are prefetched into L2 one tile ahead and loaded in software-pipelined batches
-//   warps 9-24  : 16 GELU warps (4 per TMEM lane quadrant, 16 hidden columns each): tcgen05.ld H_j, + b1, exact-erf GELU,
-//                 (packed fp16 math), write the fp16 A2 operand tile (SWIZZLE_128B); fc2 runs as an fp16 x fp16 tcgen05 GEMM
+// Persistent CTA (one per SM), 26 warps, every role loops over the CTA's 128-token tiles:
+//   warps 0-7   : output epilogue (TMEM lane quadrant w & 3, column half w >> 2): Y accumulator -> + b2 + x (+ resid2) ->
+//                 swizzled staging -> TMA store; the residual tiles are prefetched by TMA one 16-column chunk ahead
+//   warp 8      : TMEM allocator, one-time TMA load of W1/W2, fc1 issue (warp-convergent loop, elected lane). Per PAIR of 64-wide
+//                 hidden chunks: H = A1 W1^T (M128 N128 K96) into two of the four H accumulators, so the tensor core runs up
+//                 to two pairs ahead of the GELU warps
+//   warps 9-24  : 16 GELU warps in two groups on alternate chunks (4 per TMEM lane quadrant, 32 hidden columns each):
+//                 tcgen05.ld H_j, + b1, erf GELU in packed fp16 math, tcgen05.st of the fp16 result into the A2 columns of
+//                 tensor memory. The same warps LayerNorm the NEXT tile (8 rows per warp, 8 lanes per row, 3-step butterflies,
+//                 bf16 rows written straight into the SWIZZLE_64B K-major A-operand layout), group 0 after its first chunk
+//                 of the current tile and group 1 after its second
+//   warp 25     : fc2 issue: Y += A2_j W2[:, j]^T (M128 N96 K64, fp16 x fp16) with the A operand read from tensor memory
 //
-// Measured history of this kernel is in profiles/r1_ffn_fused.md: LayerNorm + epilogue on the same 4 warps serialised the
-// tile pipeline (their dependent shuffle / TMEM / TMA chains are latency-, not throughput-bound), hence the role split.
-// With everything overlapped the kernel is bound by the GELU warps' CUDA-core issue rate (~20 instructions per hidden
-// element), not by the tensor core (K = 96) and no longer by HBM.
+// Measured history of this kernel is in profiles/r1_ffn_fused.md (520 -> 251 us at M = 1,048,576): the per-role clock trace
+// (tools/ffn_trace.py) showed a dedicated LayerNorm role serialising with the fc1 issue train behind a single A1 buffer; the
+// shared-memory hand-off of the GELU output cost an async-proxy fence per chunk; row-per-thread residual loads in the epilogue
+// cost 160 us with a second residual. ncu now: issue-active 63-66 %, DRAM traffic = algorithmic.
 #include "ard_common.cuh"
 #include "ard_internal.h"
 
@@ -57,8 +58,8 @@ constexpr int FF_A1_KB = FF_BM * 64;            // 8192
 constexpr int FF_A1_OFF = FF_W2_OFF + FF_W2_BYTES;
 constexpr int FF_A1_BYTES = 3 * FF_A1_KB;       // 24576
 constexpr int FF_A2_OFF = FF_A1_OFF + FF_A1_BYTES;
-constexpr int FF_A2_BYTES = FF_BM * 128;        // 16384 per buffer (FF_A2_TMEM = 0); with the A2 tile in tensor memory the same
-                                                // 32 KB hold the TMA-prefetched residual tiles: 8 warps x {x, resid2} x (32 rows x 64 B)
+constexpr int FF_A2_BYTES = FF_BM * 128;        // the GELU output goes to fc2 through tensor memory; the 2 x 16 KB a shared-memory A2
+                                                // tile would need hold the TMA-prefetched residual tiles: 8 warps x {x, resid2} x (32 rows x 64 B)
 constexpr int FF_RB_OFF = FF_A2_OFF;
 constexpr int FF_CST_OFF = FF_A2_OFF + 2 * FF_A2_BYTES;    // 8 warps x (32 rows x 64 B)
 constexpr int FF_VEC_OFF = FF_CST_OFF + FF_EPI_WARPS * 2048;   // b1[384] b2[96] gamma[96] beta[96]
@@ -68,9 +69,6 @@ constexpr int FF_SMEM_BYTES = FF_BAR_OFF + 256 + 1024;
 constexpr int FF_NHB = 4;       // H accumulators in flight (two pairs)
 constexpr int FF_TM_H = 0;      // TMEM columns: H0..H3 @0/64/128/192, Y0 @256 (96 used), Y1 @384
 constexpr int FF_TM_Y = 256;
-#ifndef FF_A2_TMEM
-#define FF_A2_TMEM 1            // 1: the GELU output reaches fc2 through tensor memory (A operand from TMEM); 0: through shared memory (A/B)
-#endif
 constexpr int FF_TM_A2 = 352;   // A2 buffer g: 32 columns (64 fp16 per row) at 352 + 128 g, in the gaps after Y0 / Y1
 
 struct FfnParams {
@@ -154,7 +152,6 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         const int quad = warp & 3, c_begin = (warp >> 2) * 3;
         uint8_t* sbuf = smem + FF_CST_OFF + warp * 2048;
         const bool has_r2 = p.resid2 != nullptr;
-#if FF_A2_TMEM
         // The residual tiles (x, and the second residual) of a chunk are fetched by TMA one chunk ahead into this warp's two
         // 2 KB buffers: coalesced, asynchronous, no registers held across the wait. (Row-per-thread LDG.128 touches 32 lines
         // per instruction; with a second residual it cost 160 us per launch.) Chunk sequence number q = 3 * it + cc.
@@ -222,67 +219,6 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
             if (warp == 0 && lane == 0) FF_TRACE(0, it, 2);
         }
         if (lane == 0) tma_store_wait_all<0>();
-#else
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int yb = it & 1;
-            const long long row = (long long)tile * FF_BM + quad * 32 + lane;
-            const bool row_ok = row < p.M;
-            float4 r1[4], r2[4];
-            auto load_resid = [&](int c) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { r1[j] = make_float4(0.f, 0.f, 0.f, 0.f); r2[j] = r1[j]; }
-                if (row_ok) {
-                    const float4* rp = reinterpret_cast<const float4*>(p.x + row * FF_C + c * 16);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) r1[j] = rp[j];
-                    if (has_r2) {
-                        const float4* rq = reinterpret_cast<const float4*>(p.resid2 + row * FF_C + c * 16);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) r2[j] = rq[j];
-                    }
-                }
-            };
-            load_resid(c_begin);                             // in flight while fc2 of this tile finishes
-            mbar_wait_parked(&y_full[yb], (it >> 1) & 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (int cc = 0; cc < 3; ++cc) {                 // 16-column chunks
-                const int c = c_begin + cc;
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(tmem_base + FF_TM_Y + yb * 128 + c * 16 + ((uint32_t)(quad * 32) << 16), v);
-                tmem_ld_wait();
-                if (cc == 2) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&y_free[yb]);
-                }
-                float4 o[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(b2s + c * 16 + j * 4);
-                    o[j].x = __uint_as_float(v[j * 4 + 0]) + b4.x + r1[j].x + r2[j].x;
-                    o[j].y = __uint_as_float(v[j * 4 + 1]) + b4.y + r1[j].y + r2[j].y;
-                    o[j].z = __uint_as_float(v[j * 4 + 2]) + b4.z + r1[j].z + r2[j].z;
-                    o[j].w = __uint_as_float(v[j * 4 + 3]) + b4.w + r1[j].w + r2[j].w;
-                }
-                if (cc + 1 < 3) load_resid(c + 1);           // next chunk's residuals fly during the staging / TMA store below
-                if (lane == 0) tma_store_wait_read<0>();     // the previous chunk's store has read the (single) staging buffer
-                __syncwarp();
-                uint8_t* rowp = sbuf + lane * 64;
-                const int sw = (lane >> 1) & 3;              // SWIZZLE_64B: 16-byte unit index ^= (row >> 1) & 3
-#pragma unroll
-                for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(rowp + ((j ^ sw) << 4)) = o[j];
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_2d(&tmOut, sbuf, c * 16, tile * FF_BM + quad * 32);
-                    tma_store_commit();
-                }
-            }
-        }
-        if (lane == 0) tma_store_wait_all<0>();
-#endif
     } else if (warp == FF_W_MMA) {
         // ============================================================ weight load + fc1 MMA issue
         // The whole warp runs the loop (all lanes wait on the barriers) and one elected lane issues: in warp-convergent code
@@ -334,7 +270,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         // ============================================================ fc2 issuer: Y += A2_g W2[:, j]^T (same convergent pattern)
         mbar_wait_parked(w_full, 0);
         constexpr uint32_t idesc2 = umma_idesc_f16(FF_BM, FF_C);   // A2 (GELU output) and W2 are fp16
-        const uint64_t dW2 = umma_desc_sw128(smem_u32(smem + FF_W2_OFF)), dA2 = umma_desc_sw128(smem_u32(smem + FF_A2_OFF));
+        const uint64_t dW2 = umma_desc_sw128(smem_u32(smem + FF_W2_OFF));
         int g = 0;
         for (int t = 0; t < my_tiles; ++t) {
             const int yb = t & 1;
@@ -348,13 +284,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                 if (lane == 0) FF_TRACE(2, g, 2);
                 tc_fence_after();
                 if (elect_one_sync()) {
-#if FF_A2_TMEM
                     umma_f16_ts_run4(tmem_base + FF_TM_Y + yb * 128, tmem_base + FF_TM_A2 + b * 128, dW2 + (uint64_t)(j * (FF_W2_KB >> 4)), idesc2,
                                      j != 0);
-#else
-                    umma_f16_ss_run<4>(tmem_base + FF_TM_Y + yb * 128, dA2 + (uint64_t)(b * (FF_A2_BYTES >> 4)),
-                                       dW2 + (uint64_t)(j * (FF_W2_KB >> 4)), idesc2, j != 0);
-#endif
                     umma_commit(&a2_free[b]);
                     if (j == FF_NCH - 1) umma_commit(&y_full[yb]);
                 }
@@ -496,20 +427,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                 if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 2);
                 mbar_wait_parked(&a2_free[grp], ((g >> 1) & 1) ^ 1);   // fc2 MMAs that read the previous contents have retired
                 if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 3);
-#if FF_A2_TMEM
                 // 32 fp16 of this lane's row = 16 packed columns of the A2 tile in tensor memory (K pair 2c, 2c+1 in column c)
                 tmem_st_32x32b_x16(tmem_base + FF_TM_A2 + grp * 128 + half * 16 + ((uint32_t)(quad * 32) << 16), pk);
                 tmem_st_wait();
                 tc_fence_before();
                 (void)row;
-#else
-                uint8_t* rowp = smem + FF_A2_OFF + grp * FF_A2_BYTES + row * 128;
-                const int sw = row & 7;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<uint4*>(rowp + (((half * 4 + q) ^ sw) << 4)) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-                fence_proxy_async_smem();
-#endif
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a2_full[grp]);
                 if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 4);

@@ -1,6 +1,6 @@
 """Per-role timeline of the fused FFN kernel's CTA 0 (development aid).
 
-Build:  nvcc ... -DARD_FFN_TRACE -c csrc/ffn_fused.cu, link with the other objects into build/libard_trace.so
+Build:  tools/build_trace.sh   (compiles the fused FFN kernels with -DARD_FFN_TRACE into build/libard_trace.so)
 Run  :  python tools/ffn_trace.py [--r2]      -> cycles relative to the first stamp, one line per tile / chunk
 """
 import ctypes as C
