@@ -86,20 +86,33 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const __nv_bfloat
         }
         tok_lab[tid] = lab;
     }
-    for (int i = tid; i < AT_HEADS * 225; i += 128) {
-        const int hh = i / 225, idx = i - hh * 225;
-        tbl[hh][idx] = __ldg(bias_table + idx * nH + g * AT_HEADS + hh);
+    static_assert(AT_HEADS == 2, "the bias-table load below fetches both heads of the CTA as one float2");
+    for (int idx = tid; idx < 225; idx += 128) {    // nH is even, so the pair (idx, 2g), (idx, 2g+1) is 8-byte aligned
+        const float2 bb = __ldg(reinterpret_cast<const float2*>(bias_table + idx * nH + g * AT_HEADS));
+        tbl[0][idx] = bb.x;
+        tbl[1][idx] = bb.y;
     }
     __syncthreads();
 
     // ---- gather q/k/v rows of this window (token order in HBM) into swizzled smem tiles
-    for (int i = tid; i < 64 * 3 * UPR; i += 128) {
-        const int u = i % UPR;
-        const int rp = i / UPR;
-        const int part = rp % 3, t = rp / 3;
+    // UPR consecutive threads copy the UPR 16-byte units of one (token, q|k|v) segment (coalesced 96 / 128-byte runs); the unit,
+    // head and row-in-block indices are fixed per thread, so the 12 copies per thread need no index divisions (the kernel is
+    // instruction-bound: the generic `i % UPR, i / UPR, ...` loop was ~45 % of a CTA's instructions together with the rest of
+    // the prologue). 128 / UPR * UPR threads take part (96 of 128 for head_dim 24).
+    {
+        constexpr int TPB = 128 / UPR;               // tokens per pass (21 or 16)
+        const int u = tid % UPR, tb = tid / UPR;
         const int hh = u / UPH, q = u - hh * UPH;
-        const __nv_bfloat16* src = qkv + (long long)tok_row[t] * (3 * C) + part * C + (g * AT_HEADS) * HD + u * 8;
-        cp_async16(tiles + (part * AT_HEADS + hh) * 4096 + tile_off(t, q), src);
+        if (tb < TPB) {
+            const __nv_bfloat16* colp = qkv + (g * AT_HEADS) * HD + u * 8;
+            uint8_t* dst0 = tiles + hh * 4096;
+            for (int t = tb; t < 64; t += TPB) {
+                const __nv_bfloat16* rowp = colp + (long long)tok_row[t] * (3 * C);
+                const uint32_t off = tile_off(t, q);
+#pragma unroll
+                for (int part = 0; part < 3; ++part) cp_async16(dst0 + part * AT_HEADS * 4096 + off, rowp + part * C);
+            }
+        }
     }
     if constexpr (HD == 24) {  // zero the padded k-dim unit (unit 3) of every tile
         for (int i = tid; i < 3 * AT_HEADS * 64; i += 128) {
@@ -247,12 +260,18 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const __nv_bfloat
     else head_loop(std::false_type{});
     __syncwarp();
     // ---- scatter this warp's 16 output rows back to token order: (attn @ v).transpose(1,2).reshape(B_, N, C) htsat.py:354
-    for (int i = lane; i < 16 * UPR; i += 32) {
-        const int rr = warp * 16 + i / UPR;
-        const int u = i % UPR;
+    {   // UPR consecutive lanes store the UPR 16-byte units of one row (same division-free mapping as the gather)
+        constexpr int RPP = 32 / UPR;                // rows per pass (5 or 4)
+        const int u = lane % UPR, rb = lane / UPR;
         const int hh = u / UPH, q = u - hh * UPH;
-        const uint4 val = *reinterpret_cast<const uint4*>(tiles + (0 * AT_HEADS + hh) * 4096 + tile_off(rr, q));
-        *reinterpret_cast<uint4*>(out + (long long)tok_row[rr] * C + (g * AT_HEADS) * HD + u * 8) = val;
+        if (rb < RPP) {
+            __nv_bfloat16* colp = out + (g * AT_HEADS) * HD + u * 8;
+            const uint8_t* src0 = tiles + (0 * AT_HEADS + hh) * 4096;
+            for (int r = rb; r < 16; r += RPP) {
+                const int rr = warp * 16 + r;
+                *reinterpret_cast<uint4*>(colp + (long long)tok_row[rr] * C) = *reinterpret_cast<const uint4*>(src0 + tile_off(rr, q));
+            }
+        }
     }
 }
 
