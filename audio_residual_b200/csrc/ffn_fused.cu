@@ -426,6 +426,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
                 }
                 if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 2);
                 mbar_wait_parked(&a2_free[grp], ((g >> 1) & 1) ^ 1);   // fc2 MMAs that read the previous contents have retired
+                tc_fence_after();                               // order the tcgen05.st below after those MMAs' reads of the A2 columns
                 if ((ew & 7) == 0 && lane == 0) FF_TRACE(4 + grp, g, 3);
                 // 32 fp16 of this lane's row = 16 packed columns of the A2 tile in tensor memory (K pair 2c, 2c+1 in column c)
                 tmem_st_32x32b_x16(tmem_base + FF_TM_A2 + grp * 128 + half * 16 + ((uint32_t)(quad * 32) << 16), pk);

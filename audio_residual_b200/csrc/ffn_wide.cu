@@ -533,6 +533,7 @@ ffn_wide_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
                 }
                 if ((ew & 7) == 0 && lane == 0) FW_TRACE(4 + grp, (int)g, 2);
                 mbar_wait_parked(&a2_free[grp], (uint32_t)(((g >> 1) & 1) ^ 1));   // fc2 MMAs that read the previous contents have retired
+                tc_fence_after();                               // order the tcgen05.st below after those MMAs' reads of the A2 columns
                 if ((ew & 7) == 0 && lane == 0) FW_TRACE(4 + grp, (int)g, 3);
                 if constexpr (Cfg::A2T) {
                     // 32 fp16 of this lane's row = 16 packed columns of the A2 tile in tensor memory (K pair 2c, 2c+1 in column c)
