@@ -31,10 +31,21 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restri
 #pragma unroll
         for (int r = 0; r < LS_CL; ++r) acc[r] = 0.f;
         const float* wr = W + (long long)n * K;
-        for (int k = lane; k < K; k += 32) {
-            const float w = __ldg(wr + k);
+        if ((K & 3) == 0) {                           // 16-byte loads of the weight row and of the staged activations
+            for (int k = lane * 4; k < K; k += 128) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(wr + k));
 #pragma unroll
-            for (int r = 0; r < LS_CL; ++r) acc[r] = fmaf(w, xs[r * K + k], acc[r]);
+                for (int r = 0; r < LS_CL; ++r) {
+                    const float4 xv = *reinterpret_cast<const float4*>(xs + r * K + k);
+                    acc[r] = fmaf(w.x, xv.x, fmaf(w.y, xv.y, fmaf(w.z, xv.z, fmaf(w.w, xv.w, acc[r]))));
+                }
+            }
+        } else {
+            for (int k = lane; k < K; k += 32) {
+                const float w = __ldg(wr + k);
+#pragma unroll
+                for (int r = 0; r < LS_CL; ++r) acc[r] = fmaf(w, xs[r * K + k], acc[r]);
+            }
         }
 #pragma unroll
         for (int r = 0; r < LS_CL; ++r)
