@@ -244,3 +244,17 @@ def test_lambda_save_restore(tmp_path):
     load_lambdas(res, tmp_path / "lam.pt")
     for l, r in res.items():
         assert torch.allclose(r.learnable.detach(), torch.as_tensor(lam[l]))
+
+
+def test_host_pipeline_chunk_schedule():
+    """_chunk_bounds (clap.py): contiguous cover of the batch, a small first chunk (the only exposed copy), every later copy
+    sized to fit under the previous chunk's encode (next <= 22.8 + 1.156 x current, measured model), no tiny tail."""
+    m = CLAP_Module.__new__(CLAP_Module)          # the schedule needs no model state
+    for N in (65, 100, 137, 256, 512, 1000, 4096):
+        b = CLAP_Module._chunk_bounds(m, N)
+        assert b[0][0] == 0 and b[-1][1] == N and all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+        sizes = [hi - lo for lo, hi in b]
+        assert all(s > 0 for s in sizes) and sizes[0] <= 24 and max(sizes) <= 256 + 256 // 3
+        for cur, nxt in zip(sizes[:-2], sizes[1:-1]):            # the last chunk may absorb a short tail
+            assert nxt <= 22.8 + 1.156 * cur + 1, (N, sizes)
+        assert sizes[-1] >= min(8, N) or len(sizes) == 1, (N, sizes)
