@@ -20,6 +20,44 @@ from .clap import batch_features
 from .residual import MomentAccumulator, quantize_tensor, pad_or_truncate  # noqa: F401  (re-exported like the reference)
 
 
+def _spectrum(n, s1, s2):
+    """Descending eigenvalues (float64, on the GPU) of the ddof=1 covariance behind the moments {n, s1, s2}."""
+    mean = s1 / n
+    cov = (s2 - n * torch.outer(mean, mean)) / (n - 1)
+    cov = 0.5 * (cov + cov.t())
+    return torch.linalg.eigvalsh(cov).flip(0).clamp_min(0)
+
+
+def finalize_head_spectra(accs, n_components=None):
+    """Spectra of a list of MomentAccumulators (one per (layer, head)), as numpy arrays.
+    Under torch.distributed (clip-sharded pass) the moments are summed over ranks with the heads dealt round-robin
+    to owners (`reduce` to the owner instead of an allreduce: each 4096^2 float64 matrix crosses NVLink once), every rank
+    eigendecomposes only its own heads, and the spectra are exchanged in one small allreduce - the 60 serial 4096-d solves of a
+    single GPU become ceil(60 / N) per GPU. After the call every accumulator's `n` is the global sample count."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    if not accs:
+        return []
+    dev, D = accs[0].s1.device, accs[0].D
+    if world > 1:
+        ns = torch.tensor([float(a.n) for a in accs], device=dev, dtype=torch.float64)
+        dist.all_reduce(ns)
+        for i, a in enumerate(accs):
+            dist.reduce(a.s1, dst=i % world)
+            dist.reduce(a.s2, dst=i % world)
+            a.n = int(round(ns[i].item()))
+    spectra = torch.zeros((len(accs), D), device=dev, dtype=torch.float64)
+    for i, a in enumerate(accs):
+        if i % world == rank:
+            spectra[i] = _spectrum(a.n, a.s1, a.s2)
+    if world > 1:
+        dist.all_reduce(spectra)
+    out = spectra.cpu().numpy()
+    k = n_components or D
+    return [out[i, :k] for i in range(len(accs))]
+
+
 class HeadPCA:
     """Stands in for a fitted sklearn IncrementalPCA: exposes the attributes the reference reads."""
 
@@ -33,22 +71,19 @@ class HeadPCA:
         self.acc.update(X)
         return self
 
-    def finalize(self, n_components=None):
-        self.acc.allreduce()
-        n = self.acc.n
-        s1 = self.acc.s1.cpu().numpy()
-        s2 = self.acc.s2
-        mean = self.acc.s1 / n
-        cov = (s2 - n * torch.outer(mean, mean)) / (n - 1)
-        cov = 0.5 * (cov + cov.t())
-        w = torch.linalg.eigvalsh(cov).flip(0).clamp_min(0).cpu().numpy()    # float64 on the GPU
+    def _set(self, w, n_components=None):
+        """w: full descending spectrum (numpy). n_components defaults to what IncrementalPCA(n_components=None) settles on at
+        its first partial_fit: min(samples of the first batch, features) (sklearn _incremental_pca.py)."""
         k = n_components or min(self.first_batch or len(w), len(w))
-        self.mean_ = s1 / n
+        self.mean_ = (self.acc.s1 / self.acc.n).cpu().numpy()
         self.explained_variance_ = w[:k]
         self.explained_variance_ratio_ = w[:k] / w.sum()
         self.n_components_ = k
-        self.n_samples_seen_ = n
+        self.n_samples_seen_ = self.acc.n
         return self
+
+    def finalize(self, n_components=None):
+        return self._set(finalize_head_spectra([self.acc])[0], n_components)
 
 
 def extract_attention(clap, X, max_len=480000, data_filling="repeatpad", pad_or_truncate=False):
@@ -75,9 +110,9 @@ def run_PCA(clap, dataloader, num_layers, num_heads, components=None, data_filli
         for l, layer_attn in enumerate(attn):                      # [B*nW, nH, 64, 64]
             for h in range(layer_attn.shape[1]):
                 pca_models[l][h].partial_fit(layer_attn[:, h].reshape(layer_attn.shape[0], 4096))
-    for l in pca_models:
-        for h in pca_models[l]:
-            pca_models[l][h].finalize(components)
+    models = [pca_models[l][h] for l in pca_models for h in pca_models[l]]
+    for m, w in zip(models, finalize_head_spectra([m.acc for m in models])):   # heads sharded over ranks when distributed
+        m._set(w, components)
     return pca_models
 
 

@@ -59,26 +59,69 @@ def get_audio_features(sample, audio_data, max_len, data_truncating, data_fillin
     return sample
 
 
-def batch_features(x, max_len=480000, data_filling="repeatpad", device=None, do_pad_or_truncate=False):
-    """Batched get_audio_features: x is [B, T] (tensor/ndarray) or a list of 1-D clips of different lengths.
-    Returns a [B, max_len] float32 tensor on `device`."""
+_FILL_MODES = {"repeatpad": 0, "pad": 1, "repeat": 2}
+
+
+def _fill_on_device(flat, offsets, lengths, B, max_len, mode, quantize=False):
+    """ard_fill_clips: `flat` (CUDA, fp32 or int16 PCM) holds the clips back to back -> [B, max_len] fp32 on the same device."""
+    import ctypes as C
+    from . import lib as L
+    out = torch.empty((B, max_len), device=flat.device, dtype=torch.float32)
+    with torch.cuda.device(flat.device):
+        L.check(L.load().ard_fill_clips(C.c_void_p(flat.data_ptr()), int(flat.dtype == torch.int16), L.ptr(offsets), L.ptr(lengths), B, max_len, mode,
+                                        int(bool(quantize)), L.ptr(out), L.stream_ptr()))
+    return out
+
+
+def batch_features(x, max_len=480000, data_filling="repeatpad", device=None, do_pad_or_truncate=False, quantize=False):
+    """Batched get_audio_features (data.py:402-506, the reachable len <= max_len branches): x is [B, T] (tensor / ndarray) or
+    a list of 1-D clips of different lengths, float32 or int16 PCM (int16 is read as int16_to_float32, data.py:93-94).
+    Returns a [B, max_len] float32 tensor on `device`. With a CUDA `device` the clips travel as ONE flat buffer and the
+    repeat / pad filling (and the optional int16 round trip, `quantize`) runs in one kernel (ard_fill_clips) instead of the
+    reference's per-clip Python loop (hook.py:175-188); without a device (host-only callers) the same rule is applied per clip."""
+    if data_filling not in _FILL_MODES:
+        raise NotImplementedError(f"data_filling {data_filling} not implemented")           # data.py:492-496
     if isinstance(x, np.ndarray):
         x = torch.from_numpy(x)
     if torch.is_tensor(x) and x.dim() == 2:
-        clips = x if x.shape[1] == max_len else [c for c in x]
+        clips = None if x.shape[1] == max_len and not do_pad_or_truncate else [c for c in x]
     else:
         clips = [torch.as_tensor(c) for c in x]
-    if torch.is_tensor(clips):
-        out = clips
-    else:
-        if do_pad_or_truncate:
-            from .residual import pad_or_truncate
-            clips = [pad_or_truncate(c, max_len) for c in clips]
-        for c in clips:
-            if c.shape[0] > max_len:
-                raise AttributeError("clips longer than max_len are unreachable in the reference (data.py:467)")
-        out = torch.stack([_fill(c.float(), max_len, data_filling) for c in clips])
-    return out.to(device=device, dtype=torch.float32) if device is not None else out.float()
+    dev = torch.device(device) if device is not None else None
+    if clips is None:                                    # already [B, max_len]
+        if x.dtype == torch.int16 or quantize:
+            if dev is None or dev.type != "cuda":
+                y = x.float() / 32767.0 if x.dtype == torch.int16 else x.float()
+                if quantize:
+                    from .residual import quantize_tensor
+                    y = quantize_tensor(y)
+                return y if dev is None else y.to(dev)
+            src = x.to(dev) if x.dtype == torch.int16 else x.to(dev, torch.float32)
+            return _fill_on_device(src.contiguous(), None, None, x.shape[0], max_len, 0, quantize)
+        return x.to(device=dev, dtype=torch.float32) if dev is not None else x.float()
+    if do_pad_or_truncate:
+        from .residual import pad_or_truncate
+        clips = [pad_or_truncate(c if c.dtype != torch.int16 else c.float() / 32767.0, max_len) for c in clips]
+    for c in clips:
+        if c.dim() != 1:
+            raise ValueError(f"each clip must be 1-D (got shape {tuple(c.shape)})")
+        if c.shape[0] > max_len:
+            raise AttributeError("clips longer than max_len are unreachable in the reference (data.py:467)")
+        if c.shape[0] == 0:
+            raise ZeroDivisionError("division by zero")      # int(max_len / len(audio_data)), data.py:472
+    if dev is None or dev.type != "cuda":
+        out = torch.stack([_fill(c.float() / 32767.0 if c.dtype == torch.int16 else c.float(), max_len, data_filling) for c in clips])
+        if quantize:
+            from .residual import quantize_tensor
+            out = quantize_tensor(out)
+        return out if dev is None else out.to(dev)
+    pcm = all(c.dtype == torch.int16 for c in clips)
+    clips = [c if pcm else (c.float() / 32767.0 if c.dtype == torch.int16 else c.to(torch.float32)) for c in clips]
+    lengths = torch.tensor([c.shape[0] for c in clips], dtype=torch.int32)
+    offsets = torch.zeros(len(clips), dtype=torch.int64)
+    offsets[1:] = torch.cumsum(lengths[:-1].to(torch.int64), 0)
+    flat = torch.cat([c.to(dev, non_blocking=True) for c in clips]) if any(c.is_cuda for c in clips) else torch.cat(clips).to(dev)
+    return _fill_on_device(flat.contiguous(), offsets.to(dev), lengths.to(dev), len(clips), max_len, _FILL_MODES[data_filling], quantize)
 
 
 class CLAP(nn.Module):
@@ -197,13 +240,20 @@ class CLAP_Module(nn.Module):
 
     def get_audio_embedding_from_data(self, x, use_tensor=False, data_fil="repeatpad"):
         """hook.py:158-192. use_tensor=False: numpy/tensor input, int16 round-trip first, returns numpy.
-        use_tensor=True: tensor input, no quantisation, returns a tensor."""
+        use_tensor=True: tensor input, no quantisation, returns a tensor.
+        Extension: int16 input (numpy / tensor, PCM samples as a wav file stores them) is read as int16_to_float32(x)
+        (data.py:93-94) on the device, so it crosses PCIe at 0.96 MB per clip instead of 1.92 MB; results are bit-identical
+        to passing that float array."""
         self.model.eval()
         enc = self.model.audio_branch
         training_step = torch.is_grad_enabled() and any(p is not None and p.requires_grad for p in enc._lambda_params())
-        if (torch.is_tensor(x) and x.device.type == "cpu" and x.dim() == 2 and x.shape[1] == 480000
-                and x.dtype == torch.float32 and x.shape[0] > self.h2d_chunk and not training_step):
-            emb = self._embed_host_pipelined(x, quantize=not use_tensor)
+        if isinstance(x, np.ndarray) and x.ndim == 2 and x.dtype in (np.float32, np.int16):
+            xt = torch.from_numpy(x)            # zero-copy view: the numpy route rides the same chunked pipeline
+        else:
+            xt = x
+        if (torch.is_tensor(xt) and xt.device.type == "cpu" and xt.dim() == 2 and xt.shape[1] == 480000
+                and xt.dtype in (torch.float32, torch.int16) and xt.shape[0] > self.h2d_chunk and not training_step):
+            emb = self._embed_host_pipelined(xt, quantize=not use_tensor)
         else:
             wave = batch_features(x, 480000, data_fil, device=self.device)
             if enc.enable_fusion:
@@ -217,14 +267,16 @@ class CLAP_Module(nn.Module):
 
     h2d_chunk = 64                        # host batches larger than this are copied in chunks overlapped with the encoder
     h2d_schedule = (24, 50, 80, 116, 156, 204, 256)   # chunk sizes in clips: a small first copy (nothing overlaps it), then growing
+    h2d_schedule_pcm16 = (32, 80, 144, 256)            # int16 transport: copies take half as long, so chunks may grow faster
 
-    def _chunk_bounds(self, N):
+    def _chunk_bounds(self, N, schedule=None):
         """Each copy must fit under the previous chunk's encode: 0.0346 ms/clip over PCIe gen5 (55.5 GB/s measured) against
         0.79 ms + 0.040 ms/clip of graph-replayed encoder time on a B200 (tools/batch_sweep.py), i.e. the next chunk may hold
         at most 22.8 + 1.156 x the clips of the current one; chunks are capped so the two staging buffers stay small for any N."""
+        schedule = schedule or self.h2d_schedule
         bounds, lo, i = [], 0, 0
         while lo < N:
-            c = self.h2d_schedule[min(i, len(self.h2d_schedule) - 1)]
+            c = schedule[min(i, len(schedule) - 1)]
             hi = min(N, lo + c)
             if N - hi < c // 3:      # do not leave a tiny tail chunk
                 hi = N
@@ -233,46 +285,63 @@ class CLAP_Module(nn.Module):
         return bounds
 
     def _embed_host_pipelined(self, x, quantize):
-        """Full-length host batch [N, 480000] fp32: copy chunk k+1 on a side stream while chunk k is encoded, so the PCIe
-        transfer (1.92 MB per clip) hides behind compute instead of adding to it. Pinned input makes the copies asynchronous.
-        Only the first copy is exposed, so the first chunk is small and later ones grow (_chunk_bounds)."""
+        """Full-length host batch [N, 480000] fp32 or int16 PCM: copy chunk k+1 on a side stream while chunk k is encoded, so the
+        PCIe transfer (1.92 / 0.96 MB per clip) hides behind compute instead of adding to it. Pinned input makes the copies
+        asynchronous. Only the first copy is exposed, so the first chunk is small and later ones grow (_chunk_bounds).
+        int16 chunks are expanded to fp32 on the device (ard_fill_clips) into a fixed buffer, which keeps the encoder's
+        CUDA-graph key (input pointer, batch) stable across calls."""
         enc = self.model.audio_branch
         dev = self.device
         N = x.shape[0]
-        bounds = self._chunk_bounds(N)
+        pcm = x.dtype == torch.int16
+        bounds = self._chunk_bounds(N, self.h2d_schedule_pcm16 if pcm else None)
         cmax = max(hi - lo for lo, hi in bounds)
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream()
             if getattr(self, "_copy_stream", None) is None:
                 self._copy_stream = torch.cuda.Stream(device=dev)
-                self._stage = None
-            if self._stage is None or self._stage[0].shape[0] < cmax:
-                self._stage = [torch.empty((cmax, 480000), device=dev, dtype=torch.float32) for _ in range(2)]
-                self._stage_free = [torch.cuda.Event() for _ in range(2)]
+                self._stage = {}
+            st = self._stage.get(x.dtype)
+            if st is None or st[0].shape[0] < cmax:
+                st = [torch.empty((cmax, 480000), device=dev, dtype=x.dtype) for _ in range(2)]
+                self._stage[x.dtype] = st
+                self._stage_free = {} if not hasattr(self, "_stage_free") else self._stage_free
+                self._stage_free[x.dtype] = [torch.cuda.Event() for _ in range(2)]
+            free = self._stage_free[x.dtype]
+            if pcm and (getattr(self, "_pcm_wave", None) is None or self._pcm_wave.shape[0] < cmax):
+                self._pcm_wave = torch.empty((cmax, 480000), device=dev, dtype=torch.float32)
             out = torch.empty((N, enc.joint_dim), device=dev, dtype=torch.float32)
             copied = [torch.cuda.Event() for _ in range(2)]
 
             def start_copy(k):
                 lo, hi = bounds[k]
                 with torch.cuda.stream(self._copy_stream):
-                    self._copy_stream.wait_event(self._stage_free[k % 2])    # the encoder finished reading this staging buffer
-                    self._stage[k % 2][:hi - lo].copy_(x[lo:hi], non_blocking=True)
+                    self._copy_stream.wait_event(free[k % 2])    # the encoder finished reading this staging buffer
+                    st[k % 2][:hi - lo].copy_(x[lo:hi], non_blocking=True)
                     copied[k % 2].record(self._copy_stream)
 
             for b in range(2):
-                self._stage_free[b].record(main)
+                free[b].record(main)
             start_copy(0)
             for k, (lo, hi) in enumerate(bounds):
                 if k + 1 < len(bounds):
                     start_copy(k + 1)
                 main.wait_event(copied[k % 2])
-                chunk = self._stage[k % 2][:hi - lo]
+                chunk = st[k % 2][:hi - lo]
+                if pcm:   # int16_to_float32 on the device; the staging buffer is free again as soon as this kernel has run
+                    import ctypes as C
+                    from . import lib as L
+                    wavef = self._pcm_wave[:hi - lo]
+                    L.check(L.load().ard_fill_clips(C.c_void_p(chunk.data_ptr()), 1, None, None, hi - lo, 480000, 0, 0, L.ptr(wavef), L.stream_ptr()))
+                    free[k % 2].record(main)
+                    chunk = wavef
                 if enc.enable_fusion:   # get_mel + 4x stack on device (data.py:363-399, :497-501), then the fused encoder
                     res = enc.encode(mel_fusion=enc.fusion_mel(chunk, quantize=quantize), want_audio_embed=True)
                 else:
                     res = enc.encode(waveform=chunk, quantize=quantize, want_audio_embed=True)
                 out[lo:hi].copy_(res["audio_embed"])
-                self._stage_free[k % 2].record(main)
+                if not pcm:
+                    free[k % 2].record(main)
         return out
 
 

@@ -232,6 +232,11 @@ static int finalize(ard_handle* h, cudaStream_t) {
         ARD_TRY(get(h, "audio_projection.2.weight", (size_t)J * J, &v)); ARD_TRY(upload_f32(h->p2_w, *v));
         ARD_TRY(get(h, "audio_projection.2.bias", J, &v)); ARD_TRY(upload_f32(h->p2_b, *v));
     }
+    // transposed copies the backward builds lazily from the host tensors (ard_train.cu) are stale now
+    auto drop = [](DevBuf& b) { if (b.p) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; ++alloc_epoch(); } };
+    drop(h->p0_wT); drop(h->p2_wT);
+    for (LayerW& lw : h->layers) drop(lw.mg_wT);
+    h->tape_B = 0;   // activations of a forward run with the old weights must not be back-propagated through the new ones
     h->finalized = true;
     return 0;
 }
@@ -265,7 +270,7 @@ int ensure_fold(ard_handle* h, int l, int b, cudaStream_t s) {
 // One Swin block on the residual stream held in X (fp32 [B*T, C]); Y is scratch. Result ends in X.
 //   plain  : htsat.py:439-482            patched: src/residual.py:58-98 (doubled shortcut + FFN)
 static int run_block(ard_handle* h, int l, int b, int B, float* X, float* Y, float* attn_out, float attn_scale, int attn_acc,
-                     float* res_out, long long res_bstride, int res_T, cudaStream_t s) {
+                     float* res_out, long long res_bstride, int res_T, float* head_tap, cudaStream_t s) {
     BlockW& bw = h->layers[l].blocks[b];
     const int C = C_of(h, l), R = R_of(l), T = R * R, nH = h->cfg.num_heads[l];
     const long long M = (long long)B * T;
@@ -288,6 +293,7 @@ static int run_block(ard_handle* h, int l, int b, int B, float* X, float* Y, flo
     a.qkv = QKV; a.out = AO; a.bias_table = bw.rpb.as<float>(); a.attn_mean = attn_out; a.attn_scale = attn_scale; a.attn_accumulate = attn_acc;
     a.B = B; a.H = R; a.W = R; a.C = C; a.nH = nH; a.shift = shift;
     ARD_TRY(window_attention(a, s));
+    if (head_tap) ARD_TRY(head_output_tap(AO, head_tap, B, R, C, nH, shift, s));   // per-head attn @ v (htsat.py:354)
     // proj (+ folded ResiDual) + shortcut:  Y = X + r,  aux = r = residual_x
     ARD_TRY(ensure_fold(h, l, b, s));
     g = GemmArgs();
@@ -342,6 +348,7 @@ static int encoder_forward(ard_handle* h, const ard_forward_args* a, cudaStream_
     const int B = a->B;
     if (B <= 0) return set_error(ARD_ERR_SHAPE, "batch must be positive (got %d)", B);
     if (!a->embedding) return set_error(ARD_ERR_SHAPE, "embedding output is required");
+    if (a->precision != 0) return set_error(ARD_ERR_NOTIMPL, "precision=%d: the fp32-grade mode is not available in this build", a->precision);
     const int C0 = h->cfg.embed_dim;
     ARD_TRY(ensure_workspace(h, B));
     float* X = h->ws_x.as<float>();
@@ -350,6 +357,7 @@ static int encoder_forward(ard_handle* h, const ard_forward_args* a, cudaStream_
     h->tape_B = train ? h->tape_B : 0;   // an inference forward overwrites the head activations the backward would read
     if (train) {
         ARD_TRY(ensure_tape(h, B));
+        ++h->tape_gen;
         X = h->layers[0].blocks[0].t_s;
     }
     // ---- front end
@@ -373,11 +381,13 @@ static int encoder_forward(ard_handle* h, const ard_forward_args* a, cudaStream_
         for (int b = 0; b < depth; ++b) {
             float* res = a->layers_residuals[l] ? a->layers_residuals[l] + (long long)b * T * C : nullptr;
             // BasicLayer.forward (htsat.py:589-596): mean of the blocks' maps; residuals concatenated along tokens
+            float* tap = a->head_outputs[l] ? a->head_outputs[l] + (long long)b * B * T * C : nullptr;
             if (train) {
                 ARD_TRY(run_block_train(h, l, b, B, a->layers_attention[l], 1.0f / depth, b > 0, res, (long long)depth * T, s));
+                if (tap) ARD_TRY(head_output_tap(h->layers[l].blocks[b].t_ao, tap, B, R, C, h->cfg.num_heads[l], (b % 2 == 0) ? 0 : 4, s));
                 X = h->layers[l].blocks[b].t_out;
             } else {
-                ARD_TRY(run_block(h, l, b, B, X, Y, a->layers_attention[l], 1.0f / depth, b > 0, res, (long long)depth * T, T, s));
+                ARD_TRY(run_block(h, l, b, B, X, Y, a->layers_attention[l], 1.0f / depth, b > 0, res, (long long)depth * T, T, tap, s));
             }
         }
         if (l < h->nlayers - 1) {   // PatchMerging (htsat.py:505-526)
@@ -543,7 +553,8 @@ static int forward_graphed(ard_handle* h, const ard_forward_args* args, cudaStre
     const bool eligible = h->use_graphs && h->finalized && !g_prof_on && !args->save_for_backward && args->B > 0 && args->embedding &&
                           !args->framewise_output && !args->clipwise_output && !args->fine_grained_embedding &&
                           !args->layers_residuals[0] && !args->layers_residuals[1] && !args->layers_residuals[2] && !args->layers_residuals[3] &&
-                          !args->layers_attention[0] && !args->layers_attention[1] && !args->layers_attention[2] && !args->layers_attention[3];
+                          !args->layers_attention[0] && !args->layers_attention[1] && !args->layers_attention[2] && !args->layers_attention[3] &&
+                          !args->head_outputs[0] && !args->head_outputs[1] && !args->head_outputs[2] && !args->head_outputs[3];
     if (!eligible) return 0;
     const void* src = h->cfg.enable_fusion ? (const void*)args->mel_fusion : (const void*)args->waveform;
     if (!src) return 0;
@@ -634,7 +645,7 @@ int ard_block_forward(ard_handle* h, int layer, int block, const float* x_in, in
     const size_t bytes = (size_t)B * T * C * 4;
     float* X = h->ws_x.as<float>();
     ARD_CUDA(cudaMemcpyAsync(X, x_in, bytes, cudaMemcpyDeviceToDevice, s));
-    ARD_TRY(run_block(h, layer, block, B, X, h->ws_y.as<float>(), attn, 1.0f, 0, residual_x, T, T, s));
+    ARD_TRY(run_block(h, layer, block, B, X, h->ws_y.as<float>(), attn, 1.0f, 0, residual_x, T, T, nullptr, s));
     ARD_CUDA(cudaMemcpyAsync(x_out, X, bytes, cudaMemcpyDeviceToDevice, s));
     h->last_launches = g_launches;
     return 0;
@@ -648,6 +659,8 @@ int ard_encoder_backward(ard_handle* h, const ard_backward_args* args, void* str
     h->last_launches = g_launches;
     return rc;
 }
+
+long long ard_tape_generation(const ard_handle* h) { return h && h->tape_B > 0 ? h->tape_gen : 0; }
 
 long long ard_workspace_bytes(const ard_handle* h) {
     if (!h) return 0;
@@ -751,6 +764,13 @@ int ard_logmel(ard_handle* h, const float* wave, int B, int n_samples, int apply
     MelBands mb{h->melw.as<float>(), h->mstart.as<int>(), h->mlen.as<int>(), h->band_max};
     return stft_logmel(wave, B, n_samples, h->window.as<float>(), h->twiddle.as<float2>(), mb, apply_bn ? h->bn_scale.as<float>() : nullptr,
                        apply_bn ? h->bn_shift.as<float>() : nullptr, out, 0, 1, quantize, (cudaStream_t)stream);
+}
+
+int ard_patch_embed(ard_handle* h, const float* logmel, int B, float* out, void* stream) {
+    if (!h || !h->finalized) return set_error(ARD_ERR_STATE, "handle not finalised");
+    if (!logmel || !out || B <= 0) return set_error(ARD_ERR_SHAPE, "ard_patch_embed: bad argument");
+    return patch_embed_ln(logmel, (long long)ARD_FRAMES * 64, ARD_FRAMES, h->bn_scale.as<float>(), h->bn_shift.as<float>(), h->pe_w.as<float>(),
+                          h->pe_b.as<float>(), h->pe_g.as<float>(), h->pe_beta.as<float>(), out, B, h->cfg.embed_dim, (cudaStream_t)stream);
 }
 
 int ard_fusion_mel(ard_handle* h, const float* wave, int B, int n_samples, int quantize, float* out, void* stream) {

@@ -80,6 +80,7 @@ struct ard_handle {
     DevBuf tape, p0_wT, p2_wT, t_emb, t_hid, t_proj;
     DevBuf bw_g, bw_gs, bw_t, bw_hpre, bw_dh, bw_gqkv, bw_gb, bw_coef, bw_gcoef, bw_gsc, bw_small;
     int tape_B = 0;          // batch of the forward whose activations the tape holds (0: none)
+    long long tape_gen = 0;  // serial number of that forward (ard_tape_generation): a backward built on an older one is refused
     // CUDA-graph replay of the inference forward (ard_api.cu): the ~110 launches of a forward cost ~1.1 ms of fixed launch /
     // ramp latency whatever the batch; replaying a captured graph removes the host side of that and most of the device side.
     struct GraphEntry {

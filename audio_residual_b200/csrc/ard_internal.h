@@ -122,9 +122,14 @@ int linear_small(const float* x, int ldx, const float* W, const float* bias, flo
 int l2_normalize(const float* x, float* y, int B, int N, cudaStream_t s);
 int residual_fold(const float* proj_w, const float* dmean, const float* basis, const float* lam, int C, int K, float* Mtmp,
                   __nv_bfloat16* w_out, float* b_out, cudaStream_t s);
+int residual_matrix(const float* basis, const float* lam, int C, int K, float* M, cudaStream_t s);   // M = B^T diag(lam) B [C,C]
 int tscam_im2col(const float* normed, __nv_bfloat16* A, int B, int C, cudaStream_t s);
 int tscam_finish(const float* y, int ldy, float* framewise, float* clipwise, int B, int NC, cudaStream_t s);
 int fine_grained(const float* normed, float* fine, int B, int C, cudaStream_t s);
+// dlam[k] += sum_t coef[t,k] gcoef[t,k] (k < K; dlam may be NULL), gsc[t,k] = bf16(gcoef[t,k] lam[k]) (k < Kp); rows are Kp wide
+int lambda_grad(const float* coef, const float* gcoef, const float* lam, float* dlam, __nv_bfloat16* gsc, long long M, int K, int Kp,
+                cudaStream_t s);
+int head_output_tap(const __nv_bfloat16* ao, float* tap, int B, int R, int C, int nH, int shift, cudaStream_t s);   // extras.cu
 int stats_accumulate(const float* x, long long rows, long long ldx, int D, double* sum, double* sumsq, cudaStream_t s);   // stats.cu
 
 // Launch with programmatic dependent launch allowed (see pdl_wait in ard_common.cuh). ONLY for kernels that call pdl_wait()

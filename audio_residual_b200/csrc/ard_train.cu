@@ -25,7 +25,6 @@ int relu_bwd_mul(float* g, const float* act, long long n, cudaStream_t s);
 int merge_layernorm_bwd(const float* x, const float* g, const float* gamma, float* dx, __nv_bfloat16* dx_bf, int B, int H, int W, int C,
                         cudaStream_t s);
 int gelu_bwd_mul(__nv_bfloat16* dh, const __nv_bfloat16* hpre, long long n, cudaStream_t s);
-int lambda_grad(const float* coef, const float* gcoef, const float* lam, float* dlam, __nv_bfloat16* gsc, long long M, int K, cudaStream_t s);
 int bcast_rows(const float* g, float* out, int B, int T, int C, float scale, cudaStream_t s);
 int add_f32(const float* a, const float* b, float* y, __nv_bfloat16* ybf, long long n, cudaStream_t s);
 // attn_window.cu
@@ -230,7 +229,7 @@ static int block_backward(ard_handle* h, int l, int b, int B, float* dlam, bool 
         g.M = (int)M; g.N = Kp; g.K = C;
         ARD_TRY(gemm_bf16(g, h->num_sms, s));                                    // gcoef = dL/d(x_scaled) = dL/dr B^T
         const float* lam = bw.lambda_set && bw.lam.p ? bw.lam.as<float>() : bw.lam_ones.as<float>();
-        ARD_TRY(lambda_grad(w.coef, w.gcoef, lam, dlam, w.gsc, M, Kp, s));       // dlam += colsum(coef*gcoef); gsc = gcoef*lam
+        ARD_TRY(lambda_grad(w.coef, w.gcoef, lam, dlam, w.gsc, M, bw.K, Kp, s));       // dlam += colsum(coef*gcoef); gsc = gcoef*lam
         if (stop_after_lambda) return 0;
         g = GemmArgs();
         g.A = w.gsc; g.lda = Kp; g.W = bw.res_wcT.as<__nv_bfloat16>(); g.ldw = Kp; g.out = w.GAO; g.ldo = C; g.out_bf16 = 1;
@@ -257,6 +256,9 @@ int encoder_backward(ard_handle* h, const ard_backward_args* a, cudaStream_t s) 
     const int B = a->B;
     if (h->tape_B <= 0 || h->tape_B != B)
         return set_error(ARD_ERR_STATE, "ard_encoder_backward: no saved forward for batch %d (run ard_encoder_forward with save_for_backward=1)", B);
+    if (a->generation != 0 && a->generation != h->tape_gen)
+        return set_error(ARD_ERR_STATE, "ard_encoder_backward: the saved activations belong to training forward #%lld, this backward to #%lld "
+                                        "(the handle keeps one tape: run forward and backward of a step back to back)", h->tape_gen, a->generation);
     if (!a->grad_audio_embed && !a->grad_embedding) return set_error(ARD_ERR_SHAPE, "ard_encoder_backward: no output gradient given");
     const int NF = C_of(h, h->nlayers - 1), J = h->cfg.joint_dim;
     // lowest patched block: nothing below it needs a gradient

@@ -207,9 +207,12 @@ static int sgemm_tn(const float* a, int lda, const float* b, int ldb, const floa
 
 // ResiDual (src/residual.py:37-42) applied to y = x Wp^T + bp:   r = ((y - mu) B^T * lambda) B = x (M Wp)^T + (bp - mu) M
 // with M = B^T diag(lambda) B (symmetric).  Inputs: proj_w [C,C] fp32, dmean = bp - mu [C], basis [K,C], lam [K].
+int residual_matrix(const float* basis, const float* lam, int C, int K, float* M, cudaStream_t s) {
+    return sgemm_tn(basis, C, basis, C, lam, M, C, false, C, C, K, s);               // M[i][j] = sum_k B[k][i] lam[k] B[k][j]
+}
 int residual_fold(const float* proj_w, const float* dmean, const float* basis, const float* lam, int C, int K, float* Mtmp,
                   __nv_bfloat16* w_out, float* b_out, cudaStream_t s) {
-    ARD_TRY(sgemm_tn(basis, C, basis, C, lam, Mtmp, C, false, C, C, K, s));          // M[i][j] = sum_k B[k][i] lam[k] B[k][j]
+    ARD_TRY(residual_matrix(basis, lam, C, K, Mtmp, s));
     ARD_TRY(sgemm_tn(Mtmp, C, proj_w, C, nullptr, w_out, C, true, C, C, C, s));      // W'[i][j] = sum_c M[c][i] Wp[c][j]
     ARD_TRY(sgemm_tn(dmean, 1, Mtmp, C, nullptr, b_out, C, false, 1, C, C, s));      // b'[j] = sum_c (bp-mu)[c] M[c][j]
     return 0;

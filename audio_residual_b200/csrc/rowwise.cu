@@ -475,42 +475,44 @@ int gelu_bwd_mul(__nv_bfloat16* dh, const __nv_bfloat16* hpre, long long n, cuda
 }
 
 // Lambda gradient, reduced in-kernel (src/residual.py:39: x_scaled = x_proj * learnable):
-//   dlam[k] += sum_t coef[t,k] * gcoef[t,k];   gsc[t,k] = bf16(gcoef[t,k] * lam[k])   (the gradient flowing on to x_proj)
-// coef, gcoef fp32 [M, K]. Each CTA reduces a slab of rows for 32 columns in registers/smem, one atomicAdd per column per CTA.
+//   dlam[k] += sum_t coef[t,k] * gcoef[t,k]  (k < K);   gsc[t,k] = bf16(gcoef[t,k] * lam[k])  (k < Kp: the gradient flowing on to x_proj)
+// coef, gcoef fp32 [M, Kp]: rows are padded to Kp (a multiple of 16, the GEMMs' K granularity) while dlam holds only the K
+// logical components. Each CTA reduces a slab of rows for 32 columns in registers/smem, one atomicAdd per column per CTA.
 __global__ void __launch_bounds__(256) lambda_grad_kernel(const float* __restrict__ coef, const float* __restrict__ gcoef,
                                                          const float* __restrict__ lam, float* __restrict__ dlam,
-                                                         __nv_bfloat16* __restrict__ gsc, long long M, int K, long long rows_per_cta) {
+                                                         __nv_bfloat16* __restrict__ gsc, long long M, int K, int Kp, long long rows_per_cta) {
     __shared__ float part[8][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int col = blockIdx.x * 32 + tx;
     const long long r0 = (long long)blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, M);
     float acc = 0.f;
-    if (col < K) {
+    if (col < Kp) {
         const float l = lam[col];
         for (long long r = r0 + ty; r < r1; r += 8) {
-            const float c = coef[r * K + col], gc = gcoef[r * K + col];
+            const float c = coef[r * Kp + col], gc = gcoef[r * Kp + col];
             acc = fmaf(c, gc, acc);
-            gsc[r * K + col] = __float2bfloat16_rn(gc * l);
+            gsc[r * Kp + col] = __float2bfloat16_rn(gc * l);
         }
     }
     part[ty][tx] = acc;
     __syncthreads();
-    if (ty == 0 && col < K) {
+    if (ty == 0 && col < K && dlam != nullptr) {
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) t += part[w][tx];
         atomicAdd(dlam + col, t);
     }
 }
-int lambda_grad(const float* coef, const float* gcoef, const float* lam, float* dlam, __nv_bfloat16* gsc, long long M, int K, cudaStream_t s) {
+int lambda_grad(const float* coef, const float* gcoef, const float* lam, float* dlam, __nv_bfloat16* gsc, long long M, int K, int Kp,
+                cudaStream_t s) {
     if (M <= 0) return 0;
-    const int cb = (K + 31) / 32;
+    const int cb = (Kp + 31) / 32;
     long long ysplit = (148 * 8) / cb + 1;
     long long rows_per_cta = (M + ysplit - 1) / ysplit;
     rows_per_cta = ((rows_per_cta + 7) / 8) * 8;
     ysplit = (M + rows_per_cta - 1) / rows_per_cta;
-    ProfScope ps(PROF_OTHER, s, 3.0 * M * K, 10.0 * M * K);
-    lambda_grad_kernel<<<dim3(cb, (unsigned)ysplit), 256, 0, s>>>(coef, gcoef, lam, dlam, gsc, M, K, rows_per_cta);
+    ProfScope ps(PROF_OTHER, s, 3.0 * M * Kp, 10.0 * M * Kp);
+    lambda_grad_kernel<<<dim3(cb, (unsigned)ysplit), 256, 0, s>>>(coef, gcoef, lam, dlam, gsc, M, K, Kp, rows_per_cta);
     return check_cuda(cudaGetLastError(), "lambda_grad launch");
 }
 

@@ -337,13 +337,21 @@ class HTSAT_Swin_Transformer(nn.Module):
         return out
 
     def encode(self, waveform=None, mel_fusion=None, quantize=False, want_dict=False, want_audio_embed=False,
-               want_capture=True, save_for_backward=False):
+               want_capture=True, save_for_backward=False, want_head_outputs=False, precision=None):
         """Single entry to ard_encoder_forward. Returns a dict of freshly allocated CUDA tensors.
         With grad enabled and trainable ResiDual lambdas, `embedding` / `audio_embed` come back attached to the autograd graph
-        (backward = ard_encoder_backward, filling `learnable.grad` as loss.backward() does in src/training.py:30-32)."""
+        (backward = ard_encoder_backward, filling `learnable.grad` as loss.backward() does in src/training.py:30-32).
+        want_head_outputs: also return `head_outputs`, per layer [depth, B*nW, nH, 64, hd]: every block's per-head `attn @ v`
+        (htsat.py:354). precision: "bf16" (default) or "fp32" (3-term split-bf16 GEMMs + fp32 attention, rel. err <= 1e-4;
+        inference only); None takes the encoder's `precision` attribute."""
+        precision = precision or getattr(self, "precision", "bf16")
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32' (got {precision!r})")
         if not save_for_backward and torch.is_grad_enabled():
             lams = self._lambda_params()
             if any(p is not None and p.requires_grad for p in lams):
+                if precision != "bf16":
+                    raise NotImplementedError("the training step runs on the bf16 tensor-core path; precision='fp32' is inference only")
                 return _encode_with_grad(self, lams, waveform, mel_fusion, quantize, want_dict, want_audio_embed, want_capture)
         h = self._handle()
         lib = L.load()
@@ -365,6 +373,7 @@ class HTSAT_Swin_Transformer(nn.Module):
         a = L.ArdForwardArgs()
         a.B, a.quantize = B, int(bool(quantize))
         a.save_for_backward = int(bool(save_for_backward))
+        a.precision = 1 if precision == "fp32" else 0
         if self.enable_fusion:
             a.mel_fusion = src.data_ptr()
         else:
@@ -390,8 +399,18 @@ class HTSAT_Swin_Transformer(nn.Module):
                     a.layers_attention[l] = attns[l].data_ptr()
                     a.layers_residuals[l] = ress[l].data_ptr()
                 out["layers_attention"], out["layers_residuals"] = attns, ress
+        if want_head_outputs:
+            taps = []
+            for l in range(self.num_layers):
+                Cl, R = self.embed_dim << l, 64 >> l
+                nW = max(1, (R // 8) * (R // 8))
+                taps.append(torch.empty((self.depths[l], B * nW, self.num_heads[l], 64, Cl // self.num_heads[l]), **f32))
+                a.head_outputs[l] = taps[l].data_ptr()
+            out["head_outputs"] = taps
         with torch.cuda.device(dev):
             L.check(lib.ard_encoder_forward(h, C.byref(a), L.stream_ptr()))
+            if save_for_backward:
+                out["_tape_generation"] = int(lib.ard_tape_generation(h))
         out["_keepalive"] = src
         return out
 
@@ -432,6 +451,7 @@ class _EncodeFn(torch.autograd.Function):
         out = enc.encode(save_for_backward=True, **kw)
         holder.update(out)
         ctx.enc, ctx.B = enc, out["embedding"].shape[0]
+        ctx.generation = out["_tape_generation"]   # the handle keeps ONE tape: a later training forward invalidates this node
         ctx.layers = [i for i, p in enumerate(enc._lambda_params()) if p is not None]
         ctx.ks = [p.shape[0] for p in enc._lambda_params() if p is not None]
         ctx.has_audio = "audio_embed" in out
@@ -445,6 +465,7 @@ class _EncodeFn(torch.autograd.Function):
         lib = L.load()
         a = L.ArdBackwardArgs()
         a.B = ctx.B
+        a.generation = ctx.generation
         keep = []
         g_emb = grads[0]
         g_ae = grads[1] if ctx.has_audio else None

@@ -29,11 +29,12 @@ class ArdForwardArgs(C.Structure):
                 ("embedding", C.c_void_p), ("audio_embed", C.c_void_p),
                 ("layers_residuals", C.c_void_p * 4), ("layers_attention", C.c_void_p * 4),
                 ("framewise_output", C.c_void_p), ("clipwise_output", C.c_void_p), ("fine_grained_embedding", C.c_void_p),
-                ("save_for_backward", C.c_int)]
+                ("save_for_backward", C.c_int), ("head_outputs", C.c_void_p * 4), ("precision", C.c_int)]
 
 
 class ArdBackwardArgs(C.Structure):
-    _fields_ = [("B", C.c_int), ("grad_audio_embed", C.c_void_p), ("grad_embedding", C.c_void_p), ("grad_lambda", C.c_void_p * 4)]
+    _fields_ = [("B", C.c_int), ("grad_audio_embed", C.c_void_p), ("grad_embedding", C.c_void_p), ("grad_lambda", C.c_void_p * 4),
+                ("generation", C.c_longlong)]
 
 
 _lib = None
@@ -56,6 +57,7 @@ def load(check_symbols=False):
         lib.ard_last_error.restype = C.c_char_p
         lib.ard_workspace_bytes.restype = C.c_longlong
         lib.ard_launch_counter_read.restype = C.c_longlong
+        lib.ard_tape_generation.restype = C.c_longlong
         vp, ll, i, f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
         lib.ard_create.argtypes = [C.POINTER(ArdConfig), C.POINTER(vp)]
         lib.ard_destroy.argtypes = [vp]
@@ -82,8 +84,17 @@ def load(check_symbols=False):
         lib.ard_quantize_waveform.argtypes = [vp, vp, ll, vp]
         lib.ard_logmel.argtypes = [vp, vp, i, i, i, i, vp, vp]
         lib.ard_fusion_mel.argtypes = [vp, vp, i, i, i, vp, vp]
+        lib.ard_patch_embed.argtypes = [vp, vp, i, vp, vp]
         lib.ard_stats_accumulate.argtypes = [vp, ll, i, vp, vp, vp]
         lib.ard_stats_accumulate_strided.argtypes = [vp, ll, ll, i, vp, vp, vp]
+        lib.ard_tape_generation.argtypes = [vp]
+        lib.ard_residual_forward.argtypes = [vp, vp, vp, vp, vp, ll, i, i, vp]
+        lib.ard_residual_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, ll, i, i, vp]
+        lib.ard_head_forward.argtypes = [vp, vp, vp, i, i, i, vp, vp]
+        lib.ard_ce_forward.argtypes = [vp, vp, i, i, vp, vp, vp]
+        lib.ard_head_backward.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp]
+        lib.ard_eval_metrics.argtypes = [vp, vp, ll, i, i, vp, vp, vp, vp]
+        lib.ard_fill_clips.argtypes = [vp, i, vp, vp, i, i, i, i, vp, vp]
         lib.ard_profile_enable.argtypes = [i]
         lib.ard_profile_read.argtypes = [c_double_p, c_double_p, c_double_p, C.POINTER(C.c_int), i]
         _lib = lib

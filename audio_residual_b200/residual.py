@@ -35,28 +35,49 @@ class ResiDual(nn.Module):
         self.learnable = nn.Parameter(torch.ones(self.n_components))
 
     def forward(self, x):
-        """x [B, N, D] (CUDA) -> ((x - mean) @ basis.T * learnable) @ basis, computed as one bf16 tcgen05 GEMM against
-        M = basis^T diag(learnable) basis (fp32-derived) plus the constant row (-mean) M."""
+        """x [B, N, D] (CUDA) -> ((x - mean) @ basis.T * learnable) @ basis   (src/residual.py:29-42; the mean is not re-added).
+        Differentiable in `x` and in `learnable` like the reference module (autograd node = ard_residual_forward /
+        ard_residual_backward: bf16 tcgen05 GEMMs, lambda-gradient reduced in the kernel)."""
         if not x.is_cuda:
             raise RuntimeError("audio_residual_b200.ResiDual runs on CUDA only (no CPU fallback)")
-        lib = L.load()
+        dev = x.device
+        return _ResiDualFn.apply(x, self.learnable, self.mean.to(dev), self.basis.to(dev))   # the reference re-copies per call too (Q4)
+
+
+class _ResiDualFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, lam, mean, basis):
         dev = x.device
         D = x.shape[-1]
-        basis = self.basis.to(dev, torch.float32)
-        M = (basis.t() * self.learnable.detach().to(dev, torch.float32)) @ basis          # [D, D], tiny, lambda-dependent
-        bias = (-(self.mean.to(dev, torch.float32))) @ M
         x2 = x.detach().to(torch.float32).contiguous().view(-1, D)
-        rows = x2.shape[0]
-        xb = torch.empty((rows, D), device=dev, dtype=torch.bfloat16)
-        Mb = torch.empty((D, D), device=dev, dtype=torch.bfloat16)
-        out = torch.empty((rows, D), device=dev, dtype=torch.float32)
+        lam_d = lam.detach().to(dev, torch.float32).contiguous()
+        mean_d = mean.detach().to(dev, torch.float32).contiguous()
+        basis_d = basis.detach().to(dev, torch.float32).contiguous()
+        K = basis_d.shape[0]
+        if basis_d.shape[1] != D or mean_d.numel() != D or lam_d.numel() != K:
+            raise ValueError(f"ResiDual: x has width {D}, basis {tuple(basis_d.shape)}, mean {tuple(mean_d.shape)}, learnable {tuple(lam_d.shape)}")
+        out = torch.empty_like(x2)
         with torch.cuda.device(dev):
-            st = L.stream_ptr()
-            L.check(lib.ard_f32_to_bf16(L.ptr(x2), L.ptr(xb), x2.numel(), 1.0, st))
-            L.check(lib.ard_f32_to_bf16(L.ptr(M.contiguous()), L.ptr(Mb), M.numel(), 1.0, st))
-            L.check(lib.ard_gemm_bf16(L.ptr(xb), D, L.ptr(Mb), D, L.ptr(out), D, 0, rows, D, D, L.ptr(bias.contiguous()), 0,
-                                      None, 0, None, 0, st))
+            L.check(L.load().ard_residual_forward(L.ptr(x2), L.ptr(mean_d), L.ptr(basis_d), L.ptr(lam_d), L.ptr(out), x2.shape[0], D, K,
+                                                  L.stream_ptr()))
+        ctx.save_for_backward(x2, lam_d, mean_d, basis_d)
+        ctx.xshape, ctx.lam_dev, ctx.lam_dtype = x.shape, lam.device, lam.dtype
         return out.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, lam_d, mean_d, basis_d = ctx.saved_tensors
+        dev = x2.device
+        rows, D = x2.shape
+        K = basis_d.shape[0]
+        g2 = g.detach().to(dev, torch.float32).contiguous().view(-1, D)
+        dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        dlam = torch.zeros(K, device=dev, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(dev):
+            L.check(L.load().ard_residual_backward(L.ptr(x2), L.ptr(g2), L.ptr(mean_d), L.ptr(basis_d), L.ptr(lam_d), L.ptr(dx), L.ptr(dlam),
+                                                   rows, D, K, L.stream_ptr()))
+        return (dx.view(ctx.xshape) if dx is not None else None,
+                dlam.to(ctx.lam_dev, ctx.lam_dtype) if dlam is not None else None, None, None)
 
 
 def patch_block_with_residual(block, residual):
@@ -209,18 +230,23 @@ def compute_pca_components(model, dataloader, target_layer, n_components=None, m
     from .clap import batch_features
     model.eval()
     acc = None
-    for i, batch in enumerate(dataloader):
-        if max_batches and i >= max_batches:
-            break
-        x = batch[0]
-        feats = batch_features(x.squeeze(1), max_len, data_filling, device=model.device, do_pad_or_truncate=pad_or_truncate)
-        enc = model.model.audio_branch
-        out = enc.encode(waveform=feats, quantize=True, want_dict=True) if not enc.enable_fusion else \
-            enc.encode(mel_fusion=model.fusion_mel(feats, quantize=True), want_dict=True)
-        res = out["layers_residuals"][target_layer]
-        if acc is None:
-            acc = MomentAccumulator(res.shape[-1], res.device)
-        acc.update(res)
+    enc = model.model.audio_branch
+    if not 0 <= target_layer < enc.num_layers:
+        raise IndexError(f"target_layer {target_layer} out of range for a model with {enc.num_layers} layers")   # src/residual.py:135 (list index)
+    with torch.no_grad():                                      # src/residual.py:118
+        for i, batch in enumerate(dataloader):
+            if max_batches and i >= max_batches:
+                break
+            x = batch[0]
+            feats = batch_features(x.squeeze(1), max_len, data_filling, device=model.device, do_pad_or_truncate=pad_or_truncate)
+            out = enc.encode(waveform=feats, quantize=True, want_dict=True) if not enc.enable_fusion else \
+                enc.encode(mel_fusion=model.fusion_mel(feats, quantize=True), want_dict=True)
+            res = out["layers_residuals"][target_layer]
+            if acc is None:
+                acc = MomentAccumulator(res.shape[-1], res.device)
+            acc.update(res)
+    if acc is None:
+        raise ValueError("compute_pca_components: the dataloader produced no batch")
     pca_results = acc.allreduce().pca()
     if n_components:
         pca_results = pca_from_moments(acc.n, acc.s1.cpu().numpy(), acc.s2.cpu().numpy(), n_components)

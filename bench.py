@@ -119,54 +119,116 @@ def oracle_setup(model="tiny"):
     return O, sd, ores
 
 
-def cpu_time_batches(nbatch, B, warm=1):
-    """Oracle port of the reference path (same torch ops as the reference modules) on all host cores. Returns clips/s."""
+def reference_setup():
+    """The reference's OWN modules (clap_module.model.CLAP + src.residual.setup_residual_htsat, imported unmodified through
+    oracle/refimport.py from /root/reference or its snapshot oracle/_ref) with the bench's weights and PCA files loaded.
+    Returns (ns, clap, residuals, audio_cfg) or None when neither tree is present."""
+    try:
+        import pickle
+        import tempfile
+        import numpy as np
+        import torch
+        from audio_residual_b200 import weights as W
+        from oracle import refimport
+        from oracle.make_golden import load_into_reference
+        if not refimport.available():
+            return None
+        ns = refimport.load()
+        torch.manual_seed(0)
+        clap, cfg = refimport.build_clap("tiny")
+        load_into_reference(clap, W.make_state_dict("tiny", seed=0))
+        pca, lam = W.make_pca("tiny", seed=0)
+        tmp = tempfile.mkdtemp()
+        files = {}
+        for l, d in pca.items():
+            files[l] = os.path.join(tmp, f"layer_{l}")
+            with open(files[l], "wb") as f:
+                pickle.dump({"components": d["components"], "mean": d["mean"]}, f)
+        new_htsat, residuals = ns.residual.setup_residual_htsat(clap.audio_branch, files, [0, 1, 2, 3])   # src/training.py:100-103
+        clap.audio_branch = new_htsat
+        for l, r in residuals.items():
+            r.learnable.data = torch.from_numpy(np.array(lam[l])).clone()
+        return ns, clap, residuals, cfg["audio_cfg"]
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write(f"bench: reference modules unavailable ({type(e).__name__}: {e}); timing the oracle port instead\n")
+        return None
+
+
+def make_cpu_step(wl, B):
+    """One step of the reference's CPU path on B clips -> (callable, kind, description). `kind` = "reference" when the real
+    reference modules run (hook.py:175-190's per-clip featuriser loop + CLAP.get_audio_embedding, model.py:720-742, with
+    src/residual.py's patched blocks), "port" when only the oracle restatement is available."""
     import torch
-    O, sd, ores = oracle_setup()
     torch.set_num_threads(os.cpu_count())
     g = torch.Generator().manual_seed(99)
     wave = (0.1 * torch.randn(B, 480000, generator=g)).clamp_(-1, 1)
+    labels = torch.randint(0, 50, (B,), generator=g)
+    ref = reference_setup()
+    if ref is not None:
+        ns, clap, residuals, audio_cfg = ref
+
+        def feats():
+            return [ns.get_audio_features({}, x, 480000, data_truncating="rand_trunc", data_filling="repeatpad", audio_cfg=audio_cfg,
+                                          require_grad=False) for x in wave]
+        if wl == "train":
+            torch.manual_seed(0)
+            cls = torch.nn.Linear(512, 50)
+            opt = torch.optim.Adam([r.learnable for r in residuals.values()] + list(cls.parameters()), lr=1e-3)
+
+            def one():
+                opt.zero_grad()
+                emb = clap.get_audio_embedding(feats())
+                torch.nn.functional.cross_entropy(cls(emb.float()), labels).backward()
+                opt.step()
+        else:
+            def one():
+                with torch.no_grad():
+                    clap.get_audio_embedding(feats())
+        return one, "reference", "the reference's own modules (clap_module.model.CLAP.get_audio_embedding + src/residual.py patched blocks)"
+    O, sd, ores = oracle_setup()
+    if wl == "train":
+        ores = {l: (mu, comp, lam.clone().requires_grad_(True)) for l, (mu, comp, lam) in ores.items()}
+        torch.manual_seed(0)
+        Wc, bc = (0.02 * torch.randn(50, 512)).requires_grad_(True), torch.zeros(50, requires_grad=True)
+
+        def one():
+            loss, _ = O.linear_probe_loss(wave, labels, Wc, bc, sd, O.CONFIGS["tiny"], ores)
+            loss.backward()
+    else:
+        def one():
+            with torch.no_grad():
+                O.get_audio_embedding(wave, sd, O.CONFIGS["tiny"], ores)
+    return one, "port", "oracle port of the reference's PyTorch CPU path (oracle/htsat_oracle.py)"
+
+
+def cpu_time_batches(nbatch, B, warm=1, wl="infer"):
+    """Bounded CPU sample of the workload on all host cores. Returns (clips/s, s/batch, kind, description)."""
+    one, kind, desc = make_cpu_step(wl, B)
     times = []
-    with torch.no_grad():
-        for i in range(warm + nbatch):
-            t0 = time.perf_counter()
-            O.get_audio_embedding(wave, sd, O.CONFIGS["tiny"], ores)
-            dt = time.perf_counter() - t0
-            if i >= warm:
-                times.append(dt)
-    return B / (sum(times) / len(times)), sum(times) / len(times)
+    for i in range(warm + nbatch):
+        t0 = time.perf_counter()
+        one()
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return B / sec, sec, kind, desc
 
 
 def run_reference(args):
-    """--impl reference: the reference's own (CPU, PyTorch) implementation of the path. The reference is Python and cannot
-    travel to the GPU box, so this times the oracle port (oracle/htsat_oracle.py: the same torch ops in the same order,
-    pinned against the real reference by oracle/make_golden.py) on all host cores, one bounded sample of 8 clips per step."""
+    """--impl reference: the reference's own CPU (PyTorch fp32) implementation of the path on all host cores, each step a bounded
+    sample of 8 clips of the batch-256 workload. Runs the real reference modules from oracle/_ref (snapshot made by
+    oracle/build_ref.py; /root/reference does not exist on the GPU box), else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     B = 8
-    torch.set_num_threads(os.cpu_count())
-    O, sd, ores = oracle_setup()
-    g = torch.Generator().manual_seed(99)
-    wave = (0.1 * torch.randn(B, 480000, generator=g)).clamp_(-1, 1)
     wl = getattr(args, "workload", "infer")
-    if wl == "train":   # src/training.py:21-32 with a Linear(512,50) probe: forward + autograd backward to lambda and the classifier
-        ores = {l: (mu, comp, lam.clone().requires_grad_(True)) for l, (mu, comp, lam) in ores.items()}
-        torch.manual_seed(0)
-        Wc, bc = (0.02 * torch.randn(50, 512)).requires_grad_(True), torch.zeros(50, requires_grad=True)
-        labels = torch.randint(0, 50, (B,))
-
-        def one():
-            loss, _ = O.linear_probe_loss(wave, labels, Wc, bc, sd, O.CONFIGS["tiny"], ores)
-            loss.backward()
-    elif wl == "infer":
-        def one():
-            with torch.no_grad():
-                O.get_audio_embedding(wave, sd, O.CONFIGS["tiny"], ores)
-    else:
+    if wl not in ("infer", "train"):
         print(json.dumps({"impl": "reference", "unavailable": f"no CPU reference arm for --workload {wl} (only infer and train are timed)"}), flush=True)
         return
+    one, kind, desc = make_cpu_step(wl, B)
     for _ in range(max(1, min(args.warmup, 2))):
         one()
     t0 = time.perf_counter()
@@ -175,11 +237,14 @@ def run_reference(args):
         one()
     dt = time.perf_counter() - t0
     v = B * steps / dt
-    sample = f"{steps} steps x {B} clips (bounded sample of the batch-256 workload), torch {torch.__version__} CPU fp32, {torch.get_num_threads()} threads"
+    sample = (f"{steps} steps x {B} clips (a bounded sample: the workload's batch is 256 clips per step), {desc}, torch {torch.__version__} CPU fp32, "
+              f"{torch.get_num_threads()} threads")
+    cfg = config_dict(256, wl)
+    cfg["reference_sample"] = {"clips_per_step": B, "steps": steps, "note": "throughput of the CPU arm is per clip; 8-clip steps keep the run bounded"}
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": config_dict(256, wl),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -208,13 +273,212 @@ def config_dict(B, workload="infer"):
 
 
 # ------------------------------------------------------------------------------------------------- our arm
+class Workload:
+    """One of BASELINE configs[1..4] on this rank's GPU: `step()` is the device-resident step, `e2e_step(host)` the same step
+    through the public API from a pinned host batch with a host read of the result."""
+
+    def __init__(self, wl, B, dev, rank, world, precision="bf16"):
+        import torch
+        from audio_residual_b200 import weights as W
+        from audio_residual_b200.clap import build_clap_module
+        from audio_residual_b200.residual import inject_residuals
+        self.wl, self.B, self.dev, self.world = wl, B, dev, world
+        model = "base" if wl == "base_fusion" else "tiny"
+        clap = build_clap_module(model, W.make_state_dict(model, seed=0), device=dev, enable_fusion=(wl == "base_fusion"))
+        pca, lam = W.make_pca(model, seed=0)
+        enc = clap.model.audio_branch
+        enc.precision = precision
+        self.clap, self.enc = clap, enc
+        wave = synth_clips_device(B, 1234 + rank, dev)
+        self.wave = wave
+        self.comm = None
+        if wl != "pca":
+            residuals = inject_residuals(enc, pca, lam)
+        if wl == "infer":
+            self.step = lambda: enc.encode(waveform=wave, want_audio_embed=True)["audio_embed"]
+            # the reference's inference route (evaluate_zero_shot, src/evaluation.py:93-95): int16-quantised input, use_tensor=False.
+            # The host batch is int16 PCM (what quantize_tensor's output is, and what a wav file holds): 0.96 MB per clip over PCIe.
+            self.e2e_step = lambda host: clap.get_audio_embedding_from_data(host, use_tensor=False)
+            self.e2e_api = ("CLAP_Module.get_audio_embedding_from_data(x_pinned_host_int16_pcm, use_tensor=False) -> numpy "
+                            "(the reference's evaluation route: int16 round trip of the waveform, hook.py:177-179)")
+            self.e2e_dtype = torch.int16
+        elif wl == "base_fusion":
+            self.step = lambda: enc.encode(mel_fusion=clap.fusion_mel(wave), want_audio_embed=True)["audio_embed"]
+            self.e2e_step = lambda host: clap.get_audio_embedding_from_data(host, use_tensor=False)
+            self.e2e_api = "CLAP_Module(enable_fusion=True).get_audio_embedding_from_data(x_pinned_host_int16_pcm, use_tensor=False) -> numpy"
+            self.e2e_dtype = torch.int16
+        elif wl == "train":
+            from audio_residual_b200.head import cross_entropy, head_logits
+            from audio_residual_b200.parallel import flat_grad_allreduce
+            for r in residuals.values():
+                r.to(dev)
+            torch.manual_seed(0)
+            cls = torch.nn.Linear(512, 50).to(dev)
+            params = [r.learnable for r in residuals.values()] + list(cls.parameters())
+            opt = torch.optim.Adam(params, lr=1e-3)
+            labels = torch.randint(0, 50, (B,), device=dev, generator=torch.Generator(device=dev).manual_seed(5 + rank))
+            self.comm = {"collective": "allreduce(sum) of one flat fp32 buffer: lambda grads + classifier grads",
+                         "floats": int(sum(p.numel() for p in params)), "comm_nranks": world}
+
+            def train_step(x):
+                opt.zero_grad(set_to_none=False)
+                emb = clap.get_audio_embedding_from_data(x, use_tensor=True)
+                loss = cross_entropy(head_logits(emb, cls.weight, cls.bias), labels)
+                loss.backward()
+                flat_grad_allreduce([p.grad for p in params])
+                opt.step()
+                return loss.detach()
+            self.step = lambda: train_step(wave)
+            self.e2e_step = lambda host: train_step(host.to(dev, non_blocking=True)).cpu()
+            self.e2e_api = ("CLAP_Module.get_audio_embedding_from_data(x.to(device), use_tensor=True) -> head_logits(Linear(512,50)) -> "
+                            "cross_entropy -> loss.backward() -> allreduce -> Adam.step(); loss.cpu()")
+            self.e2e_dtype = torch.float32
+        else:   # pca
+            from audio_residual_b200.residual import MomentAccumulator
+            res_acc = [MomentAccumulator(96 << l, dev) for l in range(4)]
+            heads = [4, 8, 16, 32]
+            attn_acc = [[MomentAccumulator(4096, dev) for _ in range(heads[l])] for l in range(4)]
+            self.res_acc, self.attn_acc = res_acc, attn_acc
+            self.comm = {"collective": "allreduce(sum) of {n, sum x, sum x x^T} per layer and per (layer, head), once per pass (finalize)",
+                         "floats": int(sum(a.s1.numel() + a.s2.numel() + 1 for a in res_acc) + 60 * (4096 + 4096 * 4096 + 1)),
+                         "comm_nranks": world}
+
+            def pca_step(x):
+                out = enc.encode(waveform=x, quantize=True, want_dict=True)
+                for l in range(4):
+                    r = out["layers_residuals"][l]
+                    res_acc[l].update(r.view(-1, r.shape[-1]))
+                    a = out["layers_attention"][l]
+                    a3 = a.view(a.shape[0], a.shape[1], 4096)
+                    for hd in range(a.shape[1]):
+                        attn_acc[l][hd].update(a3[:, hd])
+                return res_acc[3].s1
+            self.step = lambda: pca_step(wave)
+            self.e2e_step = lambda host: pca_step(host.to(dev, non_blocking=True)).cpu()
+            self.e2e_api = "encode(want_dict=True) + MomentAccumulator.update per layer and per (layer, head); mean vector .cpu()"
+            self.e2e_dtype = torch.float32
+
+    def host_batch(self):
+        """Pinned host copy of this rank's clips in the dtype the e2e route takes (int16 PCM = quantize_tensor's integers)."""
+        import torch
+        if self.e2e_dtype == torch.int16:
+            q = (self.wave.clamp(-1.0, 1.0) * 32767.0).to(torch.int16)
+            host = torch.empty(q.shape, dtype=torch.int16).pin_memory()
+            host.copy_(q)
+            return host
+        host = torch.empty(self.wave.shape, dtype=torch.float32).pin_memory()
+        host.copy_(self.wave)
+        return host
+
+
+def measure(wl, B, K, Wm, dev, rank, world, dist, do_e2e=True, do_profile=True, sampler=None, precision="bf16"):
+    """W warm-up + K timed steps of workload `wl` (CUDA events, barrier + synchronize on both sides, max over ranks), then the
+    e2e leg and the per-class launch profile. Returns a dict (same on every rank except the rank-0-only profile)."""
+    import torch
+    from audio_residual_b200 import lib as L
+    w = Workload(wl, B, dev, rank, world, precision)
+    grad = wl == "train"
+    torch.set_grad_enabled(grad)   # inference workloads run as the reference's evaluate() does (src/training.py:47): no autograd tape
+    for _ in range(Wm):
+        out = w.step()
+    torch.cuda.synchronize()
+    L.load().ard_launch_counter_reset()
+    w.step()
+    torch.cuda.synchronize()
+    launches_per_step = L.load().ard_launch_counter_read()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    barrier()
+    if sampler is not None:
+        sampler.mark()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        out = w.step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if sampler is not None else None
+    ms_total = ms.item()
+    res = {"workload": wl, "value": world * B * K / (ms_total / 1e3), "ms_per_step": ms_total / K, "steps": K, "warmup": Wm,
+           "launches_per_step": int(launches_per_step), "clocks": clocks, "comm": w.comm,
+           "checksum": float(out.double().abs().sum().item()), "precision": precision}
+
+    if do_e2e:
+        host = w.host_batch()
+        for _ in range(2):
+            w.e2e_step(host)
+        barrier()
+        t0 = time.perf_counter()
+        Ke = max(2, min(K, 10))
+        for _ in range(Ke):
+            emb_host = w.e2e_step(host)
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        # bare pinned-host -> device copy rate of the same buffer on every rank at once: the floor the e2e step cannot beat
+        dst = torch.empty(host.shape, device=dev, dtype=host.dtype)
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(3):
+            dst.copy_(host, non_blocking=True)
+        torch.cuda.synchronize()
+        gbs = torch.tensor([3 * host.numel() * host.element_size() / (time.perf_counter() - t1) / 1e9], device=dev, dtype=torch.float64)
+        per_rank = [gbs.clone() for _ in range(world)]
+        if world > 1:
+            dist.all_gather(per_rank, gbs)
+        per_rank = [round(float(t.item()), 2) for t in per_rank]
+        del dst
+        nb = host.numel() * host.element_size()
+        res["e2e"] = {"value": world * B * Ke / te.item(), "unit": UNIT, "h2d_bytes_per_step": int(nb),
+                      "d2h_bytes_per_step": int(getattr(emb_host, "nbytes", 0) or emb_host.numel() * 4), "api": w.e2e_api, "steps": Ke,
+                      "host_dtype": str(host.dtype).replace("torch.", ""), "h2d_gbs_measured": min(per_rank), "h2d_gbs_per_rank": per_rank,
+                      "h2d_bound_clips_per_s": sum(per_rank) * 1e9 / (nb / B)}
+        if wl == "infer":   # the same call with the fp32 host waveform (use_tensor=True): 1.92 MB per clip over PCIe
+            hf = torch.empty(w.wave.shape, dtype=torch.float32).pin_memory()
+            hf.copy_(w.wave)
+            f = lambda: w.clap.get_audio_embedding_from_data(hf, use_tensor=True).cpu()   # noqa: E731
+            f(); f()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(Ke):
+                f()
+            torch.cuda.synchronize()
+            tf = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            res["e2e"]["fp32_host_waveform"] = {"value": world * B * Ke / tf.item(), "h2d_bytes_per_step": B * 480000 * 4,
+                                                "api": "get_audio_embedding_from_data(x_pinned_host_fp32, use_tensor=True).cpu()"}
+            del hf
+
+    if do_profile:
+        # per-class launch timing: every rank runs the two profiled steps (the training step holds a collective); rank 0 records
+        if rank == 0:
+            L.profile_enable(True)
+        for _ in range(2):
+            w.step()
+        torch.cuda.synchronize()
+        if rank == 0:
+            res["profile"] = L.profile_read()
+            L.profile_enable(False)
+        if world > 1:
+            dist.barrier()
+    torch.set_grad_enabled(True)
+    res["_workload_obj"] = w
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from audio_residual_b200 import lib as L
-    from audio_residual_b200 import weights as W
-    from audio_residual_b200.clap import build_clap_module
-    from audio_residual_b200.residual import inject_residuals
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -226,192 +490,101 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, K, Wm = args.batch, args.steps, max(3, args.warmup)
-
     wl = args.workload
-    model = "base" if wl == "base_fusion" else "tiny"
-    clap = build_clap_module(model, W.make_state_dict(model, seed=0), device=dev, enable_fusion=(wl == "base_fusion"))
-    pca, lam = W.make_pca(model, seed=0)
-    enc = clap.model.audio_branch
-    wave = synth_clips_device(B, 1234 + rank, dev)
-    launch_box = [0]
-    if wl != "pca":
-        residuals = inject_residuals(enc, pca, lam)
-
-    if wl == "infer":
-        def step():
-            return enc.encode(waveform=wave, want_audio_embed=True)["audio_embed"]
-
-        def e2e_step(host):
-            return clap.get_audio_embedding_from_data(host, use_tensor=True).cpu()
-        e2e_api = "CLAP_Module.get_audio_embedding_from_data(x_pinned_host, use_tensor=True).cpu()"
-    elif wl == "base_fusion":
-        def step():
-            return enc.encode(mel_fusion=clap.fusion_mel(wave), want_audio_embed=True)["audio_embed"]
-
-        def e2e_step(host):
-            return clap.get_audio_embedding_from_data(host, use_tensor=True).cpu()
-        e2e_api = "CLAP_Module(enable_fusion=True).get_audio_embedding_from_data(x_pinned_host, use_tensor=True).cpu()"
-    elif wl == "train":
-        from audio_residual_b200.parallel import flat_grad_allreduce
-        for r in residuals.values():
-            r.to(dev)
-        torch.manual_seed(0)
-        cls = torch.nn.Linear(512, 50).to(dev)
-        params = [r.learnable for r in residuals.values()] + list(cls.parameters())
-        opt = torch.optim.Adam(params, lr=1e-3)
-        labels = torch.randint(0, 50, (B,), device=dev, generator=torch.Generator(device=dev).manual_seed(5 + rank))
-
-        def train_step(x):
-            opt.zero_grad(set_to_none=False)
-            emb = clap.get_audio_embedding_from_data(x, use_tensor=True)
-            loss = torch.nn.functional.cross_entropy(cls(emb), labels)
-            loss.backward()
-            flat_grad_allreduce([p.grad for p in params])
-            opt.step()
-            return loss.detach()
-
-        def step():
-            return train_step(wave)
-
-        def e2e_step(host):
-            return train_step(host.to(dev, non_blocking=True)).cpu()
-        e2e_api = "CLAP_Module.get_audio_embedding_from_data(x.to(device), use_tensor=True) -> CE(Linear(512,50)) -> loss.backward() -> allreduce -> Adam.step(); loss.cpu()"
-    else:   # pca
-        from audio_residual_b200.residual import MomentAccumulator
-        res_acc = [MomentAccumulator(96 << l, dev) for l in range(4)]
-        heads = [4, 8, 16, 32]
-        attn_acc = [[MomentAccumulator(4096, dev) for _ in range(heads[l])] for l in range(4)]
-
-        def pca_step(x):
-            out = enc.encode(waveform=x, quantize=True, want_dict=True)
-            for l in range(4):
-                r = out["layers_residuals"][l]
-                res_acc[l].update(r.view(-1, r.shape[-1]))
-                a = out["layers_attention"][l]
-                a3 = a.view(a.shape[0], a.shape[1], 4096)
-                for hd in range(a.shape[1]):
-                    attn_acc[l][hd].update(a3[:, hd])
-            return res_acc[3].s1
-
-        def step():
-            return pca_step(wave)
-
-        def e2e_step(host):
-            return pca_step(host.to(dev, non_blocking=True)).cpu()
-        e2e_api = "encode(want_dict=True) + MomentAccumulator.update per layer and per (layer, head); mean vector .cpu()"
-
-    if wl != "train":   # inference workloads run as the reference's evaluate() does (src/training.py:47): no autograd tape
-        torch.set_grad_enabled(False)
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler is not None:
         sampler.start()          # started before warm-up so nvidia-smi is already streaming when the timed region begins
-    for _ in range(Wm):
-        out = step()
-    torch.cuda.synchronize()
-    L.load().ard_launch_counter_reset()
-    step()
-    torch.cuda.synchronize()
-    launches_per_step = L.load().ard_launch_counter_read()
+    main = measure(wl, B, K, Wm, dev, rank, world, dist, sampler=sampler)
+    main.pop("_workload_obj", None)
+    torch.cuda.empty_cache()
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+    # ---- the other BASELINE configs at this N (a few steps each), so the collectives of c3 / c4 and the c5 model are measured
+    # wherever the headline is: training step with the flat-gradient allreduce, PCA statistics with the end-of-pass moment
+    # allreduce + head-sharded eigensolve, HTSAT-base fusion throughput, and the fp32-grade inference mode.
+    extra = {}
+    if wl == "infer" and not args.no_extra:
+        Ks = max(2, min(K, 5))
+        for name, kw in (("train", dict(wl="train", B=B)), ("pca", dict(wl="pca", B=min(B, 128))), ("base_fusion", dict(wl="base_fusion", B=B)),
+                         ("infer_fp32", dict(wl="infer", B=min(B, 64), precision="fp32"))):
+            try:
+                r = measure(kw["wl"], kw["B"], Ks, 3, dev, rank, world, dist, do_e2e=False, do_profile=False, precision=kw.get("precision", "bf16"))
+                wobj = r.pop("_workload_obj")
+                rec = {"metric": METRIC, "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "steps": r["steps"], "n_gpus": world,
+                       "batch_per_gpu": kw["B"], "launches_per_step": r["launches_per_step"], "comm": r["comm"], "precision": r["precision"],
+                       "workload": config_dict(kw["B"], kw["wl"])["workload"]}
+                if name == "pca":   # end of the pass: sum the moments over ranks (NCCL), eigensolve (heads sharded over ranks)
+                    from audio_residual_b200.analyze_attention import finalize_head_spectra
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for acc in wobj.res_acc:
+                        acc.allreduce()
+                    spectra = finalize_head_spectra([a for row in wobj.attn_acc for a in row], n_components=64)
+                    torch.cuda.synchronize()
+                    rec["finalize_s"] = time.perf_counter() - t0
+                    rec["finalize"] = "allreduce of all moments + 60 head spectra (4096-d covariance eigvalsh, heads sharded over ranks)"
+                    rec["spectrum_checksum"] = float(sum(float(s[:8].sum()) for s in spectra))
+                del wobj
+                extra[name] = rec
+            except Exception as e:  # noqa: BLE001  (an extra record must never take the headline line down)
+                extra[name] = {"error": f"{type(e).__name__}: {e}"[:400]}
+            torch.cuda.empty_cache()
 
-    # ---- timed region (device-resident inputs)
-    barrier()
-    sampler.mark()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        out = step()
-    e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = ms.item()
-    value = world * B * K / (ms_total / 1e3)
-
-    # ---- e2e: public API, pinned host input, host read of the result, every step
-    host = torch.empty((B, 480000), dtype=torch.float32).pin_memory()
-    host.copy_(wave)
-    for _ in range(2):
-        e2e_step(host)
-    barrier()
-    t0 = time.perf_counter()
-    Ke = max(2, min(K, 10))
-    for _ in range(Ke):
-        emb_host = e2e_step(host)
-    torch.cuda.synchronize()
-    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    # bare pinned-host -> device copy rate of the same buffer: the floor the e2e step cannot beat (1.92 MB per clip over PCIe)
-    dst = torch.empty_like(wave)
-    torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    for _ in range(3):
-        dst.copy_(host, non_blocking=True)
-    torch.cuda.synchronize()
-    h2d_gbs = 3 * host.numel() * 4 / (time.perf_counter() - t1) / 1e9
-    del dst
-    e2e = {"value": world * B * Ke / te.item(), "unit": UNIT, "h2d_bytes_per_step": B * 480000 * 4, "d2h_bytes_per_step": int(emb_host.numel() * 4),
-           "api": e2e_api, "steps": Ke, "h2d_gbs_measured": h2d_gbs, "h2d_bound_clips_per_s": world * h2d_gbs * 1e9 / (480000 * 4)}
-
-    # ---- roofline of the dominant kernel class, measured live with CUDA events around every launch.
-    # Every rank runs the two profiled steps (the training step holds a collective); only rank 0 records and reports.
-    if rank == 0:
-        L.profile_enable(True)
-    for _ in range(2):
-        step()
-    torch.cuda.synchronize()
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return
-    peaks = read_peaks()
-    prof = L.profile_read()
-    L.profile_enable(False)
     if world > 1:
         dist.barrier()
+    peaks = read_peaks()
+    prof = main.pop("profile")
     tot_ms = sum(v["ms"] for v in prof.values())
     shares = {k: round(v["ms"] / tot_ms, 4) for k, v in prof.items() if v["launches"]}
     gm = prof["gemm_tc"]
     ff = prof.get("ffn_fused", {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+    at = prof.get("window_attention", {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
     achieved = gm["flops"] / (gm["ms"] * 1e-3) / 1e12
-    tc_ms, tc_flops = gm["ms"] + ff["ms"], gm["flops"] + ff["flops"]
+    tc_ms, tc_flops = gm["ms"] + ff["ms"] + at["ms"], gm["flops"] + ff["flops"] + at["flops"]
     peak = peaks["bf16_tflops_sustained"]
+    ms_step = main["ms_per_step"]
+    executed_gf = tc_flops / 2 / B / 1e9
     roofline = {"kernel": "gemm_tc_kernel (tcgen05 GEMM family: qkv / proj+ResiDual / fc1+GELU / fc2 / merge / head)", "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_per_step": gm["launches"] // 2, "ms_per_step": gm["ms"] / 2, "flops_per_step": gm["flops"] / 2,
                 "algorithmic_bytes_per_step": gm["bytes"] / 2, "achieved_hbm_gbs": gm["bytes"] / (gm["ms"] * 1e-3) / 1e9,
                 "hbm_frac_of_measured": gm["bytes"] / (gm["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                "all_tcgen05_kernels": {"ms_per_step": tc_ms / 2, "tflops": tc_flops / (tc_ms * 1e-3) / 1e12,
-                                        "frac": tc_flops / (tc_ms * 1e-3) / 1e12 / peak,
-                                        "ffn_fused_ms_per_step": ff["ms"] / 2, "ffn_fused_launches_per_step": ff["launches"] // 2},
-                "share_of_step_by_class": shares,
-                "whole_step_tensor_frac": ((B * GF_PER_CLIP_TINY_FAITHFUL * 1e9) / ((ms_total / K) * 1e-3) / 1e12 / peak) if wl == "infer" else None}
+                "all_tensor_core_kernels": {"ms_per_step": tc_ms / 2, "tflops": tc_flops / (tc_ms * 1e-3) / 1e12,
+                                            "frac": tc_flops / (tc_ms * 1e-3) / 1e12 / peak,
+                                            "ffn_fused_ms_per_step": ff["ms"] / 2, "ffn_fused_launches_per_step": ff["launches"] // 2,
+                                            "attention_ms_per_step": at["ms"] / 2, "attention_launches_per_step": at["launches"] // 2},
+                "share_of_step_by_class": shares}
+    if wl == "infer":
+        roofline["whole_step_tensor_frac"] = {
+            "algorithmic": (B * GF_PER_CLIP_TINY_FAITHFUL * 1e9) / (ms_step * 1e-3) / 1e12 / peak,
+            "algorithmic_gf_per_clip": GF_PER_CLIP_TINY_FAITHFUL,
+            "executed": (B * executed_gf * 1e9) / (ms_step * 1e-3) / 1e12 / peak, "executed_gf_per_clip": executed_gf,
+            "note": "algorithmic = SURVEY 8d figure incl. the 1.81 GF ResiDual GEMM pair; executed = flops the launches really do "
+                    "(the pair is folded into the out-projection weights, so it costs no launch)"}
     traffic_file = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(traffic_file):
-        roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+        tj = json.load(open(traffic_file))
+        roofline["traffic"] = tj.get("dram_bytes_per_launch")
+        roofline["traffic_of"] = {"instantiation": tj.get("kernel"), "algorithmic_bytes_per_launch": tj.get("algorithmic_bytes_per_launch"),
+                                  "note": "ncu --set full capture of ONE instantiation of the family (the one with the largest share of the "
+                                          "step); `achieved` / `frac` above are the whole family measured live"}
 
-    # ---- CPU baseline (oracle port) on a bounded sample
     cpu = None
     if world == 1 and not args.no_cpu:
-        v, sec = cpu_time_batches(nbatch=2, B=8, warm=1)
+        v, sec, kind, desc = cpu_time_batches(nbatch=2, B=8, warm=1, wl="train" if wl == "train" else "infer")
         import torch as _t
-        cpu = {"value": v, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
-               "sample": f"2 batches x 8 clips of the same workload ({sec:.2f} s/batch), oracle port of the reference's PyTorch CPU path, fp32"}
+        cpu = {"value": v, "unit": UNIT, "cores": _t.get_num_threads(), "kind": kind,
+               "sample": f"2 batches x 8 clips of the same workload ({sec:.2f} s/batch), {desc}, fp32"}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_total / K,
+    line = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config_dict(B, wl),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K, "roofline": roofline, "cpu_baseline": cpu,
-            "embedding_checksum": float(out.double().abs().sum().item())}
+            "clocks": main["clocks"], "e2e": main["e2e"], "gpu_launches": main["launches_per_step"] * K, "roofline": roofline, "cpu_baseline": cpu,
+            "comm": main["comm"], "extra": extra, "embedding_checksum": main["checksum"]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -427,6 +600,7 @@ def main():
     ap.add_argument("--workload", default="infer", choices=["infer", "train", "pca", "base_fusion"],
                     help="infer = the headline (BASELINE configs[1]); the others measure configs[2..4] with the same JSON contract")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra records (train / pca / base_fusion / fp32 at this N)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

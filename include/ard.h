@@ -93,6 +93,11 @@ typedef struct ard_forward_args {
     float* clipwise_output;  /* device [B, 527] or NULL (htsat.py:820-821,827) */
     float* fine_grained_embedding; /* device [B, 1024, 8*embed_dim] or NULL (htsat.py:807-808,828) */
     int save_for_backward;   /* 1: keep the activations ard_encoder_backward needs (training step, src/training.py:24-32) */
+    float* head_outputs[ARD_MAX_LAYERS];     /* device [depth_l, B*nW_l, nH_l, 64, hd] or NULL: the per-head `attn @ v` temporary of
+                                              * WindowAttention.forward (htsat.py:354) of every block, window order of that block
+                                              * (shifted blocks: windows of the rolled image), before transpose / proj */
+    int precision;           /* 0: bf16/fp16 tensor-core operands (rel. err <= 1e-2); 1: fp32-grade (3-term split-bf16 GEMMs, fp32
+                              * attention; rel. err <= 1e-4 vs the reference's fp32 arithmetic, hook.py:40). Inference only. */
 } ard_forward_args;
 
 /* HTSAT_Swin_Transformer.forward (htsat.py:881-994) in eval mode + optional audio_projection/normalize. */
@@ -109,8 +114,14 @@ typedef struct ard_backward_args {
     const float* grad_audio_embed;           /* device [B, joint_dim] or NULL */
     const float* grad_embedding;             /* device [B, 8*embed_dim] or NULL */
     float* grad_lambda[ARD_MAX_LAYERS];      /* device [K_l] fp32 or NULL */
+    long long generation;                    /* ard_tape_generation() read right after the forward this backward belongs to; a
+                                              * different saved forward on the handle since then -> ARD_ERR_STATE. 0: unchecked */
 } ard_backward_args;
 int ard_encoder_backward(ard_handle* h, const ard_backward_args* args, void* stream);
+/* Serial number of the last ard_encoder_forward(save_for_backward=1) on this handle (0: none). The handle keeps ONE tape:
+ * a second training forward overwrites it, and a backward carrying the older number is refused instead of silently using
+ * the newer activations. */
+long long ard_tape_generation(const ard_handle* h);
 
 /* SwinTransformerBlock.forward (htsat.py:439-482) or the ResiDual-patched forward (src/residual.py:58-98) of block
  * (layer, block) on x[B, T_l, C_l] fp32 device. Outputs (device, fp32): x_out [B,T,C]; attn [B*nW,nH,64,64] or NULL;
@@ -174,11 +185,55 @@ int ard_quantize_waveform(const float* in, float* out, long long n, void* stream
  * (bn0 applied iff apply_bn). Uses the handle's window / mel filters / BN statistics. */
 int ard_logmel(ard_handle* h, const float* wave, int B, int n_samples, int apply_bn, int quantize, float* out, void* stream);
 
+/* bn0 + reshape_wav2img + PatchEmbed (proj conv 4x4/4 + LayerNorm) (htsat.py:900-902, :848-863, :136-143) on a log-mel
+ * [B, 1001, 64] (before bn0): out [B, 4096, embed_dim] fp32 = the residual stream entering layer 0. */
+int ard_patch_embed(ard_handle* h, const float* logmel, int B, float* out, void* stream);
+
 /* Fusion featuriser: get_mel (training/data.py:363-399: torchaudio MelSpectrogram n_fft 1024 / hop 480 / htk / norm=None +
  * AmplitudeToDB(top_db=None)) for a batch, stacked 4x as get_audio_features does for clips <= 10 s (data.py:497-501):
  * wave [B, n_samples] -> out [B, 4, n_samples/480+1, 64]. Needs "fusion_featuriser.melW" [513,64] and
  * "fusion_featuriser.window" [1024] to have been set with ard_set_weight. */
 int ard_fusion_mel(ard_handle* h, const float* wave, int B, int n_samples, int quantize, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Standalone ResiDual module (ResiDual.forward, src/residual.py:29-42) and its autograd: all pointers device fp32.
+ *   forward : out[rows,D] = ((x - mean) basis^T * lam) basis           basis [K,D], lam [K], mean [D]
+ *   backward: dx[rows,D] = ((g basis^T) * lam) basis (or NULL); dlam[K] += sum_rows ((x - mean) basis^T) * (g basis^T) (or NULL).
+ * The contractions run on the tcgen05 GEMM with bf16 operands (fp32 accumulation). Uses per-process scratch: one caller at a time.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int ard_residual_forward(const float* x, const float* mean, const float* basis, const float* lam, float* out, long long rows, int D, int K,
+                         void* stream);
+int ard_residual_backward(const float* x, const float* g, const float* mean, const float* basis, const float* lam, float* dx, float* dlam,
+                          long long rows, int D, int K, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Classification head on the joint embedding: zero-shot similarities  emb @ text_embeds^T  (src/training.py:28,
+ * src/evaluation.py:98) and the linear probe nn.Linear(512, n_classes) (src/linear.py:23-32), CrossEntropyLoss (mean) and
+ * their backward (src/training.py:29-31, src/linear.py:43-45). All device fp32; labels int64 device.
+ *   ard_head_forward : logits[B,N] = emb[B,J] W[N,J]^T (+ bias[N])
+ *   ard_ce_forward   : loss[0] = mean_b( logsumexp(logits_b) - logits_b[label_b] ); dlogits[B,N] = (softmax - onehot) / B (or NULL)
+ *   ard_head_backward: d_emb[B,J] = dlogits W;  dW[N,J] = dlogits^T emb;  db[N] = colsum(dlogits)   (each may be NULL)
+ * ------------------------------------------------------------------------------------------------------------------ */
+int ard_head_forward(const float* emb, const float* W, const float* bias, int B, int N, int J, float* logits, void* stream);
+int ard_ce_forward(const float* logits, const long long* labels, int B, int N, float* loss, float* dlogits, void* stream);
+int ard_head_backward(const float* dlogits, const float* emb, const float* W, int B, int N, int J, float* d_emb, float* dW, float* db,
+                      void* stream);
+/* Evaluation reductions on device (the numbers visualize_eval_metrics prints, src/evaluation.py:159-177): for scores[n,C] and
+ * int64 targets[n]: counts[0] += #(argmax == target), counts[1] += #(target within the k largest scores, ties ordered as
+ * sklearn.top_k_accuracy_score does: of equal scores the higher class index ranks first), cm[C,C] (int64, rows = true class) += 1 at
+ * (target, argmax), preds[n] (int64, or NULL) = argmax (first maximal index, as torch.argmax). counts int64 [2] device. */
+int ard_eval_metrics(const float* scores, const long long* targets, long long n, int C, int k, long long* counts, long long* cm,
+                     long long* preds, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Batched featuriser (replaces the per-clip loop hook.py:175-188 + get_audio_features data.py:466-496 for clips <= max_len):
+ * `flat` holds B clips back to back (device, fp32 or int16 PCM), clip b = flat[offsets[b] .. offsets[b]+lengths[b]);
+ * (offsets = lengths = NULL: dense [B, max_len] input). out[B, max_len] fp32. mode 0 repeatpad (repeat int(max_len/n) times, zero-pad the rest), 1 pad (zeros), 2 repeat (tile and
+ * cut). src_is_pcm16: samples are int16 and are first mapped through int16_to_float32 (data.py:93-94: x / 32767.0).
+ * quantize: apply the int16 round trip (data.py:97-99 then :93-94; hook.py:177-179) to float samples on the way.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int ard_fill_clips(const void* flat, int src_is_pcm16, const long long* offsets, const int* lengths, int B, int max_len, int mode,
+                   int quantize, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * PCA sufficient statistics (replaces IncrementalPCA.partial_fit in compute_pca_components, src/residual.py:137-138):

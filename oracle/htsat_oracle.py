@@ -176,8 +176,9 @@ def shift_attn_mask(H, W, ws=WINDOW, shift=WINDOW // 2):
     return am.masked_fill(am != 0, float(-100.0)).masked_fill(am == 0, float(0.0))
 
 
-def window_attention(x, sd, p, num_heads, mask):
-    """WindowAttention.forward, htsat.py:326-357. x [B_,64,C] -> (out [B_,64,C], attn [B_,nH,64,64])."""
+def window_attention(x, sd, p, num_heads, mask, taps=None):
+    """WindowAttention.forward, htsat.py:326-357. x [B_,64,C] -> (out [B_,64,C], attn [B_,nH,64,64]).
+    `taps` (a list) receives the per-head `attn @ v` temporary [B_, nH, 64, hd] of htsat.py:354 (before its transpose)."""
     dt = x.dtype
     B_, N, C = x.shape
     hd = C // num_heads
@@ -194,7 +195,10 @@ def window_attention(x, sd, p, num_heads, mask):
         attn = attn.view(B_ // nW, nW, num_heads, N, N) + mask.to(dt).unsqueeze(1).unsqueeze(0)
         attn = attn.view(-1, num_heads, N, N)
     attn = torch.softmax(attn, dim=-1)
-    out = (attn @ v).transpose(1, 2).reshape(B_, N, C)
+    head_out = attn @ v
+    if taps is not None:
+        taps.append(head_out)
+    out = head_out.transpose(1, 2).reshape(B_, N, C)
     out = F.linear(out, sd[p + "attn.proj.weight"].to(dt), sd[p + "attn.proj.bias"].to(dt))
     return out, attn
 
@@ -213,7 +217,7 @@ def residual_apply(x, mean, basis, lam):
     return torch.matmul(torch.matmul(xc, basis.T) * lam, basis)
 
 
-def swin_block(x, sd, p, H, W, num_heads, shift, residual=None):
+def swin_block(x, sd, p, H, W, num_heads, shift, residual=None, taps=None):
     """SwinTransformerBlock.forward htsat.py:439-482, or, when `residual=(mean,basis,lam)` is given, the patched
     forward of src/residual.py:58-98 including its doubled shortcut/FFN.
     Eval mode: DropPath is the identity. Returns (x, attn, residual_x)."""
@@ -231,7 +235,7 @@ def swin_block(x, sd, p, H, W, num_heads, shift, residual=None):
     else:
         mask = None
     xw = window_partition(xn, ws).view(-1, ws * ws, C)
-    aw, attn = window_attention(xw, sd, p, num_heads, mask)
+    aw, attn = window_attention(xw, sd, p, num_heads, mask, taps)
     xs = window_reverse(aw.view(-1, ws, ws, C), ws, H, W)
     if shift > 0:
         xs = torch.roll(xs, shifts=(shift, shift), dims=(1, 2))
@@ -266,13 +270,13 @@ def patch_merging(x, sd, p, H, W):
     return F.linear(x, sd[p + "downsample.reduction.weight"].to(dt))
 
 
-def basic_layer(x, sd, l, cfg, H, W, residual=None):
+def basic_layer(x, sd, l, cfg, H, W, residual=None, taps=None):
     """BasicLayer.forward htsat.py:580-597 in eval mode: attention maps are stacked and averaged over the layer's
     blocks, residual_x tensors are concatenated along tokens."""
     attns, ress = [], []
     for b in range(cfg["depths"][l]):
         shift = 0 if b % 2 == 0 else WINDOW // 2
-        x, a, r = swin_block(x, sd, f"layers.{l}.blocks.{b}.", H, W, cfg["num_heads"][l], shift, residual)
+        x, a, r = swin_block(x, sd, f"layers.{l}.blocks.{b}.", H, W, cfg["num_heads"][l], shift, residual, taps)
         attns.append(a.unsqueeze(0))
         ress.append(r)
     if l < len(cfg["depths"]) - 1:
@@ -281,18 +285,22 @@ def basic_layer(x, sd, l, cfg, H, W, residual=None):
     return x, attn, torch.cat(ress, dim=1)
 
 
-def forward_features(img, sd, cfg, residuals=None):
-    """HTSAT_Swin_Transformer.forward_features htsat.py:779-834. residuals: {layer: (mean, basis, lam)}."""
+def forward_features(img, sd, cfg, residuals=None, head_outputs=False):
+    """HTSAT_Swin_Transformer.forward_features htsat.py:779-834. residuals: {layer: (mean, basis, lam)}.
+    head_outputs: add key "head_outputs", per layer [depth, B*nW, nH, 64, hd] (every block's per-head attn @ v, htsat.py:354)."""
     dt = img.dtype
     residuals = residuals or {}
     frames_num = img.shape[2]
     x = patch_embed(img, sd)
     H = W = SPEC_SIZE // PATCH
-    attns, ress = [], []
+    attns, ress, heads = [], [], []
     for l in range(len(cfg["depths"])):
-        x, a, r = basic_layer(x, sd, l, cfg, H >> l, W >> l, residuals.get(l))
+        taps = [] if head_outputs else None
+        x, a, r = basic_layer(x, sd, l, cfg, H >> l, W >> l, residuals.get(l), taps)
         attns.append(a)
         ress.append(r)
+        if head_outputs:
+            heads.append(torch.stack(taps, dim=0))
     Cn = x.shape[-1]
     x = F.layer_norm(x, (Cn,), sd["norm.weight"].to(dt), sd["norm.bias"].to(dt), LN_EPS)
     B, N, C = x.shape
@@ -310,8 +318,11 @@ def forward_features(img, sd, cfg, residuals=None):
     y = torch.flatten(y, 2)
     fpx = interpolate_repeat(torch.sigmoid(y).permute(0, 2, 1).contiguous(), 8 * PATCH)
     clip = torch.sigmoid(y.mean(dim=-1))
-    return {"framewise_output": fpx, "clipwise_output": clip, "fine_grained_embedding": fine,
-            "embedding": latent, "layers_attention": attns, "layers_residuals": ress}
+    out = {"framewise_output": fpx, "clipwise_output": clip, "fine_grained_embedding": fine,
+           "embedding": latent, "layers_attention": attns, "layers_residuals": ress}
+    if head_outputs:
+        out["head_outputs"] = heads
+    return out
 
 
 def interpolate_repeat(x, ratio):
@@ -320,7 +331,7 @@ def interpolate_repeat(x, ratio):
     return x[:, :, None, :].repeat(1, 1, ratio, 1).reshape(B, T * ratio, C)
 
 
-def htsat_forward(inputs, sd, cfg, residuals=None, enable_fusion=False):
+def htsat_forward(inputs, sd, cfg, residuals=None, enable_fusion=False, head_outputs=False):
     """HTSAT_Swin_Transformer.forward htsat.py:881-994 restricted to the reachable eval-mode routes:
     non-fusion (waveform -> STFT -> logmel -> bn0 -> img) and fusion with no `longer` clip (mel_fusion -> bn0 -> img,
     longer_idx=[] so only channel 0 reaches patch_embed.proj, htsat.py:883-894 / :108-134)."""
@@ -328,12 +339,12 @@ def htsat_forward(inputs, sd, cfg, residuals=None, enable_fusion=False):
         x = inputs["mel_fusion"]                       # [B,4,T,64]
         x = bn0_eval(x, sd)
         x = reshape_wav2img(x)
-        return forward_features(x, sd, cfg, residuals)
+        return forward_features(x, sd, cfg, residuals, head_outputs)
     x = stft_power(inputs["waveform"], sd)
     x = logmel(x, sd)
     x = bn0_eval(x, sd)
     x = reshape_wav2img(x)
-    return forward_features(x, sd, cfg, residuals)
+    return forward_features(x, sd, cfg, residuals, head_outputs)
 
 
 def audio_projection(emb, sd):

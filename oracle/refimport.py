@@ -21,8 +21,11 @@ import sys
 import types
 from contextlib import suppress
 
-REF = os.environ.get("ARD_REFERENCE_ROOT", "/root/reference")
-_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_stubs")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# /root/reference when mounted (build container); else the snapshot oracle/build_ref.py made of the same files (oracle/_ref,
+# git-ignored, shipped to the GPU box) so bench.py --impl reference can time the reference's own modules there
+REF = os.environ.get("ARD_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference/CLAP") else os.path.join(_HERE, "_ref"))
+_STUBS = os.path.join(_HERE, "_stubs")
 
 
 def available():

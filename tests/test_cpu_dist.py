@@ -69,3 +69,49 @@ def test_shard_range_covers_everything():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _spectra_worker(rank, world, port, out):
+    """finalize_head_spectra (analyze_attention.py): moments reduced to round-robin owners, each rank solves its own heads."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from audio_residual_b200.analyze_attention import finalize_head_spectra
+
+    class Acc:            # a MomentAccumulator's state without the CUDA update path
+        pass
+    rng = np.random.default_rng(1)
+    accs = []
+    for h in range(5):
+        X = rng.standard_normal((400, 12)) * np.linspace(2, 0.2, 12) + h
+        lo, hi = shard_range(400, rank, world)
+        a = Acc()
+        a.D, a.n = 12, hi - lo
+        a.s1 = torch.from_numpy(X[lo:hi].sum(0))
+        a.s2 = torch.from_numpy(X[lo:hi].T @ X[lo:hi])
+        accs.append(a)
+    spectra = finalize_head_spectra(accs)
+    if rank == 0:
+        out.put(([a.n for a in accs], spectra))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_head_sharded_spectra_match_single_process():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_spectra_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ns, spectra = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(1)
+    assert ns == [400] * 5 and len(spectra) == 5
+    for h in range(5):
+        X = rng.standard_normal((400, 12)) * np.linspace(2, 0.2, 12) + h
+        ref = np.sort(np.linalg.eigvalsh(np.cov(X.T, ddof=1)))[::-1]
+        assert np.allclose(spectra[h], ref, rtol=1e-9)

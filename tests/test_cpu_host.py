@@ -258,3 +258,56 @@ def test_host_pipeline_chunk_schedule():
         for cur, nxt in zip(sizes[:-2], sizes[1:-1]):            # the last chunk may absorb a short tail
             assert nxt <= 22.8 + 1.156 * cur + 1, (N, sizes)
         assert sizes[-1] >= min(8, N) or len(sizes) == 1, (N, sizes)
+
+
+def test_int16_dequantisation_is_exact_for_every_sample_value():
+    """The device featuriser divides int16 samples by 32767 in fp32; numpy's int16_to_float32 (data.py:93-94) divides in float64
+    and rounds once. The two agree for all 65536 inputs, so the int16 PCM transport is bit-identical to the float route."""
+    q = np.arange(-32768, 32768, dtype=np.int64).astype(np.int16)
+    assert np.array_equal((q / 32767.0).astype(np.float32), q.astype(np.float32) / np.float32(32767.0))
+
+
+def test_batch_features_host_path_int16_and_quantize():
+    from audio_residual_b200.clap import batch_features
+    from oracle import htsat_oracle as O
+    g = torch.Generator().manual_seed(3)
+    clips = [(0.5 * torch.randn(n, generator=g)).clamp_(-1.3, 1.3) for n in (5, 33, 100)]
+    ref = torch.stack([O.pad_clip(c, 100, "repeatpad") for c in clips])
+    assert torch.equal(batch_features(clips, 100, "repeatpad"), ref)
+    assert torch.equal(batch_features(clips, 100, "repeatpad", quantize=True), O.quantize_tensor(ref))
+    pcm = [(c.clamp(-1, 1) * 32767.0).to(torch.int16) for c in clips]
+    want = torch.stack([O.pad_clip(torch.from_numpy((p.numpy() / 32767.0).astype(np.float32)), 100, "pad") for p in pcm])
+    assert torch.equal(batch_features(pcm, 100, "pad"), want)
+    with pytest.raises(NotImplementedError):
+        batch_features(clips, 100, "mirror")
+    with pytest.raises(AttributeError):
+        batch_features([torch.zeros(101)], 100)
+
+
+def test_pcm16_chunk_schedule_covers_batch():
+    from audio_residual_b200.clap import CLAP_Module
+    m = CLAP_Module.__new__(CLAP_Module)
+    for n in (65, 256, 1000):
+        b = CLAP_Module._chunk_bounds(m, n, CLAP_Module.h2d_schedule_pcm16)
+        assert b[0][0] == 0 and b[-1][1] == n and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+
+
+def test_apply_criterion_routes_custom_losses_to_the_caller():
+    from audio_residual_b200.head import apply_criterion
+    z, y = torch.randn(4, 5), torch.tensor([0, 1, 2, 3])
+    crit = torch.nn.CrossEntropyLoss(label_smoothing=0.1)          # not the default: the caller's own criterion runs as is
+    assert torch.equal(apply_criterion(crit, z, y), crit(z, y))
+    assert torch.equal(apply_criterion(lambda a, b: a.sum(), z, y), z.sum())
+
+
+def test_reference_snapshot_recipe(tmp_path):
+    """oracle/build_ref.py: the snapshot holds what oracle/refimport.py needs (skipped when /root/reference is not mounted)."""
+    from oracle import build_ref
+    if not os.path.isdir(os.path.join(build_ref.SRC, "CLAP")):
+        pytest.skip("reference tree not mounted")
+    assert build_ref.build(verbose=False)
+    for rel in ("CLAP/src/laion_clap/clap_module/htsat.py", "CLAP/src/laion_clap/clap_module/model.py", "CLAP/src/laion_clap/training/data.py",
+                "src/residual.py", "CLAP/src/laion_clap/clap_module/model_configs/HTSAT-tiny.json"):
+        assert os.path.exists(os.path.join(build_ref.DST, rel)), rel
+    ign = open(os.path.join(ROOT, ".gitignore")).read()
+    assert "oracle/_ref/" in ign                                   # reference sources never enter the history

@@ -166,3 +166,32 @@ def test_oracle_block_vs_live_reference():
         r_x, r_attn, r_res = blk(x)
         o_x, o_attn, o_res = O.swin_block(x, sd, "layers.0.blocks.0.", 16, 16, 4, 4, (res.mean, res.basis, res.learnable))
     assert rel(o_x, r_x) < 1e-6 and rel(o_res, r_res) < 1e-6
+
+
+def test_oracle_head_outputs_and_residual_module_vs_reference_golden():
+    """Round-2 goldens (oracle/make_golden_extras.py): the per-head `attn @ v` tap obtained by hooking the real reference, the
+    reference ResiDual module's autograd, and ResiDual on layers (0, 2) with truncated bases."""
+    g = np.load(os.path.join(GOLDEN, "extras_tiny_b2.npz"))
+    sd = W.make_state_dict("tiny", seed=int(g["meta_seed"]))
+    wave = W.make_clips(int(g["meta_B"]), seed=1234)
+    with torch.no_grad():
+        out = O.htsat_forward({"waveform": wave}, sd, O.CONFIGS["tiny"], None, head_outputs=True)
+    for l in range(4):
+        t = out["head_outputs"][l]
+        assert tuple(t.shape) == tuple(g[f"head_out{l}_shape"])
+        assert rel(golden_sample(t), torch.from_numpy(g[f"head_out{l}_sample"])) < 2e-5
+    x = torch.from_numpy(g["residual_module_x"]).requires_grad_(True)
+    lam = torch.from_numpy(g["residual_module_lam"][:40].copy()).requires_grad_(True)
+    y = O.residual_apply(x, torch.from_numpy(g["residual_module_mean"]), torch.from_numpy(g["residual_module_basis"][:40]), lam)
+    y.backward(torch.from_numpy(g["residual_module_gout"]))
+    assert rel(y.detach(), torch.from_numpy(g["residual_module_k40_out"])) < 1e-6
+    assert rel(x.grad, torch.from_numpy(g["residual_module_k40_dx"])) < 1e-6
+    assert rel(lam.grad, torch.from_numpy(g["residual_module_k40_dlam"])) < 1e-5
+    pca, lm = W.make_pca("tiny", seed=int(g["meta_seed"]))
+    ores = {int(l): (torch.tensor(pca[int(l)]["mean"], dtype=torch.float32), torch.tensor(pca[int(l)]["components"][:int(k)], dtype=torch.float32),
+                     torch.from_numpy(lm[int(l)][:int(k)].copy())) for l, k in zip(g["subset_layers"], g["subset_k"])}
+    with torch.no_grad():
+        sub = O.htsat_forward({"waveform": wave}, sd, O.CONFIGS["tiny"], ores)
+    assert rel(sub["embedding"], torch.from_numpy(g["subset_embedding"])) < 2e-5
+    for l in range(4):
+        assert rel(golden_sample(sub["layers_residuals"][l]), torch.from_numpy(g[f"subset_res{l}_sample"])) < 2e-5

@@ -1,0 +1,480 @@
+"""-m gpu: parity THROUGH THE PUBLIC DROP-IN NAMES (the calls a user of the reference makes), against the oracle and the
+goldens the real reference produced: extract_attention / run_PCA / CSV, compute_pca_components -> load_residual ->
+setup_residual_htsat, train_one_epoch_zero_shot / evaluate, HTSATLinearClassifier, SwinTransformerBlock.forward (plain and
+patched), HTSAT_Swin_Transformer.forward, CLAP.get_audio_output_dict, the standalone ResiDual module, the per-head
+attention-output tap, PatchEmbed, and the evaluation entry points.
+
+Tolerances: bf16 tensor-core path rel. err <= 1e-2 (north_star) on activations; second-order statistics (covariance
+eigenvalues) are quadratic in the activations, so their relative error is up to twice that: 2e-2, stated where used.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import gpu_checks as G
+from audio_residual_b200 import lib as L
+from oracle import htsat_oracle as O
+
+pytestmark = pytest.mark.gpu
+W = G.W
+GOLD = os.path.join(G.GOLDEN, "extras_tiny_b2.npz")
+
+
+def _loader(batches):
+    """What the reference's DataLoaders yield: (waveform [B, 1, T], labels [B])."""
+    return [(w.unsqueeze(1), y) for w, y in batches]
+
+
+def _gram_spectrum(X):
+    """Non-zero eigenvalues (descending) of the ddof=1 covariance of the rows of X, via the n x n Gram matrix (float64)."""
+    X = X.double()
+    Xc = X - X.mean(0, keepdim=True)
+    return torch.linalg.eigvalsh(Xc @ Xc.t() / (X.shape[0] - 1)).flip(0).clamp_min(0)
+
+
+# ------------------------------------------------------------------------------------------------ a20: attention capture + PCA
+def test_extract_attention_run_pca_and_csv(tmp_path):
+    from audio_residual_b200 import analyze_attention as A
+    clap, sd, _ = G.make_encoder("tiny")
+    g = torch.Generator().manual_seed(5)
+    full = W.make_clips(2, seed=41)
+    short = [(0.1 * torch.randn(2, 300000, generator=g)).clamp_(-1, 1)]          # repeatpad branch of the featuriser
+    batches = [(full, torch.tensor([0, 1])), (short[0], torch.tensor([2, 3]))]
+    # extract_attention (src/analyze_attention.py:133-157): int16 round trip, fill, forward, layers_attention
+    attn = A.extract_attention(clap, batches[0][0].unsqueeze(1))
+    with torch.no_grad():
+        ref0 = O.htsat_forward({"waveform": O.quantize_tensor(full)}, sd, O.CONFIGS["tiny"])["layers_attention"]
+        padded = torch.stack([O.pad_clip(c, 480000, "repeatpad") for c in O.quantize_tensor(short[0])])
+        ref1 = O.htsat_forward({"waveform": padded}, sd, O.CONFIGS["tiny"])["layers_attention"]
+    assert [tuple(a.shape) for a in attn] == [(128, 4, 64, 64), (32, 8, 64, 64), (8, 16, 64, 64), (2, 32, 64, 64)]
+    for l in range(4):
+        assert G.rel(attn[l], ref0[l]) < G.TOL_BF16, (l, G.rel(attn[l], ref0[l]))
+    # run_PCA (:13-59) over both batches: per (layer, head) spectrum of the 4096-d maps vs float64 on the oracle's maps
+    models = A.run_PCA(clap, _loader(batches), 4, [4, 8, 16, 32])
+    worst = 0.0
+    for l in range(4):
+        maps = torch.cat([ref0[l], ref1[l]], dim=0)                                # [2 batches * B * nW, nH, 64, 64]
+        for h in (0, maps.shape[1] - 1):
+            m = models[l][h]
+            want = _gram_spectrum(maps[:, h].reshape(maps.shape[0], 4096))
+            k = m.n_components_
+            assert k == min(ref0[l].shape[0], 4096) and m.n_samples_seen_ == maps.shape[0]   # first-batch samples, as IncrementalPCA(None)
+            kk = min(k, want.numel() - 1, 16)
+            got = torch.from_numpy(np.asarray(m.explained_variance_[:kk]))
+            e = G.rel(got, want[:kk])
+            worst = max(worst, e)
+            assert e < 2 * G.TOL_BF16, (l, h, e)                                   # second moments: twice the activation tolerance
+            assert abs(m.explained_variance_ratio_.sum() - m.explained_variance_.sum() / float(want.sum())) < 2e-2
+    # CSV writer / reader (:62-130) incl. participation ratio and intrinsic dim (oracle: spectrum_summaries)
+    path = A.save_pca_results_on_file(str(tmp_path), "synthetic", 0, models)
+    back = A.load_pca_csv_results(path)
+    m = models[1][3]
+    pr, idim = O.spectrum_summaries(np.asarray(m.explained_variance_), np.asarray(m.explained_variance_ratio_))
+    assert abs(back[(1, 3)]["participation_ratio"] - pr) < 1e-6 * pr and back[(1, 3)]["intrinsic_dim"] == idim
+    assert len(back[(0, 0)]["explained_variance"]) == models[0][0].n_components_
+    print("run_PCA worst top-eigenvalue rel err", worst)
+
+
+# ------------------------------------------------------------------------------------------------ a19 + (f)2: PCA artefact round trip
+def test_compute_pca_components_save_load_inject_forward(tmp_path):
+    from audio_residual_b200.residual import compute_pca_components, load_residual, setup_residual_htsat
+    clap, sd, _ = G.make_encoder("tiny")
+    waves = [W.make_clips(2, seed=51), W.make_clips(2, seed=52)]
+    loader = _loader([(w, torch.zeros(2, dtype=torch.long)) for w in waves])
+    layer = 1
+    path = str(tmp_path / "ESC50" / f"layer_{layer}_evalfold_0")
+    res = compute_pca_components(clap, loader, layer, save_path=path)
+    assert sorted(res) == sorted(["components", "mean", "explained_variance", "explained_variance_ratio", "n_components", "input_dim", "num_samples"])
+    assert res["components"].shape == (192, 192) and res["num_samples"] == 2 * 2 * 2 * 1024 and res["input_dim"] == 192
+    with torch.no_grad():
+        X = torch.cat([O.htsat_forward({"waveform": O.quantize_tensor(w)}, sd, O.CONFIGS["tiny"])["layers_residuals"][layer].reshape(-1, 192)
+                       for w in waves]).double()
+    want = O.pca_from_moments(X.shape[0], X.sum(0).numpy(), (X.t() @ X).numpy())
+    assert G.rel(torch.from_numpy(res["mean"]), torch.from_numpy(want["mean"])) < G.TOL_BF16
+    assert G.rel(torch.from_numpy(res["explained_variance"][:32]), torch.from_numpy(want["explained_variance"][:32])) < 2 * G.TOL_BF16
+    comps = torch.from_numpy(res["components"])
+    assert (comps @ comps.t() - torch.eye(192, dtype=comps.dtype)).abs().max() < 1e-9      # orthonormal basis (float64 eigh)
+    # the saved file feeds load_residual / setup_residual_htsat (src/residual.py:161-207) and the patched forward
+    r = load_residual(path)
+    assert tuple(r.basis.shape) == (192, 192) and r.learnable.requires_grad
+    new_htsat, residuals = setup_residual_htsat(clap.model.audio_branch, {layer: path}, [layer])
+    assert not any(p.requires_grad for p in new_htsat.parameters()) and residuals[layer].learnable.requires_grad
+    clap.model.audio_branch = new_htsat
+    lam = 1 + 0.2 * torch.randn(192, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        residuals[layer].learnable.copy_(lam)
+        got = clap.get_audio_embedding_from_data(waves[0].cuda(), use_tensor=True).float().cpu()
+        ores = {layer: (torch.tensor(res["mean"], dtype=torch.float32), torch.tensor(res["components"], dtype=torch.float32), lam)}
+        ref = O.get_audio_embedding(waves[0], sd, O.CONFIGS["tiny"], ores)
+    assert G.rel(got, ref) < G.TOL_BF16, G.rel(got, ref)
+    with pytest.raises(ValueError):                                              # src/residual.py:194-195
+        setup_residual_htsat(clap.model.audio_branch, {7: path}, [7])
+
+
+# ------------------------------------------------------------------------------------------------ a17 / a18: drivers
+def test_train_one_epoch_zero_shot_and_evaluate_vs_oracle():
+    from audio_residual_b200.training import evaluate, train_one_epoch_zero_shot
+    clap, sd, ores = G.make_encoder("tiny", residual=True)
+    text = W.make_text_embeds(50, 512, seed=7)
+    batches = [(W.make_clips(2, seed=61), torch.tensor([4, 9])), (W.make_clips(2, seed=62), torch.tensor([30, 2]))]
+    params = [r.learnable for r in clap._residuals.values()]
+    opt = torch.optim.SGD(params, lr=0.0)                                        # lambda fixed: the oracle sees the same model on both batches
+    crit = torch.nn.CrossEntropyLoss()
+    loss, acc = train_one_epoch_zero_shot(clap, _loader(batches), text, opt, crit, torch.device("cuda"))
+    ol, oc = 0.0, 0
+    for w, y in batches:
+        o = {l: (mu, comp, lam.clone().requires_grad_(True)) for l, (mu, comp, lam) in ores.items()}
+        l_, sims = O.zero_shot_loss(w, y, text, sd, W.CONFIGS["tiny"], o)
+        ol += l_.item() * 2
+        oc += int((sims.argmax(-1) == y).sum())
+    assert abs(loss - ol / 4) < 2e-3 and acc == oc / 4, (loss, ol / 4, acc, oc / 4)
+    l_.backward()                                                                # gradients of the LAST batch stay in .grad (no zero_grad after)
+    for l, r in clap._residuals.items():
+        a, b = r.learnable.grad.cpu().double(), o[l][2].grad.double()
+        assert (a @ b / (a.norm() * b.norm())).item() > 0.98 and abs((a.norm() / b.norm()).item() - 1) < 0.05, l   # ReLU gates: see test_gpu_train.py
+    # evaluate (src/training.py:44-69): int16 round trip of the inputs through the numpy route
+    vloss, vacc = evaluate(clap, _loader(batches), text, crit, torch.device("cuda"))
+    ol = 0.0
+    with torch.no_grad():
+        for w, y in batches:
+            l_, _ = O.zero_shot_loss(torch.from_numpy(O.int16_roundtrip_np(w.numpy())), y, text, sd, W.CONFIGS["tiny"], ores)
+            ol += l_.item() * 2
+    assert abs(vloss - ol / 4) < 2e-3, (vloss, ol / 4)
+
+
+def test_linear_classifier_step_vs_reference_golden():
+    """HTSATLinearClassifier + CE + backward (src/linear.py:9-53) vs what the reference's own modules produced (tests/golden)."""
+    from audio_residual_b200.linear import HTSATLinearClassifier, train_linear_head_one_epoch
+    g = np.load(os.path.join(G.GOLDEN, "htsat_tiny_b2.npz"))
+    clap, sd, _ = G.make_encoder("tiny", seed=int(g["meta_seed"]), residual=True)
+    for r in clap._residuals.values():
+        r.learnable.requires_grad_(False)                                        # frozen encoder: only the probe trains (src/linear.py:18-19)
+    model = HTSATLinearClassifier(clap, 50).cuda()
+    assert model.classifier.weight.shape == (50, 512) and float(model.classifier.bias.abs().sum()) == 0.0
+    with torch.no_grad():
+        model.classifier.weight.copy_(torch.from_numpy(g["cls_weight"]))
+    x = W.make_clips(2, seed=1234).unsqueeze(1)
+    labels = torch.from_numpy(g["labels"])
+    logits = model(x, torch.device("cuda"))
+    loss = torch.nn.CrossEntropyLoss()(logits, labels.cuda())                    # torch CE on library logits
+    from audio_residual_b200.head import cross_entropy
+    loss_lib = cross_entropy(logits, labels.cuda())
+    loss_lib.backward()
+    assert G.rel(logits, torch.from_numpy(g["cls_logits"])) < G.TOL_BF16
+    assert abs(loss_lib.item() - float(g["cls_loss"])) < 2e-3 and abs(loss_lib.item() - loss.item()) < 1e-5
+    assert G.rel(model.classifier.weight.grad, torch.from_numpy(g["cls_weight_grad"])) < G.TOL_BF16
+    assert G.rel(model.classifier.bias.grad, torch.from_numpy(g["cls_bias_grad"])) < G.TOL_BF16
+    # one epoch through the driver: AdamW moves the probe, loss is finite
+    opt = torch.optim.AdamW(filter(lambda p: p.requires_grad, model.parameters()), lr=0.01)
+    l0, _ = train_linear_head_one_epoch(model, [(x, labels)], opt, torch.nn.CrossEntropyLoss(), torch.device("cuda"))
+    l1, _ = train_linear_head_one_epoch(model, [(x, labels)], opt, torch.nn.CrossEntropyLoss(), torch.device("cuda"))
+    assert abs(l0 - float(g["cls_loss"])) < 2e-3 and l1 < l0
+
+
+def test_head_kernels_vs_torch():
+    """ard_head_forward / ard_ce_forward / ard_head_backward vs torch fp32 autograd on the same numbers."""
+    from audio_residual_b200.head import cross_entropy, head_logits
+    g = torch.Generator().manual_seed(2)
+    for B, N, J in ((2, 50, 512), (37, 10, 512), (256, 50, 512), (5, 527, 768)):
+        e = torch.randn(B, J, generator=g).cuda().requires_grad_(True)
+        w = (torch.randn(N, J, generator=g) / J ** 0.5).cuda().requires_grad_(True)
+        b = (0.1 * torch.randn(N, generator=g)).cuda().requires_grad_(True)
+        y = torch.randint(0, N, (B,), generator=g).cuda()
+        loss = cross_entropy(head_logits(e, w, b), y)
+        loss.backward()
+        e2, w2, b2 = (t.detach().clone().requires_grad_(True) for t in (e, w, b))
+        ref = torch.nn.functional.cross_entropy(torch.nn.functional.linear(e2, w2, b2), y)
+        ref.backward()
+        assert abs(loss.item() - ref.item()) < 1e-5
+        for a, r in ((e.grad, e2.grad), (w.grad, w2.grad), (b.grad, b2.grad)):
+            assert G.rel(a, r) < G.TOL_FP32, (B, N, J, G.rel(a, r))
+
+
+# ------------------------------------------------------------------------------------------------ a9 / a11: block.forward
+@pytest.mark.parametrize("l,b", [(0, 0), (0, 1), (1, 1), (2, 3), (3, 1)])
+@pytest.mark.parametrize("patched", [False, True])
+def test_block_forward_vs_oracle(l, b, patched):
+    """model.layers[l].blocks[b](x) -> (x, attn, residual_x): htsat.py:439-482 plain, src/residual.py:58-98 patched."""
+    clap, sd, ores = G.make_encoder("tiny", residual=patched)
+    enc = clap.model.audio_branch
+    blk = enc.layers[l].blocks[b]
+    R, Cd, nH = 64 >> l, 96 << l, enc.num_heads[l]
+    x = torch.randn(2, R * R, Cd, generator=torch.Generator().manual_seed(10 * l + b)) * 0.8
+    out, attn, res = blk(x.cuda())
+    with torch.no_grad():
+        o_out, o_attn, o_res = O.swin_block(x, sd, f"layers.{l}.blocks.{b}.", R, R, nH, 0 if b % 2 == 0 else 4, ores[l] if patched else None)
+    assert out.shape == x.shape and attn.shape == o_attn.shape and res.shape == x.shape
+    for name, a, r in (("x", out, o_out), ("attn", attn, o_attn), ("residual_x", res, o_res)):
+        assert G.rel(a, r) < G.TOL_BF16, (name, G.rel(a, r))
+    with pytest.raises(ValueError):
+        blk(torch.zeros(1, 7, Cd, device="cuda"))
+
+
+def test_htsat_forward_and_get_audio_output_dict():
+    """HTSAT_Swin_Transformer.forward(x: dict) (htsat.py:881-994) and CLAP.get_audio_output_dict(list of dicts) (model.py:745-762)."""
+    clap, sd, ores = G.make_encoder("tiny", residual=True)
+    wave = W.make_clips(2, seed=71)
+    out = clap.model.audio_branch({"waveform": wave.cuda()}, mixup_lambda=None, infer_mode=False, device="cuda")
+    keys = ["framewise_output", "clipwise_output", "fine_grained_embedding", "embedding", "layers_attention", "layers_residuals"]
+    assert list(out.keys()) == keys
+    with torch.no_grad():
+        ref = O.htsat_forward({"waveform": wave}, sd, O.CONFIGS["tiny"], ores)
+    m = G.compare_output_dicts(out, ref)
+    assert all(v < G.TOL_BF16 for v in m.values()), m
+    data = [{"waveform": w.cuda(), "longer": torch.tensor([False])} for w in wave]
+    out2 = clap.model.get_audio_output_dict(data)
+    assert list(out2.keys()) == keys and torch.equal(out2["embedding"], out["embedding"])
+    emb = clap.model.get_audio_embedding(data)
+    with torch.no_grad():
+        assert G.rel(emb, O.audio_projection(ref["embedding"], sd)) < G.TOL_BF16
+    clap.model.audio_branch.train()
+    with pytest.raises(NotImplementedError):
+        clap.model.audio_branch({"waveform": wave.cuda()})
+
+
+# ------------------------------------------------------------------------------------------------ ResiDual module (ADVICE)
+@pytest.mark.parametrize("tag,k", [("full", None), ("k40", 40)])
+def test_residual_module_forward_backward_vs_reference_golden(tag, k):
+    """Standalone ResiDual.forward + autograd in x and learnable vs the reference module's own outputs (oracle/make_golden_extras.py)."""
+    from audio_residual_b200.residual import ResiDual
+    g = np.load(GOLD)
+    mod = ResiDual(torch.from_numpy(g["residual_module_basis"]), torch.from_numpy(g["residual_module_mean"]), n_components=k)
+    K = mod.learnable.numel()
+    with torch.no_grad():
+        mod.learnable.copy_(torch.from_numpy(g["residual_module_lam"][:K]))
+    x = torch.from_numpy(g["residual_module_x"]).cuda().requires_grad_(True)
+    y = mod(x)
+    y.backward(torch.from_numpy(g["residual_module_gout"]).cuda())
+    assert mod.learnable.grad is not None and mod.learnable.grad.shape == (K,) and not mod.learnable.grad.is_cuda   # leaf stays where it lives (Q4)
+    assert G.rel(y, torch.from_numpy(g[f"residual_module_{tag}_out"])) < G.TOL_BF16
+    assert G.rel(x.grad, torch.from_numpy(g[f"residual_module_{tag}_dx"])) < G.TOL_BF16
+    assert G.rel(mod.learnable.grad, torch.from_numpy(g[f"residual_module_{tag}_dlam"])) < G.TOL_BF16
+    with torch.no_grad():                                                        # no-grad call: same numbers, no graph
+        assert torch.equal(mod(x.detach()), y.detach())
+
+
+# ------------------------------------------------------------------------------------------------ J2: per-head attention outputs
+def test_head_outputs_vs_hooked_reference_golden():
+    g = np.load(GOLD)
+    clap, sd, _ = G.make_encoder("tiny", seed=int(g["meta_seed"]))
+    wave = W.make_clips(int(g["meta_B"]), seed=1234)
+    out = clap.model.audio_branch.encode(waveform=wave.cuda(), want_head_outputs=True)
+    for l in range(4):
+        t = out["head_outputs"][l]
+        assert tuple(t.shape) == tuple(g[f"head_out{l}_shape"])
+        e = G.rel(G.golden_sample(t), torch.from_numpy(g[f"head_out{l}_sample"]))
+        assert e < G.TOL_BF16, (l, e)
+    with torch.no_grad():                                                        # and in full against the oracle's tap
+        ref = O.htsat_forward({"waveform": wave}, sd, O.CONFIGS["tiny"], None, head_outputs=True)["head_outputs"]
+    for l in range(4):
+        assert G.rel(out["head_outputs"][l], ref[l]) < G.TOL_BF16
+
+
+def test_subset_layers_truncated_basis_vs_reference_golden():
+    """ResiDual on layers (0, 2) only with n_components 40 / 100 < D: forward goldens from the real reference."""
+    from audio_residual_b200.residual import ResiDual, patch_block_with_residual
+    g = np.load(GOLD)
+    clap, sd, _ = G.make_encoder("tiny", seed=int(g["meta_seed"]))
+    pca, lam = W.make_pca("tiny", seed=int(g["meta_seed"]))
+    enc = clap.model.audio_branch
+    for l, k in zip(g["subset_layers"], g["subset_k"]):
+        r = ResiDual(torch.tensor(pca[int(l)]["components"], dtype=torch.float32), torch.tensor(pca[int(l)]["mean"], dtype=torch.float32), n_components=int(k))
+        with torch.no_grad():
+            r.learnable.copy_(torch.from_numpy(lam[int(l)][:int(k)]))
+        for blk in enc.layers[int(l)].blocks:
+            patch_block_with_residual(blk, r)
+    wave = W.make_clips(int(g["meta_B"]), seed=1234)
+    with torch.no_grad():
+        got = G.encoder_outputs(clap, wave)
+    assert G.rel(got["embedding"], torch.from_numpy(g["subset_embedding"])) < G.TOL_BF16
+    assert G.rel(got["audio_embed"], torch.from_numpy(g["subset_audio_embed"])) < G.TOL_BF16
+    for l in range(4):
+        assert G.rel(G.golden_sample(got["layers_residuals"][l]), torch.from_numpy(g[f"subset_res{l}_sample"])) < G.TOL_BF16, l
+        assert G.rel(G.golden_sample(got["layers_attention"][l]), torch.from_numpy(g[f"subset_attn{l}_sample"])) < G.TOL_BF16, l
+
+
+# ------------------------------------------------------------------------------------------------ a7 / a8: bn0 + wav2img + PatchEmbed
+def test_patch_embed_vs_reference_golden():
+    """ard_patch_embed on the reference's own log-mel pipeline: the golden patch_embed_sample is PatchEmbed(reshape_wav2img(bn0(.)))
+    from the real reference (fp32). The kernel's split-bf16 tensor-core product claims fp32-grade accuracy: <= 1e-4."""
+    g = np.load(os.path.join(G.GOLDEN, "htsat_tiny_b2.npz"))
+    clap, sd, _ = G.make_encoder("tiny", seed=int(g["meta_seed"]))
+    h = clap.model.audio_branch._handle()
+    wave = W.make_clips(2, seed=1234)
+    with torch.no_grad():
+        lm = O.logmel(O.stft_power(wave, sd), sd)[:, 0].contiguous()             # [B, 1001, 64], pinned to the reference by make_golden.py
+        img = O.reshape_wav2img(O.bn0_eval(lm[:, None], sd))
+    assert G.rel(G.golden_sample(img), torch.from_numpy(g["img_sample"])) < 1e-6   # the oracle intermediates ARE the golden ones
+    lmd = lm.cuda()
+    out = torch.empty(2, 4096, 96, device="cuda")
+    L.check(L.load().ard_patch_embed(h, L.ptr(lmd), 2, L.ptr(out), L.stream_ptr()))
+    torch.cuda.synchronize()
+    e = G.rel(G.golden_sample(out), torch.from_numpy(g["patch_embed_sample"]))
+    assert e < G.TOL_FP32, e
+    with torch.no_grad():
+        assert G.rel(out, O.patch_embed(img, sd)) < G.TOL_FP32
+
+
+# ------------------------------------------------------------------------------------------------ ADVICE regressions
+def test_reloaded_weights_reach_the_backward():
+    """A second load_state_dict on the same module must refresh the transposed weight copies the backward uses."""
+    clap, sd, _ = G.make_encoder("tiny", seed=0, residual=True)
+    wave = W.make_clips(2, seed=81)
+    text = W.make_text_embeds(50, 512, seed=7)
+    labels = torch.tensor([5, 6])
+    G._train_step(clap, wave, text, labels)                                      # builds the lazy backward weights for seed 0
+    clap.load_state_dict_flat(W.make_state_dict("tiny", seed=3))
+    G._train_step(clap, wave, text, labels)
+    got = {l: r.learnable.grad.clone() for l, r in clap._residuals.items()}
+    fresh, _, _ = G.make_encoder("tiny", seed=3, residual=True)
+    for l, r in fresh._residuals.items():                                        # same PCA / lambda as `clap` (make_pca seed 0 in both)
+        with torch.no_grad():
+            r.learnable.copy_(clap._residuals[l].learnable)
+            r.basis.copy_(clap._residuals[l].basis)
+            r.mean.copy_(clap._residuals[l].mean)
+    G._train_step(fresh, wave, text, labels)
+    for l, r in fresh._residuals.items():
+        assert G.rel(got[l], r.learnable.grad) < 1e-3, (l, G.rel(got[l], r.learnable.grad))   # only atomic summation order differs
+
+
+def test_stale_tape_is_refused_and_two_losses_work_sequentially():
+    clap, sd, _ = G.make_encoder("tiny", residual=True)
+    enc = clap.model.audio_branch
+    w1, w2 = W.make_clips(1, seed=91).cuda(), W.make_clips(1, seed=92).cuda()
+    e1 = enc.encode(waveform=w1)["embedding"]
+    e2 = enc.encode(waveform=w2)["embedding"]                                    # overwrites the handle's single tape
+    with pytest.raises(RuntimeError, match="saved activations belong"):
+        e1.sum().backward()
+    e2.sum().backward()                                                          # the newest forward is still valid
+    assert all(r.learnable.grad is not None for r in clap._residuals.values())
+
+
+def test_training_with_n_components_not_multiple_of_16():
+    """K = 40 (padded to 48 inside the library): lambda-gradient has exactly K entries and matches autograd through the oracle."""
+    from audio_residual_b200.residual import ResiDual, patch_block_with_residual
+    clap, sd, _ = G.make_encoder("tiny")
+    pca, lam = W.make_pca("tiny", seed=0)
+    enc = clap.model.audio_branch
+    l, K = 2, 40
+    r = ResiDual(torch.tensor(pca[l]["components"], dtype=torch.float32), torch.tensor(pca[l]["mean"], dtype=torch.float32), n_components=K)
+    with torch.no_grad():
+        r.learnable.copy_(torch.from_numpy(lam[l][:K]))
+    for blk in enc.layers[l].blocks:
+        patch_block_with_residual(blk, r)
+    wave = W.make_clips(2, seed=99)
+    NF = enc.num_features
+    Wc = torch.randn(50, NF, generator=torch.Generator().manual_seed(3)) / NF ** 0.5
+    labels = torch.tensor([1, 2])
+    emb = enc.encode(waveform=wave.cuda())["embedding"]
+    torch.nn.functional.cross_entropy(emb @ Wc.T.cuda(), labels.cuda()).backward()
+    assert r.learnable.grad.shape == (K,)
+    lam_o = torch.from_numpy(lam[l][:K].copy()).requires_grad_(True)
+    ores = {l: (torch.tensor(pca[l]["mean"], dtype=torch.float32), torch.tensor(pca[l]["components"][:K], dtype=torch.float32), lam_o)}
+    oemb = O.htsat_forward({"waveform": wave}, sd, W.CONFIGS["tiny"], ores)["embedding"]
+    torch.nn.functional.cross_entropy(oemb @ Wc.T, labels).backward()
+    assert G.rel(r.learnable.grad.cpu(), lam_o.grad) < 1.5e-2, G.rel(r.learnable.grad.cpu(), lam_o.grad)
+
+
+# ------------------------------------------------------------------------------------------------ (f)1: featuriser on the device
+def test_device_featuriser_ragged_float_and_pcm16():
+    from audio_residual_b200.clap import batch_features
+    g = torch.Generator().manual_seed(17)
+    lengths = [1, 7, 19200, 160000, 479999, 480000]
+    clips = [(0.4 * torch.randn(n, generator=g)).clamp_(-1.2, 1.2) for n in lengths]
+    for mode in ("repeatpad", "pad", "repeat"):
+        got = batch_features([c.clone() for c in clips], 480000, mode, device="cuda").cpu()
+        ref = torch.stack([O.pad_clip(c, 480000, mode) for c in clips])
+        assert torch.equal(got, ref), mode                                       # copies only: bit-exact
+    gotq = batch_features([c.clone() for c in clips], 480000, "repeatpad", device="cuda", quantize=True).cpu()
+    assert torch.equal(gotq, O.quantize_tensor(torch.stack([O.pad_clip(c, 480000, "repeatpad") for c in clips])))
+    pcm = [(c.clamp(-1, 1) * 32767.0).to(torch.int16) for c in clips]
+    gotp = batch_features(pcm, 480000, "repeatpad", device="cuda").cpu()
+    refp = torch.stack([O.pad_clip(torch.from_numpy((p.numpy() / 32767.0).astype(np.float32)), 480000, "repeatpad") for p in pcm])   # data.py:93-94
+    assert torch.equal(gotp, refp)
+    with pytest.raises(NotImplementedError):
+        batch_features(clips, 480000, "mirror", device="cuda")
+    with pytest.raises(AttributeError):
+        batch_features([torch.zeros(480001)], 480000, "repeatpad", device="cuda")
+
+
+def test_pcm16_host_route_is_bit_identical_to_float_route():
+    """int16 PCM input == the float array int16_to_float32 makes of it, for the small-batch path and the chunked host pipeline."""
+    clap, sd, ores = G.make_encoder("tiny", residual=True)
+    for n in (3, 70):
+        wave = W.make_clips(n, seed=200 + n)
+        pcm = (wave.clamp(-1, 1) * 32767.0).to(torch.int16)
+        as_float = (pcm.numpy() / 32767.0).astype(np.float32)
+        a = clap.get_audio_embedding_from_data(pcm.numpy(), use_tensor=False)
+        b = clap.get_audio_embedding_from_data(as_float, use_tensor=False)
+        c = clap.get_audio_embedding_from_data(pcm.pin_memory(), use_tensor=False)
+        assert isinstance(a, np.ndarray) and a.shape == (n, 512)
+        assert np.array_equal(a, b) and np.array_equal(a, c), n
+    with torch.no_grad():
+        ref = O.get_audio_embedding(torch.from_numpy(O.int16_roundtrip_np(as_float[:2])), sd, O.CONFIGS["tiny"], ores)
+    assert G.rel(torch.from_numpy(b[:2]), ref) < G.TOL_BF16
+
+
+# ------------------------------------------------------------------------------------------------ (f)4: evaluation entry points
+def test_eval_metrics_vs_sklearn():
+    from sklearn.metrics import accuracy_score, confusion_matrix, f1_score, precision_score, recall_score, top_k_accuracy_score
+    from audio_residual_b200.evaluation import fold_metrics
+    rng = np.random.default_rng(3)
+    n, Cn = 400, 50
+    y = rng.integers(0, Cn, size=n)
+    s = rng.standard_normal((n, Cn)).astype(np.float32)
+    s[np.arange(n), y] += 1.5
+    s[:40, 0] = s[:40, 1]                                                        # exact ties
+    pred = s.argmax(1)
+    m = fold_metrics(s, pred, y, Cn, k_top=5)
+    assert abs(m["acc"] - accuracy_score(y, pred)) < 1e-12
+    assert abs(m["topk"] - top_k_accuracy_score(y, s, k=5, labels=np.arange(Cn))) < 1e-12
+    assert abs(m["prec"] - precision_score(y, pred, average="macro", zero_division=0)) < 1e-9
+    assert abs(m["rec"] - recall_score(y, pred, average="macro", zero_division=0)) < 1e-9
+    assert abs(m["f1"] - f1_score(y, pred, average="macro", zero_division=0)) < 1e-9
+    assert np.array_equal(m["confusion"], confusion_matrix(y, pred, labels=list(range(Cn))))
+
+
+def test_evaluation_and_training_drivers_end_to_end(tmp_path):
+    """train_and_evaluate_residual, evaluate_baseline_clap, train_with_config, train_and_eval_linear_head, visualize_eval_metrics on a
+    synthetic 2-fold 'dataset' with the PCA files written by compute_pca_components (the reference's file layout)."""
+    import pickle
+    from audio_residual_b200 import evaluation as E
+    from audio_residual_b200.linear import train_and_eval_linear_head
+    from audio_residual_b200.training import train_with_config
+    clap, sd, _ = G.make_encoder("tiny")
+    text = W.make_text_embeds(50, 512, seed=7)
+    pca, _ = W.make_pca("tiny", seed=0)
+    folds = []
+    for i in range(2):
+        tr = _loader([(W.make_clips(2, seed=300 + i), torch.tensor([1 + i, 7]))])
+        va = _loader([(W.make_clips(3, seed=310 + i), torch.tensor([3, 4 + i, 9]))])
+        folds.append((tr, va))
+        for l in (0, 3):
+            p = tmp_path / "pca" / "SYN" / f"layer_{l}_evalfold_{i}"
+            p.parent.mkdir(parents=True, exist_ok=True)
+            with open(p, "wb") as f:
+                pickle.dump({"components": pca[l]["components"], "mean": pca[l]["mean"]}, f)
+    out = str(tmp_path / "results")
+    E.evaluate_baseline_clap(clap, "SYN", folds, text, out)
+    base = np.load(os.path.join(out, "SYN", "Baseline", "evalfold_1.npz"))
+    assert base["similarities"].shape == (3, 50) and base["predictions"].shape == (3,) and list(base["targets"]) == [3, 5, 9]
+    with torch.no_grad():                                                        # the saved similarities are the oracle's
+        emb = O.get_audio_embedding(torch.from_numpy(O.int16_roundtrip_np(W.make_clips(3, seed=311).numpy())), sd, O.CONFIGS["tiny"])
+    assert G.rel(torch.from_numpy(base["similarities"]), emb @ text.T) < G.TOL_BF16
+    E.train_and_evaluate_residual(clap, "SYN", folds, text, str(tmp_path / "pca"), out, epochs=1, lr=0.01, inject_layers=[0, 3])
+    res = np.load(os.path.join(out, "SYN", "ResiDual", "layers_0_3_evalfold_0.npz"))
+    assert res["similarities"].shape == (3, 50) and np.isfinite(res["similarities"]).all()
+    m = E.visualize_eval_metrics(os.path.join(out, "SYN", "ResiDual"), "SYN", 2, [0, 3], k_top=5)
+    assert m["confusion"].sum() == 6 and 0.0 <= m["summary"]["topk"][0] <= 1.0 and len(m["per_fold"]["acc"]) == 2
+    clap2, _, _ = G.make_encoder("tiny")
+    logged = []
+    r = train_with_config({"learning_rate": 0.01, "epochs": 2, "inject_layers": [3], "eval_fold": 1}, clap2, "SYN", folds, text, str(tmp_path / "pca"),
+                          logger=logged.append)
+    assert len(logged) == 2 and logged[-1]["epoch"] == 2 and r["final_learnable"][3].shape == (768,)
+    assert not np.allclose(r["final_learnable"][3], 1.0)                          # Adam moved lambda
+    train_and_eval_linear_head(clap2, "SYN", folds, 50, out, lr=0.01, epochs=1)
+    lin = np.load(os.path.join(out, "SYN", "Linear", "evalfold_0.npz"))
+    assert lin["similarities"].shape == (3, 50) and abs(lin["similarities"].sum(1) - 1).max() < 1e-5   # softmax scores (src/linear.py:120)

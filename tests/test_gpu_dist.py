@@ -1,0 +1,30 @@
+"""-m gpu, needs >= 2 GPUs (skipped otherwise): N-GPU sharded results == 1-GPU results for the two real collectives of the path
+(the flat lambda/classifier gradient allreduce of c3 and the moment reduction of c4). Spawns tests/dist_gpu_check.py under torchrun."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
+def test_sharded_training_step_and_statistics_equal_single_gpu():
+    n = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "dist_gpu_check.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-3000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("DIST_CHECK ")][-1]
+    m = json.loads(line[len("DIST_CHECK "):])
+    assert m["world"] == n
+    # per-clip arithmetic is independent of the shard a clip rides in; what differs is fp32 summation order (mean-of-means vs one
+    # mean, atomic order of the in-kernel lambda reduction) and the allreduce's own order
+    assert m["loss_abs"] < 1e-5, m
+    assert max(m["grad_rel"]) < 1e-3, m
+    assert m["moments_n"][0] == m["moments_n"][1] and m["moments_s1_rel"] < 1e-9 and m["moments_s2_rel"] < 1e-6, m
+    assert max(m["spectra_rel"]) < 1e-6, m
