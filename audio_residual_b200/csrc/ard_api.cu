@@ -262,7 +262,7 @@ int ensure_fold(ard_handle* h, int l, int b, cudaStream_t s) {
     for (int i = 0; i < bw.K; ++i) ones[i] = 1.0f;
     ARD_TRY(upload_f32(bw.lam_ones, ones));
     ARD_TRY(residual_fold(bw.proj_w_f32.as<float>(), bw.res_dmean.as<float>(), bw.res_basis.as<float>(), bw.lam_ones.as<float>(), C, bw.K,
-                          bw.res_M.as<float>(), bw.proj_w_fold.as<__nv_bfloat16>(), bw.proj_b_fold.as<float>(), s));
+                          bw.res_M.as<float>(), bw.proj_w_fold.as<__nv_bfloat16>(), bw.proj_b_fold.as<float>(), s, bw.proj_w_fold_f32.as<float>()));
     bw.lambda_set = true;
     return 0;
 }
@@ -348,7 +348,10 @@ static int encoder_forward(ard_handle* h, const ard_forward_args* a, cudaStream_
     const int B = a->B;
     if (B <= 0) return set_error(ARD_ERR_SHAPE, "batch must be positive (got %d)", B);
     if (!a->embedding) return set_error(ARD_ERR_SHAPE, "embedding output is required");
-    if (a->precision != 0) return set_error(ARD_ERR_NOTIMPL, "precision=%d: the fp32-grade mode is not available in this build", a->precision);
+    if (a->precision != 0 && a->precision != 1) return set_error(ARD_ERR_SHAPE, "precision must be 0 (bf16) or 1 (fp32-grade), got %d", a->precision);
+    const bool fp32 = a->precision == 1;
+    if (fp32 && a->save_for_backward)
+        return set_error(ARD_ERR_NOTIMPL, "the training step (save_for_backward) runs on the bf16 path; precision=1 is inference only");
     const int C0 = h->cfg.embed_dim;
     ARD_TRY(ensure_workspace(h, B));
     float* X = h->ws_x.as<float>();
@@ -376,7 +379,8 @@ static int encoder_forward(ard_handle* h, const ard_forward_args* a, cudaStream_
                                X, B, C0, s));
     }
     // ---- swin stages
-    for (int l = 0; l < h->nlayers; ++l) {
+    if (fp32) ARD_TRY(encoder_stages_fp32(h, a, X, Y, &X, s));
+    for (int l = 0; l < h->nlayers && !fp32; ++l) {
         const int C = C_of(h, l), R = R_of(l), T = R * R, depth = h->cfg.depths[l];
         for (int b = 0; b < depth; ++b) {
             float* res = a->layers_residuals[l] ? a->layers_residuals[l] + (long long)b * T * C : nullptr;
@@ -425,13 +429,17 @@ static int encoder_forward(ard_handle* h, const ard_forward_args* a, cudaStream_
         if (a->framewise_output || a->clipwise_output) {
             if (!h->tscam_w.p) return set_error(ARD_ERR_STATE, "tscam_conv weights were never set");
             const int ldy = 528;
-            ARD_TRY(h->ws_tscam_a.ensure((size_t)B * 32 * NF * 6 * 2));
             ARD_TRY(h->ws_tscam_y.ensure((size_t)B * 32 * ldy * 4));
-            ARD_TRY(tscam_im2col(normed, h->ws_tscam_a.as<__nv_bfloat16>(), B, NF, s));
-            GemmArgs g;
-            g.A = h->ws_tscam_a.as<__nv_bfloat16>(); g.lda = 6LL * NF; g.W = h->tscam_w.as<__nv_bfloat16>(); g.ldw = 6LL * NF;
-            g.out = h->ws_tscam_y.as<float>(); g.ldo = ldy; g.M = B * 32; g.N = ARD_CLASS_NUM; g.K = 6 * NF; g.bias = h->tscam_b.as<float>();
-            ARD_TRY(gemm_bf16(g, h->num_sms, s));
+            if (fp32) {
+                ARD_TRY(tscam_gemm_fp32(h, normed, h->ws_tscam_y.as<float>(), ldy, B, s));
+            } else {
+                ARD_TRY(h->ws_tscam_a.ensure((size_t)B * 32 * NF * 6 * 2));
+                ARD_TRY(tscam_im2col(normed, h->ws_tscam_a.as<__nv_bfloat16>(), B, NF, s));
+                GemmArgs g;
+                g.A = h->ws_tscam_a.as<__nv_bfloat16>(); g.lda = 6LL * NF; g.W = h->tscam_w.as<__nv_bfloat16>(); g.ldw = 6LL * NF;
+                g.out = h->ws_tscam_y.as<float>(); g.ldo = ldy; g.M = B * 32; g.N = ARD_CLASS_NUM; g.K = 6 * NF; g.bias = h->tscam_b.as<float>();
+                ARD_TRY(gemm_bf16(g, h->num_sms, s));
+            }
             ARD_TRY(tscam_finish(h->ws_tscam_y.as<float>(), ldy, a->framewise_output, a->clipwise_output, B, ARD_CLASS_NUM, s));
         }
     }
@@ -472,6 +480,7 @@ int ard_create(const ard_config* cfg, ard_handle** out) {
 }
 
 int ard_destroy(ard_handle* h) {
+    if (h) fp32_release(h);
     delete h;
     return 0;
 }
@@ -504,6 +513,7 @@ int ard_set_block_residual(ard_handle* h, int layer, int block, const float* mea
     ARD_TRY(upload(bw.res_basis, basis, (size_t)K * D * 4));
     ARD_TRY(bw.res_M.ensure((size_t)C * C * 4));
     ARD_TRY(bw.proj_w_fold.ensure((size_t)C * C * 2));
+    ARD_TRY(bw.proj_w_fold_f32.ensure((size_t)C * C * 4));
     ARD_TRY(bw.proj_b_fold.ensure((size_t)C * 4));
     char key[96];
     snprintf(key, sizeof(key), "layers.%d.blocks.%d.attn.proj.bias", layer, block);
@@ -533,7 +543,8 @@ int ard_set_block_lambda(ard_handle* h, int layer, int block, const float* lambd
     const int C = C_of(h, layer);
     g_launches = 0;
     ARD_TRY(residual_fold(bw.proj_w_f32.as<float>(), bw.res_dmean.as<float>(), bw.res_basis.as<float>(), lambda_dev, C, bw.K,
-                          bw.res_M.as<float>(), bw.proj_w_fold.as<__nv_bfloat16>(), bw.proj_b_fold.as<float>(), (cudaStream_t)stream));
+                          bw.res_M.as<float>(), bw.proj_w_fold.as<__nv_bfloat16>(), bw.proj_b_fold.as<float>(), (cudaStream_t)stream,
+                          bw.proj_w_fold_f32.as<float>()));
     // keep a (zero-padded) copy of lambda for the backward: gsc = gcoef * lambda
     const int Kp = (bw.K + 15) & ~15;
     ARD_TRY(bw.lam.ensure((size_t)Kp * 4));
@@ -550,7 +561,7 @@ int ard_set_block_lambda(ard_handle* h, int layer, int block, const float* lambd
 // (weights, ResiDual injection, a larger workspace) bumps an epoch and the entry is re-captured.
 static int forward_graphed(ard_handle* h, const ard_forward_args* args, cudaStream_t s, bool* handled) {
     *handled = false;
-    const bool eligible = h->use_graphs && h->finalized && !g_prof_on && !args->save_for_backward && args->B > 0 && args->embedding &&
+    const bool eligible = h->use_graphs && h->finalized && !g_prof_on && !args->save_for_backward && args->precision == 0 && args->B > 0 && args->embedding &&
                           !args->framewise_output && !args->clipwise_output && !args->fine_grained_embedding &&
                           !args->layers_residuals[0] && !args->layers_residuals[1] && !args->layers_residuals[2] && !args->layers_residuals[3] &&
                           !args->layers_attention[0] && !args->layers_attention[1] && !args->layers_attention[2] && !args->layers_attention[3] &&

@@ -38,7 +38,7 @@ struct BlockW {
     bool has_res = false, lambda_set = false;
     int K = 0;
     std::vector<float> h_mean, h_basis;
-    DevBuf res_basis, res_dmean, res_M, proj_w_fold, proj_b_fold, lam_ones;
+    DevBuf res_basis, res_dmean, res_M, proj_w_fold, proj_w_fold_f32, proj_b_fold, lam_ones;
     // training (ard_train.cu): current lambda (padded to Kp), transposed / folded weights for the dgrad GEMMs, built lazily
     int Kp = 0;
     bool bwd_ready = false;
@@ -128,4 +128,8 @@ int ensure_tape(ard_handle* h, int B);
 int run_block_train(ard_handle* h, int l, int b, int B, float* attn_out, float attn_scale, int attn_acc, float* res_out,
                     long long res_bstride, cudaStream_t s);
 int encoder_backward(ard_handle* h, const ard_backward_args* a, cudaStream_t s);
+// fp32-grade mode (fp32_mode.cu)
+int encoder_stages_fp32(ard_handle* h, const ard_forward_args* a, float* X, float* Y, float** x_final, cudaStream_t s);
+int tscam_gemm_fp32(ard_handle* h, const float* normed, float* y, int ldy, int B, cudaStream_t s);
+void fp32_release(const ard_handle* h);
 }  // namespace ard

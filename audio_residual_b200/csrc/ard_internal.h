@@ -80,6 +80,9 @@ int add_layernorm_bf16(const float* x, const float* add, float* sum_out, const f
 // PatchMerging gather (htsat.py:516-521) + LayerNorm(4C) -> bf16 [B*(H/2)*(W/2), 4C]
 int merge_layernorm_bf16(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int B, int H, int W, int C,
                          cudaStream_t s);
+// fp32-grade mode: LayerNorm output written as split-bf16 rows [hi | hi | lo], 3C wide (rowwise.cu)
+int layernorm_split3(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out3, long long rows, int C, cudaStream_t s);
+int merge_layernorm_split3(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out3, int B, int H, int W, int C, cudaStream_t s);
 // final LayerNorm + token mean (htsat.py:797, :810-811): x[B, T, C] -> emb[B, C]; optionally the normalised tokens (fp32) too
 int final_norm_mean(const float* x, const float* gamma, const float* beta, float* emb, float* normed, int B, int T, int C, cudaStream_t s);
 int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, float scale, cudaStream_t s);
@@ -121,7 +124,7 @@ int quantize_waveform(const float* in, float* out, long long n, cudaStream_t s);
 int linear_small(const float* x, int ldx, const float* W, const float* bias, float* y, int ldy, int B, int N, int K, int act, cudaStream_t s);
 int l2_normalize(const float* x, float* y, int B, int N, cudaStream_t s);
 int residual_fold(const float* proj_w, const float* dmean, const float* basis, const float* lam, int C, int K, float* Mtmp,
-                  __nv_bfloat16* w_out, float* b_out, cudaStream_t s);
+                  __nv_bfloat16* w_out, float* b_out, cudaStream_t s, float* w_out_f32 = nullptr);
 int residual_matrix(const float* basis, const float* lam, int C, int K, float* M, cudaStream_t s);   // M = B^T diag(lam) B [C,C]
 int tscam_im2col(const float* normed, __nv_bfloat16* A, int B, int C, cudaStream_t s);
 int tscam_finish(const float* y, int ldy, float* framewise, float* clipwise, int B, int NC, cudaStream_t s);

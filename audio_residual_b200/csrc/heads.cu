@@ -211,9 +211,14 @@ int residual_matrix(const float* basis, const float* lam, int C, int K, float* M
     return sgemm_tn(basis, C, basis, C, lam, M, C, false, C, C, K, s);               // M[i][j] = sum_k B[k][i] lam[k] B[k][j]
 }
 int residual_fold(const float* proj_w, const float* dmean, const float* basis, const float* lam, int C, int K, float* Mtmp,
-                  __nv_bfloat16* w_out, float* b_out, cudaStream_t s) {
+                  __nv_bfloat16* w_out, float* b_out, cudaStream_t s, float* w_out_f32) {
     ARD_TRY(residual_matrix(basis, lam, C, K, Mtmp, s));
-    ARD_TRY(sgemm_tn(Mtmp, C, proj_w, C, nullptr, w_out, C, true, C, C, C, s));      // W'[i][j] = sum_c M[c][i] Wp[c][j]
+    if (w_out_f32 != nullptr) {   // keep the fp32 fold too (the fp32-grade mode splits it into bf16 terms); bf16(acc) is unchanged
+        ARD_TRY(sgemm_tn(Mtmp, C, proj_w, C, nullptr, w_out_f32, C, false, C, C, C, s));
+        ARD_TRY(f32_to_bf16(w_out_f32, w_out, (long long)C * C, 1.0f, s));
+    } else {
+        ARD_TRY(sgemm_tn(Mtmp, C, proj_w, C, nullptr, w_out, C, true, C, C, C, s));  // W'[i][j] = sum_c M[c][i] Wp[c][j]
+    }
     ARD_TRY(sgemm_tn(dmean, 1, Mtmp, C, nullptr, b_out, C, false, 1, C, C, s));      // b'[j] = sum_c (bp-mu)[c] M[c][j]
     return 0;
 }

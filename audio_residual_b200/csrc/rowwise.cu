@@ -39,6 +39,19 @@ ARD_DEVINL void store_bf16_vec(__nv_bfloat16* p, const float* r) {
     }
 }
 
+// fp32-grade mode: a value is carried as two bf16 terms, hi = bf16(x), lo = bf16(x - hi) (16 significant bits); an activation
+// row of width C is laid out [hi | hi | lo] (3C wide) so that ONE GEMM against the weight rows [W_hi | W_lo | W_hi] accumulates
+// hi*hi + hi*lo + lo*hi in fp32 (the dropped lo*lo term is 2^-18 relative).
+template <int VEC>
+ARD_DEVINL void store_split3_vec(__nv_bfloat16* row_base, int C, int e, const float* r) {
+    float lo[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) lo[k] = r[k] - __bfloat162float(__float2bfloat16_rn(r[k]));
+    store_bf16_vec<VEC>(row_base + e, r);
+    store_bf16_vec<VEC>(row_base + C + e, r);
+    store_bf16_vec<VEC>(row_base + 2 * C + e, lo);
+}
+
 // Row r of the logical [rows, C] matrix; element offset e (multiple of VEC) -> source pointer.
 struct PlainRows {
     const float* x;
@@ -61,7 +74,7 @@ struct MergeRows {
     }
 };
 
-template <int VEC, int NV, class Rows>
+template <int VEC, int NV, class Rows, bool SPLIT3 = false>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(Rows rows, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             __nv_bfloat16* __restrict__ out, long long nrows) {
     pdl_launch_dependents();
@@ -96,7 +109,8 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(Rows rows, const fl
         load_vec<VEC>(beta + e, b);
 #pragma unroll
         for (int k = 0; k < VEC; ++k) o[k] = fmaf((v[i][k] - mean) * rstd, g[k], b[k]);
-        store_bf16_vec<VEC>(out + row * C + e, o);
+        if constexpr (SPLIT3) store_split3_vec<VEC>(out + row * (3 * C), C, e, o);
+        else store_bf16_vec<VEC>(out + row * C + e, o);
     }
 }
 
@@ -176,13 +190,13 @@ int add_layernorm_bf16(const float* x, const float* add, float* sum_out, const f
     return check_cuda(cudaGetLastError(), "add_layernorm launch");
 }
 
-template <class Rows>
+template <class Rows, bool SPLIT3 = false>
 static int launch_ln(Rows rows, const float* gamma, const float* beta, __nv_bfloat16* out, long long nrows, int C, cudaStream_t s) {
     const int wpb = 8;
     const unsigned grid = (unsigned)((nrows + wpb - 1) / wpb);
-    ProfScope ps(PROF_LN, s, 8.0 * nrows * C, 6.0 * nrows * C);
+    ProfScope ps(PROF_LN, s, 8.0 * nrows * C, (SPLIT3 ? 10.0 : 6.0) * nrows * C);
 #define ARD_LN_CASE(c, vec, nv) \
-    case c: ARD_CUDA(enqueue_pdl(layernorm_rows_kernel<vec, nv, Rows>, dim3(grid), dim3(wpb * 32), 0, s, rows, gamma, beta, out, nrows)); break;
+    case c: ARD_CUDA(enqueue_pdl(layernorm_rows_kernel<vec, nv, Rows, SPLIT3>, dim3(grid), dim3(wpb * 32), 0, s, rows, gamma, beta, out, nrows)); break;
     switch (C) {
         ARD_LN_CASE(96, 1, 3)
         ARD_LN_CASE(128, 4, 1)
@@ -210,6 +224,17 @@ int merge_layernorm_bf16(const float* x, const float* gamma, const float* beta, 
     if ((H & 1) || (W & 1)) return set_error(ARD_ERR_SHAPE, "x size (%d*%d) are not even.", H, W);  // htsat.py:512
     const long long rows = (long long)B * (H / 2) * (W / 2);
     return launch_ln(MergeRows{x, H, W, C}, gamma, beta, out, rows, 4 * C, s);
+}
+
+// fp32-grade mode: LayerNorm output as split-bf16 rows [hi | hi | lo] (3C wide)
+int layernorm_split3(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out3, long long rows, int C, cudaStream_t s) {
+    if (rows <= 0) return 0;
+    return launch_ln<PlainRows, true>(PlainRows{x, C}, gamma, beta, out3, rows, C, s);
+}
+int merge_layernorm_split3(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out3, int B, int H, int W, int C, cudaStream_t s) {
+    if ((H & 1) || (W & 1)) return set_error(ARD_ERR_SHAPE, "x size (%d*%d) are not even.", H, W);  // htsat.py:512
+    const long long rows = (long long)B * (H / 2) * (W / 2);
+    return launch_ln<MergeRows, true>(MergeRows{x, H, W, C}, gamma, beta, out3, rows, 4 * C, s);
 }
 
 // ---------------------------------------------------------------------------------------------- final norm + token mean
