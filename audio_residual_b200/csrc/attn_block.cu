@@ -1,0 +1,561 @@
+// Window-resident attention block of the 96-channel stage, one kernel:
+//
+//     y = x + proj'( window_attention( LayerNorm1(x) ) )        proj' = out-projection with the ResiDual fold (M W_p, (b_p - mu) M)
+//
+// Reference: SwinTransformerBlock.forward htsat.py:449-476 (norm1, roll, window_partition, WindowAttention :326-357,
+// window_reverse, roll back, shortcut add) and the patched form src/residual.py:58-92 (ResiDual on the attention output,
+// folded into the projection for the current lambda: ard_api.cu::ensure_fold).
+//
+// Unfused this is four kernels (ln_qkv, window_attention, proj GEMM) that move 30 B per token-channel through HBM: the bf16
+// qkv tensor is written and re-read, so is the attention output. Here a CTA owns a PAIR of 8x8 windows (128 tokens = one
+// UMMA M tile); x is read once, y written once (8 B per token-channel) and every contraction runs on tcgen05 with its
+// accumulator in tensor memory:
+//
+//   A   = LayerNorm1(x rows of the two windows, gathered with the cyclic shift)      bf16, SWIZZLE_64B K-major, smem
+//   QK  = A  Wqk_pad^T      M128 N256 K96   per-head padded layout: head h -> columns 32h..32h+23 (hd 24 -> 32, zero rows),
+//                                           q rows carry head_dim^-0.5 * log2(e)
+//   V^T = Wv_pad A^T        M128 N128 K96   computed TRANSPOSED (weights as the A operand, tokens as N) so that the epilogue
+//                                           thread of channel c writes row c of V^T[channel, key]: the K-major B operand of P V
+//   S_h = Q_h K_h^T         M128 N128 K32   both windows at once; the two cross-window 64x64 blocks are computed and ignored
+//   P_h = softmax(S_h + rel-pos bias + shift mask)   one thread per query row (TMEM lane): 64 logits in registers, exp2,
+//                                           probabilities written back to TENSOR MEMORY as the bf16 A operand (zeros in the
+//                                           cross-window half), S double-buffered so head h+1's S MMA overlaps head h's softmax
+//   O_h = P_h V_h           M128 N32  K128  A from TMEM, B = rows 32h.. of V^T
+//   Y   = O_pad Wp_pad^T    M128 N96  K128  + b' + x -> y (fp32, token order: window_reverse / roll back are address arithmetic)
+//
+// TMEM (512 columns): QK accumulator 0-255, V^T accumulator 256-383, O 384-511; after the QKV drain S[0], S[1] reuse 0-255,
+// P[0], P[1] reuse 256-383 (64 columns each: 128 bf16 per row), Y reuses 0-95.
+// Warp roles (13 warps): 0-7 tensor-memory warps (lane quadrant w & 3, half w >> 2: drain QKV, softmax of heads {half, half+2},
+// drain O, output epilogue), 8 = TMA weights + MMA issue (warp-convergent, elected lane), 9-12 = LayerNorm of the NEXT tile
+// (it overlaps the attention phase: the A tile is free as soon as the QK / V^T MMAs have read it).
+#include "ard_common.cuh"
+#include "ard_handle.h"
+
+namespace ard {
+
+constexpr int AB_C = 96, AB_NH = 4, AB_HD = 24;
+constexpr int AB_TM_WARPS = 8, AB_W_MMA = 8, AB_W_LN = 9, AB_LN_WARPS = 4;
+constexpr int AB_THREADS = (AB_W_LN + AB_LN_WARPS) * 32;   // 416
+
+constexpr int AB_KB = 128 * 64;                    // bytes of a 128-row x 32-element (64 B) SWIZZLE_64B k-block
+constexpr int AB_WQK_OFF = 0, AB_WQK_KB = 256 * 64;               // 3 k-blocks of [256 rows x 64 B]
+constexpr int AB_WV_OFF = AB_WQK_OFF + 3 * AB_WQK_KB;             // 49152: 3 k-blocks of [128 x 64 B]
+constexpr int AB_WP_OFF = AB_WV_OFF + 3 * AB_KB, AB_WP_KB = 96 * 64;   // 73728: 4 k-blocks of [96 x 64 B]
+constexpr int AB_A_OFF = AB_WP_OFF + 4 * AB_WP_KB;                // 98304: 3 k-blocks
+constexpr int AB_Q_OFF = AB_A_OFF + 3 * AB_KB;                    // 122880: 4 k-blocks (one per head); later the O_pad operand
+constexpr int AB_K_OFF = AB_Q_OFF + 4 * AB_KB;                    // 155648
+constexpr int AB_VT_OFF = AB_K_OFF + 4 * AB_KB;                   // 188416: 4 k-blocks of 32 keys, rows = padded channel
+constexpr int AB_VEC_OFF = AB_VT_OFF + 4 * AB_KB;                 // 221184: bqk[256] bv[128] bp[96] gamma[96] beta[96]
+constexpr int AB_TAB_OFF = AB_VEC_OFF + (256 + 128 + 3 * 96) * 4; // rel-pos bias table [4][225] (x log2 e)
+constexpr int AB_BAR_OFF = AB_TAB_OFF + 4 * 225 * 4 + 16;         // (16: keep 8-byte alignment margin)
+constexpr int AB_SMEM_BYTES = ((AB_BAR_OFF + 7) & ~7) + 256 + 1024;
+static_assert(AB_SMEM_BYTES <= 227 * 1024, "attn_block: shared memory budget");
+
+constexpr uint32_t AB_TM_QK = 0, AB_TM_VT = 256, AB_TM_O = 384, AB_TM_S = 0, AB_TM_P = 256, AB_TM_Y = 0;
+constexpr float AB_LOG2E = 1.4426950408889634f;
+
+struct AttnBlockParams {
+    const float* x;       // [B*R*R, 96] fp32, token order
+    float* out;           // [B*R*R, 96] fp32
+    const float* bqk;     // [256] padded q/k bias (q part scaled)
+    const float* bv;      // [128]
+    const float* bp;      // [96]  (folded) projection bias
+    const float* gamma;   // norm1
+    const float* beta;
+    const float* table;   // [4][225] relative-position bias x log2(e)
+    int R, shift, n_tiles;   // tokens per side (64), cyclic shift (0 / 4), number of window pairs
+};
+
+// D (+)= A_tmem * B for ONE k-step (A: 128 lanes x 8 columns of packed bf16 pairs)
+ARD_DEVINL void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+ARD_DEVINL float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// byte offset of element (row r, column c) in a SWIZZLE_64B K-major tile made of k-blocks of `kb_bytes`
+ARD_DEVINL int sw64_off(int r, int c, int kb_bytes) {
+    const int kb = c >> 5, cc = c & 31;
+    return kb * kb_bytes + r * 64 + ((((cc >> 3) ^ (r >> 1)) & 3) << 4) + (cc & 7) * 2;
+}
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_constant__ CUtensorMap tmWv, const __grid_constant__ CUtensorMap tmWp,
+                  const AttnBlockParams p) {
+    pdl_launch_dependents();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* bqk_s = reinterpret_cast<float*>(smem + AB_VEC_OFF);
+    float* bv_s = bqk_s + 256;
+    float* bp_s = bv_s + 128;
+    float* g_s = bp_s + 96;
+    float* b_s = g_s + 96;
+    float* tab_s = reinterpret_cast<float*>(smem + AB_TAB_OFF);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ((AB_BAR_OFF + 7) & ~7));
+    uint64_t* w_full = bars + 0;
+    uint64_t* a_full = bars + 1;
+    uint64_t* a_free = bars + 2;
+    uint64_t* acc_full = bars + 3;
+    uint64_t* qkv_ready = bars + 4;
+    uint64_t* s_full = bars + 5;    // [2]
+    uint64_t* s_free = bars + 7;    // [2]
+    uint64_t* p_full = bars + 9;    // [2]
+    uint64_t* p_free = bars + 11;   // [2]
+    uint64_t* o_full = bars + 13;
+    uint64_t* ao_ready = bars + 14;
+    uint64_t* y_full = bars + 15;
+    uint64_t* y_free = bars + 16;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 17);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int R = p.R, nWr = R >> 3, nW = nWr * nWr;
+
+    for (int i = threadIdx.x; i < 256; i += AB_THREADS) bqk_s[i] = p.bqk[i];
+    for (int i = threadIdx.x; i < 128; i += AB_THREADS) bv_s[i] = p.bv[i];
+    for (int i = threadIdx.x; i < 96; i += AB_THREADS) {
+        bp_s[i] = p.bp[i];
+        g_s[i] = p.gamma[i];
+        b_s[i] = p.beta[i];
+    }
+    for (int i = threadIdx.x; i < 4 * 225; i += AB_THREADS) tab_s[i] = p.table[i];
+    if (warp == AB_W_MMA && lane == 0) {
+        tma_prefetch_desc(&tmWqk);
+        tma_prefetch_desc(&tmWv);
+        tma_prefetch_desc(&tmWp);
+        mbar_init(w_full, 1);
+        mbar_init(a_full, AB_LN_WARPS);
+        mbar_init(a_free, 1);
+        mbar_init(acc_full, 1);
+        mbar_init(qkv_ready, AB_TM_WARPS);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_free[i], 4);
+            mbar_init(&p_full[i], 4);
+            mbar_init(&p_free[i], 1);
+        }
+        mbar_init(o_full, 1);
+        mbar_init(ao_ready, AB_TM_WARPS);
+        mbar_init(y_full, 1);
+        mbar_init(y_free, AB_TM_WARPS);
+        fence_barrier_init();
+    }
+    if (warp == AB_W_MMA) {
+        tmem_alloc(tmem_ptr_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();
+
+    // token (row r of tile `tile`) -> row index of x / out: window pair -> (clip, wy, wx), roll by -shift (htsat.py:452-460)
+    auto token_row = [&](int tile, int r) -> long long {
+        const int widx = tile * 2 + (r >> 6);
+        const int b = widx / nW, win = widx - b * nW;
+        const int wy = win / nWr, wx = win - wy * nWr;
+        const int i = r & 63;
+        int y = wy * 8 + (i >> 3) + p.shift, x = wx * 8 + (i & 7) + p.shift;
+        if (y >= R) y -= R;
+        if (x >= R) x -= R;
+        return ((long long)b * R + y) * R + x;
+    };
+
+    if (warp < AB_TM_WARPS) {
+        // ============================================================ tensor-memory warps
+        const int quad = warp & 3, half = warp >> 2;
+        const int row = quad * 32 + lane;                 // TMEM lane == row of the tile (token, or padded channel for V^T)
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const int sw = (row >> 1) & 3;
+        const int win_in_tile = quad >> 1;
+        const int qi = row & 63, ty = qi >> 3, tx = qi & 7;
+        const int ci = ty * 15 + tx + 112;                // bias index = ci - (jy * 15 + jx)   (relative_position_index, htsat.py:301-316)
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            // ---- 1. drain the QK / V^T accumulators into their shared-memory operand tiles (bf16)
+            mbar_wait_parked(acc_full, (uint32_t)(it & 1));
+            tc_fence_after();
+            {
+                uint8_t* dst = smem + (half == 0 ? AB_Q_OFF : AB_K_OFF);
+#pragma unroll 1
+                for (int h = 0; h < 4; ++h) {             // 32 padded columns of head h -> k-block h, this thread's row
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(lane_addr + AB_TM_QK + half * 128 + h * 32, v);
+                    tmem_ld_wait();
+                    const float* bb = bqk_s + half * 128 + h * 32;
+                    uint8_t* rowp = dst + h * AB_KB + row * 64;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            pk[k] = pack_bf16x2(__uint_as_float(v[q * 8 + 2 * k]) + bb[q * 8 + 2 * k], __uint_as_float(v[q * 8 + 2 * k + 1]) + bb[q * 8 + 2 * k + 1]);
+                        *reinterpret_cast<uint4*>(rowp + ((q ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+                const float bvr = bv_s[row];               // V^T: lane = padded channel, columns = tokens (keys)
+#pragma unroll 1
+                for (int kq = 0; kq < 2; ++kq) {
+                    const int kb = half * 2 + kq;
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(lane_addr + AB_TM_VT + kb * 32, v);
+                    tmem_ld_wait();
+                    uint8_t* rowp = smem + AB_VT_OFF + kb * AB_KB + row * 64;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) pk[k] = pack_bf16x2(__uint_as_float(v[q * 8 + 2 * k]) + bvr, __uint_as_float(v[q * 8 + 2 * k + 1]) + bvr);
+                        *reinterpret_cast<uint4*>(rowp + ((q ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(qkv_ready);
+
+            // ---- 2. softmax of heads {half, half + 2}: one query row per thread
+            const int widx = tile * 2 + win_in_tile;
+            const int win = widx % nW;
+            const bool rowmask = p.shift > 0 && (win / nWr) == nWr - 1;   // windows that straddle the roll seam (htsat.py:414-433)
+            const bool colmask = p.shift > 0 && (win % nWr) == nWr - 1;
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {
+                const int h = 2 * hh + half;
+                const uint32_t u = (uint32_t)(2 * it + hh);
+                mbar_wait_parked(&s_full[half], u & 1);
+                tc_fence_after();
+                uint32_t v[64];
+                {
+                    uint32_t t0[32], t1[32];
+                    tmem_ld_32x32b_x32(lane_addr + AB_TM_S + half * 128 + win_in_tile * 64, t0);
+                    tmem_ld_32x32b_x32(lane_addr + AB_TM_S + half * 128 + win_in_tile * 64 + 32, t1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { v[j] = t0[j]; v[32 + j] = t1[j]; }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_free[half]);
+                const float* tb = tab_s + h * 225 + ci;
+                float s[64];
+                float m = -INFINITY;
+                if (rowmask || colmask) {
+                    const bool my_y = ty >= 4, my_x = tx >= 4;
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) {
+                        const bool masked = (rowmask && (my_y != (j >= 32))) || (colmask && (my_x != ((j & 7) >= 4)));
+                        s[j] = __uint_as_float(v[j]) + tb[-((j >> 3) * 15 + (j & 7))] + (masked ? -100.0f * AB_LOG2E : 0.0f);
+                        m = fmaxf(m, s[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) {
+                        s[j] = __uint_as_float(v[j]) + tb[-((j >> 3) * 15 + (j & 7))];
+                        m = fmaxf(m, s[j]);
+                    }
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                    s[j] = ex2_approx(s[j] - m);
+                    sum += s[j];
+                }
+                const float inv = 1.0f / sum;
+                uint32_t pk[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(s[2 * j] * inv, s[2 * j + 1] * inv);
+                mbar_wait_parked(&p_free[half], (u & 1) ^ 1);     // the P V MMAs that read the previous contents have retired
+                tc_fence_after();
+                const uint32_t pbase = lane_addr + AB_TM_P + half * 64;
+                const uint32_t own = pbase + win_in_tile * 32, other = pbase + (win_in_tile ^ 1) * 32;
+                {
+                    uint32_t a[16], z[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { a[j] = pk[j]; z[j] = 0u; }
+                    tmem_st_32x32b_x16(own, a);
+                    tmem_st_32x32b_x16(other, z);
+                    tmem_st_32x32b_x16(other + 16, z);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) a[j] = pk[16 + j];
+                    tmem_st_32x32b_x16(own + 16, a);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[half]);
+            }
+
+            // ---- 3. drain O (heads 2 half, 2 half + 1) -> O_pad operand of the projection (reuses the Q tile)
+            mbar_wait_parked(o_full, (uint32_t)(it & 1));
+            tc_fence_after();
+#pragma unroll 1
+            for (int hq = 0; hq < 2; ++hq) {
+                const int h = half * 2 + hq;
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(lane_addr + AB_TM_O + h * 32, v);
+                tmem_ld_wait();
+                uint8_t* rowp = smem + AB_Q_OFF + h * AB_KB + row * 64;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) pk[k] = pack_bf16x2(__uint_as_float(v[q * 8 + 2 * k]), __uint_as_float(v[q * 8 + 2 * k + 1]));
+                    *reinterpret_cast<uint4*>(rowp + ((q ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ao_ready);
+
+            // ---- 4. output: y = Y + b' + x  (48 of the 96 channels per thread: columns [48 half, 48 half + 48))
+            const long long grow = token_row(tile, row);
+            const float* xr = p.x + grow * AB_C + half * 48;
+            float4 xv[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) xv[j] = __ldg(reinterpret_cast<const float4*>(xr) + j);   // shortcut (an L2 hit: read by the LayerNorm warps)
+            mbar_wait_parked(y_full, (uint32_t)(it & 1));
+            tc_fence_after();
+            uint32_t ya[32], yb[16];
+            tmem_ld_32x32b_x32(lane_addr + AB_TM_Y + half * 48, ya);
+            tmem_ld_32x32b_x16(lane_addr + AB_TM_Y + half * 48 + 32, yb);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(y_free);
+            float* orow = p.out + grow * AB_C + half * 48;
+            const float* bb = bp_s + half * 48;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                float4 o;
+                const uint32_t* src = j < 8 ? &ya[j * 4] : &yb[(j - 8) * 4];
+                o.x = __uint_as_float(src[0]) + bb[j * 4 + 0] + xv[j].x;
+                o.y = __uint_as_float(src[1]) + bb[j * 4 + 1] + xv[j].y;
+                o.z = __uint_as_float(src[2]) + bb[j * 4 + 2] + xv[j].z;
+                o.w = __uint_as_float(src[3]) + bb[j * 4 + 3] + xv[j].w;
+                *(reinterpret_cast<float4*>(orow) + j) = o;
+            }
+        }
+    } else if (warp == AB_W_MMA) {
+        // ============================================================ weight load + MMA issue (warp-convergent, elected lane)
+        if (elect_one_sync()) {
+            mbar_expect_tx(w_full, 3 * AB_WQK_KB + 3 * AB_KB + 4 * AB_WP_KB);
+            for (int kb = 0; kb < 3; ++kb) {
+                tma_load_2d(smem + AB_WQK_OFF + kb * AB_WQK_KB, &tmWqk, w_full, kb * 32, 0);
+                tma_load_2d(smem + AB_WV_OFF + kb * AB_KB, &tmWv, w_full, kb * 32, 0);
+            }
+            for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + AB_WP_OFF + kb * AB_WP_KB, &tmWp, w_full, kb * 32, 0);
+        }
+        __syncwarp();
+        mbar_wait(w_full, 0);
+        constexpr uint32_t id_qk = umma_idesc_bf16(128, 256), id_vt = umma_idesc_bf16(128, 128), id_s = umma_idesc_bf16(128, 128),
+                           id_pv = umma_idesc_bf16(128, 32), id_y = umma_idesc_bf16(128, 96);
+        const uint64_t dWqk = umma_desc_sw64(smem_u32(smem + AB_WQK_OFF)), dWv = umma_desc_sw64(smem_u32(smem + AB_WV_OFF)),
+                       dWp = umma_desc_sw64(smem_u32(smem + AB_WP_OFF)), dA = umma_desc_sw64(smem_u32(smem + AB_A_OFF)),
+                       dQ = umma_desc_sw64(smem_u32(smem + AB_Q_OFF)), dK = umma_desc_sw64(smem_u32(smem + AB_K_OFF)),
+                       dVT = umma_desc_sw64(smem_u32(smem + AB_VT_OFF));
+        for (int it = 0; it < my_tiles; ++it) {
+            mbar_wait_parked(a_full, (uint32_t)(it & 1));
+            mbar_wait_parked(y_free, (uint32_t)((it & 1) ^ 1));       // the previous tile's Y (and with it S / P) has been read out of TMEM
+            tc_fence_after();
+            if (elect_one_sync()) {
+#pragma unroll
+                for (int kb = 0; kb < 3; ++kb)
+                    umma_f16_ss_run<2>(tmem_base + AB_TM_QK, dA + (uint64_t)(kb * (AB_KB >> 4)), dWqk + (uint64_t)(kb * (AB_WQK_KB >> 4)), id_qk, kb != 0);
+#pragma unroll
+                for (int kb = 0; kb < 3; ++kb)
+                    umma_f16_ss_run<2>(tmem_base + AB_TM_VT, dWv + (uint64_t)(kb * (AB_KB >> 4)), dA + (uint64_t)(kb * (AB_KB >> 4)), id_vt, kb != 0);
+                umma_commit(acc_full);
+                umma_commit(a_free);
+            }
+            __syncwarp();
+            mbar_wait_parked(qkv_ready, (uint32_t)(it & 1));
+            tc_fence_after();
+            if (elect_one_sync()) {
+                for (int h = 0; h < 2; ++h) {
+                    umma_f16_ss_run<2>(tmem_base + AB_TM_S + h * 128, dQ + (uint64_t)(h * (AB_KB >> 4)), dK + (uint64_t)(h * (AB_KB >> 4)), id_s, 0);
+                    umma_commit(&s_full[h]);
+                }
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int h = 0; h < 4; ++h) {
+                const int b = h & 1;
+                const uint32_t u = (uint32_t)(2 * it + (h >> 1));
+                if (h + 2 < 4) {                                     // S of head h+2 goes where head h's logits were: they are in registers by now
+                    mbar_wait_parked(&s_free[b], u & 1);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        umma_f16_ss_run<2>(tmem_base + AB_TM_S + b * 128, dQ + (uint64_t)((h + 2) * (AB_KB >> 4)), dK + (uint64_t)((h + 2) * (AB_KB >> 4)), id_s, 0);
+                        umma_commit(&s_full[b]);
+                    }
+                    __syncwarp();
+                }
+                mbar_wait_parked(&p_full[b], u & 1);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t d = tmem_base + AB_TM_O + h * 32, a = tmem_base + AB_TM_P + b * 64;
+                    const uint64_t dv = dVT + (uint64_t)((h * 32 * 64) >> 4);   // rows 32h.. of every 32-key k-block of V^T
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_bf16_ts(d, a + ks * 8, dv + (uint64_t)((ks >> 1) * (AB_KB >> 4) + (ks & 1) * 2), id_pv, ks != 0);
+                    umma_commit(&p_free[b]);
+                    if (h == 3) umma_commit(o_full);
+                }
+                __syncwarp();
+            }
+            mbar_wait_parked(ao_ready, (uint32_t)(it & 1));
+            tc_fence_after();
+            if (elect_one_sync()) {
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb)
+                    umma_f16_ss_run<2>(tmem_base + AB_TM_Y, dQ + (uint64_t)(kb * (AB_KB >> 4)), dWp + (uint64_t)(kb * (AB_WP_KB >> 4)), id_y, kb != 0);
+                umma_commit(y_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ============================================================ LayerNorm warps: 32 rows each, 8 lanes per row (12 channels per lane)
+        const int lw = warp - AB_W_LN;
+        const int l8 = lane & 7, rsub = lane >> 3;
+        uint8_t* a1 = smem + AB_A_OFF;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+#pragma unroll 1
+            for (int bt = 0; bt < 2; ++bt) {              // two batches of 16 rows (4 row groups of 4)
+                float4 v[4][3];
+                int rr[4];
+#pragma unroll
+                for (int gi = 0; gi < 4; ++gi) {
+                    rr[gi] = lw * 32 + bt * 16 + gi * 4 + rsub;
+                    const float4* xr = reinterpret_cast<const float4*>(p.x + token_row(tile, rr[gi]) * AB_C + l8 * 12);
+                    v[gi][0] = __ldg(xr); v[gi][1] = __ldg(xr + 1); v[gi][2] = __ldg(xr + 2);
+                }
+                if (bt == 0) mbar_wait_parked(a_free, (uint32_t)((it & 1) ^ 1));   // the previous tile's QK / V^T MMAs have read A
+#pragma unroll
+                for (int gi = 0; gi < 4; ++gi) {
+                    float sm = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) sm += (v[gi][q].x + v[gi][q].y) + (v[gi][q].z + v[gi][q].w);
+#pragma unroll
+                    for (int sh = 4; sh > 0; sh >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, sh);
+                    const float mean = sm * (1.0f / AB_C);
+                    float qv = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        v[gi][q].x -= mean; v[gi][q].y -= mean; v[gi][q].z -= mean; v[gi][q].w -= mean;
+                        qv += (v[gi][q].x * v[gi][q].x + v[gi][q].y * v[gi][q].y) + (v[gi][q].z * v[gi][q].z + v[gi][q].w * v[gi][q].w);
+                    }
+#pragma unroll
+                    for (int sh = 4; sh > 0; sh >>= 1) qv += __shfl_xor_sync(0xffffffffu, qv, sh);
+                    const float rstd = rsqrtf(qv * (1.0f / AB_C) + 1e-5f);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const int c0 = l8 * 12 + q * 4;
+                        const float4 gm = *reinterpret_cast<const float4*>(g_s + c0);
+                        const float4 bta = *reinterpret_cast<const float4*>(b_s + c0);
+                        uint2 pk;
+                        pk.x = pack_bf16x2(fmaf(v[gi][q].x * rstd, gm.x, bta.x), fmaf(v[gi][q].y * rstd, gm.y, bta.y));
+                        pk.y = pack_bf16x2(fmaf(v[gi][q].z * rstd, gm.z, bta.z), fmaf(v[gi][q].w * rstd, gm.w, bta.w));
+                        *reinterpret_cast<uint2*>(a1 + sw64_off(rr[gi], c0, AB_KB)) = pk;
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == AB_W_MMA) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+// Wp_pad[n][32 h + d] = Wp[n][24 h + d] (zero elsewhere): the projection consumes the per-head padded O layout
+__global__ void pad_proj_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out, int C, int nH, int hd, int hdp) {
+    const int total = C * nH * hdp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int d = i % hdp, h = (i / hdp) % nH, n = i / (hdp * nH);
+        out[i] = d < hd ? w[n * C + h * hd + d] : __float2bfloat16_rn(0.f);
+    }
+}
+int attn_block_pad_proj(const __nv_bfloat16* w, __nv_bfloat16* out, int C, int nH, cudaStream_t s) {
+    const int hd = C / nH;
+    pad_proj_kernel<<<(C * nH * 32 + 255) / 256, 256, 0, s>>>(w, out, C, nH, hd, 32);
+    return check_cuda(cudaGetLastError(), "pad_proj launch");
+}
+
+// Host packing of the padded q/k/v weights of one block from the reference tensors (attn.qkv.weight [3C, C], attn.qkv.bias [3C],
+// relative_position_bias_table [225, nH]); q rows carry head_dim^-0.5 (htsat.py:295,331) * log2(e) (the softmax runs in base 2).
+int attn_block_pack(AttnBlockW& w, const std::vector<float>& qkv_w, const std::vector<float>& qkv_b, const std::vector<float>& rpb, int C, int nH) {
+    const int hd = C / nH;
+    if (C != AB_C || nH != AB_NH || hd != AB_HD) return set_error(ARD_ERR_SHAPE, "attn_block: built for C=96, 4 heads of 24");
+    const float qs = AB_LOG2E / sqrtf((float)hd);
+    std::vector<float> wqk((size_t)256 * C, 0.f), bqk(256, 0.f), wv((size_t)128 * C, 0.f), bv(128, 0.f), tab((size_t)nH * 225);
+    for (int h = 0; h < nH; ++h)
+        for (int d = 0; d < hd; ++d) {
+            const int src = h * hd + d, dst = h * 32 + d;
+            for (int k = 0; k < C; ++k) {
+                wqk[(size_t)dst * C + k] = qkv_w[(size_t)src * C + k] * qs;
+                wqk[(size_t)(128 + dst) * C + k] = qkv_w[(size_t)(C + src) * C + k];
+                wv[(size_t)dst * C + k] = qkv_w[(size_t)(2 * C + src) * C + k];
+            }
+            bqk[dst] = qkv_b[src] * qs;
+            bqk[128 + dst] = qkv_b[C + src];
+            bv[dst] = qkv_b[2 * C + src];
+        }
+    for (int h = 0; h < nH; ++h)
+        for (int i = 0; i < 225; ++i) tab[(size_t)h * 225 + i] = rpb[(size_t)i * nH + h] * AB_LOG2E;
+    ARD_TRY(upload_bf16(w.wqk, wqk));
+    ARD_TRY(upload_f32(w.bqk, bqk));
+    ARD_TRY(upload_bf16(w.wv, wv));
+    ARD_TRY(upload_f32(w.bv, bv));
+    ARD_TRY(upload_f32(w.table, tab));
+    w.ready = true;
+    return 0;
+}
+
+// y = x + proj'(window_attention(LayerNorm(x))) for B clips of R x R tokens, C = 96. wp_pad [96, 128] bf16, bp [96] fp32 (device).
+int attn_block_96(const float* x, float* out, const AttnBlockW& w, const __nv_bfloat16* wp_pad, const float* bp, const float* gamma,
+                  const float* beta, int B, int R, int shift, int num_sms, cudaStream_t stream) {
+    if (B <= 0) return 0;
+    if (!w.ready) return set_error(ARD_ERR_STATE, "attn_block: weights not packed");
+    if (R % 16 != 0) return set_error(ARD_ERR_SHAPE, "attn_block: needs an even number of windows per row (R %% 16 == 0), got R=%d", R);
+    const long long windows = (long long)B * (R / 8) * (R / 8);
+    if (windows / 2 > 0x3fffffffLL) return set_error(ARD_ERR_SHAPE, "attn_block: batch too large");
+    CUtensorMap tqk, tv, tp;
+    ARD_TRY(make_tmap_2d(&tqk, w.wqk.p, 2, AB_C, 256, (uint64_t)AB_C * 2, 32, 256, 64));
+    ARD_TRY(make_tmap_2d(&tv, w.wv.p, 2, AB_C, 128, (uint64_t)AB_C * 2, 32, 128, 64));
+    ARD_TRY(make_tmap_2d(&tp, wp_pad, 2, 128, AB_C, (uint64_t)128 * 2, 32, AB_C, 64));
+    static bool attr_set = false;
+    if (!attr_set) {
+        ARD_CUDA(cudaFuncSetAttribute(attn_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
+        attr_set = true;
+    }
+    AttnBlockParams p;
+    p.x = x; p.out = out; p.bqk = w.bqk.as<float>(); p.bv = w.bv.as<float>(); p.bp = bp; p.gamma = gamma; p.beta = beta;
+    p.table = w.table.as<float>(); p.R = R; p.shift = R > 8 ? shift : 0; p.n_tiles = (int)(windows / 2);
+    const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+    const double M = (double)B * R * R;
+    // executed tensor work: QK (N 256) + V^T (N 128) K 96, S (128x128x32) + PV (128x32x128) per head, proj K 128 N 96, per 128 tokens
+    ProfScope ps(PROF_ATTN, stream, M * 2.0 * (384.0 * 96 + 4.0 * (128.0 * 32 + 32.0 * 128) + 128.0 * 96), M * AB_C * 8.0);
+    ARD_CUDA(enqueue_pdl(attn_block_kernel, dim3(grid), dim3(AB_THREADS), AB_SMEM_BYTES, stream, tqk, tv, tp, p));
+    return check_cuda(cudaGetLastError(), "attn_block launch");
+}
+
+}  // namespace ard
