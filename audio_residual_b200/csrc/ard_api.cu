@@ -199,6 +199,15 @@ static int finalize(ard_handle* h, cudaStream_t) {
             ARD_TRY(get(h, p + "mlp.fc2.weight", (size_t)4 * C * C, &v)); ARD_TRY(upload_f16(bw.fc2_w, *v));   // hidden activations are fp16
             ARD_TRY(get(h, p + "mlp.fc2.bias", C, &v)); ARD_TRY(upload_f32(bw.fc2_b, *v));
             ARD_TRY(get(h, p + "attn.relative_position_bias_table", (size_t)225 * nH, &v)); ARD_TRY(upload_f32(bw.rpb, *v));
+            if (C == 96 && nH == 4) {   // window-resident attention block kernel: per-head padded q/k/v weights + padded projection
+                const std::vector<float>*qw, *qb;
+                ARD_TRY(get(h, p + "attn.qkv.weight", (size_t)3 * C * C, &qw));
+                ARD_TRY(get(h, p + "attn.qkv.bias", (size_t)3 * C, &qb));
+                ARD_TRY(attn_block_pack(bw.ab, *qw, *qb, *v, C, nH));
+                ARD_TRY(bw.ab.wp_plain.ensure((size_t)C * 128 * 2));
+                ARD_TRY(bw.ab.wp_fold.ensure((size_t)C * 128 * 2));
+                ARD_TRY(attn_block_pad_proj(bw.proj_w.as<__nv_bfloat16>(), bw.ab.wp_plain.as<__nv_bfloat16>(), C, nH, nullptr));
+            }
             if (bw.has_res) {   // proj bias may have changed: refresh (b_proj - mean) and force a re-fold
                 std::vector<float> dm(C);
                 const std::vector<float>* pb;
@@ -263,6 +272,7 @@ int ensure_fold(ard_handle* h, int l, int b, cudaStream_t s) {
     ARD_TRY(upload_f32(bw.lam_ones, ones));
     ARD_TRY(residual_fold(bw.proj_w_f32.as<float>(), bw.res_dmean.as<float>(), bw.res_basis.as<float>(), bw.lam_ones.as<float>(), C, bw.K,
                           bw.res_M.as<float>(), bw.proj_w_fold.as<__nv_bfloat16>(), bw.proj_b_fold.as<float>(), s, bw.proj_w_fold_f32.as<float>()));
+    if (bw.ab.ready) ARD_TRY(attn_block_pad_proj(bw.proj_w_fold.as<__nv_bfloat16>(), bw.ab.wp_fold.as<__nv_bfloat16>(), C, h->cfg.num_heads[l], s));
     bw.lambda_set = true;
     return 0;
 }
@@ -281,6 +291,15 @@ static int run_block(ard_handle* h, int l, int b, int B, float* X, float* Y, flo
     const int shift = (b % 2 == 0) ? 0 : 4;   // htsat.py:563
 
     GemmArgs g;
+    const bool fused_attn = h->use_attn_block && bw.ab.ready && !attn_out && !res_out && !head_tap && (R % 16) == 0;
+    if (fused_attn) {
+        // norm1 + qkv + window attention + (folded) projection + shortcut in ONE kernel: Y = X + r. q/k/v, the attention
+        // probabilities and the attention output never reach HBM (capture outputs need them: those calls take the path below)
+        ARD_TRY(ensure_fold(h, l, b, s));
+        ARD_TRY(attn_block_96(X, Y, bw.ab, (bw.has_res ? bw.ab.wp_fold : bw.ab.wp_plain).as<__nv_bfloat16>(),
+                              (bw.has_res ? bw.proj_b_fold : bw.proj_b).as<float>(), bw.ln1_g.as<float>(), bw.ln1_b.as<float>(), B, R, shift,
+                              h->num_sms, s));
+    } else {
     if (C == 96 && h->use_ln_qkv) {   // norm1 + qkv in one kernel: the bf16 LayerNorm output never reaches HBM
         ARD_TRY(ln_qkv_96(X, bw.ln1_g.as<float>(), bw.ln1_b.as<float>(), bw.qkv_w.as<__nv_bfloat16>(), bw.qkv_b.as<float>(), QKV, M, h->num_sms, s));
     } else {
@@ -303,6 +322,7 @@ static int run_block(ard_handle* h, int l, int b, int B, float* X, float* Y, flo
     g.resid1 = X; g.ldr1 = C;
     if (res_out) { g.aux = res_out; g.ld_aux = C; g.aux_T = T; g.aux_bstride = res_bstride; (void)res_T; }
     ARD_TRY(gemm_bf16(g, h->num_sms, s));
+    }
     // FFN: (Y) -> LN2 -> fc1+GELU -> fc2
     // one FFN: out = in + mlp(norm2(in)) (+ r2 inside the fused kernel). `pre_add`: the LayerNorm input is in + pre_add, written back to `in`.
     // ffn_wide (weights streamed from L2) is used where it measures faster than LayerNorm + two GEMMs: both FFNs of the
@@ -475,6 +495,7 @@ int ard_create(const ard_config* cfg, ard_handle** out) {
     if (const char* e = getenv("ARD_FUSED_FFN_WIDE")) h->use_fused_ffn_wide = atoi(e);
     if (const char* e = getenv("ARD_GRAPHS")) h->use_graphs = atoi(e);
     if (const char* e = getenv("ARD_LN_QKV")) h->use_ln_qkv = atoi(e) != 0;
+    if (const char* e = getenv("ARD_ATTN_BLOCK")) h->use_attn_block = atoi(e) != 0;
     *out = h;
     return 0;
 }
@@ -545,6 +566,8 @@ int ard_set_block_lambda(ard_handle* h, int layer, int block, const float* lambd
     ARD_TRY(residual_fold(bw.proj_w_f32.as<float>(), bw.res_dmean.as<float>(), bw.res_basis.as<float>(), lambda_dev, C, bw.K,
                           bw.res_M.as<float>(), bw.proj_w_fold.as<__nv_bfloat16>(), bw.proj_b_fold.as<float>(), (cudaStream_t)stream,
                           bw.proj_w_fold_f32.as<float>()));
+    if (bw.ab.ready)
+        ARD_TRY(attn_block_pad_proj(bw.proj_w_fold.as<__nv_bfloat16>(), bw.ab.wp_fold.as<__nv_bfloat16>(), C, h->cfg.num_heads[layer], (cudaStream_t)stream));
     // keep a (zero-padded) copy of lambda for the backward: gsc = gcoef * lambda
     const int Kp = (bw.K + 15) & ~15;
     ARD_TRY(bw.lam.ensure((size_t)Kp * 4));
@@ -660,6 +683,24 @@ int ard_block_forward(ard_handle* h, int layer, int block, const float* x_in, in
     ARD_CUDA(cudaMemcpyAsync(x_out, X, bytes, cudaMemcpyDeviceToDevice, s));
     h->last_launches = g_launches;
     return 0;
+}
+
+int ard_attention_block(ard_handle* h, int layer, int block, const float* x_in, int B, float* x_out, void* stream) {
+    if (!h || !x_in || !x_out) return set_error(ARD_ERR_SHAPE, "null argument");
+    if (!h->finalized) return set_error(ARD_ERR_STATE, "ard_finalize_weights has not been called");
+    if (layer < 0 || layer >= h->nlayers || block < 0 || block >= h->cfg.depths[layer]) return set_error(ARD_ERR_SHAPE, "bad block index");
+    if (B <= 0) return set_error(ARD_ERR_SHAPE, "batch must be positive");
+    BlockW& bw = h->layers[layer].blocks[block];
+    if (!bw.ab.ready) return set_error(ARD_ERR_NOTIMPL, "the window-resident attention block kernel covers the 96-channel stage (layer 0 of HTSAT-tiny)");
+    cudaStream_t s = (cudaStream_t)stream;
+    g_launches = 0;
+    ARD_TRY(ensure_fold(h, layer, block, s));
+    const int R = R_of(layer);
+    const int rc = attn_block_96(x_in, x_out, bw.ab, (bw.has_res ? bw.ab.wp_fold : bw.ab.wp_plain).as<__nv_bfloat16>(),
+                                 (bw.has_res ? bw.proj_b_fold : bw.proj_b).as<float>(), bw.ln1_g.as<float>(), bw.ln1_b.as<float>(), B, R,
+                                 (block % 2 == 0) ? 0 : 4, h->num_sms, s);
+    h->last_launches = g_launches;
+    return rc;
 }
 
 int ard_encoder_backward(ard_handle* h, const ard_backward_args* args, void* stream) {

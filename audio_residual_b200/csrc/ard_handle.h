@@ -31,6 +31,12 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// padded per-head q/k/v weights of the window-resident attention block kernel (attn_block.cu), 96-channel stage
+struct AttnBlockW {
+    DevBuf wqk, bqk, wv, bv, table, wp_plain, wp_fold;   // [256,96] bf16, [256] f32, [128,96] bf16, [128] f32, [4,225] f32, 2 x [96,128] bf16
+    bool ready = false;
+};
+
 struct BlockW {
     DevBuf ln1_g, ln1_b, ln2_g, ln2_b;
     DevBuf qkv_w, qkv_b, proj_w, proj_b, proj_w_f32, fc1_w, fc1_b, fc1_b_half, fc2_w, fc2_b, rpb;
@@ -39,6 +45,7 @@ struct BlockW {
     int K = 0;
     std::vector<float> h_mean, h_basis;
     DevBuf res_basis, res_dmean, res_M, proj_w_fold, proj_w_fold_f32, proj_b_fold, lam_ones;
+    AttnBlockW ab;
     // training (ard_train.cu): current lambda (padded to Kp), transposed / folded weights for the dgrad GEMMs, built lazily
     int Kp = 0;
     bool bwd_ready = false;
@@ -75,6 +82,7 @@ struct ard_handle {
     int last_launches = 0;
     bool use_fused_ffn = true;   // ARD_FUSED_FFN=0 disables the fused 96-channel FFN kernel (A/B measurements)
     bool use_ln_qkv = true;      // ARD_LN_QKV=0: LayerNorm kernel + qkv GEMM instead of ln_qkv_96 (A/B measurements)
+    bool use_attn_block = true;  // ARD_ATTN_BLOCK=0: ln_qkv + window_attention + proj GEMM instead of attn_block_96 (A/B measurements)
     int use_fused_ffn_wide = 1;    // ARD_FUSED_FFN_WIDE: 0 never, 1 where it measures faster (default), 2 for every C = 192 / 384 FFN
     // training state
     DevBuf tape, p0_wT, p2_wT, t_emb, t_hid, t_proj;
@@ -128,6 +136,11 @@ int ensure_tape(ard_handle* h, int B);
 int run_block_train(ard_handle* h, int l, int b, int B, float* attn_out, float attn_scale, int attn_acc, float* res_out,
                     long long res_bstride, cudaStream_t s);
 int encoder_backward(ard_handle* h, const ard_backward_args* a, cudaStream_t s);
+// window-resident attention block (attn_block.cu)
+int attn_block_pack(AttnBlockW& w, const std::vector<float>& qkv_w, const std::vector<float>& qkv_b, const std::vector<float>& rpb, int C, int nH);
+int attn_block_pad_proj(const __nv_bfloat16* w, __nv_bfloat16* out, int C, int nH, cudaStream_t s);
+int attn_block_96(const float* x, float* out, const AttnBlockW& w, const __nv_bfloat16* wp_pad, const float* bp, const float* gamma,
+                  const float* beta, int B, int R, int shift, int num_sms, cudaStream_t stream);
 // fp32-grade mode (fp32_mode.cu)
 int encoder_stages_fp32(ard_handle* h, const ard_forward_args* a, float* X, float* Y, float** x_final, cudaStream_t s);
 int tscam_gemm_fp32(ard_handle* h, const float* normed, float* y, int ldy, int B, cudaStream_t s);

@@ -118,6 +118,7 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
     const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int R = p.R, nWr = R >> 3, nW = nWr * nWr;
 
+    pdl_wait();   // the folded projection bias / weights may have been written by the kernel just before this one (lambda update)
     for (int i = threadIdx.x; i < 256; i += AB_THREADS) bqk_s[i] = p.bqk[i];
     for (int i = threadIdx.x; i < 128; i += AB_THREADS) bv_s[i] = p.bv[i];
     for (int i = threadIdx.x; i < 96; i += AB_THREADS) {
@@ -155,7 +156,6 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
-    pdl_wait();
 
     // token (row r of tile `tile`) -> row index of x / out: window pair -> (clip, wy, wx), roll by -shift (htsat.py:452-460)
     auto token_row = [&](int tile, int r) -> long long {
@@ -318,32 +318,35 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(ao_ready);
 
-            // ---- 4. output: y = Y + b' + x  (48 of the 96 channels per thread: columns [48 half, 48 half + 48))
+            // ---- 4. output: y = Y + b' + x. 48 of the 96 channels per thread: columns [32 half, +32) and [64 + 16 half, +16)
             const long long grow = token_row(tile, row);
-            const float* xr = p.x + grow * AB_C + half * 48;
+            const int cA = 32 * half, cB = 64 + 16 * half;
+            const float* xr = p.x + grow * AB_C;
             float4 xv[12];
 #pragma unroll
-            for (int j = 0; j < 12; ++j) xv[j] = __ldg(reinterpret_cast<const float4*>(xr) + j);   // shortcut (an L2 hit: read by the LayerNorm warps)
+            for (int j = 0; j < 8; ++j) xv[j] = __ldg(reinterpret_cast<const float4*>(xr + cA) + j);   // shortcut (an L2 hit: read by the LayerNorm warps)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xv[8 + j] = __ldg(reinterpret_cast<const float4*>(xr + cB) + j);
             mbar_wait_parked(y_full, (uint32_t)(it & 1));
             tc_fence_after();
             uint32_t ya[32], yb[16];
-            tmem_ld_32x32b_x32(lane_addr + AB_TM_Y + half * 48, ya);
-            tmem_ld_32x32b_x16(lane_addr + AB_TM_Y + half * 48 + 32, yb);
+            tmem_ld_32x32b_x32(lane_addr + AB_TM_Y + cA, ya);
+            tmem_ld_32x32b_x16(lane_addr + AB_TM_Y + cB, yb);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(y_free);
-            float* orow = p.out + grow * AB_C + half * 48;
-            const float* bb = bp_s + half * 48;
+            float* orow = p.out + grow * AB_C;
 #pragma unroll
             for (int j = 0; j < 12; ++j) {
                 float4 o;
                 const uint32_t* src = j < 8 ? &ya[j * 4] : &yb[(j - 8) * 4];
-                o.x = __uint_as_float(src[0]) + bb[j * 4 + 0] + xv[j].x;
-                o.y = __uint_as_float(src[1]) + bb[j * 4 + 1] + xv[j].y;
-                o.z = __uint_as_float(src[2]) + bb[j * 4 + 2] + xv[j].z;
-                o.w = __uint_as_float(src[3]) + bb[j * 4 + 3] + xv[j].w;
-                *(reinterpret_cast<float4*>(orow) + j) = o;
+                const int c = j < 8 ? cA + j * 4 : cB + (j - 8) * 4;
+                o.x = __uint_as_float(src[0]) + bp_s[c + 0] + xv[j].x;
+                o.y = __uint_as_float(src[1]) + bp_s[c + 1] + xv[j].y;
+                o.z = __uint_as_float(src[2]) + bp_s[c + 2] + xv[j].z;
+                o.w = __uint_as_float(src[3]) + bp_s[c + 3] + xv[j].w;
+                *reinterpret_cast<float4*>(orow + c) = o;
             }
         }
     } else if (warp == AB_W_MMA) {

@@ -69,6 +69,7 @@ def load(check_symbols=False):
         lib.ard_encoder_forward.argtypes = [vp, C.POINTER(ArdForwardArgs), vp]
         lib.ard_encoder_backward.argtypes = [vp, C.POINTER(ArdBackwardArgs), vp]
         lib.ard_block_forward.argtypes = [vp, i, i, vp, i, vp, vp, vp, vp]
+        lib.ard_attention_block.argtypes = [vp, i, i, vp, i, vp, vp]
         lib.ard_workspace_bytes.argtypes = [vp]
         lib.ard_last_launch_count.argtypes = [vp]
         lib.ard_gemm_bf16.argtypes = [vp, ll, vp, ll, vp, ll, i, i, i, i, vp, i, vp, ll, vp, ll, vp]

@@ -129,6 +129,12 @@ long long ard_tape_generation(const ard_handle* h);
 int ard_block_forward(ard_handle* h, int layer, int block, const float* x_in, int B, float* x_out, float* attn, float* residual_x,
                       void* stream);
 
+/* The attention half of a Swin block as ONE kernel (the window-resident tcgen05 attention block, 96-channel stage):
+ * x_out = x + proj'(WindowAttention(norm1(x))) with roll / window_partition / window_reverse as address arithmetic
+ * (htsat.py:449-476; proj' carries the ResiDual fold of src/residual.py:88-92 when the block is patched). x_in, x_out
+ * [B, T_l, C_l] fp32 device. ARD_ERR_NOTIMPL for layers the kernel does not cover (the encoder uses the unfused chain there). */
+int ard_attention_block(ard_handle* h, int layer, int block, const float* x_in, int B, float* x_out, void* stream);
+
 /* Bytes of device workspace the handle currently holds (grown on demand by forward calls). */
 long long ard_workspace_bytes(const ard_handle* h);
 /* Number of kernels launched by the last ard_encoder_forward / ard_block_forward on this handle. */

@@ -507,3 +507,23 @@ def check_argmax_vs_golden(fname="htsat_tiny_b2.npz"):
     return {"zero_shot_argmax_mismatch": int((sims.argmax(-1) != ref_sims.argmax(-1)).sum()),
             "clipwise_argmax_mismatch": int((clip.argmax(-1).cpu() != ref_clip.argmax(-1)).sum()),
             "reference_top1_top2_margin": margin, "sims_max_abs_err": (sims - ref_sims).abs().max().item()}
+
+
+def check_attention_block(B=2, block=0, residual=False, seed=0):
+    """ard_attention_block (LayerNorm1 + qkv + window attention + (folded) projection + shortcut in one tcgen05 kernel) vs the
+    oracle's x + residual_x of the same block (htsat.py:449-476, src/residual.py:58-92), and vs the unfused kernel chain."""
+    clap, sd, ores = make_encoder("tiny", seed=seed, residual=residual)
+    enc = clap.model.audio_branch
+    h = enc._handle()
+    l, R, Cd = 0, 64, 96
+    x = torch.randn(B, R * R, Cd, generator=torch.Generator().manual_seed(100 + block)) * 0.8 + 0.1
+    xd = x.cuda().contiguous()
+    out = torch.empty_like(xd)
+    L.check(L.load().ard_attention_block(h, l, block, L.ptr(xd), B, L.ptr(out), L.stream_ptr()))
+    torch.cuda.synchronize()
+    _, _, res_unfused = enc.layers[l].blocks[block](xd)                       # ard_block_forward: unfused chain (capture path)
+    with torch.no_grad():
+        _, _, o_res = O.swin_block(x, sd, f"layers.{l}.blocks.{block}.", R, R, enc.num_heads[l], 0 if block % 2 == 0 else 4,
+                                   ores[l] if residual else None)
+    got_r = out.cpu() - x
+    return {"out": rel(out, x + o_res), "branch": rel(got_r, o_res), "branch_vs_unfused": rel(got_r, res_unfused.cpu())}

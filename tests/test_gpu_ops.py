@@ -82,3 +82,23 @@ def test_stats_accumulate(rows, D, strided, calls):
 
 def test_quantize_waveform_bit_exact():
     assert G.check_quantize_waveform() == 0
+
+
+@pytest.mark.parametrize("B,block,residual", [(1, 0, False), (2, 1, False), (3, 0, True), (2, 1, True), (150, 1, True)])
+def test_attention_block_fused(B, block, residual):
+    """The window-resident tcgen05 attention block of the 96-channel stage (shifted and unshifted windows, plain and
+    ResiDual-folded projection, more tiles than SMs) vs the oracle and vs the unfused kernel chain."""
+    if B > 8:
+        # the oracle at B=150 takes minutes: compare with the unfused kernel chain only
+        import torch
+        clap, sd, _ = G.make_encoder("tiny", residual=residual)
+        enc = clap.model.audio_branch
+        x = (torch.randn(B, 4096, 96, generator=torch.Generator().manual_seed(1)) * 0.8).cuda()
+        out = torch.empty_like(x)
+        G.L.check(G.L.load().ard_attention_block(enc._handle(), 0, block, G.L.ptr(x), B, G.L.ptr(out), G.L.stream_ptr()))
+        _, _, res = enc.layers[0].blocks[block](x)
+        torch.cuda.synchronize()
+        assert G.rel(out - x, res) < G.TOL_BF16
+        return
+    m = G.check_attention_block(B, block, residual)
+    assert m["out"] < 2e-3 and m["branch"] < G.TOL_BF16 and m["branch_vs_unfused"] < G.TOL_BF16, m
