@@ -206,7 +206,10 @@ static int finalize(ard_handle* h, cudaStream_t) {
                 ARD_TRY(attn_block_pack(bw.ab, *qw, *qb, *v, C, nH));
                 ARD_TRY(bw.ab.wp_plain.ensure((size_t)C * 128 * 2));
                 ARD_TRY(bw.ab.wp_fold.ensure((size_t)C * 128 * 2));
-                ARD_TRY(attn_block_pad_proj(bw.proj_w.as<__nv_bfloat16>(), bw.ab.wp_plain.as<__nv_bfloat16>(), C, nH, nullptr));
+                ARD_TRY(bw.ab.bp_plain.ensure((size_t)C * 4));
+                ARD_TRY(bw.ab.bp_fold.ensure((size_t)C * 4));
+                ARD_TRY(attn_block_pad_proj(bw.proj_w.as<__nv_bfloat16>(), bw.proj_b.as<float>(), bw.ab.bv.as<float>(), bw.ab.wp_plain.as<__nv_bfloat16>(),
+                                            bw.ab.bp_plain.as<float>(), C, nH, nullptr));
             }
             if (bw.has_res) {   // proj bias may have changed: refresh (b_proj - mean) and force a re-fold
                 std::vector<float> dm(C);
@@ -272,7 +275,9 @@ int ensure_fold(ard_handle* h, int l, int b, cudaStream_t s) {
     ARD_TRY(upload_f32(bw.lam_ones, ones));
     ARD_TRY(residual_fold(bw.proj_w_f32.as<float>(), bw.res_dmean.as<float>(), bw.res_basis.as<float>(), bw.lam_ones.as<float>(), C, bw.K,
                           bw.res_M.as<float>(), bw.proj_w_fold.as<__nv_bfloat16>(), bw.proj_b_fold.as<float>(), s, bw.proj_w_fold_f32.as<float>()));
-    if (bw.ab.ready) ARD_TRY(attn_block_pad_proj(bw.proj_w_fold.as<__nv_bfloat16>(), bw.ab.wp_fold.as<__nv_bfloat16>(), C, h->cfg.num_heads[l], s));
+    if (bw.ab.ready)
+        ARD_TRY(attn_block_pad_proj(bw.proj_w_fold.as<__nv_bfloat16>(), bw.proj_b_fold.as<float>(), bw.ab.bv.as<float>(), bw.ab.wp_fold.as<__nv_bfloat16>(),
+                                    bw.ab.bp_fold.as<float>(), C, h->cfg.num_heads[l], s));
     bw.lambda_set = true;
     return 0;
 }
@@ -297,7 +302,7 @@ static int run_block(ard_handle* h, int l, int b, int B, float* X, float* Y, flo
         // probabilities and the attention output never reach HBM (capture outputs need them: those calls take the path below)
         ARD_TRY(ensure_fold(h, l, b, s));
         ARD_TRY(attn_block_96(X, Y, bw.ab, (bw.has_res ? bw.ab.wp_fold : bw.ab.wp_plain).as<__nv_bfloat16>(),
-                              (bw.has_res ? bw.proj_b_fold : bw.proj_b).as<float>(), bw.ln1_g.as<float>(), bw.ln1_b.as<float>(), B, R, shift,
+                              (bw.has_res ? bw.ab.bp_fold : bw.ab.bp_plain).as<float>(), bw.ln1_g.as<float>(), bw.ln1_b.as<float>(), B, R, shift,
                               h->num_sms, s));
     } else {
     if (C == 96 && h->use_ln_qkv) {   // norm1 + qkv in one kernel: the bf16 LayerNorm output never reaches HBM
@@ -567,7 +572,8 @@ int ard_set_block_lambda(ard_handle* h, int layer, int block, const float* lambd
                           bw.res_M.as<float>(), bw.proj_w_fold.as<__nv_bfloat16>(), bw.proj_b_fold.as<float>(), (cudaStream_t)stream,
                           bw.proj_w_fold_f32.as<float>()));
     if (bw.ab.ready)
-        ARD_TRY(attn_block_pad_proj(bw.proj_w_fold.as<__nv_bfloat16>(), bw.ab.wp_fold.as<__nv_bfloat16>(), C, h->cfg.num_heads[layer], (cudaStream_t)stream));
+        ARD_TRY(attn_block_pad_proj(bw.proj_w_fold.as<__nv_bfloat16>(), bw.proj_b_fold.as<float>(), bw.ab.bv.as<float>(), bw.ab.wp_fold.as<__nv_bfloat16>(),
+                                    bw.ab.bp_fold.as<float>(), C, h->cfg.num_heads[layer], (cudaStream_t)stream));
     // keep a (zero-padded) copy of lambda for the backward: gsc = gcoef * lambda
     const int Kp = (bw.K + 15) & ~15;
     ARD_TRY(bw.lam.ensure((size_t)Kp * 4));
@@ -697,7 +703,7 @@ int ard_attention_block(ard_handle* h, int layer, int block, const float* x_in, 
     ARD_TRY(ensure_fold(h, layer, block, s));
     const int R = R_of(layer);
     const int rc = attn_block_96(x_in, x_out, bw.ab, (bw.has_res ? bw.ab.wp_fold : bw.ab.wp_plain).as<__nv_bfloat16>(),
-                                 (bw.has_res ? bw.proj_b_fold : bw.proj_b).as<float>(), bw.ln1_g.as<float>(), bw.ln1_b.as<float>(), B, R,
+                                 (bw.has_res ? bw.ab.bp_fold : bw.ab.bp_plain).as<float>(), bw.ln1_g.as<float>(), bw.ln1_b.as<float>(), B, R,
                                  (block % 2 == 0) ? 0 : 4, h->num_sms, s);
     h->last_launches = g_launches;
     return rc;

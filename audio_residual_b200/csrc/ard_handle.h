@@ -33,7 +33,8 @@ struct DevBuf {
 
 // padded per-head q/k/v weights of the window-resident attention block kernel (attn_block.cu), 96-channel stage
 struct AttnBlockW {
-    DevBuf wqk, bqk, wv, bv, table, wp_plain, wp_fold;   // [256,96] bf16, [256] f32, [128,96] bf16, [128] f32, [4,225] f32, 2 x [96,128] bf16
+    DevBuf wqk, bq, wv, bv, table, wp_plain, wp_fold, bp_plain, bp_fold;   // [256,96] bf16, [128] f32, [128,96] bf16, [96] f32 (un-padded v bias),
+                                                                           // [4,15,24] f32, 2 x [96,128] bf16, 2 x [96] f32 (bias + Wp' bv)
     bool ready = false;
 };
 
@@ -138,7 +139,7 @@ int run_block_train(ard_handle* h, int l, int b, int B, float* attn_out, float a
 int encoder_backward(ard_handle* h, const ard_backward_args* a, cudaStream_t s);
 // window-resident attention block (attn_block.cu)
 int attn_block_pack(AttnBlockW& w, const std::vector<float>& qkv_w, const std::vector<float>& qkv_b, const std::vector<float>& rpb, int C, int nH);
-int attn_block_pad_proj(const __nv_bfloat16* w, __nv_bfloat16* out, int C, int nH, cudaStream_t s);
+int attn_block_pad_proj(const __nv_bfloat16* w, const float* bp, const float* bv, __nv_bfloat16* out, float* bp_eff, int C, int nH, cudaStream_t s);
 int attn_block_96(const float* x, float* out, const AttnBlockW& w, const __nv_bfloat16* wp_pad, const float* bp, const float* gamma,
                   const float* beta, int B, int R, int shift, int num_sms, cudaStream_t stream);
 // fp32-grade mode (fp32_mode.cu)

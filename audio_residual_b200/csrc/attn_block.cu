@@ -24,7 +24,10 @@
 //   Y   = O_pad Wp_pad^T    M128 N96  K128  + b' + x -> y (fp32, token order: window_reverse / roll back are address arithmetic)
 //
 // TMEM (512 columns): QK accumulator 0-255, V^T accumulator 256-383, O 384-511; after the QKV drain S[0], S[1] reuse 0-255,
-// P[0], P[1] reuse 256-383 (64 columns each: 128 bf16 per row), Y reuses 0-95.
+// P[0], P[1] reuse 256-383 (64 columns each: 128 bf16 per row); Y reuses the O columns (384-479) once O is in shared memory, so
+// the NEXT tile's QK / V^T MMAs (columns 0-383) run underneath this tile's output epilogue.
+// Row sums ride on the tensor core: padded channel 24 of every head of V^T is set to ones, so column 24 of O_h is sum_j P~_ij of
+// the bf16 probabilities actually multiplied; the O drain divides by it (no per-element sum / normalise in the softmax).
 // Warp roles (13 warps): 0-7 tensor-memory warps (lane quadrant w & 3, half w >> 2: drain QKV, softmax of heads {half, half+2},
 // drain O, output epilogue), 8 = TMA weights + MMA issue (warp-convergent, elected lane), 9-12 = LayerNorm of the NEXT tile
 // (it overlaps the attention phase: the A tile is free as soon as the QK / V^T MMAs have read it).
@@ -32,6 +35,14 @@
 #include "ard_handle.h"
 
 namespace ard {
+
+// Development aid (tools/ab_trace.py builds a separate library with -DARD_AB_TRACE): per-role clock64() stamps of CTA 0.
+#ifdef ARD_AB_TRACE
+__device__ long long g_ab_trace[4][32][24];   // [role][tile index][event]
+#define AB_TRACE(role, idx, field) do { if (blockIdx.x == 0 && lane == 0 && (idx) < 32) g_ab_trace[role][idx][field] = clock64(); } while (0)
+#else
+#define AB_TRACE(role, idx, field) do { } while (0)
+#endif
 
 constexpr int AB_C = 96, AB_NH = 4, AB_HD = 24;
 constexpr int AB_TM_WARPS = 8, AB_W_MMA = 8, AB_W_LN = 9, AB_LN_WARPS = 4;
@@ -45,24 +56,29 @@ constexpr int AB_A_OFF = AB_WP_OFF + 4 * AB_WP_KB;                // 98304: 3 k-
 constexpr int AB_Q_OFF = AB_A_OFF + 3 * AB_KB;                    // 122880: 4 k-blocks (one per head); later the O_pad operand
 constexpr int AB_K_OFF = AB_Q_OFF + 4 * AB_KB;                    // 155648
 constexpr int AB_VT_OFF = AB_K_OFF + 4 * AB_KB;                   // 188416: 4 k-blocks of 32 keys, rows = padded channel
-constexpr int AB_VEC_OFF = AB_VT_OFF + 4 * AB_KB;                 // 221184: bqk[256] bv[128] bp[96] gamma[96] beta[96]
-constexpr int AB_TAB_OFF = AB_VEC_OFF + (256 + 128 + 3 * 96) * 4; // rel-pos bias table [4][225] (x log2 e)
-constexpr int AB_BAR_OFF = AB_TAB_OFF + 4 * 225 * 4 + 16;         // (16: keep 8-byte alignment margin)
-constexpr int AB_SMEM_BYTES = ((AB_BAR_OFF + 7) & ~7) + 256 + 1024;
+constexpr int AB_VEC_OFF = AB_VT_OFF + 4 * AB_KB;                 // 221184: bq[128] bp[96] gamma[96] beta[96]
+constexpr int AB_TAB_STRIDE = 24, AB_TAB_N = 15 * AB_TAB_STRIDE;  // rel-pos bias table per head as [15][24]: index (dy+7)*24 + (dx+7); the
+                                                                  // stride 24 puts the 32 rows of a warp (4 ty x 8 tx) on 32 different banks
+constexpr int AB_TAB_OFF = AB_VEC_OFF + (128 + 3 * 96) * 4;       // [4][360] floats (x log2 e)
+constexpr int AB_ROW_OFF = AB_TAB_OFF + 4 * AB_TAB_N * 4;         // int[128]: row of x / out of each token of the tile
+constexpr int AB_BAR_OFF = AB_ROW_OFF + 128 * 4;
+constexpr int AB_SMEM_BYTES = AB_BAR_OFF + 256 + 1024;
+constexpr int AB_STAGE_OFF = AB_Q_OFF, AB_STAGE_LD = 400;         // output staging [128][100] fp32 over the (by then dead) Q / K tiles
+static_assert(128 * AB_STAGE_LD <= 8 * AB_KB, "attn_block: staging tile must fit in the Q + K tiles");
 static_assert(AB_SMEM_BYTES <= 227 * 1024, "attn_block: shared memory budget");
 
-constexpr uint32_t AB_TM_QK = 0, AB_TM_VT = 256, AB_TM_O = 384, AB_TM_S = 0, AB_TM_P = 256, AB_TM_Y = 0;
+constexpr uint32_t AB_TM_QK = 0, AB_TM_VT = 256, AB_TM_O = 384, AB_TM_S = 0, AB_TM_P = 256, AB_TM_Y = 384;
 constexpr float AB_LOG2E = 1.4426950408889634f;
 
 struct AttnBlockParams {
     const float* x;       // [B*R*R, 96] fp32, token order
     float* out;           // [B*R*R, 96] fp32
-    const float* bqk;     // [256] padded q/k bias (q part scaled)
-    const float* bv;      // [128]
-    const float* bp;      // [96]  (folded) projection bias
+    const float* bq;      // [128] padded q bias (scaled). The k bias cancels in the softmax (constant per query row) and the v bias
+                          // passes through P (rows sum to 1): it is folded into bp on the host side (attn_block_pad_proj)
+    const float* bp;      // [96]  (folded) projection bias + Wp' bv
     const float* gamma;   // norm1
     const float* beta;
-    const float* table;   // [4][225] relative-position bias x log2(e)
+    const float* table;   // [4][15][24] relative-position bias x log2(e)
     int R, shift, n_tiles;   // tokens per side (64), cyclic shift (0 / 4), number of window pairs
 };
 
@@ -92,13 +108,13 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    float* bqk_s = reinterpret_cast<float*>(smem + AB_VEC_OFF);
-    float* bv_s = bqk_s + 256;
-    float* bp_s = bv_s + 128;
+    float* bq_s = reinterpret_cast<float*>(smem + AB_VEC_OFF);
+    float* bp_s = bq_s + 128;
     float* g_s = bp_s + 96;
     float* b_s = g_s + 96;
     float* tab_s = reinterpret_cast<float*>(smem + AB_TAB_OFF);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ((AB_BAR_OFF + 7) & ~7));
+    int* rowidx_s = reinterpret_cast<int*>(smem + AB_ROW_OFF);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AB_BAR_OFF);
     uint64_t* w_full = bars + 0;
     uint64_t* a_full = bars + 1;
     uint64_t* a_free = bars + 2;
@@ -119,14 +135,13 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
     const int R = p.R, nWr = R >> 3, nW = nWr * nWr;
 
     pdl_wait();   // the folded projection bias / weights may have been written by the kernel just before this one (lambda update)
-    for (int i = threadIdx.x; i < 256; i += AB_THREADS) bqk_s[i] = p.bqk[i];
-    for (int i = threadIdx.x; i < 128; i += AB_THREADS) bv_s[i] = p.bv[i];
+    for (int i = threadIdx.x; i < 128; i += AB_THREADS) bq_s[i] = p.bq[i];
     for (int i = threadIdx.x; i < 96; i += AB_THREADS) {
         bp_s[i] = p.bp[i];
         g_s[i] = p.gamma[i];
         b_s[i] = p.beta[i];
     }
-    for (int i = threadIdx.x; i < 4 * 225; i += AB_THREADS) tab_s[i] = p.table[i];
+    for (int i = threadIdx.x; i < 4 * AB_TAB_N; i += AB_THREADS) tab_s[i] = p.table[i];
     if (warp == AB_W_MMA && lane == 0) {
         tma_prefetch_desc(&tmWqk);
         tma_prefetch_desc(&tmWv);
@@ -177,51 +192,59 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
         const int sw = (row >> 1) & 3;
         const int win_in_tile = quad >> 1;
         const int qi = row & 63, ty = qi >> 3, tx = qi & 7;
-        const int ci = ty * 15 + tx + 112;                // bias index = ci - (jy * 15 + jx)   (relative_position_index, htsat.py:301-316)
+        const int ci = ty * AB_TAB_STRIDE + tx + 7 * AB_TAB_STRIDE + 7;   // bias index = ci - (jy * 24 + jx)   (relative_position_index, htsat.py:301-316)
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             // ---- 1. drain the QK / V^T accumulators into their shared-memory operand tiles (bf16)
+            const int trole = (quad == 0) ? half : 3;     // trace: warps 0 and 4
+            if (quad == 0) AB_TRACE(trole, it, 0);
             mbar_wait_parked(acc_full, (uint32_t)(it & 1));
+            if (quad == 0) AB_TRACE(trole, it, 1);
             tc_fence_after();
             {
-                uint8_t* dst = smem + (half == 0 ? AB_Q_OFF : AB_K_OFF);
-#pragma unroll 1
-                for (int h = 0; h < 4; ++h) {             // 32 padded columns of head h -> k-block h, this thread's row
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(lane_addr + AB_TM_QK + half * 128 + h * 32, v);
-                    tmem_ld_wait();
-                    const float* bb = bqk_s + half * 128 + h * 32;
-                    uint8_t* rowp = dst + h * AB_KB + row * 64;
+                auto put = [&](const uint32_t (&v)[32], uint8_t* rowp, const float* bb, bool ones) {   // 32 fp32 (+ bias) -> one 64-byte bf16 row, SWIZZLE_64B
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         uint32_t pk[4];
+                        float bq8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (bb != nullptr) {                  // two broadcast LDS.128 instead of eight LDS.32: the drain is shared-memory-pipe bound
+                            const float4 b0 = *reinterpret_cast<const float4*>(bb + q * 8), b1 = *reinterpret_cast<const float4*>(bb + q * 8 + 4);
+                            bq8[0] = b0.x; bq8[1] = b0.y; bq8[2] = b0.z; bq8[3] = b0.w; bq8[4] = b1.x; bq8[5] = b1.y; bq8[6] = b1.z; bq8[7] = b1.w;
+                        }
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            pk[k] = pack_bf16x2(__uint_as_float(v[q * 8 + 2 * k]) + bb[q * 8 + 2 * k], __uint_as_float(v[q * 8 + 2 * k + 1]) + bb[q * 8 + 2 * k + 1]);
+                        for (int k = 0; k < 4; ++k) {
+                            const float a0 = __uint_as_float(v[q * 8 + 2 * k]) + bq8[2 * k], a1 = __uint_as_float(v[q * 8 + 2 * k + 1]) + bq8[2 * k + 1];
+                            pk[k] = ones ? 0x3F803F80u : pack_bf16x2(a0, a1);
+                        }
                         *reinterpret_cast<uint4*>(rowp + ((q ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
+                };
+#pragma unroll
+                for (int hq = 0; hq < 2; ++hq) {          // heads 2 half, 2 half + 1: q (with bias) and k chunks of this thread's row
+                    const int h = half * 2 + hq;
+                    uint32_t vq[32], vk[32];
+                    tmem_ld_32x32b_x32(lane_addr + AB_TM_QK + h * 32, vq);
+                    tmem_ld_32x32b_x32(lane_addr + AB_TM_QK + 128 + h * 32, vk);
+                    tmem_ld_wait();
+                    put(vq, smem + AB_Q_OFF + h * AB_KB + row * 64, bq_s + h * 32, false);
+                    put(vk, smem + AB_K_OFF + h * AB_KB + row * 64, nullptr, false);
                 }
-                const float bvr = bv_s[row];               // V^T: lane = padded channel, columns = tokens (keys)
-#pragma unroll 1
-                for (int kq = 0; kq < 2; ++kq) {
-                    const int kb = half * 2 + kq;
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(lane_addr + AB_TM_VT + kb * 32, v);
+                {                                         // V^T: lane = padded channel, columns = tokens (keys)
+                    uint32_t v0[32], v1[32];
+                    tmem_ld_32x32b_x32(lane_addr + AB_TM_VT + half * 64, v0);
+                    tmem_ld_32x32b_x32(lane_addr + AB_TM_VT + half * 64 + 32, v1);
                     tmem_ld_wait();
-                    uint8_t* rowp = smem + AB_VT_OFF + kb * AB_KB + row * 64;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) pk[k] = pack_bf16x2(__uint_as_float(v[q * 8 + 2 * k]) + bvr, __uint_as_float(v[q * 8 + 2 * k + 1]) + bvr);
-                        *reinterpret_cast<uint4*>(rowp + ((q ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    }
+                    const bool ones = (row & 31) == AB_HD;    // padded channel 24 of each head: the all-ones row that makes O_h[:, 24] the row sum
+                    put(v0, smem + AB_VT_OFF + (half * 2) * AB_KB + row * 64, nullptr, ones);
+                    put(v1, smem + AB_VT_OFF + (half * 2 + 1) * AB_KB + row * 64, nullptr, ones);
                 }
             }
+            if (half == 0) rowidx_s[row] = (int)token_row(tile, row);   // read by the output epilogue (after a bar.sync of these warps)
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(qkv_ready);
+            if (quad == 0) AB_TRACE(trole, it, 2);
 
             // ---- 2. softmax of heads {half, half + 2}: one query row per thread
             const int widx = tile * 2 + win_in_tile;
@@ -233,6 +256,7 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
                 const int h = 2 * hh + half;
                 const uint32_t u = (uint32_t)(2 * it + hh);
                 mbar_wait_parked(&s_full[half], u & 1);
+                if (quad == 0) AB_TRACE(trole, it, 3 + 5 * hh);
                 tc_fence_after();
                 uint32_t v[64];
                 {
@@ -246,35 +270,32 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_free[half]);
-                const float* tb = tab_s + h * 225 + ci;
+                if (quad == 0) AB_TRACE(trole, it, 4 + 5 * hh);
+                const float* tb = tab_s + h * AB_TAB_N + ci;
                 float s[64];
-                float m = -INFINITY;
+                float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains: 16-deep instead of 64-deep
                 if (rowmask || colmask) {
                     const bool my_y = ty >= 4, my_x = tx >= 4;
 #pragma unroll
                     for (int j = 0; j < 64; ++j) {
                         const bool masked = (rowmask && (my_y != (j >= 32))) || (colmask && (my_x != ((j & 7) >= 4)));
-                        s[j] = __uint_as_float(v[j]) + tb[-((j >> 3) * 15 + (j & 7))] + (masked ? -100.0f * AB_LOG2E : 0.0f);
-                        m = fmaxf(m, s[j]);
+                        s[j] = __uint_as_float(v[j]) + tb[-((j >> 3) * AB_TAB_STRIDE + (j & 7))] + (masked ? -100.0f * AB_LOG2E : 0.0f);
+                        mx[j & 3] = fmaxf(mx[j & 3], s[j]);
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 64; ++j) {
-                        s[j] = __uint_as_float(v[j]) + tb[-((j >> 3) * 15 + (j & 7))];
-                        m = fmaxf(m, s[j]);
+                        s[j] = __uint_as_float(v[j]) + tb[-((j >> 3) * AB_TAB_STRIDE + (j & 7))];
+                        mx[j & 3] = fmaxf(mx[j & 3], s[j]);
                     }
                 }
-                float sum = 0.f;
+                const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+                uint32_t pk[32];                               // un-normalised probabilities (<= 1); the row sum comes back in O_h[:, 24]
 #pragma unroll
-                for (int j = 0; j < 64; ++j) {
-                    s[j] = ex2_approx(s[j] - m);
-                    sum += s[j];
-                }
-                const float inv = 1.0f / sum;
-                uint32_t pk[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(s[2 * j] * inv, s[2 * j + 1] * inv);
+                for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(ex2_approx(s[2 * j] - m), ex2_approx(s[2 * j + 1] - m));
+                if (quad == 0) AB_TRACE(trole, it, 5 + 5 * hh);
                 mbar_wait_parked(&p_free[half], (u & 1) ^ 1);     // the P V MMAs that read the previous contents have retired
+                if (quad == 0) AB_TRACE(trole, it, 6 + 5 * hh);
                 tc_fence_after();
                 const uint32_t pbase = lane_addr + AB_TM_P + half * 64;
                 const uint32_t own = pbase + win_in_tile * 32, other = pbase + (win_in_tile ^ 1) * 32;
@@ -293,10 +314,12 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[half]);
+                if (quad == 0) AB_TRACE(trole, it, 7 + 5 * hh);
             }
 
             // ---- 3. drain O (heads 2 half, 2 half + 1) -> O_pad operand of the projection (reuses the Q tile)
             mbar_wait_parked(o_full, (uint32_t)(it & 1));
+            if (quad == 0) AB_TRACE(trole, it, 13);
             tc_fence_after();
 #pragma unroll 1
             for (int hq = 0; hq < 2; ++hq) {
@@ -304,50 +327,71 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(lane_addr + AB_TM_O + h * 32, v);
                 tmem_ld_wait();
+                const float inv = 1.0f / __uint_as_float(v[AB_HD]);   // sum_j P~_ij (>= the max term, 1)
                 uint8_t* rowp = smem + AB_Q_OFF + h * AB_KB + row * 64;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < 3; ++q) {                 // 24 channels = three 16-byte units; the fourth (padding) is zero
                     uint32_t pk[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) pk[k] = pack_bf16x2(__uint_as_float(v[q * 8 + 2 * k]), __uint_as_float(v[q * 8 + 2 * k + 1]));
+                    for (int k = 0; k < 4; ++k) pk[k] = pack_bf16x2(__uint_as_float(v[q * 8 + 2 * k]) * inv, __uint_as_float(v[q * 8 + 2 * k + 1]) * inv);
                     *reinterpret_cast<uint4*>(rowp + ((q ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
+                *reinterpret_cast<uint4*>(rowp + ((3 ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
             }
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(ao_ready);
+            if (quad == 0) AB_TRACE(trole, it, 14);
 
-            // ---- 4. output: y = Y + b' + x. 48 of the 96 channels per thread: columns [32 half, +32) and [64 + 16 half, +16)
-            const long long grow = token_row(tile, row);
-            const int cA = 32 * half, cB = 64 + 16 * half;
-            const float* xr = p.x + grow * AB_C;
+            // ---- 4. output: y = Y + b' + x. Each thread adds the bias to 48 channels of its row (columns [32 half, +32) and
+            // [64 + 16 half, +16)) and parks them in a padded fp32 staging tile over the dead Q / K tiles; the 256 threads then
+            // walk the tile in row-major float4 order so that x is read and y written in 384-byte coalesced runs (a row-per-thread
+            // LDG / STG touches 32 different lines per instruction: measured 3.7 k cycles each per tile, 40 % of the first version).
+            // The x loads are issued before the wait for the projection MMA, so their L2 latency hides behind it.
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight tensor-memory warps: row indices visible
             float4 xv[12];
+            int goff[12];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) xv[j] = __ldg(reinterpret_cast<const float4*>(xr + cA) + j);   // shortcut (an L2 hit: read by the LayerNorm warps)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) xv[8 + j] = __ldg(reinterpret_cast<const float4*>(xr + cB) + j);
-            mbar_wait_parked(y_full, (uint32_t)(it & 1));
-            tc_fence_after();
-            uint32_t ya[32], yb[16];
-            tmem_ld_32x32b_x32(lane_addr + AB_TM_Y + cA, ya);
-            tmem_ld_32x32b_x16(lane_addr + AB_TM_Y + cB, yb);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(y_free);
-            float* orow = p.out + grow * AB_C;
-#pragma unroll
-            for (int j = 0; j < 12; ++j) {
-                float4 o;
-                const uint32_t* src = j < 8 ? &ya[j * 4] : &yb[(j - 8) * 4];
-                const int c = j < 8 ? cA + j * 4 : cB + (j - 8) * 4;
-                o.x = __uint_as_float(src[0]) + bp_s[c + 0] + xv[j].x;
-                o.y = __uint_as_float(src[1]) + bp_s[c + 1] + xv[j].y;
-                o.z = __uint_as_float(src[2]) + bp_s[c + 2] + xv[j].z;
-                o.w = __uint_as_float(src[3]) + bp_s[c + 3] + xv[j].w;
-                *reinterpret_cast<float4*>(orow + c) = o;
+            for (int i = 0; i < 12; ++i) {
+                const int f = (int)threadIdx.x + 256 * i;       // float4 index in the [128][24] tile
+                const int r = f / 24, c4 = f - r * 24;
+                goff[i] = rowidx_s[r] * AB_C + c4 * 4;
+                xv[i] = __ldg(reinterpret_cast<const float4*>(p.x + goff[i]));   // shortcut (an L2 hit: read by the LayerNorm warps)
             }
+            const int cA = 32 * half, cB = 64 + 16 * half;
+            if (quad == 0) AB_TRACE(trole, it, 15);
+            mbar_wait_parked(y_full, (uint32_t)(it & 1));
+            if (quad == 0) AB_TRACE(trole, it, 16);
+            tc_fence_after();
+            {
+                uint32_t ya[32], yb[16];
+                tmem_ld_32x32b_x32(lane_addr + AB_TM_Y + cA, ya);
+                tmem_ld_32x32b_x16(lane_addr + AB_TM_Y + cB, yb);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(y_free);
+                uint8_t* srow = smem + AB_STAGE_OFF + row * AB_STAGE_LD;
+#pragma unroll
+                for (int j = 0; j < 12; ++j) {
+                    const uint32_t* src = j < 8 ? &ya[j * 4] : &yb[(j - 8) * 4];
+                    const int c = j < 8 ? cA + j * 4 : cB + (j - 8) * 4;
+                    const float4 b4 = *reinterpret_cast<const float4*>(bp_s + c);
+                    *reinterpret_cast<float4*>(srow + c * 4) = make_float4(__uint_as_float(src[0]) + b4.x, __uint_as_float(src[1]) + b4.y,
+                                                                           __uint_as_float(src[2]) + b4.z, __uint_as_float(src[3]) + b4.w);
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // staging tile complete
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                const int f = (int)threadIdx.x + 256 * i;
+                const int r = f / 24, c4 = f - r * 24;
+                const float4 yv = *reinterpret_cast<const float4*>(smem + AB_STAGE_OFF + r * AB_STAGE_LD + c4 * 16);
+                *reinterpret_cast<float4*>(p.out + goff[i]) = make_float4(xv[i].x + yv.x, xv[i].y + yv.y, xv[i].z + yv.z, xv[i].w + yv.w);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // staging tile read out: the next tile's drain may overwrite Q / K
+            if (quad == 0) AB_TRACE(trole, it, 17);
         }
     } else if (warp == AB_W_MMA) {
         // ============================================================ weight load + MMA issue (warp-convergent, elected lane)
@@ -367,9 +411,8 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
                        dWp = umma_desc_sw64(smem_u32(smem + AB_WP_OFF)), dA = umma_desc_sw64(smem_u32(smem + AB_A_OFF)),
                        dQ = umma_desc_sw64(smem_u32(smem + AB_Q_OFF)), dK = umma_desc_sw64(smem_u32(smem + AB_K_OFF)),
                        dVT = umma_desc_sw64(smem_u32(smem + AB_VT_OFF));
-        for (int it = 0; it < my_tiles; ++it) {
+        auto issue_qkv = [&](int it) {                       // QK and V^T accumulators of local tile `it` (TMEM columns 0-383)
             mbar_wait_parked(a_full, (uint32_t)(it & 1));
-            mbar_wait_parked(y_free, (uint32_t)((it & 1) ^ 1));       // the previous tile's Y (and with it S / P) has been read out of TMEM
             tc_fence_after();
             if (elect_one_sync()) {
 #pragma unroll
@@ -382,7 +425,12 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
                 umma_commit(a_free);
             }
             __syncwarp();
+        };
+        if (my_tiles > 0) issue_qkv(0);
+        for (int it = 0; it < my_tiles; ++it) {
+            AB_TRACE(2, it, 3);
             mbar_wait_parked(qkv_ready, (uint32_t)(it & 1));
+            AB_TRACE(2, it, 4);
             tc_fence_after();
             if (elect_one_sync()) {
                 for (int h = 0; h < 2; ++h) {
@@ -391,6 +439,7 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
                 }
             }
             __syncwarp();
+            mbar_wait_parked(y_free, (uint32_t)((it & 1) ^ 1));       // the previous tile's Y has left the O columns
 #pragma unroll 1
             for (int h = 0; h < 4; ++h) {
                 const int b = h & 1;
@@ -404,7 +453,9 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
                     }
                     __syncwarp();
                 }
+                AB_TRACE(2, it, 5 + 3 * h);
                 mbar_wait_parked(&p_full[b], u & 1);
+                AB_TRACE(2, it, 6 + 3 * h);
                 tc_fence_after();
                 if (elect_one_sync()) {
                     const uint32_t d = tmem_base + AB_TM_O + h * 32, a = tmem_base + AB_TM_P + b * 64;
@@ -416,8 +467,10 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
                     if (h == 3) umma_commit(o_full);
                 }
                 __syncwarp();
+                AB_TRACE(2, it, 7 + 3 * h);
             }
             mbar_wait_parked(ao_ready, (uint32_t)(it & 1));
+            AB_TRACE(2, it, 17);
             tc_fence_after();
             if (elect_one_sync()) {
 #pragma unroll
@@ -426,6 +479,10 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
                 umma_commit(y_full);
             }
             __syncwarp();
+            AB_TRACE(2, it, 18);
+            // the next tile's QK / V^T MMAs run underneath this tile's output epilogue: S / P (columns 0-383) are dead (every P V MMA
+            // was issued after its p_full and executes before these), Y lives in the O columns
+            if (it + 1 < my_tiles) issue_qkv(it + 1);
         }
     } else {
         // ============================================================ LayerNorm warps: 32 rows each, 8 lanes per row (12 channels per lane)
@@ -434,6 +491,12 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
         uint8_t* a1 = smem + AB_A_OFF;
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
+            if (it + 1 < my_tiles) {                      // pull the next tile's 32 rows of this warp into L2: 3 lines of 128 B per row
+                const char* nr = reinterpret_cast<const char*>(p.x + token_row(tile + gridDim.x, lw * 32 + lane) * AB_C);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nr));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nr + 128));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nr + 256));
+            }
 #pragma unroll 1
             for (int bt = 0; bt < 2; ++bt) {              // two batches of 16 rows (4 row groups of 4)
                 float4 v[4][3];
@@ -444,7 +507,9 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
                     const float4* xr = reinterpret_cast<const float4*>(p.x + token_row(tile, rr[gi]) * AB_C + l8 * 12);
                     v[gi][0] = __ldg(xr); v[gi][1] = __ldg(xr + 1); v[gi][2] = __ldg(xr + 2);
                 }
+                if (lw == 0 && bt == 0) AB_TRACE(3, it, 20);
                 if (bt == 0) mbar_wait_parked(a_free, (uint32_t)((it & 1) ^ 1));   // the previous tile's QK / V^T MMAs have read A
+                if (lw == 0 && bt == 0) AB_TRACE(3, it, 21);
 #pragma unroll
                 for (int gi = 0; gi < 4; ++gi) {
                     float sm = 0.f;
@@ -477,6 +542,7 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full);
+            if (lw == 0) AB_TRACE(3, it, 22);
         }
     }
 
@@ -489,17 +555,30 @@ attn_block_kernel(const __grid_constant__ CUtensorMap tmWqk, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-// Wp_pad[n][32 h + d] = Wp[n][24 h + d] (zero elsewhere): the projection consumes the per-head padded O layout
-__global__ void pad_proj_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out, int C, int nH, int hd, int hdp) {
-    const int total = C * nH * hdp;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int d = i % hdp, h = (i / hdp) % nH, n = i / (hdp * nH);
-        out[i] = d < hd ? w[n * C + h * hd + d] : __float2bfloat16_rn(0.f);
+// Wp_pad[n][32 h + d] = Wp[n][24 h + d] (zero elsewhere): the projection consumes the per-head padded O layout.
+// bp_eff[n] = bp[n] + sum_c Wp[n][c] bv[c]: the v bias rides through the attention (softmax rows sum to 1) into the projection bias.
+__global__ void pad_proj_kernel(const __nv_bfloat16* __restrict__ w, const float* __restrict__ bp, const float* __restrict__ bv,
+                                __nv_bfloat16* __restrict__ out, float* __restrict__ bp_eff, int C, int nH, int hd, int hdp) {
+    const int n = blockIdx.x;                 // one CTA per output channel
+    __shared__ float red[128];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < nH * hdp; i += blockDim.x) {
+        const int d = i % hdp, h = i / hdp;
+        const __nv_bfloat16 v = d < hd ? w[n * C + h * hd + d] : __float2bfloat16_rn(0.f);
+        out[n * nH * hdp + i] = v;
+        if (d < hd) acc = fmaf(__bfloat162float(v), bv[h * hd + d], acc);
     }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bp_eff[n] = bp[n] + red[0];
 }
-int attn_block_pad_proj(const __nv_bfloat16* w, __nv_bfloat16* out, int C, int nH, cudaStream_t s) {
+int attn_block_pad_proj(const __nv_bfloat16* w, const float* bp, const float* bv, __nv_bfloat16* out, float* bp_eff, int C, int nH, cudaStream_t s) {
     const int hd = C / nH;
-    pad_proj_kernel<<<(C * nH * 32 + 255) / 256, 256, 0, s>>>(w, out, C, nH, hd, 32);
+    pad_proj_kernel<<<C, 128, 0, s>>>(w, bp, bv, out, bp_eff, C, nH, hd, 32);
     return check_cuda(cudaGetLastError(), "pad_proj launch");
 }
 
@@ -509,7 +588,7 @@ int attn_block_pack(AttnBlockW& w, const std::vector<float>& qkv_w, const std::v
     const int hd = C / nH;
     if (C != AB_C || nH != AB_NH || hd != AB_HD) return set_error(ARD_ERR_SHAPE, "attn_block: built for C=96, 4 heads of 24");
     const float qs = AB_LOG2E / sqrtf((float)hd);
-    std::vector<float> wqk((size_t)256 * C, 0.f), bqk(256, 0.f), wv((size_t)128 * C, 0.f), bv(128, 0.f), tab((size_t)nH * 225);
+    std::vector<float> wqk((size_t)256 * C, 0.f), bq(128, 0.f), wv((size_t)128 * C, 0.f), bv(C, 0.f), tab((size_t)nH * AB_TAB_N, 0.f);
     for (int h = 0; h < nH; ++h)
         for (int d = 0; d < hd; ++d) {
             const int src = h * hd + d, dst = h * 32 + d;
@@ -518,14 +597,15 @@ int attn_block_pack(AttnBlockW& w, const std::vector<float>& qkv_w, const std::v
                 wqk[(size_t)(128 + dst) * C + k] = qkv_w[(size_t)(C + src) * C + k];
                 wv[(size_t)dst * C + k] = qkv_w[(size_t)(2 * C + src) * C + k];
             }
-            bqk[dst] = qkv_b[src] * qs;
-            bqk[128 + dst] = qkv_b[C + src];
-            bv[dst] = qkv_b[2 * C + src];
+            bq[dst] = qkv_b[src] * qs;     // the k bias cancels in the softmax; the v bias (un-padded) is folded into the projection bias
+            bv[src] = qkv_b[2 * C + src];
         }
     for (int h = 0; h < nH; ++h)
-        for (int i = 0; i < 225; ++i) tab[(size_t)h * 225 + i] = rpb[(size_t)i * nH + h] * AB_LOG2E;
+        for (int dy = 0; dy < 15; ++dy)
+            for (int dx = 0; dx < 15; ++dx)
+                tab[(size_t)h * AB_TAB_N + dy * AB_TAB_STRIDE + dx] = rpb[(size_t)(dy * 15 + dx) * nH + h] * AB_LOG2E;
     ARD_TRY(upload_bf16(w.wqk, wqk));
-    ARD_TRY(upload_f32(w.bqk, bqk));
+    ARD_TRY(upload_f32(w.bq, bq));
     ARD_TRY(upload_bf16(w.wv, wv));
     ARD_TRY(upload_f32(w.bv, bv));
     ARD_TRY(upload_f32(w.table, tab));
@@ -533,7 +613,8 @@ int attn_block_pack(AttnBlockW& w, const std::vector<float>& qkv_w, const std::v
     return 0;
 }
 
-// y = x + proj'(window_attention(LayerNorm(x))) for B clips of R x R tokens, C = 96. wp_pad [96, 128] bf16, bp [96] fp32 (device).
+// y = x + proj'(window_attention(LayerNorm(x))) for B clips of R x R tokens, C = 96. wp_pad [96, 128] bf16, bp [96] fp32 = the
+// effective bias attn_block_pad_proj produced (device).
 int attn_block_96(const float* x, float* out, const AttnBlockW& w, const __nv_bfloat16* wp_pad, const float* bp, const float* gamma,
                   const float* beta, int B, int R, int shift, int num_sms, cudaStream_t stream) {
     if (B <= 0) return 0;
@@ -551,7 +632,7 @@ int attn_block_96(const float* x, float* out, const AttnBlockW& w, const __nv_bf
         attr_set = true;
     }
     AttnBlockParams p;
-    p.x = x; p.out = out; p.bqk = w.bqk.as<float>(); p.bv = w.bv.as<float>(); p.bp = bp; p.gamma = gamma; p.beta = beta;
+    p.x = x; p.out = out; p.bq = w.bq.as<float>(); p.bp = bp; p.gamma = gamma; p.beta = beta;
     p.table = w.table.as<float>(); p.R = R; p.shift = R > 8 ? shift : 0; p.n_tiles = (int)(windows / 2);
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
     const double M = (double)B * R * R;
@@ -562,3 +643,9 @@ int attn_block_96(const float* x, float* out, const AttnBlockW& w, const __nv_bf
 }
 
 }  // namespace ard
+
+#ifdef ARD_AB_TRACE
+extern "C" int ard_debug_ab_trace(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, ard::g_ab_trace, sizeof(long long) * 4 * 32 * 24);
+}
+#endif

@@ -149,6 +149,24 @@ def bench_attn():
             report(f"stage{l} window_attention shift={shift} M={M} C={C}", us, 4.0 * M * 64 * C, 8.0 * M * C)
 
 
+def bench_attn_block():
+    """Window-resident attention block (attn_block.cu) vs the unfused chain it replaces (ln_qkv + window_attention + proj GEMM)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import gpu_checks as G
+    clap, sd, _ = G.make_encoder("tiny", residual=True)
+    enc = clap.model.audio_branch
+    h = enc._handle()
+    lib = L.load()
+    st = L.stream_ptr()
+    M = B * 4096
+    x = torch.randn(B, 4096, 96, device=dev)
+    out = torch.empty_like(x)
+    for blk in (0, 1):
+        us = timeit(lambda: L.check(lib.ard_attention_block(h, 0, blk, L.ptr(x), B, L.ptr(out), st)))
+        fl = M * 2.0 * (384.0 * 96 + 4.0 * (128.0 * 32 + 32.0 * 128) + 128.0 * 96)
+        report(f"attn_block_96 block={blk} (shift={4 * blk}) M={M}", us, fl, 8.0 * M * 96)
+
+
 def bench_ln():
     lib = L.load()
     st = L.stream_ptr()
@@ -185,4 +203,4 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "ffn", "ffnw", "attn", "ln", "front"]
     print(torch.cuda.get_device_name(0), "B =", B, flush=True)
     for w in which:
-        {"gemm": bench_gemm, "ffn": bench_ffn, "ffnw": bench_ffn_wide, "lnqkv": bench_lnqkv, "attn": bench_attn, "ln": bench_ln, "front": bench_front}[w]()
+        {"gemm": bench_gemm, "ffn": bench_ffn, "ffnw": bench_ffn_wide, "lnqkv": bench_lnqkv, "attn": bench_attn, "ab": bench_attn_block, "ln": bench_ln, "front": bench_front}[w]()

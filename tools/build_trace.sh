@@ -4,9 +4,11 @@
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p build/trace
-F="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -DARD_FFN_TRACE"
-nvcc $F -c audio_residual_b200/csrc/ffn_fused.cu -o build/trace/ffn_fused.o
-nvcc $F -c audio_residual_b200/csrc/ffn_wide.cu -o build/trace/ffn_wide.o
-nvcc --shared -gencode arch=compute_100a,code=sm_100a -o build/libard_trace.so build/trace/ffn_fused.o build/trace/ffn_wide.o \
-    $(ls build/*.cu.o | grep -v "ffn_fused\|ffn_wide")
+F="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -DARD_FFN_TRACE -DARD_AB_TRACE"
+nvcc $F -c audio_residual_b200/csrc/ffn_fused.cu -o build/trace/ffn_fused.o &
+nvcc $F -c audio_residual_b200/csrc/ffn_wide.cu -o build/trace/ffn_wide.o &
+nvcc $F -c audio_residual_b200/csrc/attn_block.cu -o build/trace/attn_block.o &
+wait
+nvcc --shared -gencode arch=compute_100a,code=sm_100a -o build/libard_trace.so build/trace/ffn_fused.o build/trace/ffn_wide.o build/trace/attn_block.o \
+    $(ls build/*.cu.o | grep -v "ffn_fused\|ffn_wide\|attn_block")
 ls -la build/libard_trace.so
