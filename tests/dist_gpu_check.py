@@ -70,7 +70,8 @@ def main():
     dist.all_reduce(loss_sum)
     # ---- c4: sharded statistics (plain encoder, capture)
     with torch.no_grad():
-        clap2, _, _ = G.make_encoder("tiny")
+        from audio_residual_b200.clap import build_clap_module
+        clap2 = build_clap_module("tiny", W.make_state_dict("tiny", seed=0), device=dev)      # plain encoder on THIS rank's GPU
         o = clap2.model.audio_branch.encode(waveform=wave_all[lo:hi].to(dev), quantize=True, want_dict=True)
         racc = MomentAccumulator(192, dev)
         racc.update(o["layers_residuals"][1])

@@ -26,5 +26,7 @@ def test_sharded_training_step_and_statistics_equal_single_gpu():
     # mean, atomic order of the in-kernel lambda reduction) and the allreduce's own order
     assert m["loss_abs"] < 1e-5, m
     assert max(m["grad_rel"]) < 1e-3, m
-    assert m["moments_n"][0] == m["moments_n"][1] and m["moments_s1_rel"] < 1e-9 and m["moments_s2_rel"] < 1e-6, m
+    # second moments: each ard_stats_accumulate call accumulates its rows in fp32 on the tensor core before the float64 fold, so
+    # 2 x 4096 rows and 1 x 8192 rows differ at the fp32-accumulation level (measured 2e-5; both are ~5e-6 from float64)
+    assert m["moments_n"][0] == m["moments_n"][1] and m["moments_s1_rel"] < 1e-9 and m["moments_s2_rel"] < 1e-4, m
     assert max(m["spectra_rel"]) < 1e-6, m
