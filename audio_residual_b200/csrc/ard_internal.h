@@ -52,8 +52,15 @@ struct GemmArgs {
     int out_f16 = 0;                   // with out_bf16=1 and act=GELU: GELU in packed fp16, fp16 output
     const __nv_bfloat16* mul_gelu_bwd = nullptr;   // bf16 [M, ld_mul]: out = acc * gelu'(this), bf16 output only (FFN backward)
     long long ld_mul = 0;
+    int splitk = 0;                    // > 1: split the K range over `splitk` partial outputs, partial s at rows [s * split_rows, +M) of `out`
+    int split_rows = 0;                //      (fp32 [splitk * split_rows, ldo], split_rows % 256 == 0, >= M; plain epilogue only)
+                                       //      number of partials actually written: gemm_splitk_used(K, splitk)
 };
 int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream);
+inline int gemm_splitk_used(int K, int splitk) {   // empty trailing splits are dropped
+    const int num_kb = (K + 63) / 64, per = (num_kb + splitk - 1) / splitk;
+    return (num_kb + per - 1) / per;
+}
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                  uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
 

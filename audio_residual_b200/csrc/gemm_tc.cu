@@ -71,6 +71,9 @@ struct GemmKernelParams {
     int ab_f16;          // A and W hold fp16 (else bf16)
     int out_f16;         // 16-bit output holds fp16 (GELU evaluated in packed fp16), else bf16
     int mul_gelu_bwd;    // 16-bit output only: out = acc * gelu'(h), h = the bf16 [M,N] tensor behind tmR (FFN backward: dh = (g W2) * gelu'(hpre))
+    int splitk;          // >= 1. Split s works on k-blocks [s * kb_per_split, ...) of every tile and stores its partial tile `split_rows`
+    int kb_per_split;    // rows further down the output (out is [splitk * split_rows, N] fp32, no bias / residuals): long-K, few-tile
+    int split_rows;      // problems (X^T X over a million rows with a 96 x 96 result) would otherwise run on a single CTA
 };
 
 template <int BN, bool OUT_BF16, bool PAIR, bool MUL, int NEPI>
@@ -98,7 +101,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int lane = threadIdx.x & 31;
     const int m_blocks = (p.M + TILE_M - 1) / TILE_M;
     const int n_blocks = (p.N + BN - 1) / BN;
-    const int num_tiles = m_blocks * n_blocks;
+    const int mn_tiles = m_blocks * n_blocks;
+    const int num_tiles = mn_tiles * p.splitk;
     const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
 
     if (warp == 0 && lane == 0) {
@@ -139,8 +143,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
-                const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int ks = tile / mn_tiles, t2 = tile - ks * mn_tiles;
+                const int m_blk = t2 / n_blocks, n_blk = t2 % n_blocks;
+                const int kb_begin = ks * p.kb_per_split, kb_end = min(num_kb, kb_begin + p.kb_per_split);
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
@@ -179,7 +185,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 else mbar_wait(&tempty_bar[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * Cfg::ACC_COLS;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb_begin = (tile / mn_tiles) * p.kb_per_split, kb_end = min(num_kb, kb_begin + p.kb_per_split);
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -188,20 +195,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int ksteps = min(GEMM_BK, p.K - kb * GEMM_BK) >> 4;   // 4, or 1..3 in the last k-block (K % 16 == 0)
                     if (elect_one_sync()) {
                         if (ksteps == 4) {
-                            umma_f16_ss_run<4, PAIR>(d_tmem, da, db, idesc, kb != 0);
+                            umma_f16_ss_run<4, PAIR>(d_tmem, da, db, idesc, kb != kb_begin);
                         } else {
-                            if (ksteps >= 2) umma_f16_ss_run<2, PAIR>(d_tmem, da, db, idesc, kb != 0);
+                            if (ksteps >= 2) umma_f16_ss_run<2, PAIR>(d_tmem, da, db, idesc, kb != kb_begin);
                             if (ksteps & 1) {
                                 const int k = ksteps - 1;
-                                if constexpr (PAIR) umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                                else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                                if constexpr (PAIR) umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, ((kb - kb_begin) | k) != 0);
+                                else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, ((kb - kb_begin) | k) != 0);
                             }
                         }
                         // frees the smem slot (in both CTAs of a pair) when these MMAs retire
                         if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
                         else umma_commit(&empty_bar[stage]);
                         // accumulator ready (each CTA's epilogue reads its own 128 rows out of its own TMEM)
-                        if (kb == num_kb - 1) {
+                        if (kb == kb_end - 1) {
                             if constexpr (PAIR) umma_commit_pair(&tfull_bar[as]);
                             else umma_commit(&tfull_bar[as]);
                         }
@@ -228,7 +235,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // pre-activation whose gelu' multiplies the result (FFN backward). The same buffer is then handed to the TMA store.
         const bool tma_resid = MUL || (!OUT_BF16 && p.resid1 != nullptr);
         auto issue_resid = [&](int t, int cc, int b) {   // lane 0 only
-            const int mb = t / n_blocks, nb = t % n_blocks;
+            const int t2 = t % mn_tiles;
+            const int mb = t2 / n_blocks, nb = t2 % n_blocks;
             mbar_expect_tx(&rbar[b], Cfg::CST);
             tma_load_2d(cst + b * Cfg::CST, &tmR, &rbar[b], nb * BN + cc * 32, mb * TILE_M + (int)pair_rank * GEMM_BM + quad * 32);
         };
@@ -243,7 +251,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tma_store_wait_read<1>();          // buffer (i+1)%3 was last stored two chunks ago
                 if (ntile < num_tiles) issue_resid(ntile, nc, (i + 1) % NBUF);
             }
-            const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+            const int ks = tile / mn_tiles, t2 = tile - ks * mn_tiles;
+            const int m_blk = t2 / n_blocks, n_blk = t2 % n_blocks;
             const int as = it % NACC;
             if (c == grp) {                        // first chunk of this tile for this warp
                 mbar_wait(&tfull_bar[as], (it / NACC) & 1);
@@ -368,7 +377,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                tma_store_2d(&tmC, sbuf, col0, row0);
+                tma_store_2d(&tmC, sbuf, col0, row0 + ks * p.split_rows);
                 tma_store_commit();
             }
             ++i;
@@ -433,7 +442,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
         attr_set = true;
     }
     constexpr int TILE_M = PAIR ? 2 * GEMM_BM : GEMM_BM;
-    const int tiles = ((kp.M + TILE_M - 1) / TILE_M) * ((kp.N + BN - 1) / BN);
+    const int tiles = ((kp.M + TILE_M - 1) / TILE_M) * ((kp.N + BN - 1) / BN) * kp.splitk;
     if constexpr (PAIR) {
         // one CTA pair (cluster of 2, same TPC) per 256 x BN tile
         const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
@@ -496,10 +505,16 @@ int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     if (int rc = make_tmap_2d(&ta, a.A, 2, a.K, a.M, (uint64_t)a.lda * 2, GEMM_BK, GEMM_BM, 128)) return rc;
     const bool pair = a.mul_gelu_bwd == nullptr && pick_pair(a, BN);
     if (int rc = make_tmap_2d(&tb, a.W, 2, a.K, a.N, (uint64_t)a.ldw * 2, GEMM_BK, pair ? BN / 2 : BN, 128)) return rc;
+    const int splitk = a.splitk > 1 ? a.splitk : 1;
+    if (splitk > 1) {
+        if (a.out_bf16 || a.bias || a.act || a.resid1 || a.resid2 || a.aux || a.mul_gelu_bwd || a.split_rows < a.M || (a.split_rows % 256) != 0)
+            return set_error(ARD_ERR_SHAPE, "gemm: split-K needs a plain fp32 output and split_rows (a multiple of 256) >= M");
+    }
     if (a.out_bf16) {
         if (int rc = make_tmap_2d(&tc, a.out, 2, a.N, a.M, (uint64_t)a.ldo * 2, 32, 32, 64)) return rc;
     } else {
-        if (int rc = make_tmap_2d(&tc, a.out, 4, a.N, a.M, (uint64_t)a.ldo * 4, 32, 32, 128)) return rc;
+        const uint64_t out_rows = splitk > 1 ? (uint64_t)splitk * a.split_rows : (uint64_t)a.M;
+        if (int rc = make_tmap_2d(&tc, a.out, 4, a.N, out_rows, (uint64_t)a.ldo * 4, 32, 32, 128)) return rc;
     }
     tr = tc;
     if (!a.out_bf16 && a.resid1 != nullptr) {
@@ -517,6 +532,13 @@ int gemm_bf16(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     kp.resid1 = a.resid1; kp.ldr1 = a.ldr1; kp.resid2 = a.resid2; kp.ldr2 = a.ldr2;
     kp.aux = a.aux; kp.ld_aux = a.ld_aux; kp.aux_T = a.aux_T > 0 ? a.aux_T : a.M; kp.aux_bstride = a.aux_bstride;
     kp.ab_f16 = a.ab_f16; kp.out_f16 = a.out_f16; kp.mul_gelu_bwd = a.mul_gelu_bwd != nullptr;
+    {
+        const int num_kb = (a.K + GEMM_BK - 1) / GEMM_BK;
+        kp.splitk = splitk;
+        kp.kb_per_split = (num_kb + splitk - 1) / splitk;
+        kp.splitk = (num_kb + kp.kb_per_split - 1) / kp.kb_per_split;   // no empty splits (an empty k-range would never commit its accumulator)
+        kp.split_rows = splitk > 1 ? a.split_rows : 0;
+    }
     const double osz = a.out_bf16 ? 2.0 : 4.0;
     ProfScope ps(PROF_GEMM, stream, 2.0 * a.M * a.N * a.K,
                  2.0 * a.M * a.K + 2.0 * a.N * a.K + osz * a.M * a.N + (a.resid1 ? 4.0 * a.M * a.N : 0.0) + (a.resid2 ? 4.0 * a.M * a.N : 0.0) +

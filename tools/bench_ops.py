@@ -167,6 +167,32 @@ def bench_attn_block():
         report(f"attn_block_96 block={blk} (shift={4 * blk}) M={M}", us, fl, 8.0 * M * 96)
 
 
+def bench_stats():
+    """ard_stats_accumulate_strided at the c4 shapes (one head's 4096-d attention maps out of layers_attention, B clips)."""
+    from audio_residual_b200.residual import MomentAccumulator
+    import torch.cuda as tc
+    for l, (nW, nH) in enumerate([(64, 4), (16, 8), (4, 16), (1, 32)]):
+        rows = B * nW
+        a = torch.rand(rows, nH, 4096, device=dev)
+        acc = MomentAccumulator(4096, a.device)
+        lib = L.load()
+        L.profile_enable(True)
+        for _ in range(3):
+            acc.update(a[:, 1])
+        pr = L.profile_read()
+        L.profile_enable(False)
+        us = timeit(lambda: acc.update(a[:, 1]), reps=5)
+        report(f"stats layer{l} rows={rows} D=4096 (gemm {pr['gemm_tc']['ms'] / 3 * 1e3:.0f} us, split+fold {pr['other']['ms'] / 3 * 1e3:.0f} us)", us,
+               2.0 * 2 * rows * 4096 * 4096, 12.0 * rows * 4096 + 24.0 * 4096 * 4096)
+        del a, acc
+    for D, rows in ((96, B * 8192), (192, B * 2048), (384, B * 1536), (768, B * 128)):
+        x = torch.rand(rows, D, device=dev)
+        acc = MomentAccumulator(D, x.device)
+        us = timeit(lambda: acc.update(x), reps=5)
+        report(f"stats residuals rows={rows} D={D}", us, 2.0 * 2 * rows * D * D, 12.0 * rows * D)
+        del x, acc
+
+
 def bench_ln():
     lib = L.load()
     st = L.stream_ptr()
@@ -203,4 +229,4 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "ffn", "ffnw", "attn", "ln", "front"]
     print(torch.cuda.get_device_name(0), "B =", B, flush=True)
     for w in which:
-        {"gemm": bench_gemm, "ffn": bench_ffn, "ffnw": bench_ffn_wide, "lnqkv": bench_lnqkv, "attn": bench_attn, "ab": bench_attn_block, "ln": bench_ln, "front": bench_front}[w]()
+        {"gemm": bench_gemm, "ffn": bench_ffn, "ffnw": bench_ffn_wide, "lnqkv": bench_lnqkv, "attn": bench_attn, "ab": bench_attn_block, "stats": bench_stats, "ln": bench_ln, "front": bench_front}[w]()
