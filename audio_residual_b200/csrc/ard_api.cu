@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <cmath>
 #include <map>
 #include <string>
@@ -501,6 +502,7 @@ int ard_create(const ard_config* cfg, ard_handle** out) {
     if (const char* e = getenv("ARD_GRAPHS")) h->use_graphs = atoi(e);
     if (const char* e = getenv("ARD_LN_QKV")) h->use_ln_qkv = atoi(e) != 0;
     if (const char* e = getenv("ARD_ATTN_BLOCK")) h->use_attn_block = atoi(e) != 0;
+    if (const char* e = getenv("ARD_DUAL_GEMM")) h->use_dual_gemm = atoi(e);
     *out = h;
     return 0;
 }
@@ -561,6 +563,21 @@ int ard_clear_block_residual(ard_handle* h, int layer, int block) {
     return 0;
 }
 
+// what a block needs after its fold changed: the padded copies of the attention-block kernel, and lambda for the backward
+static int after_fold(ard_handle* h, int layer, BlockW& bw, const float* lambda_dev, cudaStream_t s) {
+    const int C = C_of(h, layer);
+    if (bw.ab.ready)
+        ARD_TRY(attn_block_pad_proj(bw.proj_w_fold.as<__nv_bfloat16>(), bw.proj_b_fold.as<float>(), bw.ab.bv.as<float>(), bw.ab.wp_fold.as<__nv_bfloat16>(),
+                                    bw.ab.bp_fold.as<float>(), C, h->cfg.num_heads[layer], s));
+    // keep a (zero-padded) copy of lambda for the backward: gsc = gcoef * lambda
+    const int Kp = (bw.K + 15) & ~15;
+    ARD_TRY(bw.lam.ensure((size_t)Kp * 4));
+    ARD_CUDA(cudaMemsetAsync(bw.lam.p, 0, (size_t)Kp * 4, s));
+    ARD_CUDA(cudaMemcpyAsync(bw.lam.p, lambda_dev, (size_t)bw.K * 4, cudaMemcpyDeviceToDevice, s));
+    bw.lambda_set = true;
+    return 0;
+}
+
 int ard_set_block_lambda(ard_handle* h, int layer, int block, const float* lambda_dev, void* stream) {
     if (!h || layer < 0 || layer >= h->nlayers || block < 0 || block >= h->cfg.depths[layer]) return set_error(ARD_ERR_SHAPE, "bad block index");
     if (!h->finalized) return set_error(ARD_ERR_STATE, "ard_finalize_weights has not been called");
@@ -571,15 +588,38 @@ int ard_set_block_lambda(ard_handle* h, int layer, int block, const float* lambd
     ARD_TRY(residual_fold(bw.proj_w_f32.as<float>(), bw.res_dmean.as<float>(), bw.res_basis.as<float>(), lambda_dev, C, bw.K,
                           bw.res_M.as<float>(), bw.proj_w_fold.as<__nv_bfloat16>(), bw.proj_b_fold.as<float>(), (cudaStream_t)stream,
                           bw.proj_w_fold_f32.as<float>()));
-    if (bw.ab.ready)
-        ARD_TRY(attn_block_pad_proj(bw.proj_w_fold.as<__nv_bfloat16>(), bw.proj_b_fold.as<float>(), bw.ab.bv.as<float>(), bw.ab.wp_fold.as<__nv_bfloat16>(),
-                                    bw.ab.bp_fold.as<float>(), C, h->cfg.num_heads[layer], (cudaStream_t)stream));
-    // keep a (zero-padded) copy of lambda for the backward: gsc = gcoef * lambda
-    const int Kp = (bw.K + 15) & ~15;
-    ARD_TRY(bw.lam.ensure((size_t)Kp * 4));
-    ARD_CUDA(cudaMemsetAsync(bw.lam.p, 0, (size_t)Kp * 4, (cudaStream_t)stream));
-    ARD_CUDA(cudaMemcpyAsync(bw.lam.p, lambda_dev, (size_t)bw.K * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    bw.lambda_set = true;
+    return after_fold(h, layer, bw, lambda_dev, (cudaStream_t)stream);
+}
+
+// The reference builds ONE ResiDual per layer and shares it between the layer's blocks (src/residual.py:170-186), so
+// M = B^T diag(lambda) B is a per-layer matrix: it is formed once and the folds of all patched blocks of the layer run as one
+// batched launch each (3 launches per layer instead of 3 per block; the training step re-folds every layer every step).
+int ard_set_layer_lambda(ard_handle* h, int layer, const float* lambda_dev, void* stream) {
+    if (!h || layer < 0 || layer >= h->nlayers) return set_error(ARD_ERR_SHAPE, "bad layer index");
+    if (!h->finalized) return set_error(ARD_ERR_STATE, "ard_finalize_weights has not been called");
+    const int C = C_of(h, layer);
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<BlockW*> pb;
+    for (BlockW& bw : h->layers[layer].blocks)
+        if (bw.has_res) pb.push_back(&bw);
+    if (pb.empty()) return set_error(ARD_ERR_STATE, "layer %d has no ResiDual injected", layer);
+    for (BlockW* bw : pb)   // the caller states the blocks share one ResiDual: same basis and mean (host copies kept by ard_set_block_residual)
+        if (bw->K != pb[0]->K || bw->h_basis != pb[0]->h_basis || bw->h_mean != pb[0]->h_mean)
+            return set_error(ARD_ERR_STATE, "layer %d: its blocks carry different ResiDual bases; use ard_set_block_lambda per block", layer);
+    g_launches = 0;
+    for (size_t i0 = 0; i0 < pb.size(); i0 += 8) {
+        const int nb = (int)std::min<size_t>(8, pb.size() - i0);
+        const float *pw[8], *dm[8];
+        __nv_bfloat16* wo[8];
+        float *bo[8], *wf[8];
+        for (int z = 0; z < nb; ++z) {
+            BlockW& bw = *pb[i0 + z];
+            pw[z] = bw.proj_w_f32.as<float>(); dm[z] = bw.res_dmean.as<float>(); wo[z] = bw.proj_w_fold.as<__nv_bfloat16>();
+            bo[z] = bw.proj_b_fold.as<float>(); wf[z] = bw.proj_w_fold_f32.as<float>();
+        }
+        ARD_TRY(residual_fold_batch(pw, dm, pb[0]->res_basis.as<float>(), lambda_dev, C, pb[0]->K, pb[0]->res_M.as<float>(), wo, bo, wf, nb, s));
+    }
+    for (BlockW* bw : pb) ARD_TRY(after_fold(h, layer, *bw, lambda_dev, s));
     return 0;
 }
 
@@ -745,6 +785,20 @@ int ard_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, vo
     g.M = M; g.N = N; g.K = K; g.bias = bias; g.act = act; g.resid1 = resid1; g.ldr1 = ldr1; g.resid2 = resid2; g.ldr2 = ldr2;
     if (act == ARD_ACT_GELU_F16) { g.act = ARD_ACT_GELU; g.out_f16 = 1; }
     return gemm_bf16(g, sms, (cudaStream_t)stream);
+}
+
+int ard_gemm_dual(int mode, const void* A1, long long lda1, const void* W1, long long ldw1, const void* A2, long long lda2, const void* W2,
+                  long long ldw2, void* out, long long ldo, int M, int N, int K, const float* vec1, const float* vec2, float* dlam, int Kvalid,
+                  void* stream) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return set_error(ARD_ERR_CUDA, "no CUDA device");
+    if (mode != 0 && mode != 1) return set_error(ARD_ERR_SHAPE, "ard_gemm_dual: mode must be 0 (gelu backward) or 1 (lambda gradient)");
+    DualArgs d;
+    d.A1 = (const __nv_bfloat16*)A1; d.lda1 = lda1; d.W1 = (const __nv_bfloat16*)W1; d.ldw1 = ldw1;
+    d.A2 = (const __nv_bfloat16*)A2; d.lda2 = lda2; d.W2 = (const __nv_bfloat16*)W2; d.ldw2 = ldw2;
+    d.out = (__nv_bfloat16*)out; d.ldo = ldo; d.M = M; d.N = N; d.K = K; d.vec1 = vec1; d.vec2 = vec2; d.dlam = dlam; d.Kvalid = Kvalid;
+    return mode == 0 ? gemm_dual_gelu_bwd(d, sms, (cudaStream_t)stream) : gemm_dual_lambda(d, sms, (cudaStream_t)stream);
 }
 
 int ard_gemm_f16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int out_is_bf16, int M, int N,

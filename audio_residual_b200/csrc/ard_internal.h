@@ -61,6 +61,20 @@ inline int gemm_splitk_used(int K, int splitk) {   // empty trailing splits are 
     const int num_kb = (K + 63) / 64, per = (num_kb + splitk - 1) / splitk;
     return (num_kb + per - 1) / per;
 }
+// Two GEMMs of one shape meeting in the epilogue (gemm_dual.cu): acc1 = A1 W1^T, acc2 = A2 W2^T, bf16 [M, ldo] output.
+struct DualArgs {
+    const __nv_bfloat16 *A1 = nullptr, *W1 = nullptr, *A2 = nullptr, *W2 = nullptr;   // A [M, lda] and W [N, ldw] row-major (K-major)
+    long long lda1 = 0, ldw1 = 0, lda2 = 0, ldw2 = 0;
+    __nv_bfloat16* out = nullptr;
+    long long ldo = 0;
+    int M = 0, N = 0, K = 0;
+    const float* vec1 = nullptr;   // gelu_bwd: bias of GEMM 2 (fc1 bias) [N];  lambda: bias of GEMM 1 (c0) [N]
+    const float* vec2 = nullptr;   // lambda: lambda [N] (zero beyond Kvalid)
+    float* dlam = nullptr;         // lambda: [Kvalid], += column sums of (acc1 + vec1) * acc2
+    int Kvalid = 0;
+};
+int gemm_dual_gelu_bwd(const DualArgs& a, int num_sms, cudaStream_t stream);   // out = acc1 * gelu'(acc2 + vec1)
+int gemm_dual_lambda(const DualArgs& a, int num_sms, cudaStream_t stream);     // dlam += colsum((acc1 + vec1) * acc2), out = acc2 * vec2
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                  uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
 
@@ -132,6 +146,8 @@ int linear_small(const float* x, int ldx, const float* W, const float* bias, flo
 int l2_normalize(const float* x, float* y, int B, int N, cudaStream_t s);
 int residual_fold(const float* proj_w, const float* dmean, const float* basis, const float* lam, int C, int K, float* Mtmp,
                   __nv_bfloat16* w_out, float* b_out, cudaStream_t s, float* w_out_f32 = nullptr);
+int residual_fold_batch(const float* const* proj_w, const float* const* dmean, const float* basis, const float* lam, int C, int K, float* Mtmp,
+                        __nv_bfloat16* const* w_out, float* const* b_out, float* const* w_out_f32, int nb, cudaStream_t s);   // nb <= 8 blocks sharing M
 int residual_matrix(const float* basis, const float* lam, int C, int K, float* M, cudaStream_t s);   // M = B^T diag(lam) B [C,C]
 int tscam_im2col(const float* normed, __nv_bfloat16* A, int B, int C, cudaStream_t s);
 int tscam_finish(const float* y, int ldy, float* framewise, float* clipwise, int B, int NC, cudaStream_t s);

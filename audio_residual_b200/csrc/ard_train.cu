@@ -193,6 +193,16 @@ static int ffn_backward(ard_handle* h, BlockW& bw, int C, long long M, const flo
                         const BwdBufs& w, cudaStream_t s) {
     ARD_TRY(layernorm_bf16(x, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), w.XN, M, C, s));
     GemmArgs f;
+    if (h->use_dual_gemm && C <= 192) {
+        // dh = (g W2) * gelu'(fc1(norm2(x))): both products in one kernel, the re-computed pre-activation never reaches HBM.
+        // (C >= 384: a 128 x 128 tile of two K = C products moves 4 x 128 x C operand bytes per 16 K outputs out of L2 -
+        //  more than the two separate GEMMs with their wider tiles, which stay.)
+        DualArgs d;
+        d.A1 = w.GB; d.lda1 = C; d.W1 = bw.fc2_wT.as<__nv_bfloat16>(); d.ldw1 = C;
+        d.A2 = w.XN; d.lda2 = C; d.W2 = bw.fc1_w.as<__nv_bfloat16>(); d.ldw2 = C;
+        d.vec1 = bw.fc1_b.as<float>(); d.out = w.DH; d.ldo = 4 * C; d.M = (int)M; d.N = 4 * C; d.K = C;
+        ARD_TRY(gemm_dual_gelu_bwd(d, h->num_sms, s));
+    } else {
     f.A = w.XN; f.lda = C; f.W = bw.fc1_w.as<__nv_bfloat16>(); f.ldw = C; f.out = w.HPRE; f.ldo = 4 * C; f.out_bf16 = 1;
     f.M = (int)M; f.N = 4 * C; f.K = C; f.bias = bw.fc1_b.as<float>();
     ARD_TRY(gemm_bf16(f, h->num_sms, s));                                       // hpre = fc1(norm2(x)), recomputed
@@ -200,6 +210,7 @@ static int ffn_backward(ard_handle* h, BlockW& bw, int C, long long M, const flo
     f.A = w.GB; f.lda = C; f.W = bw.fc2_wT.as<__nv_bfloat16>(); f.ldw = C; f.out = w.DH; f.ldo = 4 * C; f.out_bf16 = 1;
     f.M = (int)M; f.N = 4 * C; f.K = C; f.mul_gelu_bwd = w.HPRE; f.ld_mul = 4 * C;
     ARD_TRY(gemm_bf16(f, h->num_sms, s));                                       // dh = (g W2) * gelu'(hpre), multiplied in the epilogue
+    }
     f = GemmArgs();
     f.A = w.DH; f.lda = 4 * C; f.W = bw.fc1_wT.as<__nv_bfloat16>(); f.ldw = 4 * C; f.out = w.T; f.ldo = C;
     f.M = (int)M; f.N = C; f.K = 4 * C;
@@ -221,6 +232,17 @@ static int block_backward(ard_handle* h, int l, int b, int B, float* dlam, bool 
         // shortcut sum dL/ds so far = dL/dx3 + dL/dx1 = 2 G + FFN'(G) is written straight into G
         ARD_TRY(ffn_backward(h, bw, C, M, bw.t_x1, w.G, w.G, 2.0f, w, s));
         const int Kp = bw.Kp;
+        const float* lam = bw.lambda_set && bw.lam.p ? bw.lam.as<float>() : bw.lam_ones.as<float>();
+        if (h->use_dual_gemm) {
+            // coef = x_proj = ao Wc^T + c0 and gcoef = dL/d(x_scaled) = dL/dr B^T meet in the epilogue of one kernel:
+            // dlam += colsum(coef * gcoef), gsc = gcoef * lam; neither [M, K] fp32 matrix reaches HBM
+            DualArgs d;
+            d.A1 = bw.t_ao; d.lda1 = C; d.W1 = bw.res_wc.as<__nv_bfloat16>(); d.ldw1 = C;
+            d.A2 = w.GB; d.lda2 = C; d.W2 = bw.res_basis_bf16.as<__nv_bfloat16>(); d.ldw2 = C;
+            d.vec1 = bw.res_c0.as<float>(); d.vec2 = lam; d.dlam = dlam; d.Kvalid = bw.K;
+            d.out = w.gsc; d.ldo = Kp; d.M = (int)M; d.N = Kp; d.K = C;
+            ARD_TRY(gemm_dual_lambda(d, h->num_sms, s));
+        } else {
         g.A = bw.t_ao; g.lda = C; g.W = bw.res_wc.as<__nv_bfloat16>(); g.ldw = C; g.out = w.coef; g.ldo = Kp;
         g.M = (int)M; g.N = Kp; g.K = C; g.bias = bw.res_c0.as<float>();
         ARD_TRY(gemm_bf16(g, h->num_sms, s));                                    // coef = x_proj
@@ -228,8 +250,8 @@ static int block_backward(ard_handle* h, int l, int b, int B, float* dlam, bool 
         g.A = w.GB; g.lda = C; g.W = bw.res_basis_bf16.as<__nv_bfloat16>(); g.ldw = C; g.out = w.gcoef; g.ldo = Kp;
         g.M = (int)M; g.N = Kp; g.K = C;
         ARD_TRY(gemm_bf16(g, h->num_sms, s));                                    // gcoef = dL/d(x_scaled) = dL/dr B^T
-        const float* lam = bw.lambda_set && bw.lam.p ? bw.lam.as<float>() : bw.lam_ones.as<float>();
         ARD_TRY(lambda_grad(w.coef, w.gcoef, lam, dlam, w.gsc, M, bw.K, Kp, s));       // dlam += colsum(coef*gcoef); gsc = gcoef*lam
+        }
         if (stop_after_lambda) return 0;
         g = GemmArgs();
         g.A = w.gsc; g.lda = Kp; g.W = bw.res_wcT.as<__nv_bfloat16>(); g.ldw = Kp; g.out = w.GAO; g.ldo = C; g.out_bf16 = 1;
@@ -282,8 +304,10 @@ int encoder_backward(ard_handle* h, const ard_backward_args* a, cudaStream_t s) 
     ARD_TRY(h->bw_t.ensure(MC * 4));
     ARD_TRY(h->bw_dh.ensure(MC * 4 * 2));
     ARD_TRY(h->bw_gb.ensure(MC * 2));
-    ARD_TRY(h->bw_coef.ensure(MC * 4));
-    ARD_TRY(h->bw_gcoef.ensure(MC * 4));
+    if (!h->use_dual_gemm) {   // the fp32 coefficient matrices only exist on the separate-GEMM path
+        ARD_TRY(h->bw_coef.ensure(MC * 4));
+        ARD_TRY(h->bw_gcoef.ensure(MC * 4));
+    }
     ARD_TRY(h->bw_gsc.ensure(MC * 2));
     ARD_TRY(h->bw_small.ensure((size_t)B * (2 * J + NF) * 4 + 1024));
     BwdBufs w;

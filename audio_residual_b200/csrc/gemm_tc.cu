@@ -307,9 +307,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const float h0 = __uint_as_float(w4[k] << 16), h1 = __uint_as_float(w4[k] & 0xffff0000u);
-                            f[q * 8 + 2 * k] *= gelu_erf_grad(h0);
-                            f[q * 8 + 2 * k + 1] *= gelu_erf_grad(h1);
+                            const float2 gd = gelu_erf_grad_bf16x2(w4[k]);   // packed fp16 evaluation, fp32 product (gradients underflow fp16)
+                            f[q * 8 + 2 * k] *= gd.x;
+                            f[q * 8 + 2 * k + 1] *= gd.y;
                         }
                     }
                 }

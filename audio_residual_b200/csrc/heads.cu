@@ -141,86 +141,141 @@ int relu_bwd_mul(float* g, const float* act, long long n, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------ fp32 "TN" GEMM
-// out[i][j] = sum_k a[k*lda + i] * (scale ? scale[k] : 1) * b[k*ldb + j];  i < Ma, j < Nb. 64x64 tile, 4x4 per thread.
-// Only used to re-derive the folded ResiDual projection when lambda changes (C^3 flops, off the per-clip path).
-template <bool OUT_BF16>
-__global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
-                                                      const float* __restrict__ scale, void* __restrict__ out, int ldo, int Ma, int Nb,
-                                                      int K) {
-    __shared__ float As[16][64 + 4];
-    __shared__ float Bs[16][64 + 4];
+// out_z[i][j] = sum_k a[k*lda + i] * (scale ? scale[k] : 1) * b_z[k*ldb + j];  i < Ma, j < Nb, z = blockIdx.z (up to 8 right-hand
+// sides share `a`: the blocks of a layer share one ResiDual, so W'_b = M Wp_b for every block b is ONE launch).
+// 64x64 tile, 4x4 per thread, 16-deep k-tiles double-buffered through registers (one __syncthreads per k-tile), 16-byte
+// shared-memory reads. Only used to re-derive the folded ResiDual projection when lambda changes: C^3 flops per block, off the
+// per-clip path, but once per training step - 3.6 GFLOP per step for HTSAT-tiny, all layers patched.
+struct FoldBatch {
+    const float* b[8];
+    float* out_f32[8];          // either may be null
+    __nv_bfloat16* out_bf16[8];
+};
+__global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__ a, int lda, FoldBatch fb, int ldb,
+                                                      const float* __restrict__ scale, int ldo, int Ma, int Nb, int K) {
+    __shared__ __align__(16) float As[2][16][64];
+    __shared__ __align__(16) float Bs[2][16][64];
+    const float* __restrict__ b = fb.b[blockIdx.z];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
-    float acc[4][4] = {};
-    for (int k0 = 0; k0 < K; k0 += 16) {
-        for (int t = threadIdx.x; t < 16 * 64; t += 256) {
-            const int kk = t >> 6, c = t & 63;
-            const int k = k0 + kk;
-            float av = 0.f, bv = 0.f;
-            if (k < K) {
-                if (i0 + c < Ma) av = a[(long long)k * lda + i0 + c] * (scale ? scale[k] : 1.0f);
-                if (j0 + c < Nb) bv = b[(long long)k * ldb + j0 + c];
+    const int lk = threadIdx.x >> 4, lc = (threadIdx.x & 15) * 4;   // this thread's float4 of a k-tile: row lk, columns lc..lc+3
+    const bool a_ok = i0 + lc < Ma, b_ok = j0 + lc < Nb;            // Ma, Nb, lda, ldb are multiples of 4 (checked by the launcher)
+    auto fetch = [&](int k0, float4& av, float4& bv) {
+        const int k = k0 + lk;
+        av = make_float4(0.f, 0.f, 0.f, 0.f);
+        bv = av;
+        if (k < K) {
+            if (a_ok) {
+                av = *reinterpret_cast<const float4*>(a + (long long)k * lda + i0 + lc);
+                if (scale != nullptr) { const float sc = scale[k]; av.x *= sc; av.y *= sc; av.z *= sc; av.w *= sc; }
             }
-            As[kk][c] = av;
-            Bs[kk][c] = bv;
+            if (b_ok) bv = *reinterpret_cast<const float4*>(b + (long long)k * ldb + j0 + lc);
         }
-        __syncthreads();
+    };
+    float acc[4][4] = {};
+    float4 av, bv;
+    fetch(0, av, bv);
+    *reinterpret_cast<float4*>(&As[0][lk][lc]) = av;
+    *reinterpret_cast<float4*>(&Bs[0][lk][lc]) = bv;
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        const bool more = k0 + 16 < K;
+        if (more) fetch(k0 + 16, av, bv);
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) {
-            float ar[4], br[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                ar[r] = As[kk][ty * 4 + r];
-                br[r] = Bs[kk][tx * 4 + r];
-            }
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            const float ar[4] = {a4.x, a4.y, a4.z, a4.w}, br[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(ar[r], br[c], acc[r][c]);
         }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int i = i0 + ty * 4 + r, j = j0 + tx * 4 + c;
-            if (i < Ma && j < Nb) {
-                if constexpr (OUT_BF16)
-                    reinterpret_cast<__nv_bfloat16*>(out)[(long long)i * ldo + j] = __float2bfloat16_rn(acc[r][c]);
-                else
-                    reinterpret_cast<float*>(out)[(long long)i * ldo + j] = acc[r][c];
-            }
+        if (more) {
+            *reinterpret_cast<float4*>(&As[buf ^ 1][lk][lc]) = av;
+            *reinterpret_cast<float4*>(&Bs[buf ^ 1][lk][lc]) = bv;
         }
+        __syncthreads();
+        buf ^= 1;
+    }
+    float* of = fb.out_f32[blockIdx.z];
+    __nv_bfloat16* ob = fb.out_bf16[blockIdx.z];
+    const int j = j0 + tx * 4;
+    if (j >= Nb) return;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + ty * 4 + r;
+        if (i >= Ma) break;
+        if (of != nullptr) *reinterpret_cast<float4*>(of + (long long)i * ldo + j) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        if (ob != nullptr) {
+            uint2 pk;
+            pk.x = pack_bf16x2(acc[r][0], acc[r][1]);
+            pk.y = pack_bf16x2(acc[r][2], acc[r][3]);
+            *reinterpret_cast<uint2*>(ob + (long long)i * ldo + j) = pk;
+        }
+    }
 }
 
-static int sgemm_tn(const float* a, int lda, const float* b, int ldb, const float* scale, void* out, int ldo, bool out_bf16, int Ma, int Nb,
-                    int K, cudaStream_t s) {
-    dim3 grid((Nb + 63) / 64, (Ma + 63) / 64);
-    ProfScope ps(PROF_OTHER, s, 2.0 * Ma * Nb * K, 4.0 * ((double)Ma * K + (double)Nb * K + (double)Ma * Nb));
-    if (out_bf16)
-        sgemm_tn_kernel<true><<<grid, 256, 0, s>>>(a, lda, b, ldb, scale, out, ldo, Ma, Nb, K);
-    else
-        sgemm_tn_kernel<false><<<grid, 256, 0, s>>>(a, lda, b, ldb, scale, out, ldo, Ma, Nb, K);
+static int sgemm_tn(const float* a, int lda, const FoldBatch& fb, int nbatch, int ldb, const float* scale, int ldo, int Ma, int Nb, int K,
+                    cudaStream_t s) {
+    if ((Ma | Nb | lda | ldb | ldo) & 3) return set_error(ARD_ERR_SHAPE, "sgemm_tn: extents must be multiples of 4 (got %d x %d)", Ma, Nb);
+    if (nbatch < 1 || nbatch > 8) return set_error(ARD_ERR_SHAPE, "sgemm_tn: batch of %d", nbatch);
+    dim3 grid((Nb + 63) / 64, (Ma + 63) / 64, nbatch);
+    ProfScope ps(PROF_OTHER, s, 2.0 * Ma * Nb * K * nbatch, 4.0 * ((double)Ma * K + ((double)Nb * K + (double)Ma * Nb) * nbatch));
+    sgemm_tn_kernel<<<grid, 256, 0, s>>>(a, lda, fb, ldb, scale, ldo, Ma, Nb, K);
     return check_cuda(cudaGetLastError(), "sgemm_tn launch");
+}
+
+// b'_z[j] = sum_c d_z[c] M[c][j]   (the folded bias of up to 8 blocks sharing M): grid (C / 64, nbatch), 4 c-slices per column
+struct FoldBiasBatch {
+    const float* d[8];
+    float* out[8];
+};
+__global__ void __launch_bounds__(256) fold_bias_kernel(FoldBiasBatch fb, const float* __restrict__ M, int C) {
+    __shared__ float part[4][64];
+    const float* __restrict__ d = fb.d[blockIdx.y];
+    const int jj = threadIdx.x & 63, cs = threadIdx.x >> 6;
+    const int j = blockIdx.x * 64 + jj;
+    float acc = 0.f;
+    if (j < C) {
+#pragma unroll 4
+        for (int c = cs; c < C; c += 4) acc = fmaf(d[c], M[(long long)c * C + j], acc);
+    }
+    part[cs][jj] = acc;
+    __syncthreads();
+    if (cs == 0 && j < C) fb.out[blockIdx.y][j] = (part[0][jj] + part[1][jj]) + (part[2][jj] + part[3][jj]);
 }
 
 // ResiDual (src/residual.py:37-42) applied to y = x Wp^T + bp:   r = ((y - mu) B^T * lambda) B = x (M Wp)^T + (bp - mu) M
 // with M = B^T diag(lambda) B (symmetric).  Inputs: proj_w [C,C] fp32, dmean = bp - mu [C], basis [K,C], lam [K].
 int residual_matrix(const float* basis, const float* lam, int C, int K, float* M, cudaStream_t s) {
-    return sgemm_tn(basis, C, basis, C, lam, M, C, false, C, C, K, s);               // M[i][j] = sum_k B[k][i] lam[k] B[k][j]
+    FoldBatch fb = {};
+    fb.b[0] = basis; fb.out_f32[0] = M;
+    return sgemm_tn(basis, C, fb, 1, C, lam, C, C, C, K, s);                         // M[i][j] = sum_k B[k][i] lam[k] B[k][j]
+}
+// One ResiDual shared by `nb` blocks of a layer (src/residual.py:170-186 builds one per layer): M once, then every block's
+// W'_b = M Wp_b (fp32 and / or bf16 copies) and b'_b = (bp_b - mu) M in one launch each.
+int residual_fold_batch(const float* const* proj_w, const float* const* dmean, const float* basis, const float* lam, int C, int K, float* Mtmp,
+                        __nv_bfloat16* const* w_out, float* const* b_out, float* const* w_out_f32, int nb, cudaStream_t s) {
+    if (nb < 1 || nb > 8) return set_error(ARD_ERR_SHAPE, "residual_fold_batch: %d blocks", nb);
+    ARD_TRY(residual_matrix(basis, lam, C, K, Mtmp, s));
+    FoldBatch fb = {};
+    FoldBiasBatch bb = {};
+    for (int z = 0; z < nb; ++z) {
+        fb.b[z] = proj_w[z];
+        fb.out_bf16[z] = w_out[z];
+        fb.out_f32[z] = w_out_f32 ? w_out_f32[z] : nullptr;   // the fp32-grade mode splits the fp32 fold into bf16 terms
+        bb.d[z] = dmean[z];
+        bb.out[z] = b_out[z];
+    }
+    ARD_TRY(sgemm_tn(Mtmp, C, fb, nb, C, nullptr, C, C, C, C, s));                   // W'[i][j] = sum_c M[c][i] Wp[c][j]
+    fold_bias_kernel<<<dim3((C + 63) / 64, nb), 256, 0, s>>>(bb, Mtmp, C);           // b'[j] = sum_c (bp-mu)[c] M[c][j]
+    return check_cuda(cudaGetLastError(), "fold_bias launch");
 }
 int residual_fold(const float* proj_w, const float* dmean, const float* basis, const float* lam, int C, int K, float* Mtmp,
                   __nv_bfloat16* w_out, float* b_out, cudaStream_t s, float* w_out_f32) {
-    ARD_TRY(residual_matrix(basis, lam, C, K, Mtmp, s));
-    if (w_out_f32 != nullptr) {   // keep the fp32 fold too (the fp32-grade mode splits it into bf16 terms); bf16(acc) is unchanged
-        ARD_TRY(sgemm_tn(Mtmp, C, proj_w, C, nullptr, w_out_f32, C, false, C, C, C, s));
-        ARD_TRY(f32_to_bf16(w_out_f32, w_out, (long long)C * C, 1.0f, s));
-    } else {
-        ARD_TRY(sgemm_tn(Mtmp, C, proj_w, C, nullptr, w_out, C, true, C, C, C, s));  // W'[i][j] = sum_c M[c][i] Wp[c][j]
-    }
-    ARD_TRY(sgemm_tn(dmean, 1, Mtmp, C, nullptr, b_out, C, false, 1, C, C, s));      // b'[j] = sum_c (bp-mu)[c] M[c][j]
-    return 0;
+    return residual_fold_batch(&proj_w, &dmean, basis, lam, C, K, Mtmp, &w_out, &b_out, w_out_f32 ? &w_out_f32 : nullptr, 1, s);
 }
 
 // ------------------------------------------------------------------------------------------------ token-semantic head

@@ -286,6 +286,7 @@ class HTSAT_Swin_Transformer(nn.Module):
     def _sync_residuals(self, lib):
         hb, dev = self._hb, self._device()
         for l, layer in enumerate(self.layers):
+            stale = []   # patched blocks whose folded projection must be re-derived: (block index, ResiDual, basis signature, lambda signature)
             for b, blk in enumerate(layer.blocks):
                 res = blk._residual
                 key = (l, b)
@@ -303,10 +304,23 @@ class HTSAT_Swin_Transformer(nn.Module):
                     L.check(lib.ard_set_block_residual(hb.h, l, b, L.ptr(mean), L.ptr(basis), basis.shape[0], basis.shape[1]))
                     old = None
                 if old is None or old[1] != lsig:
-                    lam = res.learnable.detach().to(dev, torch.float32).contiguous()   # reference re-copies per call (Q4)
+                    stale.append((b, res, bsig, lsig))
+            if not stale:
+                continue
+            patched = [blk._residual for blk in layer.blocks if blk._residual is not None]
+            shared = len(stale) == len(patched) and len(patched) > 1 and all(r is patched[0] for r in patched)
+            if shared:
+                # one ResiDual per layer shared by its blocks (src/residual.py:170-186): M once, the blocks' folds batched
+                res = patched[0]
+                lam = res.learnable.detach().to(dev, torch.float32).contiguous()   # reference re-copies per call (Q4)
+                L.check(lib.ard_set_layer_lambda(hb.h, l, L.ptr(lam), L.stream_ptr()))
+                res._lam_dev = lam
+            for b, res, bsig, lsig in stale:
+                if not shared:
+                    lam = res.learnable.detach().to(dev, torch.float32).contiguous()
                     L.check(lib.ard_set_block_lambda(hb.h, l, b, L.ptr(lam), L.stream_ptr()))
                     res._lam_dev = lam
-                hb.res_sig[key] = (bsig, lsig)
+                hb.res_sig[(l, b)] = (bsig, lsig)
 
     # ------------------------------------------------------------------ compute
     def _block_forward(self, blk, x):

@@ -66,6 +66,7 @@ def load(check_symbols=False):
         lib.ard_set_block_residual.argtypes = [vp, i, i, vp, vp, i, i]
         lib.ard_clear_block_residual.argtypes = [vp, i, i]
         lib.ard_set_block_lambda.argtypes = [vp, i, i, vp, vp]
+        lib.ard_set_layer_lambda.argtypes = [vp, i, vp, vp]
         lib.ard_encoder_forward.argtypes = [vp, C.POINTER(ArdForwardArgs), vp]
         lib.ard_encoder_backward.argtypes = [vp, C.POINTER(ArdBackwardArgs), vp]
         lib.ard_block_forward.argtypes = [vp, i, i, vp, i, vp, vp, vp, vp]
@@ -73,6 +74,7 @@ def load(check_symbols=False):
         lib.ard_workspace_bytes.argtypes = [vp]
         lib.ard_last_launch_count.argtypes = [vp]
         lib.ard_gemm_bf16.argtypes = [vp, ll, vp, ll, vp, ll, i, i, i, i, vp, i, vp, ll, vp, ll, vp]
+        lib.ard_gemm_dual.argtypes = [i, vp, ll, vp, ll, vp, ll, vp, ll, vp, ll, i, i, i, vp, vp, vp, i, vp]
         lib.ard_gemm_f16.argtypes = [vp, ll, vp, ll, vp, ll, i, i, i, i, vp, i, vp, ll, vp, ll, vp]
         lib.ard_layernorm_bf16.argtypes = [vp, vp, vp, vp, ll, i, vp]
         lib.ard_ffn_fused_96.argtypes = [vp, vp, vp, ll, vp, vp, vp, vp, vp, vp, vp]

@@ -79,6 +79,10 @@ int ard_clear_block_residual(ard_handle* h, int layer, int block);
 /* lambda = ResiDual.learnable [K] (src/residual.py:27), float32 DEVICE pointer; re-derives the fused
  * projection  W' = M W_proj, b' = (b_proj - mean) M  with  M = B^T diag(lambda) B. */
 int ard_set_block_lambda(ard_handle* h, int layer, int block, const float* lambda_dev, void* stream);
+/* Same for every patched block of `layer` at once, when they share one ResiDual as setup_residual_htsat builds them
+ * (src/residual.py:170-186: one ResiDual per layer, patched into each of its blocks): M is formed once per layer and the
+ * blocks' folds run batched. ARD_ERR_STATE if the blocks carry different bases / means (then set them block by block). */
+int ard_set_layer_lambda(ard_handle* h, int layer, const float* lambda_dev, void* stream);
 
 typedef struct ard_forward_args {
     const float* waveform;   /* device [B, 480000] fp32 (non-fusion route) */
@@ -149,6 +153,14 @@ long long ard_launch_counter_read(void);
 /* out[M,N] = act(A[M,K] W[N,K]^T + bias) (+ resid1 + resid2); A, W bf16 device; out bf16 or fp32.  nn.Linear semantics. */
 int ard_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int out_is_bf16, int M, int N,
                   int K, const float* bias, int act, const float* resid1, long long ldr1, const float* resid2, long long ldr2,
+                  void* stream);
+/* Two contractions of one shape meeting in the epilogue (training backward; bf16 operands, bf16 [M,N] output):
+ *   acc1 = A1[M,K] W1[N,K]^T, acc2 = A2[M,K] W2[N,K]^T
+ *   mode 0: out = acc1 * gelu'(acc2 + vec1)   - FFN backward dh = (g W2) * gelu'(fc1(norm2(x))), autograd of Mlp htsat.py:146-164
+ *   mode 1: dlam[n] += sum_m (acc1 + vec1) * acc2 for n < Kvalid, out = acc2 * vec2[n]
+ *           - ResiDual backward, autograd of src/residual.py:37-40: coef = x_proj, acc2 = dL/d x_scaled, vec2 = learnable */
+int ard_gemm_dual(int mode, const void* A1, long long lda1, const void* W1, long long ldw1, const void* A2, long long lda2, const void* W2,
+                  long long ldw2, void* out, long long ldo, int M, int N, int K, const float* vec1, const float* vec2, float* dlam, int Kvalid,
                   void* stream);
 /* Same contraction with fp16 A and W operands (fp32 accumulation): the fc2 GEMM, whose input is the fp16 GELU output. */
 int ard_gemm_f16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int out_is_bf16, int M, int N,

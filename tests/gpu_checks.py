@@ -77,6 +77,36 @@ def check_gemm(M, N, K, out_bf16, act=0, bias=True, nres=0, seed=0):
     return rel(got, ref), (got - ref).abs().max().item()
 
 
+def check_gemm_dual(mode, M, N, K, Kvalid=None, seed=0):
+    """ard_gemm_dual vs torch fp32 on bf16-rounded operands. mode 0: out = (A1 W1^T) * gelu'(A2 W2^T + b); mode 1: dlam += colsum((A1 W1^T + c0)
+    * (A2 W2^T)), out = (A2 W2^T) * lam. Returns (rel err of out, rel err of dlam or 0)."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(seed)
+    A1, A2 = torch.randn(M, K, generator=g), torch.randn(M, K, generator=g)
+    W1, W2 = torch.randn(N, K, generator=g) / K ** 0.5, 1.5 * torch.randn(N, K, generator=g) / K ** 0.5
+    v1, v2 = 0.3 * torch.randn(N, generator=g), 1 + 0.2 * torch.randn(N, generator=g)
+    Kvalid = N if Kvalid is None else Kvalid
+    acc1, acc2 = bf16r(A1) @ bf16r(W1).t(), bf16r(A2) @ bf16r(W2).t()
+    d = lambda t: t.cuda().contiguous()   # noqa: E731
+    A1d, A2d, W1d, W2d = (d(t).to(torch.bfloat16) for t in (A1, A2, W1, W2))
+    v1d, v2d = d(v1), d(v2)
+    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    dlam = torch.full((Kvalid,), 0.5, device="cuda")   # accumulated into
+    if mode == 0:
+        h = (acc2 + v1).double()
+        gd = 0.5 * (1 + torch.erf(h / 2 ** 0.5)) + h * torch.exp(-h * h / 2) / (2 * torch.pi) ** 0.5
+        ref, ref_dl = acc1 * gd.float(), None
+    else:
+        ref = acc2 * v2
+        ref_dl = ((acc1 + v1).double() * acc2.double()).sum(0)[:Kvalid].float() + 0.5
+    L.check(lib.ard_gemm_dual(mode, L.ptr(A1d), K, L.ptr(W1d), K, L.ptr(A2d), K, L.ptr(W2d), K, L.ptr(out), N, M, N, K, L.ptr(v1d), L.ptr(v2d),
+                              L.ptr(dlam) if mode == 1 else None, Kvalid, L.stream_ptr()))
+    torch.cuda.synchronize()
+    r_out = rel(out.float().cpu(), ref)
+    r_dl = rel(dlam.cpu(), ref_dl) if mode == 1 else 0.0
+    return r_out, r_dl
+
+
 def check_ffn_fused(M=5000, resid2=True, seed=0, Cd=96, alias=False):
     """ard_ffn_fused_96 / ard_ffn_fused_wide (LN + fc1 + GELU + fc2 + residuals in one kernel) vs torch fp32 on bf16/fp16-rounded
     weights. `alias`: the output overwrites x (how the forward schedule calls it)."""

@@ -478,3 +478,40 @@ def test_evaluation_and_training_drivers_end_to_end(tmp_path):
     train_and_eval_linear_head(clap2, "SYN", folds, 50, out, lr=0.01, epochs=1)
     lin = np.load(os.path.join(out, "SYN", "Linear", "evalfold_0.npz"))
     assert lin["similarities"].shape == (3, 50) and abs(lin["similarities"].sum(1) - 1).max() < 1e-5   # softmax scores (src/linear.py:120)
+
+
+# ------------------------------------------------------------------------------------------------ per-layer batched lambda fold
+def test_layer_lambda_fold_matches_per_block_fold():
+    """ard_set_layer_lambda (M once per layer, the blocks' folds batched) against ard_set_block_lambda block by block: the same
+    kernels on the same numbers, so the embeddings are bit-identical; blocks with different bases are refused."""
+    import copy
+    from audio_residual_b200.residual import patch_block_with_residual
+    wave = W.make_clips(2, seed=77).cuda()
+    clap_a, _, _ = G.make_encoder("tiny", residual=True)                  # one ResiDual object per layer -> ard_set_layer_lambda
+    clap_b, _, _ = G.make_encoder("tiny", residual=True)
+    enc_b = clap_b.model.audio_branch
+    for layer in enc_b.layers:                                            # equal but distinct objects per block -> ard_set_block_lambda
+        for blk in layer.blocks:
+            patch_block_with_residual(blk, copy.deepcopy(blk._residual))
+    with torch.no_grad():
+        ea = clap_a.get_audio_embedding_from_data(wave, use_tensor=True)
+        eb = clap_b.get_audio_embedding_from_data(wave, use_tensor=True)
+    assert torch.equal(ea, eb)
+    # a lambda update reaches every block of the layer through the batched fold
+    with torch.no_grad():
+        for ca in (clap_a, clap_b):
+            for layer in ca.model.audio_branch.layers:
+                for blk in layer.blocks:
+                    blk._residual.learnable.mul_(1.25)
+                    if ca is clap_a:
+                        break                                            # shared object: scale once
+        ea2 = clap_a.get_audio_embedding_from_data(wave, use_tensor=True)
+        eb2 = clap_b.get_audio_embedding_from_data(wave, use_tensor=True)
+    assert torch.equal(ea2, eb2) and not torch.equal(ea, ea2)
+    lib = L.load()
+    lam = torch.ones(384, device="cuda")
+    h = enc_b._handle()
+    basis = torch.linalg.qr(torch.randn(384, 384))[0].contiguous()
+    mean = torch.zeros(384)
+    L.check(lib.ard_set_block_residual(h, 2, 1, L.ptr(mean), L.ptr(basis), 384, 384))
+    assert lib.ard_set_layer_lambda(h, 2, L.ptr(lam), L.stream_ptr()) == L.ARD_ERR_STATE

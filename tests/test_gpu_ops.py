@@ -50,6 +50,23 @@ def test_ln_qkv_96(M):
     assert G.check_ln_qkv(M) < 4e-3, M          # bf16 output rounding (2^-9) on top of bf16 operands
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 384, 96), (4096 + 64, 384, 96), (3000, 768, 192), (20000, 1536, 384), (640, 512, 128)])
+def test_gemm_dual_gelu_backward(M, N, K):
+    """dh = (g W2) * gelu'(fc1(norm2(x)) + b1) in one kernel (FFN backward): packed-fp16 gelu' (fit error 1.2e-4, fp16 evaluation
+    4e-4) on top of the bf16 output rounding."""
+    r, _ = G.check_gemm_dual(0, M, N, K)
+    assert r < 4e-3, r
+
+
+@pytest.mark.parametrize("M,N,K,Kvalid", [(4096, 96, 96, 96), (4096 + 64, 48, 96, 40), (3000, 192, 192, 192), (2048, 384, 384, 384),
+                                          (1100, 768, 768, 768), (200000, 96, 96, 96)])
+def test_gemm_dual_lambda_gradient(M, N, K, Kvalid):
+    """ResiDual backward: dlam += colsum(x_proj * dL/d x_scaled) reduced in the kernel (registers -> shared -> one atomic per column
+    per CTA), gsc = gcoef * lambda as the bf16 output. N = component count padded to 16, Kvalid = the real one."""
+    r_out, r_dl = G.check_gemm_dual(1, M, N, K, Kvalid)
+    assert r_out < 4e-3 and r_dl < 1e-4, (r_out, r_dl)
+
+
 def test_gemm_f16_hidden_chain():
     r_h, r_out = G.check_gemm_f16_chain()
     assert r_h < 1e-3 and r_out < 2e-3, (r_h, r_out)                # fp16 hidden: 10-bit mantissa

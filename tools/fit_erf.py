@@ -84,3 +84,49 @@ if __name__ == "__main__" and "--tanh" in __import__("sys").argv:
     c, e_erf, e_gelu = fit_tanh()
     print("tanh form: coeffs", c, "max|erf err| %.2e max|gelu err| %.2e" % (e_erf, e_gelu))
     print("fp16 evaluation rel l2 error: %.3e (exact tanh), %.3e (MUFU noise 2^-11)" % (emulate_f16(c, 0.0), emulate_f16(c)))
+
+
+# ------------------------------------------------------------------------------------------------ packed-fp16 gelu' (--grad)
+def fit_grad():
+    """gelu_erf_grad_bf16x2 in csrc/ard_common.cuh:  gelu'(x) = 1/2 + t/2 + (1 - t^2) x (d0 + d1 x^2) / 2,  t = tanh(x (c0 + c1 x^2)),
+    the four constants fitted (iteratively re-weighted least squares -> near-minimax) to the exact Phi(x) + x phi(x)."""
+    from scipy.optimize import least_squares
+    x = np.linspace(-8, 8, 400001)
+    exact = 0.5 * (1 + erf(x / np.sqrt(2))) + x * np.exp(-x * x / 2) / np.sqrt(2 * np.pi)
+
+    def model(c):
+        x2 = x * x
+        t = np.tanh(x * (c[0] + c[1] * x2))
+        return 0.5 + 0.5 * t + 0.5 * (1 - t * t) * x * (c[2] + c[3] * x2)
+    c = np.array([0.80015708, 0.03470089, 0.80015708, 3 * 0.03470089])
+    w = np.ones_like(x)
+    for _ in range(30):
+        c = least_squares(lambda cc: (model(cc) - exact) * w, c, xtol=1e-15, ftol=1e-15).x
+        e = np.abs(model(c) - exact)
+        w = w * (1 + 2 * e / e.max())
+        w /= w.mean()
+    return c, np.abs(model(c) - exact).max()
+
+
+def emulate_grad_f16(c, n=2_000_000, sigma=1.5):
+    import torch
+    h = np.float16
+    xs = np.random.default_rng(0).normal(0, sigma, n)
+    xb = torch.tensor(xs, dtype=torch.float32).bfloat16().double().numpy()   # hpre is stored as bf16
+    ex = lambda v: 0.5 * (1 + erf(v / np.sqrt(2))) + v * np.exp(-v * v / 2) / np.sqrt(2 * np.pi)   # noqa: E731
+    x = xb.astype(h)
+    x2 = np.minimum((x * x).astype(h), h(64))
+    u = (x * (h(c[1]) * x2 + h(c[0])).astype(h)).astype(h)
+    t = np.tanh(u.astype(np.float64)).astype(h)
+    wv = (x * (h(0.5 * c[3]) * x2 + h(0.5 * c[2])).astype(h)).astype(h)
+    s = (h(1) - (t * t).astype(h)).astype(h)
+    r = (t * h(0.5) + h(0.5)).astype(h)
+    g = ((s * wv).astype(h) + r).astype(h).astype(np.float64)
+    return (np.linalg.norm(g - ex(xb)) / np.linalg.norm(ex(xb)), np.abs(g - ex(xb)).max(),
+            np.linalg.norm(ex(xb) - ex(xs)) / np.linalg.norm(ex(xs)))
+
+
+if __name__ == "__main__" and "--grad" in __import__("sys").argv:
+    c, e = fit_grad()
+    print("gelu' tanh-derivative form: c0 c1 d0 d1 =", c, "max |error| %.2e" % e)
+    print("fp16 evaluation on bf16 inputs: rel l2 %.3e, max abs %.2e; bf16 rounding of the input alone: rel l2 %.3e" % emulate_grad_f16(c))
