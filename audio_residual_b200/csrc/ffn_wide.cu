@@ -39,40 +39,44 @@ constexpr int FW_EPI_WARPS = 8;
 constexpr int FW_GELU_WARPS = 16;
 constexpr int FW_W_MMA = FW_EPI_WARPS, FW_W_TMA = FW_W_MMA + 1, FW_W_GELU = FW_W_TMA + 1, FW_W_MMA2 = FW_W_GELU + FW_GELU_WARPS;
 constexpr int FW_THREADS = (FW_W_MMA2 + 1) * 32;   // 864
-constexpr int FW_SLOT = 24576;                     // ring slot: 3 k-blocks of W1 [64 x 64] or one W2 block [192 x 64], 16-bit
 constexpr int FW_TM_H = 384;                       // TMEM columns: Y (C, or 2 x 192) from 0, H0 / H1 at 384 / 448
 
 template <int C>
 struct FwCfg {
-    static_assert(C == 192 || C == 384, "ffn_wide: C = 192 or 384");
+    static_assert(C == 128 || C == 192 || C == 256 || C == 384, "ffn_wide: C = 128, 192, 256 or 384");
     static constexpr int HD = 4 * C;
-    static constexpr int NCH = HD / 64;              // hidden chunks per tile (12 / 24)
-    static constexpr int NS = C / 192;               // slots per ring entry (1 / 2)
-    static constexpr int KB1 = C / 64;               // fc1 k-blocks (3 / 6)
+    static constexpr int NCH = HD / 64;              // hidden chunks per tile (8 / 12 / 16 / 24)
+    // Ring slot = one YW-wide piece of the channel axis: KBS k-blocks of a W1 chunk [64 x 64 each] or one W2 block [YW x 64].
+    // YW is also the N of the fc2 MMAs. 192 for the HTSAT-tiny widths (192, 384 = 2 x 192); the HTSAT-base widths 128 / 256 are one piece.
+    static constexpr int YW = (C % 192 == 0) ? 192 : C;
+    static constexpr int KBS = YW / 64;              // k-blocks per slot (2 / 3 / 4)
+    static constexpr int SLOT = YW * 128;            // bytes: 16 / 24 / 32 KB
+    static constexpr int NS = C / YW;                // slots per ring entry (2 at C = 384, else 1)
+    static constexpr int KB1 = C / 64;               // fc1 k-blocks
     static constexpr int NYB = 1;                    // Y accumulators
     // C = 192: the GELU output reaches fc2 through TENSOR MEMORY (A operand from TMEM; Y 0-191, A2 192-255, H 384-511) and the
     // 32 KB of shared memory that held the A2 tiles hold the TMA-prefetched residual tiles of the epilogue instead (see
     // ffn_fused.cu: 372 -> 251 us there). At C = 384, Y + H fill all 512 TMEM columns: A2 and the residual loads stay as before.
-    static constexpr bool A2T = C == 192;
-    static constexpr int TM_A2 = 192;
+    static constexpr bool A2T = C <= 256;            // Y 0..C-1, A2 C..C+63, H 384-511
+    static constexpr int TM_A2 = C;
     // LayerNorm operand buffers / ring slots. Measured at C = 192 (B = 256, M = 262144): one A1 buffer + 5 slots 249 us, two A1
     // buffers (next tile's LayerNorm overlapped) + 3 slots 277 us: the ring depth is worth more than the overlap.
     static constexpr int NA1 = 1;
-    static constexpr int NSLOT = C == 192 ? 5 : 3;
+    static constexpr int NSLOT = C == 128 ? 8 : C == 192 ? 5 : 3;
     static constexpr int A1_KB = FW_BM * 128;        // 16384 bytes per 64-wide k-block of A1
     static constexpr int A1_OFF = 0;
     static constexpr int A1_BYTES = KB1 * A1_KB;
     static constexpr int A2_OFF = A1_OFF + NA1 * A1_BYTES;
     static constexpr int A2_BYTES = FW_BM * 128;     // 16384 per buffer
     static constexpr int RING_OFF = A2_OFF + 2 * A2_BYTES;
-    static constexpr int CST_OFF = RING_OFF + NSLOT * FW_SLOT;   // 8 warps x (32 rows x 64 B)
+    static constexpr int CST_OFF = RING_OFF + NSLOT * SLOT;   // 8 warps x (32 rows x 64 B)
     static constexpr int VEC_OFF = CST_OFF + FW_EPI_WARPS * 2048;   // b2[C] gamma[C] beta[C]
     static constexpr int BAR_OFF = VEC_OFF + 3 * C * 4;
-    static constexpr int SMEM_BYTES = BAR_OFF + 320 + 1024;
+    static constexpr int SMEM_BYTES = BAR_OFF + 384 + 1024;
     static_assert(SMEM_BYTES <= 227 * 1024, "ffn_wide: shared memory budget");
     static constexpr int LN_CH = C / 16;             // channels per lane in the LayerNorm mapping (16 lanes per row)
     static constexpr int LN_V4 = LN_CH / 4;          // float4 per lane per row (3 / 6)
-    static constexpr int LN_STEPS = 48 / LN_CH;      // row-pairs held in registers at once (4 / 2): 48 fp32 registers
+    static constexpr int LN_STEPS = LN_CH <= 12 ? 4 : 2;   // row-pairs held in registers at once (of the warp's 4): 32-48 fp32 registers
 };
 
 struct FwParams {
@@ -98,18 +102,18 @@ ffn_wide_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
     float* gs = b2s + C;
     float* bs = gs + C;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
-    uint64_t* ring_full = bars + 0;     // [5]
-    uint64_t* ring_empty = bars + 5;    // [5]
-    uint64_t* a1_full = bars + 10;      // [2]
-    uint64_t* a1_free = bars + 12;      // [2]
-    uint64_t* h_full = bars + 14;       // [2]
-    uint64_t* h_free = bars + 16;       // [2]
-    uint64_t* a2_full = bars + 18;      // [2]
-    uint64_t* a2_free = bars + 20;      // [2]
-    uint64_t* y_full = bars + 22;       // [2]
-    uint64_t* y_free = bars + 24;       // [2]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 26);
-    uint64_t* rbar = bars + 28;         // [8] residual tiles landed (one per epilogue warp)
+    uint64_t* ring_full = bars + 0;     // [8]
+    uint64_t* ring_empty = bars + 8;    // [8]
+    uint64_t* a1_full = bars + 16;      // [2]
+    uint64_t* a1_free = bars + 18;      // [2]
+    uint64_t* h_full = bars + 20;       // [2]
+    uint64_t* h_free = bars + 22;       // [2]
+    uint64_t* a2_full = bars + 24;      // [2]
+    uint64_t* a2_free = bars + 26;      // [2]
+    uint64_t* y_full = bars + 28;       // [2]
+    uint64_t* y_free = bars + 30;       // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 32);
+    uint64_t* rbar = bars + 34;         // [8] residual tiles landed (one per epilogue warp)
 
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -304,14 +308,14 @@ ffn_wide_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
                     mbar_wait_parked(&ring_empty[slot], par ^ 1);
                     if (lane == 0) FW_TRACE(6, (int)n, 1);
                     if (elect_one_sync()) {
-                        uint8_t* dst = smem + Cfg::RING_OFF + slot * FW_SLOT;
-                        mbar_expect_tx(&ring_full[slot], FW_SLOT);
+                        uint8_t* dst = smem + Cfg::RING_OFF + slot * Cfg::SLOT;
+                        mbar_expect_tx(&ring_full[slot], Cfg::SLOT);
                         if (is_w2) {
-                            tma_load_2d(dst, &tmW2, &ring_full[slot], j * 64, s * 192);              // W2[192 s.., 64 j..]
+                            tma_load_2d(dst, &tmW2, &ring_full[slot], j * 64, s * Cfg::YW);          // W2[YW s.., 64 j..]
                         } else {
 #pragma unroll
-                            for (int kb = 0; kb < 3; ++kb)                                           // W1[64 j.., 192 s + 64 kb..]
-                                tma_load_2d(dst + kb * 8192, &tmW1, &ring_full[slot], s * 192 + kb * 64, j * 64);
+                            for (int kb = 0; kb < Cfg::KBS; ++kb)                                    // W1[64 j.., YW s + 64 kb..]
+                                tma_load_2d(dst + kb * 8192, &tmW1, &ring_full[slot], s * Cfg::YW + kb * 64, j * 64);
                         }
                     }
                     __syncwarp();
@@ -344,10 +348,10 @@ ffn_wide_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
                     tc_fence_after();
                     if (elect_one_sync()) {
                         const uint32_t d = tmem_base + FW_TM_H + hb * 64;
-                        const uint64_t db = umma_desc_sw128(ring_u32 + slot * FW_SLOT);
+                        const uint64_t db = umma_desc_sw128(ring_u32 + slot * Cfg::SLOT);
 #pragma unroll
-                        for (int kb = 0; kb < 3; ++kb)       // descriptor start-address field is in 16-byte units
-                            umma_f16_ss_run<4>(d, dA1 + (uint64_t)((ab * Cfg::KB1 + s * 3 + kb) * (Cfg::A1_KB >> 4)), db + (uint64_t)(kb * (8192 >> 4)), idesc1,
+                        for (int kb = 0; kb < Cfg::KBS; ++kb)   // descriptor start-address field is in 16-byte units
+                            umma_f16_ss_run<4>(d, dA1 + (uint64_t)((ab * Cfg::KB1 + s * Cfg::KBS + kb) * (Cfg::A1_KB >> 4)), db + (uint64_t)(kb * (8192 >> 4)), idesc1,
                                                (s | kb) != 0);
                         umma_commit(&ring_empty[slot]);
                         if (s == NS - 1) {
@@ -362,7 +366,7 @@ ffn_wide_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
         }
     } else if (warp == FW_W_MMA2) {
         // ============================================================ fc2 MMA issue: Y[:, 192 s..] += A2_j W2[192 s.., 64 j..]^T
-        constexpr uint32_t idesc2 = umma_idesc_f16(FW_BM, 192);   // A2 (GELU output) and W2 are fp16
+        constexpr uint32_t idesc2 = umma_idesc_f16(FW_BM, Cfg::YW);   // A2 (GELU output) and W2 are fp16
         const uint64_t dA2 = umma_desc_sw128(smem_u32(smem + Cfg::A2_OFF));
         const uint32_t ring_u32 = smem_u32(smem + Cfg::RING_OFF);
         long long g = 0;
@@ -387,11 +391,11 @@ ffn_wide_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
                     tc_fence_after();
                     if (elect_one_sync()) {
                         if constexpr (Cfg::A2T)
-                            umma_f16_ts_run4(tmem_base + yb * 192 + s * 192, tmem_base + Cfg::TM_A2 + b * 32,
-                                             umma_desc_sw128(ring_u32 + slot * FW_SLOT), idesc2, j != 0);
+                            umma_f16_ts_run4(tmem_base + yb * 192 + s * Cfg::YW, tmem_base + Cfg::TM_A2 + b * 32,
+                                             umma_desc_sw128(ring_u32 + slot * Cfg::SLOT), idesc2, j != 0);
                         else
-                            umma_f16_ss_run<4>(tmem_base + yb * 192 + s * 192, dA2 + (uint64_t)(b * (Cfg::A2_BYTES >> 4)),
-                                               umma_desc_sw128(ring_u32 + slot * FW_SLOT), idesc2, j != 0);
+                            umma_f16_ss_run<4>(tmem_base + yb * 192 + s * Cfg::YW, dA2 + (uint64_t)(b * (Cfg::A2_BYTES >> 4)),
+                                               umma_desc_sw128(ring_u32 + slot * Cfg::SLOT), idesc2, j != 0);
                         umma_commit(&ring_empty[slot]);
                         if (s == NS - 1) {
                             umma_commit(&a2_free[b]);
@@ -575,7 +579,7 @@ static int launch_ffn_wide(const float* x, const float* resid2, float* out, long
     using Cfg = FwCfg<C>;
     CUtensorMap t1, t2, to;
     ARD_TRY(make_tmap_2d(&t1, w1, 2, C, Cfg::HD, (uint64_t)C * 2, 64, 64, 128));
-    ARD_TRY(make_tmap_2d(&t2, w2_f16, 2, Cfg::HD, C, (uint64_t)Cfg::HD * 2, 64, 192, 128));
+    ARD_TRY(make_tmap_2d(&t2, w2_f16, 2, Cfg::HD, C, (uint64_t)Cfg::HD * 2, 64, Cfg::YW, 128));
     ARD_TRY(make_tmap_2d(&to, out, 4, C, (uint64_t)M, (uint64_t)C * 4, 16, 32, 64));
     CUtensorMap tx, tr;
     ARD_TRY(make_tmap_2d(&tx, x, 4, C, (uint64_t)M, (uint64_t)C * 4, 16, 32, 64));
@@ -601,9 +605,11 @@ int ffn_fused_wide(const float* x, const float* resid2, float* out, long long M,
                    const __nv_bfloat16* w1, const float* b1_half, const __half* w2_f16, const float* b2, int num_sms, cudaStream_t stream) {
     if (M <= 0) return 0;
     if (M > 0x7fffffffLL) return set_error(ARD_ERR_SHAPE, "ffn_wide: too many rows");
+    if (C == 128) return launch_ffn_wide<128>(x, resid2, out, M, gamma, beta, w1, b1_half, w2_f16, b2, num_sms, stream);
     if (C == 192) return launch_ffn_wide<192>(x, resid2, out, M, gamma, beta, w1, b1_half, w2_f16, b2, num_sms, stream);
+    if (C == 256) return launch_ffn_wide<256>(x, resid2, out, M, gamma, beta, w1, b1_half, w2_f16, b2, num_sms, stream);
     if (C == 384) return launch_ffn_wide<384>(x, resid2, out, M, gamma, beta, w1, b1_half, w2_f16, b2, num_sms, stream);
-    return set_error(ARD_ERR_SHAPE, "ffn_wide: C = %d not supported (192, 384)", C);
+    return set_error(ARD_ERR_SHAPE, "ffn_wide: C = %d not supported (128, 192, 256, 384)", C);
 }
 
 }  // namespace ard

@@ -39,7 +39,9 @@ def test_ffn_fused_96(M, resid2):
 
 
 @pytest.mark.parametrize("C,M,resid2,alias", [(192, 128, False, False), (192, 5000, True, True), (192, 148 * 128 * 3 + 77, True, False),
-                                             (384, 100, False, True), (384, 5000, True, False), (384, 148 * 128 * 2 + 300, False, True)])
+                                             (384, 100, False, True), (384, 5000, True, False), (384, 148 * 128 * 2 + 300, False, True),
+                                             (128, 128, False, False), (128, 5000, True, True), (128, 148 * 128 * 3 + 77, True, False),
+                                             (256, 100, False, True), (256, 5000, True, False), (256, 148 * 128 * 2 + 300, False, True)])
 def test_ffn_fused_wide(C, M, resid2, alias):
     r_out, r_branch = G.check_ffn_fused(M, resid2, Cd=C, alias=alias)
     assert r_out < 2e-3 and r_branch < 5e-3, (C, M, r_out, r_branch)
