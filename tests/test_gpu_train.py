@@ -1,13 +1,17 @@
 """-m gpu: the ResiDual training step (config c3): backward kernels vs autograd, lambda gradients vs the reference's
 loss.backward() (golden) and vs autograd through the oracle.
 
-Tolerances. The backward runs on the same bf16 tensor-core GEMMs as the forward, so gradients carry the forward's bf16
-error (<= 1e-2, north_star) plus their own. For a loss on `embedding` (GELU/LayerNorm/softmax only: smooth) the lambda
-gradients agree with the fp32 oracle to <= 1e-2. For the zero-shot loss on `audio_embed` the path crosses the ReLU of
-audio_projection (model.py:539-543): a bf16-sized perturbation of the 768-d embedding flips the gate of the few hidden
-units that sit within that perturbation of zero, and each flipped gate changes the gradient discontinuously, so the
-element-wise bound there is looser (2e-2 on the committed golden case, where it was measured at 9.8e-3) and the
-oracle comparison on other seeds asserts direction (cosine) and norm instead.
+Tolerances (relative l2 error of each layer's lambda-gradient vector; measured values from tools/train_tol_report.py on B200).
+The backward runs on the same bf16 tensor-core GEMMs as the forward, so gradients carry the forward's bf16 error (<= 1e-2,
+north_star) plus their own.
+* Loss on `embedding` (GELU / LayerNorm / softmax only: smooth): <= 1e-2 against autograd through the fp32 oracle
+  (measured 4.9e-3 ... 8.7e-3 over the three cases).
+* Zero-shot loss on `audio_embed`, committed golden of the reference's own loss.backward(): measured 8.7e-3 ... 9.7e-3 per layer,
+  asserted <= 1.2e-2 (the path crosses the ReLU of audio_projection, model.py:539-543: a bf16-sized perturbation of the 768-d
+  embedding flips the gate of the few hidden units that sit within that perturbation of zero, each flip changes the gradient
+  discontinuously; the bound leaves 20 % over the measured value rather than the factor 2 it had in round 1).
+* The same loss on another seed / a subset of layers (one flipped gate there: element-wise 1.5e-2): direction and norm are
+  asserted (cosine > 0.999, measured 0.99989; norm ratio within 1 %, measured 0.998) plus the element-wise bound 2e-2.
 """
 import pytest
 import torch
@@ -34,7 +38,7 @@ def test_training_step_vs_golden():
     m = G.check_training_step_vs_golden("htsat_tiny_b2.npz")
     assert m["loss_abs"] < 2e-3 and m["sims"] < G.TOL_BF16, m
     for l in range(4):
-        assert m[f"lambda_grad{l}"] < 2e-2, m
+        assert m[f"lambda_grad{l}"] < 1.2e-2, m
 
 
 @pytest.mark.parametrize("layers,B,wseed", [((0, 1, 2, 3), 3, 99), ((2, 3), 2, 1234), ((1,), 2, 7)])
@@ -42,13 +46,13 @@ def test_embedding_loss_lambda_grads_vs_oracle(layers, B, wseed):
     m = G.check_embedding_grad_vs_oracle("tiny", B, layers, 0, wseed)
     assert m["embedding"] < G.TOL_BF16, m
     for l in layers:
-        assert m[f"lambda_grad{l}"] < 1.5e-2, m
+        assert m[f"lambda_grad{l}"] < 1e-2, m
 
 
 def test_zero_shot_step_subset_of_layers_vs_oracle():
     m = G.check_training_step_vs_oracle("tiny", 2, (1,), cosine=True)
     assert m["loss_abs"] < 2e-3 and m["sims"] < G.TOL_BF16, m
-    assert m["lambda_cos1"] > 0.98 and abs(m["lambda_norm_ratio1"] - 1) < 0.05, m
+    assert m["lambda_cos1"] > 0.999 and abs(m["lambda_norm_ratio1"] - 1) < 0.01 and m["lambda_grad1"] < 2e-2, m
 
 
 def test_backward_requires_saved_forward():
