@@ -441,7 +441,10 @@ def measure(wl, B, K, Wm, dev, rank, world, dist, do_e2e=True, do_profile=True, 
         res["e2e"] = {"value": world * B * Ke / te.item(), "unit": UNIT, "h2d_bytes_per_step": int(nb),
                       "d2h_bytes_per_step": int(getattr(emb_host, "nbytes", 0) or emb_host.numel() * 4), "api": w.e2e_api, "steps": Ke,
                       "host_dtype": str(host.dtype).replace("torch.", ""), "h2d_gbs_measured": min(per_rank), "h2d_gbs_per_rank": per_rank,
-                      "h2d_bound_clips_per_s": sum(per_rank) * 1e9 / (nb / B)}
+                      "h2d_bound_clips_per_s": sum(per_rank) * 1e9 / (nb / B),
+                      "host_chunks_rank0": [hi - lo for lo, hi in getattr(w.clap, "_last_bounds", [])],
+                      "host_chunks_note": "chunk sizes (clips) of rank 0's last timed call: each rank picks the compute-bound or the tapered "
+                                          "(copy-bound) schedule from the copy / encode times it measured on its previous call"}
         if wl == "infer":   # the same call with the fp32 host waveform (use_tensor=True): 1.92 MB per clip over PCIe
             hf = torch.empty(w.wave.shape, dtype=torch.float32).pin_memory()
             hf.copy_(w.wave)

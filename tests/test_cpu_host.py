@@ -292,6 +292,28 @@ def test_pcm16_chunk_schedule_covers_batch():
         assert b[0][0] == 0 and b[-1][1] == n and all(x[1] == y[0] for x, y in zip(b, b[1:]))
 
 
+def test_tapered_chunk_schedule_for_copy_bound_ranks():
+    """_chunk_bounds_tapered: contiguous cover, small first AND last chunks (a copy-bound call ends one encode of the last chunk
+    after the last byte arrives); _pick_bounds switches on measured copy / encode time with hysteresis."""
+    from audio_residual_b200.clap import CLAP_Module
+    for n in (256, 300, 1000, 4096):
+        b = CLAP_Module._chunk_bounds_tapered(n)
+        sizes = [hi - lo for lo, hi in b]
+        assert b[0][0] == 0 and b[-1][1] == n and all(x[1] == y[0] for x, y in zip(b, b[1:])), (n, b)
+        assert sizes[0] == 32 and sizes[-2:] == [40, 24] and max(sizes) <= 80 and min(sizes) >= 24, (n, sizes)
+    assert CLAP_Module._chunk_bounds_tapered(100) is None            # too short to taper: the ordinary schedule is used
+    m = CLAP_Module.__new__(CLAP_Module)
+    normal = CLAP_Module._chunk_bounds(m, 256, CLAP_Module.h2d_schedule_pcm16)
+    assert m._pick_bounds(256, torch.int16) == normal                # nothing measured yet
+    m._pipe_rates = {torch.int16: {"copy_ms": 10.5, "enc_ms": 10.4, "pending": None}}
+    assert m._pick_bounds(256, torch.int16) == CLAP_Module._chunk_bounds_tapered(256)
+    m._pipe_rates[torch.int16].update(copy_ms=8.0, enc_ms=11.5)      # 0.70: stays tapered (hysteresis), a fresh module would not taper
+    assert m._pick_bounds(256, torch.int16) == CLAP_Module._chunk_bounds_tapered(256)
+    m._pipe_rates[torch.int16].update(copy_ms=4.5, enc_ms=11.0)      # compute-bound again
+    assert m._pick_bounds(256, torch.int16) == normal
+    assert m._pick_bounds(256, torch.float32) == CLAP_Module._chunk_bounds(m, 256)
+
+
 def test_apply_criterion_routes_custom_losses_to_the_caller():
     from audio_residual_b200.head import apply_criterion
     z, y = torch.randn(4, 5), torch.tensor([0, 1, 2, 3])

@@ -17,6 +17,13 @@ def test_tiny_vs_oracle(residual):
     _assert_all(G.check_encoder_vs_oracle("tiny", 2, residual))
 
 
+@pytest.mark.parametrize("residual", [False, True])
+def test_base_waveform_route_vs_oracle(residual):
+    """HTSAT-base WITHOUT feature fusion (waveform -> log-mel -> encoder; C = 128 / 256 / 512 / 1024, head dim 32): the fused FFN of
+    stages 0-1 (`ffn_wide<128|256>`), the unfused chain of stages 2-3."""
+    _assert_all(G.check_encoder_vs_oracle("base", 2, residual))
+
+
 def test_tiny_vs_golden():
     _assert_all(G.check_encoder_vs_golden("htsat_tiny_b2.npz"))
 
@@ -52,6 +59,26 @@ def test_host_batch_pipelined_equals_device_batch():
             assert got.shape == ref.shape
             # per-clip arithmetic is independent of the batch it rides in: bit-identical
             assert torch.equal(got, ref), (n, (got - ref).abs().max().item())
+
+
+def test_tapered_host_schedule_is_bit_identical():
+    """The copy-bound (tapered) chunk schedule, forced through the measured-rate state, against one device-resident call; then a
+    real call's CUDA-event timings are read back and the schedule decision is made from them."""
+    import torch
+    clap, sd, _ = G.make_encoder("tiny", residual=True)
+    n = 200
+    wave = G.W.make_clips(n, seed=9)
+    pcm = (wave.clamp(-1, 1) * 32767.0).to(torch.int16).pin_memory()
+    with torch.no_grad():
+        ref = clap.model.audio_branch.encode(waveform=(pcm.float() / 32767.0).cuda(), quantize=True, want_audio_embed=True)["audio_embed"].cpu().numpy()
+        clap._pipe_rates = {torch.int16: {"copy_ms": 2.0, "enc_ms": 1.0, "pending": None}}
+        assert len(clap._pick_bounds(n, torch.int16)) == 5            # 32, 52, 52, 40, 24 -> tapered
+        got = clap.get_audio_embedding_from_data(pcm, use_tensor=False)
+        assert (got == ref).all()
+        torch.cuda.synchronize()
+        clap._pick_bounds(n, torch.int16)                             # reads the events of the call above
+        r = clap._pipe_rates[torch.int16]
+        assert r["pending"] is None and r["copy_ms"] > 0 and r["enc_ms"] > 0, r
 
 
 def test_argmax_predictions_identical_to_reference():
