@@ -284,45 +284,85 @@ class CLAP_Module(nn.Module):
             lo, i = hi, i + 1
         return bounds
 
-    h2d_taper = (32, 80, 40, 24)          # copy-bound schedule: first chunk, middle chunks, and the two-chunk tail
+    # ---- adaptive schedule. The fixed schedules above assume this GPU has the host to itself (55 GB/s). With 8 ranks on one socket
+    # the pinned-host copy rate per GPU was measured at 23-36 GB/s: copies no longer fit under the previous chunk's encode, the
+    # encoder stalls between chunks, and the call ends one encode of a LARGE last chunk after the last byte arrives (8 GPUs:
+    # e2e 14.8 ms per 256 clips against 11.9 ms alone). So every pipelined call times its own copies and encodes with CUDA events
+    # (waits excluded), the next call fits  copy(n) = c n  and  encode(n) = a + b n  to them, simulates the two-stream pipeline
+    # for a family of candidate schedules (first chunk, growth factor, optional tapered tail) and takes the fastest.
+    @staticmethod
+    def _simulate(sizes, c, a, b, pcm):
+        """End time (ms) of the last encode. Copy k needs staging buffer k % 2: free once chunk k-2 has been expanded (int16: at
+        the start of its encode) or encoded (fp32)."""
+        copy_done, enc_start, enc_done = [], [], []
+        for k, n in enumerate(sizes):
+            t = copy_done[k - 1] if k else 0.0
+            if k >= 2:
+                t = max(t, (enc_start[k - 2] + 0.02) if pcm else enc_done[k - 2])
+            copy_done.append(t + 0.01 + c * n)
+            st = max(copy_done[k], enc_done[k - 1] if k else 0.0)
+            enc_start.append(st)
+            enc_done.append(st + a + b * n)
+        return enc_done[-1]
 
-    @classmethod
-    def _chunk_bounds_tapered(cls, N):
-        """Schedule for a COPY-bound rank (the host feeds this GPU slower than it encodes: 23 GB/s per GPU measured with 8 ranks
-        on one socket against 55 GB/s alone). The copies then run back to back whatever the chunking and the call ends one
-        encode of the LAST chunk after the last byte arrives, so the tail is small (40, 24 clips) where the compute-bound
-        schedule grows its chunks."""
-        first, mid, t1, t2 = cls.h2d_taper
-        rem = N - first - t1 - t2
-        if rem < mid // 2:
-            return None
-        k = max(1, -(-rem // mid))
-        sizes = [first] + [rem // k + (1 if i < rem % k else 0) for i in range(k)] + [t1, t2]
-        bounds, lo = [], 0
-        for c in sizes:
-            bounds.append((lo, lo + c))
-            lo += c
-        return bounds
+    @staticmethod
+    def _candidates(N):
+        out = []
+        for first in (16, 24, 32, 48):
+            for growth in (1.0, 1.4, 1.8, 2.4):
+                for tail in ((), (40, 24), (64, 32), (24,)):
+                    body = N - sum(tail)
+                    if body < first:
+                        continue
+                    sizes, cur, left = [], float(first), body
+                    while left > 0:
+                        n = min(left, int(round(cur)))
+                        if left - n < 12:          # no tiny remainder
+                            n = left
+                        sizes.append(n)
+                        left -= n
+                        cur = min(cur * growth if growth > 1.0 else 64.0, 160.0)
+                    out.append(tuple(sizes) + tuple(tail))
+        return out
 
     def _pick_bounds(self, N, dtype):
-        """Compute-bound schedule unless the previous pipelined call of this dtype measured its copies (CUDA events around each
-        chunk's cudaMemcpyAsync, waits excluded) at more than 0.85 x its encodes: then the tapered one."""
+        """Fixed compute-bound schedule until a call of this dtype has been measured; then the simulated-fastest candidate."""
         pcm = dtype == torch.int16
+        default = self._chunk_bounds(N, self.h2d_schedule_pcm16 if pcm else None)
         rates = getattr(self, "_pipe_rates", {}).get(dtype)
-        if rates is not None:
-            pending = rates.get("pending")
-            if pending is not None and all(e.query() for pair in pending for e in pair[:2]):
-                copy_ms = sum(a.elapsed_time(b) for a, b, kind in pending if kind == "copy")
-                enc_ms = sum(a.elapsed_time(b) for a, b, kind in pending if kind == "enc")
-                rates.update(copy_ms=copy_ms, enc_ms=enc_ms, pending=None)
-            if rates.get("enc_ms", 0.0) > 0.0:   # hysteresis: the tapered schedule has more chunks, so its encodes sum higher
-                ratio = rates["copy_ms"] / rates["enc_ms"]
-                rates["tapered"] = ratio > (0.6 if rates.get("tapered") else 0.85)
-            if rates.get("tapered"):
-                tb = self._chunk_bounds_tapered(N)
-                if tb is not None:
-                    return tb
-        return self._chunk_bounds(N, self.h2d_schedule_pcm16 if pcm else None)
+        if rates is None:
+            return default
+        pending = rates.get("pending")
+        if pending is not None and all(e.query() for rec in pending for e in rec[:2]):
+            cp = [(n, e0.elapsed_time(e1)) for e0, e1, kind, n in pending if kind == "copy"]
+            en = [(n, e0.elapsed_time(e1)) for e0, e1, kind, n in pending if kind == "enc"]
+            rates["pending"] = None
+            if cp and en:
+                rates["c"] = sum(t for _, t in cp) / sum(n for n, _ in cp)
+                xs, ys = [float(n) for n, _ in en], [t for _, t in en]
+                mx, my = sum(xs) / len(xs), sum(ys) / len(ys)
+                sxx = sum((x - mx) ** 2 for x in xs)
+                bb = sum((x - mx) * (y - my) for x, y in zip(xs, ys)) / sxx if sxx > 0 else 0.0
+                if bb <= 0.0 or my - bb * mx < 0.0:          # one chunk size, or noise: keep the slope of a proportional model
+                    bb, aa = 0.9 * my / mx, 0.1 * my
+                else:
+                    aa = my - bb * mx
+                rates["a"], rates["b"] = aa, bb
+        if "c" not in rates:
+            return default
+        c, a, b = rates["c"], rates["a"], rates["b"]
+        best, best_t = [hi - lo for lo, hi in default], None
+        best_t = self._simulate(best, c, a, b, pcm)
+        for sizes in self._candidates(N):
+            t = self._simulate(sizes, c, a, b, pcm)
+            if t < 0.985 * best_t:                             # switch only for a real gain (the measurements are noisy)
+                best, best_t = list(sizes), t
+        rates["predicted_ms"] = best_t
+        bounds, lo = [], 0
+        for n in best:
+            bounds.append((lo, lo + n))
+            lo += n
+        return bounds
 
     def _embed_host_pipelined(self, x, quantize):
         """Full-length host batch [N, 480000] fp32 or int16 PCM: copy chunk k+1 on a side stream while chunk k is encoded, so the
@@ -363,7 +403,7 @@ class CLAP_Module(nn.Module):
                     e0.record(self._copy_stream)
                     st[k % 2][:hi - lo].copy_(x[lo:hi], non_blocking=True)
                     e1.record(self._copy_stream)
-                    timing.append((e0, e1, "copy"))
+                    timing.append((e0, e1, "copy", hi - lo))
                     copied[k % 2].record(self._copy_stream)
 
             for b in range(2):
@@ -389,12 +429,12 @@ class CLAP_Module(nn.Module):
                     res = enc.encode(waveform=chunk, quantize=quantize, want_audio_embed=True)
                 out[lo:hi].copy_(res["audio_embed"])
                 t1.record(main)
-                timing.append((t0, t1, "enc"))
+                timing.append((t0, t1, "enc", hi - lo))
                 if not pcm:
                     free[k % 2].record(main)
             if not hasattr(self, "_pipe_rates"):
                 self._pipe_rates = {}
-            self._pipe_rates.setdefault(x.dtype, {"copy_ms": 0.0, "enc_ms": 0.0})["pending"] = timing
+            self._pipe_rates.setdefault(x.dtype, {})["pending"] = timing
         return out
 
 
