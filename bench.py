@@ -421,9 +421,17 @@ def measure(wl, B, K, Wm, dev, rank, world, dist, do_e2e=True, do_profile=True, 
         for _ in range(Ke):
             emb_host = w.e2e_step(host)
         torch.cuda.synchronize()
-        te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        t_mine = time.perf_counter() - t0
+        te = torch.tensor([t_mine], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        # per-rank view of the e2e leg: wall time of the Ke calls and the pipeline fit (copy ms/clip, encode a + b n) each rank measured
+        fit = (getattr(w.clap, "_pipe_rates", {}).get(host.dtype) or {}) if hasattr(w, "clap") else {}
+        mine = torch.tensor([t_mine, fit.get("c", 0.0), fit.get("a", 0.0), fit.get("b", 0.0),
+                             float(len(getattr(w.clap, "_last_bounds", []) or []))], device=dev, dtype=torch.float64)
+        allr = [mine.clone() for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allr, mine)
         # bare pinned-host -> device copy rate of the same buffer on every rank at once: the floor the e2e step cannot beat
         dst = torch.empty(host.shape, device=dev, dtype=host.dtype)
         barrier()
@@ -442,9 +450,13 @@ def measure(wl, B, K, Wm, dev, rank, world, dist, do_e2e=True, do_profile=True, 
                       "d2h_bytes_per_step": int(getattr(emb_host, "nbytes", 0) or emb_host.numel() * 4), "api": w.e2e_api, "steps": Ke,
                       "host_dtype": str(host.dtype).replace("torch.", ""), "h2d_gbs_measured": min(per_rank), "h2d_gbs_per_rank": per_rank,
                       "h2d_bound_clips_per_s": sum(per_rank) * 1e9 / (nb / B),
+                      "per_rank": [{"ms_per_call": round(1e3 * float(t[0]) / Ke, 3), "copy_ms_per_clip": round(float(t[1]), 5),
+                                    "enc_fixed_ms": round(float(t[2]), 4), "enc_ms_per_clip": round(float(t[3]), 5), "chunks": int(t[4])} for t in allr],
                       "host_chunks_rank0": [hi - lo for lo, hi in getattr(w.clap, "_last_bounds", [])],
-                      "host_chunks_note": "chunk sizes (clips) of rank 0's last timed call: each rank picks the compute-bound or the tapered "
-                                          "(copy-bound) schedule from the copy / encode times it measured on its previous call"}
+                      "host_pipe_fit_rank0": {k: round(float(v), 5) for k, v in (getattr(w.clap, "_pipe_rates", {}).get(host.dtype) or {}).items()
+                                              if k in ("c", "a", "b", "predicted_ms")},
+                      "host_chunks_note": "chunk sizes (clips) of rank 0's last timed call: each rank fits copy(n) = c n and encode(n) = a + b n (ms) "
+                                          "to the CUDA-event timings of its previous call and takes the schedule its pipeline simulation predicts fastest"}
         if wl == "infer":   # the same call with the fp32 host waveform (use_tensor=True): 1.92 MB per clip over PCIe
             hf = torch.empty(w.wave.shape, dtype=torch.float32).pin_memory()
             hf.copy_(w.wave)
