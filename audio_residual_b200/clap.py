@@ -394,6 +394,15 @@ class CLAP_Module(nn.Module):
                 self._pcm_wave = torch.empty((cmax, 480000), device=dev, dtype=torch.float32)
             out = torch.empty((N, enc.joint_dim), device=dev, dtype=torch.float32)
             copied = [torch.cuda.Event() for _ in range(2)]
+            import ctypes as C
+            from . import lib as L
+            lib = L.load()
+            if not enc.enable_fusion:
+                hnd = enc._handle()
+                emb_scratch = torch.empty((cmax, enc.num_features), device=dev, dtype=torch.float32)
+                fa = L.ArdForwardArgs()
+                fa.quantize = int(bool(quantize))
+                fa.precision = 1 if getattr(enc, "precision", "bf16") == "fp32" else 0
 
             def start_copy(k):
                 lo, hi = bounds[k]
@@ -417,17 +426,21 @@ class CLAP_Module(nn.Module):
                 t0.record(main)
                 chunk = st[k % 2][:hi - lo]
                 if pcm:   # int16_to_float32 on the device; the staging buffer is free again as soon as this kernel has run
-                    import ctypes as C
-                    from . import lib as L
                     wavef = self._pcm_wave[:hi - lo]
-                    L.check(L.load().ard_fill_clips(C.c_void_p(chunk.data_ptr()), 1, None, None, hi - lo, 480000, 0, 0, L.ptr(wavef), L.stream_ptr()))
+                    L.check(lib.ard_fill_clips(C.c_void_p(chunk.data_ptr()), 1, None, None, hi - lo, 480000, 0, 0, L.ptr(wavef), L.stream_ptr()))
                     free[k % 2].record(main)
                     chunk = wavef
                 if enc.enable_fusion:   # get_mel + 4x stack on device (data.py:363-399, :497-501), then the fused encoder
                     res = enc.encode(mel_fusion=enc.fusion_mel(chunk, quantize=quantize), want_audio_embed=True)
+                    out[lo:hi].copy_(res["audio_embed"])
                 else:
-                    res = enc.encode(waveform=chunk, quantize=quantize, want_audio_embed=True)
-                out[lo:hi].copy_(res["audio_embed"])
+                    # lean per-chunk call: the handle was validated once for this call (weights / ResiDuals cannot change inside
+                    # it), the embedding lands straight in its rows of `out`. Keeps the host side of a chunk to two ctypes calls:
+                    # on a loaded host (8 ranks on one socket) the Python around encode() was what the GPU waited for
+                    fa.B, fa.waveform = hi - lo, chunk.data_ptr()
+                    fa.embedding = emb_scratch.data_ptr()
+                    fa.audio_embed = out.data_ptr() + lo * out.shape[1] * 4
+                    L.check(lib.ard_encoder_forward(hnd, C.byref(fa), L.stream_ptr()))
                 t1.record(main)
                 timing.append((t0, t1, "enc", hi - lo))
                 if not pcm:
