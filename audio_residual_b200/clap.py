@@ -7,6 +7,8 @@
   instead of the reference's per-clip Python loop.
 Text towers, checkpoint download and tokenisers are out of scope (they need the network and are not on the path).
 """
+import functools
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -306,6 +308,7 @@ class CLAP_Module(nn.Module):
         return enc_done[-1]
 
     @staticmethod
+    @functools.lru_cache(maxsize=32)
     def _candidates(N):
         out = []
         for first in (16, 24, 32, 48):
@@ -323,35 +326,44 @@ class CLAP_Module(nn.Module):
                         left -= n
                         cur = min(cur * growth if growth > 1.0 else 64.0, 160.0)
                     out.append(tuple(sizes) + tuple(tail))
-        return out
+        return tuple(out)
 
     def _pick_bounds(self, N, dtype):
-        """Fixed compute-bound schedule until a call of this dtype has been measured; then the simulated-fastest candidate."""
+        """The schedule planned for (N, dtype) by an earlier call's _plan_next, else the fixed compute-bound schedule."""
+        plan = getattr(self, "_pipe_plan", {}).get((N, dtype))
+        if plan is not None:
+            return plan
+        return self._chunk_bounds(N, self.h2d_schedule_pcm16 if dtype == torch.int16 else None)
+
+    def _plan_next(self, N, dtype):
+        """Fit the rates to the newest COMPLETED call's events and plan the next call's schedule. Called at the end of a pipelined
+        call, when all of its work is queued: the planning (a few hundred Python steps) runs while the GPU is busy, not in front
+        of the first copy."""
         pcm = dtype == torch.int16
-        default = self._chunk_bounds(N, self.h2d_schedule_pcm16 if pcm else None)
         rates = getattr(self, "_pipe_rates", {}).get(dtype)
         if rates is None:
-            return default
-        pending = rates.get("pending")
-        if pending is not None and all(e.query() for rec in pending for e in rec[:2]):
-            cp = [(n, e0.elapsed_time(e1)) for e0, e1, kind, n in pending if kind == "copy"]
-            en = [(n, e0.elapsed_time(e1)) for e0, e1, kind, n in pending if kind == "enc"]
-            rates["pending"] = None
-            if cp and en:
-                rates["c"] = sum(t for _, t in cp) / sum(n for n, _ in cp)
-                xs, ys = [float(n) for n, _ in en], [t for _, t in en]
-                mx, my = sum(xs) / len(xs), sum(ys) / len(ys)
-                sxx = sum((x - mx) ** 2 for x in xs)
-                bb = sum((x - mx) * (y - my) for x, y in zip(xs, ys)) / sxx if sxx > 0 else 0.0
-                if bb <= 0.0 or my - bb * mx < 0.0:          # one chunk size, or noise: keep the slope of a proportional model
-                    bb, aa = 0.9 * my / mx, 0.1 * my
-                else:
-                    aa = my - bb * mx
-                rates["a"], rates["b"] = aa, bb
-        if "c" not in rates:
-            return default
-        c, a, b = rates["c"], rates["a"], rates["b"]
-        best, best_t = [hi - lo for lo, hi in default], None
+            return
+        done = rates.get("done")
+        if done is None or not all(e.query() for rec in done for e in rec[:2]):
+            return
+        rates["done"] = None
+        cp = [(n, e0.elapsed_time(e1)) for e0, e1, kind, n in done if kind == "copy"]
+        en = [(n, e0.elapsed_time(e1)) for e0, e1, kind, n in done if kind == "enc"]
+        if not cp or not en:
+            return
+        rates["c"] = sum(t for _, t in cp) / sum(n for n, _ in cp)
+        xs, ys = [float(n) for n, _ in en], [t for _, t in en]
+        mx, my = sum(xs) / len(xs), sum(ys) / len(ys)
+        sxx = sum((x - mx) ** 2 for x in xs)
+        bb = sum((x - mx) * (y - my) for x, y in zip(xs, ys)) / sxx if sxx > 0 else 0.0
+        if bb <= 0.0 or my - bb * mx < 0.0:          # one chunk size, or noise: keep the slope of a proportional model
+            bb, aa = 0.9 * my / mx, 0.1 * my
+        else:
+            aa = my - bb * mx
+        rates["a"], rates["b"] = aa, bb
+        c, a, b = rates["c"], aa, bb
+        default = self._chunk_bounds(N, self.h2d_schedule_pcm16 if pcm else None)
+        best = [hi - lo for lo, hi in default]
         best_t = self._simulate(best, c, a, b, pcm)
         for sizes in self._candidates(N):
             t = self._simulate(sizes, c, a, b, pcm)
@@ -362,7 +374,9 @@ class CLAP_Module(nn.Module):
         for n in best:
             bounds.append((lo, lo + n))
             lo += n
-        return bounds
+        if not hasattr(self, "_pipe_plan"):
+            self._pipe_plan = {}
+        self._pipe_plan[(N, dtype)] = bounds
 
     def _embed_host_pipelined(self, x, quantize):
         """Full-length host batch [N, 480000] fp32 or int16 PCM: copy chunk k+1 on a side stream while chunk k is encoded, so the
@@ -447,7 +461,9 @@ class CLAP_Module(nn.Module):
                     free[k % 2].record(main)
             if not hasattr(self, "_pipe_rates"):
                 self._pipe_rates = {}
-            self._pipe_rates.setdefault(x.dtype, {})["pending"] = timing
+            rates = self._pipe_rates.setdefault(x.dtype, {})
+            self._plan_next(N, x.dtype)          # from the previous call's events (complete by now), while this call's work runs
+            rates["done"] = timing
         return out
 
 

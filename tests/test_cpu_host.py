@@ -292,11 +292,33 @@ def test_pcm16_chunk_schedule_covers_batch():
         assert b[0][0] == 0 and b[-1][1] == n and all(x[1] == y[0] for x, y in zip(b, b[1:]))
 
 
+class _FakeEvent:
+    """CUDA-event stand-in for the planner: completed, with a given timestamp (ms)."""
+
+    def __init__(self, t):
+        self.t = t
+
+    def query(self):
+        return True
+
+    def elapsed_time(self, other):
+        return other.t - self.t
+
+
+def _fake_call(sizes, c, a, b):
+    rec, t = [], 0.0
+    for n in sizes:
+        rec.append((_FakeEvent(t), _FakeEvent(t + c * n), "copy", n))
+        rec.append((_FakeEvent(t), _FakeEvent(t + a + b * n), "enc", n))
+        t += 100.0
+    return rec
+
+
 def test_adaptive_chunk_schedule_from_measured_rates():
-    """_pick_bounds: the fixed schedule until a call has been measured; then the candidate the two-stream pipeline simulation
-    (copy(n) = c n, encode(n) = a + b n, double-buffered staging) predicts fastest. With the host to itself (55 GB/s:
-    c = 0.0175 ms/clip for int16) that IS the fixed schedule; at the 23 GB/s per GPU of an 8-rank box the chunks shrink and the
-    tail tapers, and the prediction beats the fixed schedule by > 10 %."""
+    """_plan_next / _pick_bounds: the fixed schedule until a call has been measured; then the candidate the two-stream pipeline
+    simulation (copy(n) = c n, encode(n) = a + b n, double-buffered staging) predicts fastest. With the host to itself
+    (55 GB/s: c = 0.0175 ms/clip for int16) that IS the fixed schedule; at the 23 GB/s per GPU of a saturated 8-rank host the
+    chunks shrink and the tail tapers, and the prediction beats the fixed schedule by > 10 %."""
     from audio_residual_b200.clap import CLAP_Module
     m = CLAP_Module.__new__(CLAP_Module)
     fixed = CLAP_Module._chunk_bounds(m, 256, CLAP_Module.h2d_schedule_pcm16)
@@ -304,14 +326,18 @@ def test_adaptive_chunk_schedule_from_measured_rates():
     for n in (65, 256, 300, 1000):
         for sizes in CLAP_Module._candidates(n):
             assert sum(sizes) == n and min(sizes) >= 12, (n, sizes)
-    m._pipe_rates = {torch.int16: {"c": 0.0175, "a": 0.55, "b": 0.0375, "pending": None}}
+    m._pipe_rates = {torch.int16: {"done": _fake_call([32, 80, 144], 0.0175, 0.55, 0.0375)}}
+    m._plan_next(256, torch.int16)
+    r = m._pipe_rates[torch.int16]
+    assert abs(r["c"] - 0.0175) < 1e-9 and abs(r["a"] - 0.55) < 1e-6 and abs(r["b"] - 0.0375) < 1e-8 and r["done"] is None, r
     assert m._pick_bounds(256, torch.int16) == fixed
     t_fixed = CLAP_Module._simulate([32, 80, 144], 0.041, 0.55, 0.0375, True)
-    m._pipe_rates[torch.int16].update(c=0.041)
+    r["done"] = _fake_call([32, 80, 144], 0.041, 0.55, 0.0375)
+    m._plan_next(256, torch.int16)
     b = m._pick_bounds(256, torch.int16)
     sizes = [hi - lo for lo, hi in b]
     assert b[0][0] == 0 and b[-1][1] == 256 and all(x[1] == y[0] for x, y in zip(b, b[1:]))
-    assert sizes[-1] <= 64 and m._pipe_rates[torch.int16]["predicted_ms"] < 0.9 * t_fixed, (sizes, t_fixed)
+    assert sizes[-1] <= 64 and r["predicted_ms"] < 0.9 * t_fixed, (sizes, t_fixed)
     # the simulation itself: copies back to back, an encode starts when its copy AND the previous encode are done
     assert abs(CLAP_Module._simulate([10, 10], 0.05, 1.0, 0.0, True) - (0.51 + 1.0 + 1.0)) < 1e-9        # copy 1 (0.51) hides under encode 0
     assert abs(CLAP_Module._simulate([10, 10], 0.5, 1.0, 0.0, True) - (2 * 5.01 + 1.0)) < 1e-9           # copy-bound: last copy + one encode

@@ -71,14 +71,16 @@ def test_adaptive_host_schedule_is_bit_identical():
     pcm = (wave.clamp(-1, 1) * 32767.0).to(torch.int16).pin_memory()
     with torch.no_grad():
         ref = clap.model.audio_branch.encode(waveform=(pcm.float() / 32767.0).cuda(), quantize=True, want_audio_embed=True)["audio_embed"].cpu().numpy()
-        clap._pipe_rates = {torch.int16: {"c": 0.045, "a": 0.55, "b": 0.0375, "pending": None}}
-        assert len(clap._pick_bounds(n, torch.int16)) >= 4            # copy-bound: more, smaller chunks than (32, 80, 88)
+        from audio_residual_b200.clap import CLAP_Module
+        clap._pipe_plan = {(n, torch.int16): [(0, 24), (24, 58), (58, 105), (105, 160), (160, 200)]}   # as a copy-bound rank would plan
         got = clap.get_audio_embedding_from_data(pcm, use_tensor=False)
+        assert (got == ref).all() and clap._last_bounds == clap._pipe_plan[(n, torch.int16)]
+        got = clap.get_audio_embedding_from_data(pcm, use_tensor=False)   # its end-of-call planner reads the first call's events
         assert (got == ref).all()
-        torch.cuda.synchronize()
-        clap._pick_bounds(n, torch.int16)                             # reads the events of the call above
         r = clap._pipe_rates[torch.int16]
-        assert r["pending"] is None and 0.005 < r["c"] < 0.2 and r["a"] >= 0 and 0.01 < r["b"] < 0.2, r
+        assert 0.005 < r["c"] < 0.2 and r["a"] >= 0 and 0.01 < r["b"] < 0.2 and r["predicted_ms"] > 0, r
+        b = clap._pick_bounds(n, torch.int16)
+        assert b[0][0] == 0 and b[-1][1] == n and b == CLAP_Module._pick_bounds(clap, n, torch.int16)
 
 
 def test_argmax_predictions_identical_to_reference():
