@@ -8,6 +8,7 @@
 Text towers, checkpoint download and tokenisers are out of scope (they need the network and are not on the path).
 """
 import functools
+import os
 
 import numpy as np
 import torch
@@ -267,6 +268,7 @@ class CLAP_Module(nn.Module):
             emb = emb.detach().cpu().numpy()
         return emb
 
+    h2d_adapt = os.environ.get("ARD_PIPE_ADAPT", "1") != "0"
     h2d_chunk = 64                        # host batches larger than this are copied in chunks overlapped with the encoder
     h2d_schedule = (24, 50, 80, 116, 156, 204, 256)   # chunk sizes in clips: a small first copy (nothing overlaps it), then growing
     h2d_schedule_pcm16 = (32, 80, 144, 256)            # int16 transport: copies take half as long, so chunks may grow faster
@@ -347,6 +349,14 @@ class CLAP_Module(nn.Module):
         if done is None or not all(e.query() for rec in done for e in rec[:2]):
             return
         rates["done"] = None
+        # The first two calls on a schedule are not representative: a new chunk size runs kernel by kernel once and is captured
+        # into a CUDA graph on its second use (ard_api.cu::forward_graphed). Fitting those would re-plan on garbage, and every
+        # re-plan brings new chunk sizes: the schedule would never settle (measured: ranks that flapped spent 20 ms per call).
+        key = (N, dtype)
+        seen = rates.setdefault("calls_on_plan", {})
+        seen[key] = seen.get(key, 0) + 1
+        if seen[key] <= 2 or rates.setdefault("replans", {}).get(key, 0) >= 3:
+            return
         cp = [(n, e0.elapsed_time(e1)) for e0, e1, kind, n in done if kind == "copy"]
         en = [(n, e0.elapsed_time(e1)) for e0, e1, kind, n in done if kind == "enc"]
         if not cp or not en:
@@ -363,12 +373,16 @@ class CLAP_Module(nn.Module):
         rates["a"], rates["b"] = aa, bb
         c, a, b = rates["c"], aa, bb
         default = self._chunk_bounds(N, self.h2d_schedule_pcm16 if pcm else None)
-        best = [hi - lo for lo, hi in default]
-        best_t = self._simulate(best, c, a, b, pcm)
-        for sizes in self._candidates(N):
-            t = self._simulate(sizes, c, a, b, pcm)
-            if t < 0.985 * best_t:                             # switch only for a real gain (the measurements are noisy)
+        cur = [hi - lo for lo, hi in self._pick_bounds(N, dtype)]
+        cur_t = self._simulate(cur, c, a, b, pcm)
+        best, best_t = cur, cur_t
+        for sizes in ([hi - lo for lo, hi in default],) + self._candidates(N):
+            t = self._simulate(list(sizes), c, a, b, pcm)
+            if t < best_t:
                 best, best_t = list(sizes), t
+        rates["predicted_ms"] = cur_t
+        if best_t >= 0.95 * cur_t:                             # re-plan only for a real gain: new chunk sizes cost an eager run + a capture
+            return
         rates["predicted_ms"] = best_t
         bounds, lo = [], 0
         for n in best:
@@ -376,7 +390,9 @@ class CLAP_Module(nn.Module):
             lo += n
         if not hasattr(self, "_pipe_plan"):
             self._pipe_plan = {}
-        self._pipe_plan[(N, dtype)] = bounds
+        self._pipe_plan[key] = bounds
+        seen[key] = 0
+        rates["replans"][key] = rates["replans"].get(key, 0) + 1
 
     def _embed_host_pipelined(self, x, quantize):
         """Full-length host batch [N, 480000] fp32 or int16 PCM: copy chunk k+1 on a side stream while chunk k is encoded, so the
@@ -391,7 +407,8 @@ class CLAP_Module(nn.Module):
         bounds = self._pick_bounds(N, x.dtype)
         self._last_bounds = bounds
         cmax = max(hi - lo for lo, hi in bounds)
-        timing = []                       # (start, end, "copy" | "enc") CUDA events of this call, read by the next call's _pick_bounds
+        timing = []                       # (start, end, "copy" | "enc", clips) CUDA events of this call, fitted by a later call's _plan_next
+        adapt = self.h2d_adapt            # ARD_PIPE_ADAPT=0: fixed schedule, no event timing (A/B measurements)
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream()
             if getattr(self, "_copy_stream", None) is None:
@@ -422,11 +439,13 @@ class CLAP_Module(nn.Module):
                 lo, hi = bounds[k]
                 with torch.cuda.stream(self._copy_stream):
                     self._copy_stream.wait_event(free[k % 2])    # the encoder finished reading this staging buffer
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record(self._copy_stream)
+                    if adapt:
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(self._copy_stream)
                     st[k % 2][:hi - lo].copy_(x[lo:hi], non_blocking=True)
-                    e1.record(self._copy_stream)
-                    timing.append((e0, e1, "copy", hi - lo))
+                    if adapt:
+                        e1.record(self._copy_stream)
+                        timing.append((e0, e1, "copy", hi - lo))
                     copied[k % 2].record(self._copy_stream)
 
             for b in range(2):
@@ -436,8 +455,9 @@ class CLAP_Module(nn.Module):
                 if k + 1 < len(bounds):
                     start_copy(k + 1)
                 main.wait_event(copied[k % 2])
-                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                t0.record(main)
+                if adapt:
+                    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    t0.record(main)
                 chunk = st[k % 2][:hi - lo]
                 if pcm:   # int16_to_float32 on the device; the staging buffer is free again as soon as this kernel has run
                     wavef = self._pcm_wave[:hi - lo]
@@ -455,15 +475,17 @@ class CLAP_Module(nn.Module):
                     fa.embedding = emb_scratch.data_ptr()
                     fa.audio_embed = out.data_ptr() + lo * out.shape[1] * 4
                     L.check(lib.ard_encoder_forward(hnd, C.byref(fa), L.stream_ptr()))
-                t1.record(main)
-                timing.append((t0, t1, "enc", hi - lo))
+                if adapt:
+                    t1.record(main)
+                    timing.append((t0, t1, "enc", hi - lo))
                 if not pcm:
                     free[k % 2].record(main)
             if not hasattr(self, "_pipe_rates"):
                 self._pipe_rates = {}
-            rates = self._pipe_rates.setdefault(x.dtype, {})
-            self._plan_next(N, x.dtype)          # from the previous call's events (complete by now), while this call's work runs
-            rates["done"] = timing
+            if adapt:
+                rates = self._pipe_rates.setdefault(x.dtype, {})
+                self._plan_next(N, x.dtype)      # from the previous call's events (complete by now), while this call's work runs
+                rates["done"] = timing
         return out
 
 

@@ -326,18 +326,27 @@ def test_adaptive_chunk_schedule_from_measured_rates():
     for n in (65, 256, 300, 1000):
         for sizes in CLAP_Module._candidates(n):
             assert sum(sizes) == n and min(sizes) >= 12, (n, sizes)
-    m._pipe_rates = {torch.int16: {"done": _fake_call([32, 80, 144], 0.0175, 0.55, 0.0375)}}
-    m._plan_next(256, torch.int16)
+    m._pipe_rates = {torch.int16: {}}
     r = m._pipe_rates[torch.int16]
+
+    def feed(sizes, c, a, b, calls=3):       # the first two calls on a schedule (eager run, graph capture) are not fitted
+        for _ in range(calls):
+            r["done"] = _fake_call(sizes, c, a, b)
+            m._plan_next(256, torch.int16)
+
+    feed([32, 80, 144], 0.0175, 0.55, 0.0375, calls=2)
+    assert "c" not in r
+    feed([32, 80, 144], 0.0175, 0.55, 0.0375, calls=1)
     assert abs(r["c"] - 0.0175) < 1e-9 and abs(r["a"] - 0.55) < 1e-6 and abs(r["b"] - 0.0375) < 1e-8 and r["done"] is None, r
-    assert m._pick_bounds(256, torch.int16) == fixed
+    assert m._pick_bounds(256, torch.int16) == fixed                 # host to itself: the fixed schedule stays
     t_fixed = CLAP_Module._simulate([32, 80, 144], 0.041, 0.55, 0.0375, True)
-    r["done"] = _fake_call([32, 80, 144], 0.041, 0.55, 0.0375)
-    m._plan_next(256, torch.int16)
+    feed([32, 80, 144], 0.041, 0.55, 0.0375, calls=1)                # the copy rate drops (saturated host): re-plan
     b = m._pick_bounds(256, torch.int16)
     sizes = [hi - lo for lo, hi in b]
     assert b[0][0] == 0 and b[-1][1] == 256 and all(x[1] == y[0] for x, y in zip(b, b[1:]))
     assert sizes[-1] <= 64 and r["predicted_ms"] < 0.9 * t_fixed, (sizes, t_fixed)
+    feed(sizes, 0.041, 0.55, 0.0375, calls=3)                        # same rates measured on the new schedule: it stays
+    assert m._pick_bounds(256, torch.int16) == b and r["replans"][(256, torch.int16)] == 1
     # the simulation itself: copies back to back, an encode starts when its copy AND the previous encode are done
     assert abs(CLAP_Module._simulate([10, 10], 0.05, 1.0, 0.0, True) - (0.51 + 1.0 + 1.0)) < 1e-9        # copy 1 (0.51) hides under encode 0
     assert abs(CLAP_Module._simulate([10, 10], 0.5, 1.0, 0.0, True) - (2 * 5.01 + 1.0)) < 1e-9           # copy-bound: last copy + one encode

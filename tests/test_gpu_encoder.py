@@ -75,12 +75,13 @@ def test_adaptive_host_schedule_is_bit_identical():
         clap._pipe_plan = {(n, torch.int16): [(0, 24), (24, 58), (58, 105), (105, 160), (160, 200)]}   # as a copy-bound rank would plan
         got = clap.get_audio_embedding_from_data(pcm, use_tensor=False)
         assert (got == ref).all() and clap._last_bounds == clap._pipe_plan[(n, torch.int16)]
-        got = clap.get_audio_embedding_from_data(pcm, use_tensor=False)   # its end-of-call planner reads the first call's events
-        assert (got == ref).all()
+        for _ in range(4):                                            # calls 1-2 on a schedule (eager, capture) are not fitted; call 3 is
+            got = clap.get_audio_embedding_from_data(pcm, use_tensor=False)
+            assert (got == ref).all()
         r = clap._pipe_rates[torch.int16]
         assert 0.005 < r["c"] < 0.2 and r["a"] >= 0 and 0.01 < r["b"] < 0.2 and r["predicted_ms"] > 0, r
         b = clap._pick_bounds(n, torch.int16)
-        assert b[0][0] == 0 and b[-1][1] == n and b == CLAP_Module._pick_bounds(clap, n, torch.int16)
+        assert b[0][0] == 0 and b[-1][1] == n
 
 
 def test_argmax_predictions_identical_to_reference():
