@@ -28,29 +28,72 @@ def _spectrum(n, s1, s2):
     return torch.linalg.eigvalsh(cov).flip(0).clamp_min(0)
 
 
+def _gram_spectrum(rows, n_total, D):
+    """Descending ddof=1 covariance spectrum (length D, zero-padded) of the samples `rows` [n, D] with n < D, from the n x n Gram
+    matrix of the centred rows (float64): same non-zero eigenvalues as the D x D covariance at (n / D)^3 of the eigen-solve."""
+    X = rows.double()
+    Xc = X - X.mean(0, keepdim=True)
+    w = torch.linalg.eigvalsh(Xc @ Xc.t() / (n_total - 1)).flip(0).clamp_min(0)
+    out = torch.zeros(D, device=rows.device, dtype=torch.float64)
+    out[:w.numel()] = w[:D]
+    return out
+
+
 def finalize_head_spectra(accs, n_components=None):
     """Spectra of a list of MomentAccumulators (one per (layer, head)), as numpy arrays.
     Under torch.distributed (clip-sharded pass) the moments are summed over ranks with the heads dealt round-robin
     to owners (`reduce` to the owner instead of an allreduce: each 4096^2 float64 matrix crosses NVLink once), every rank
     eigendecomposes only its own heads, and the spectra are exchanged in one small allreduce - the 60 serial 4096-d solves of a
-    single GPU become ceil(60 / N) per GPU. After the call every accumulator's `n` is the global sample count."""
+    single GPU become ceil(60 / N) per GPU. After the call every accumulator's `n` is the global sample count.
+    Heads that saw fewer samples than dimensions and still hold them all (MomentAccumulator.parked_rows: the last HTSAT layer
+    has ONE window per clip, so a 2000-clip pass gives its 32 heads 2000 samples of 4096 dimensions) take the Gram route: the
+    rows (not the D x D matrix) go to the owner and the eigen-solve is n x n (9 instead of 79 ms at n = 2000)."""
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
     if not accs:
         return []
-    dev, D = accs[0].s1.device, accs[0].D
+    dev, D = accs[0]._s1.device, accs[0].D
+    rows = [a.parked_rows() for a in accs]
+    counts = torch.tensor([[float(a.n), 1.0 if r is not None else 0.0] for a, r in zip(accs, rows)], device=dev, dtype=torch.float64)
+    n_loc = counts[:, 0].clone()
     if world > 1:
-        ns = torch.tensor([float(a.n) for a in accs], device=dev, dtype=torch.float64)
-        dist.all_reduce(ns)
-        for i, a in enumerate(accs):
-            dist.reduce(a.s1, dst=i % world)
-            dist.reduce(a.s2, dst=i % world)
-            a.n = int(round(ns[i].item()))
+        both = [counts.clone() for _ in range(world)]
+        dist.all_gather(both, counts)
+        n_all = torch.stack([b[:, 0] for b in both])                  # [world, heads]
+        n_tot = n_all.sum(0)
+        parked = torch.stack([b[:, 1] for b in both]).min(0).values    # every rank still holds its rows
+    else:
+        n_all, n_tot, parked = n_loc[None], n_loc, counts[:, 1]
+    gram = [bool(parked[i] > 0) and 1 < int(n_tot[i]) < D for i in range(len(accs))]
+    # global means (HeadPCA.mean_): one small allreduce of the first moments, taken before the per-head reductions below
+    s1 = torch.stack([a._s1 + (a._buf[:a._fill].double().sum(0) if a._fill else 0.0) for a in accs])
+    if world > 1:
+        dist.all_reduce(s1)
     spectra = torch.zeros((len(accs), D), device=dev, dtype=torch.float64)
     for i, a in enumerate(accs):
-        if i % world == rank:
-            spectra[i] = _spectrum(a.n, a.s1, a.s2)
+        owner = i % world
+        n_i = int(round(n_tot[i].item()))
+        if gram[i]:
+            r = rows[i]
+            if world > 1:
+                nmax = int(n_all[:, i].max().item())
+                pad = torch.zeros((nmax, D), device=dev, dtype=torch.float32)
+                pad[:r.shape[0]] = r
+                parts = [torch.empty_like(pad) for _ in range(world)] if rank == owner else None
+                dist.gather(pad, parts, dst=owner)
+                if rank == owner:
+                    r = torch.cat([parts[k][:int(n_all[k, i].item())] for k in range(world)])
+            if rank == owner:
+                spectra[i] = _gram_spectrum(r, n_i, D)
+        else:
+            if world > 1:
+                dist.reduce(a.s1, dst=owner)
+                dist.reduce(a.s2, dst=owner)
+            if rank == owner:
+                spectra[i] = _spectrum(n_i, a.s1, a.s2)
+        a.n = n_i
+        a.mean_global = s1[i] / max(n_i, 1)
     if world > 1:
         dist.all_reduce(spectra)
     out = spectra.cpu().numpy()
@@ -75,7 +118,8 @@ class HeadPCA:
         """w: full descending spectrum (numpy). n_components defaults to what IncrementalPCA(n_components=None) settles on at
         its first partial_fit: min(samples of the first batch, features) (sklearn _incremental_pca.py)."""
         k = n_components or min(self.first_batch or len(w), len(w))
-        self.mean_ = (self.acc.s1 / self.acc.n).cpu().numpy()
+        mean = getattr(self.acc, "mean_global", None)
+        self.mean_ = (mean if mean is not None else self.acc.s1 / self.acc.n).cpu().numpy()
         self.explained_variance_ = w[:k]
         self.explained_variance_ratio_ = w[:k] / w.sum()
         self.n_components_ = k

@@ -335,7 +335,7 @@ static int run_block(ard_handle* h, int l, int b, int B, float* X, float* Y, flo
     // 192-channel stage (217 / 255 us plain / with second residual vs 341 / 339 us at B = 256). At C = 384 (254 vs 200 us: three
     // ring slots cannot cover the L2 latency) the unfused chain stays. ARD_FUSED_FFN_WIDE=2 forces it for C = 384 too (A/B
     // measurements), =0 disables it.
-    const bool wide = ((C == 128 || C == 192 || C == 256) && h->use_fused_ffn_wide >= 1) || (C == 384 && h->use_fused_ffn_wide == 2);
+    const bool wide = (((C == 128 || C == 192 || C == 256) && h->use_fused_ffn_wide >= 1) || (C == 384 && h->use_fused_ffn_wide == 2)) && C != h->wide_skip;
     auto ffn = [&](float* in, float* out, const float* r2, const float* pre_add) -> int {
         if (C == 96 && h->use_fused_ffn && pre_add == nullptr)   // whole FFN in one kernel, hidden activation never leaves the SM
             return ffn_fused_96(in, r2, out, M, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), bw.fc1_w.as<__nv_bfloat16>(), bw.fc1_b.as<float>(),
@@ -503,6 +503,7 @@ int ard_create(const ard_config* cfg, ard_handle** out) {
     if (const char* e = getenv("ARD_LN_QKV")) h->use_ln_qkv = atoi(e) != 0;
     if (const char* e = getenv("ARD_ATTN_BLOCK")) h->use_attn_block = atoi(e) != 0;
     if (const char* e = getenv("ARD_DUAL_GEMM")) h->use_dual_gemm = atoi(e);
+    if (const char* e = getenv("ARD_FFN_WIDE_SKIP")) h->wide_skip = atoi(e);   // development: one width back on the unfused chain
     *out = h;
     return 0;
 }

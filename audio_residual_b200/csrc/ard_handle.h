@@ -85,6 +85,7 @@ struct ard_handle {
     bool use_ln_qkv = true;      // ARD_LN_QKV=0: LayerNorm kernel + qkv GEMM instead of ln_qkv_96 (A/B measurements)
     bool use_attn_block = true;  // ARD_ATTN_BLOCK=0: ln_qkv + window_attention + proj GEMM instead of attn_block_96 (A/B measurements)
     int use_dual_gemm = 1;       // ARD_DUAL_GEMM: backward with gemm_dual (1, default) or the separate GEMMs + lambda_grad kernel (0; A/B measurements)
+    int wide_skip = 0;           // ARD_FFN_WIDE_SKIP=<C>: that width takes the unfused FFN chain (development)
     int use_fused_ffn_wide = 1;    // ARD_FUSED_FFN_WIDE: 0 never, 1 where it measures faster (default), 2 for every C = 192 / 384 FFN
     // training state
     DevBuf tape, p0_wT, p2_wT, t_emb, t_hid, t_proj;

@@ -209,6 +209,15 @@ class MomentAccumulator:
         if self._fill:
             self._accumulate(self._buf[:self._fill], self.D)
             self._fill = 0
+            self._flushed = True
+
+    def parked_rows(self):
+        """The samples themselves, [n, D] fp32, while every one of them is still parked (nothing folded into s2 yet), else None.
+        With fewer samples than dimensions the covariance spectrum is the spectrum of the n x n Gram matrix of the centred rows:
+        analyze_attention.finalize_head_spectra takes that route instead of a D x D eigen-solve."""
+        if getattr(self, "_flushed", False) or self._buf is None or self._fill != self.n:
+            return None
+        return self._buf[:self._fill]
 
     def update(self, x):
         x = x.detach()
@@ -220,7 +229,9 @@ class MomentAccumulator:
         rows = x2.shape[0]
         self.n += rows
         if rows >= self.min_rows:
+            self.flush()
             self._accumulate(x2, ldx)
+            self._flushed = True
             return
         if self._buf is None:
             self._buf = torch.empty(self.min_rows, self.D, device=self._s1.device, dtype=torch.float32)

@@ -371,11 +371,44 @@ class Workload:
         return host
 
 
-def measure(wl, B, K, Wm, dev, rank, world, dist, do_e2e=True, do_profile=True, sampler=None, precision="bf16"):
+class RankGuard:
+    """CPU-side (gloo) agreement between ranks for the EXTRA records: a rank whose CUDA context died (a kernel fault is sticky)
+    cannot take part in an NCCL barrier any more, and the healthy ranks would wait in it until the NCCL watchdog fires. The extras
+    therefore synchronise through a gloo group: every rank reports whether its phase succeeded, all of them learn the minimum, and
+    if any failed they all abandon that record together. The headline measurement keeps the NCCL barrier the contract asks for."""
+
+    def __init__(self, dist, world):
+        self.dist, self.world = dist, world
+        self.group = dist.new_group(backend="gloo") if world > 1 else None
+
+    def all_ok(self, ok):
+        import torch
+        if self.world == 1:
+            return bool(ok)
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+        return bool(t.item())
+
+    def max(self, value):
+        import torch
+        if self.world == 1:
+            return float(value)
+        t = torch.tensor([float(value)], dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return float(t.item())
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+
+
+def measure(wl, B, K, Wm, dev, rank, world, dist, do_e2e=True, do_profile=True, sampler=None, precision="bf16", guard=None):
     """W warm-up + K timed steps of workload `wl` (CUDA events, barrier + synchronize on both sides, max over ranks), then the
     e2e leg and the per-class launch profile. Returns a dict (same on every rank except the rank-0-only profile)."""
     import torch
     from audio_residual_b200 import lib as L
+    if guard is not None:
+        return _measure_guarded(wl, B, K, Wm, dev, rank, world, precision, guard)
     w = Workload(wl, B, dev, rank, world, precision)
     grad = wl == "train"
     torch.set_grad_enabled(grad)   # inference workloads run as the reference's evaluate() does (src/training.py:47): no autograd tape
@@ -492,6 +525,60 @@ def measure(wl, B, K, Wm, dev, rank, world, dist, do_e2e=True, do_profile=True, 
     return res
 
 
+def _measure_guarded(wl, B, K, Wm, dev, rank, world, precision, guard):
+    """measure() for the extra records (no e2e / profile legs): same W warm-up + K timed steps with CUDA events and the max over
+    ranks, but every synchronisation point is a RankGuard agreement, so one rank's failure ends the record on ALL ranks instead of
+    leaving the others in a barrier. (The training step's gradient allreduce and the PCA finalize are NCCL collectives of the
+    workload itself and stay what they are.)"""
+    import torch
+    from audio_residual_b200 import lib as L
+    state = {}
+
+    def phase(fn, what):
+        ok, err = True, None
+        try:
+            fn()
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            ok, err = False, f"{type(e).__name__}: {e}"
+        if not guard.all_ok(ok):
+            raise RuntimeError(f"extra '{wl}' abandoned on every rank: {what} failed on " + ("this rank: " + err[:300] if err else "another rank"))
+
+    def setup():
+        if os.environ.get("ARD_BENCH_INJECT_FAULT") == f"{rank}:{wl}":          # test hook: one rank fails its warm-up
+            raise RuntimeError("injected failure (ARD_BENCH_INJECT_FAULT)")
+        state["w"] = Workload(wl, B, dev, rank, world, precision)
+        torch.set_grad_enabled(wl == "train")
+        for _ in range(Wm):
+            state["w"].step()
+        torch.cuda.synchronize()
+        L.load().ard_launch_counter_reset()
+        state["w"].step()
+        torch.cuda.synchronize()
+        state["launches"] = L.load().ard_launch_counter_read()
+
+    def timed():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            state["out"] = state["w"].step()
+        e1.record()
+        torch.cuda.synchronize()
+        state["ms"] = e0.elapsed_time(e1)
+        state["checksum"] = float(state["out"].double().abs().sum().item())
+
+    try:
+        phase(setup, "set-up / warm-up")        # doubles as the barrier in front of the timed region
+        phase(timed, "the timed steps")
+    finally:
+        torch.set_grad_enabled(True)
+    ms_total = guard.max(state["ms"])
+    w = state["w"]
+    return {"workload": wl, "value": world * B * K / (ms_total / 1e3), "ms_per_step": ms_total / K, "steps": K, "warmup": Wm,
+            "launches_per_step": int(state["launches"]), "clocks": None, "comm": w.comm, "checksum": state["checksum"],
+            "precision": precision, "_workload_obj": w}
+
+
 def pin_rank_to_cores(local_rank, world):
     """One contiguous block of host cores per rank (torchrun does not pin). Measured on an 8-GPU box with 32 vCPUs: un-pinned, three
     of the eight ranks spent 20 ms per e2e call against 12.4-12.8 ms for the others - their Python threads were what their GPUs
@@ -526,6 +613,7 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler is not None:
         sampler.start()          # started before warm-up so nvidia-smi is already streaming when the timed region begins
+    guard = RankGuard(dist, world)
     main = measure(wl, B, K, Wm, dev, rank, world, dist, sampler=sampler)
     main.pop("_workload_obj", None)
     torch.cuda.empty_cache()
@@ -536,10 +624,11 @@ def run_ours(args):
     extra = {}
     if wl == "infer" and not args.no_extra:
         Ks = max(2, min(K, 5))
-        for name, kw in (("train", dict(wl="train", B=B)), ("pca", dict(wl="pca", B=min(B, 128))), ("base_fusion", dict(wl="base_fusion", B=B)),
-                         ("infer_fp32", dict(wl="infer", B=min(B, 64), precision="fp32"))):
+        for name, kw in (("train", dict(wl="train", B=B)), ("pca", dict(wl="pca", B=min(B, 128))),
+                         ("infer_fp32", dict(wl="infer", B=min(B, 64), precision="fp32")), ("base_fusion", dict(wl="base_fusion", B=B))):
             try:
-                r = measure(kw["wl"], kw["B"], Ks, 3, dev, rank, world, dist, do_e2e=False, do_profile=False, precision=kw.get("precision", "bf16"))
+                r = measure(kw["wl"], kw["B"], Ks, 3, dev, rank, world, dist, do_e2e=False, do_profile=False, precision=kw.get("precision", "bf16"),
+                            guard=guard)
                 wobj = r.pop("_workload_obj")
                 rec = {"metric": METRIC, "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "steps": r["steps"], "n_gpus": world,
                        "batch_per_gpu": kw["B"], "launches_per_step": r["launches_per_step"], "comm": r["comm"], "precision": r["precision"],
@@ -559,15 +648,21 @@ def run_ours(args):
                 extra[name] = rec
             except Exception as e:  # noqa: BLE001  (an extra record must never take the headline line down)
                 extra[name] = {"error": f"{type(e).__name__}: {e}"[:400]}
-            torch.cuda.empty_cache()
+            try:
+                torch.cuda.empty_cache()
+            except Exception:  # noqa: BLE001  (a dead CUDA context: the remaining extras will report it, the headline is already measured)
+                pass
 
     if rank != 0:
         if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+            guard.barrier()          # gloo: a rank that lost its CUDA context in an extra can still leave in step with the others
+            try:
+                dist.destroy_process_group()
+            except Exception:  # noqa: BLE001
+                pass
         return
     if world > 1:
-        dist.barrier()
+        guard.barrier()
     peaks = read_peaks()
     prof = main.pop("profile")
     tot_ms = sum(v["ms"] for v in prof.values())
@@ -619,7 +714,10 @@ def run_ours(args):
             "comm": main["comm"], "extra": extra, "embedding_checksum": main["checksum"]}
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 def main():

@@ -515,3 +515,29 @@ def test_layer_lambda_fold_matches_per_block_fold():
     mean = torch.zeros(384)
     L.check(lib.ard_set_block_residual(h, 2, 1, L.ptr(mean), L.ptr(basis), 384, 384))
     assert lib.ard_set_layer_lambda(h, 2, L.ptr(lam), L.stream_ptr()) == L.ARD_ERR_STATE
+
+
+# ------------------------------------------------------------------------------------------------ Gram route of the head spectra
+def test_head_spectrum_gram_route_matches_moment_route():
+    """Fewer samples than dimensions (the last layer's heads: one window per clip): finalize_head_spectra eigen-solves the n x n Gram
+    matrix of the parked rows instead of the 4096 x 4096 covariance. Same spectrum as the moment route and as float64 torch."""
+    from audio_residual_b200.analyze_attention import HeadPCA, finalize_head_spectra
+    g = torch.Generator().manual_seed(11)
+    X = (torch.rand(300, 4096, generator=g) ** 3).cuda()              # attention-map-like: non-negative, skewed
+    a, b = HeadPCA(4096, X.device), HeadPCA(4096, X.device)
+    b.acc.min_rows = 0                                                # moments from the first row on: the D x D route
+    for lo in range(0, 300, 100):
+        a.partial_fit(X[lo:lo + 100])
+        b.partial_fit(X[lo:lo + 100])
+    assert a.acc.parked_rows() is not None and b.acc.parked_rows() is None
+    wa, wb = finalize_head_spectra([a.acc])[0], finalize_head_spectra([b.acc])[0]
+    ref = _gram_spectrum(X.cpu()).numpy()
+    assert wa.shape == (4096,) and np.all(wa[299:] == 0.0)
+    assert np.linalg.norm(wa[:299] - ref[:299]) / np.linalg.norm(ref[:299]) < 1e-6
+    assert np.linalg.norm(wb[:299] - ref[:299]) / np.linalg.norm(ref[:299]) < 2e-5   # split-bf16 second moments: fp32-grade
+    a._set(wa)
+    assert np.allclose(a.mean_, X.double().mean(0).cpu().numpy(), rtol=0, atol=1e-6) and a.n_samples_seen_ == 300
+    # once a batch has been folded into the moments the rows are gone: the accumulator says so
+    c = HeadPCA(4096, X.device)
+    c.partial_fit(X[:100]).partial_fit(torch.cat([X] * 7)[:2048])
+    assert c.acc.parked_rows() is None
