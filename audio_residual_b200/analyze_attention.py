@@ -80,10 +80,13 @@ def finalize_head_spectra(accs, n_components=None):
                 nmax = int(n_all[:, i].max().item())
                 pad = torch.zeros((nmax, D), device=dev, dtype=torch.float32)
                 pad[:r.shape[0]] = r
-                parts = [torch.empty_like(pad) for _ in range(world)] if rank == owner else None
-                dist.gather(pad, parts, dst=owner)
+                # all_gather (the ring the allreduces already use) rather than gather to the owner: NCCL builds point-to-point
+                # channels lazily and the first gather paid ~2 s for them; the rows of one head are a few MB per rank
+                parts = [torch.empty_like(pad) for _ in range(world)]
+                dist.all_gather(parts, pad)
                 if rank == owner:
                     r = torch.cat([parts[k][:int(n_all[k, i].item())] for k in range(world)])
+                del parts
             if rank == owner:
                 spectra[i] = _gram_spectrum(r, n_i, D)
         else:
