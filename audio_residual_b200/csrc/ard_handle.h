@@ -86,7 +86,7 @@ struct ard_handle {
     bool use_attn_block = true;  // ARD_ATTN_BLOCK=0: ln_qkv + window_attention + proj GEMM instead of attn_block_96 (A/B measurements)
     int use_dual_gemm = 1;       // ARD_DUAL_GEMM: backward with gemm_dual (1, default) or the separate GEMMs + lambda_grad kernel (0; A/B measurements)
     int wide_skip = 0;           // ARD_FFN_WIDE_SKIP=<C>: that width takes the unfused FFN chain (development)
-    int use_fused_ffn_wide = 1;    // ARD_FUSED_FFN_WIDE: 0 never, 1 where it measures faster (default), 2 for every C = 192 / 384 FFN
+    int use_fused_ffn_wide = 1;    // ARD_FUSED_FFN_WIDE: 0 never, 1 C = 192 (default), 2 also C = 384, 3 also the HTSAT-base widths 128 / 256 (opt-in, see ard_api.cu)
     // training state
     DevBuf tape, p0_wT, p2_wT, t_emb, t_hid, t_proj;
     DevBuf bw_g, bw_gs, bw_t, bw_hpre, bw_dh, bw_gqkv, bw_gb, bw_coef, bw_gcoef, bw_gsc, bw_small;

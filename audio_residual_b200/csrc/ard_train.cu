@@ -162,7 +162,7 @@ int run_block_train(ard_handle* h, int l, int b, int B, float* attn_out, float a
         if (C == 96 && h->use_fused_ffn)
             return ffn_fused_96(in, r2, out, M, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), bw.fc1_w.as<__nv_bfloat16>(), bw.fc1_b.as<float>(),
                                 bw.fc2_w.as<__half>(), bw.fc2_b.as<float>(), h->num_sms, s);
-        if (((C == 128 || C == 192 || C == 256) && h->use_fused_ffn_wide >= 1) || (C == 384 && h->use_fused_ffn_wide == 2))
+        if (((C == 192 && h->use_fused_ffn_wide >= 1) || ((C == 128 || C == 256) && h->use_fused_ffn_wide >= 3)) || (C == 384 && h->use_fused_ffn_wide >= 2))
             return ffn_fused_wide(in, r2, out, M, C, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), bw.fc1_w.as<__nv_bfloat16>(),
                                   bw.fc1_b_half.as<float>(), bw.fc2_w.as<__half>(), bw.fc2_b.as<float>(), h->num_sms, s);
         ARD_TRY(layernorm_bf16(in, bw.ln2_g.as<float>(), bw.ln2_b.as<float>(), XN, M, C, s));

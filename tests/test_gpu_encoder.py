@@ -17,10 +17,12 @@ def test_tiny_vs_oracle(residual):
     _assert_all(G.check_encoder_vs_oracle("tiny", 2, residual))
 
 
-@pytest.mark.parametrize("residual", [False, True])
-def test_base_waveform_route_vs_oracle(residual):
-    """HTSAT-base WITHOUT feature fusion (waveform -> log-mel -> encoder; C = 128 / 256 / 512 / 1024, head dim 32): the fused FFN of
-    stages 0-1 (`ffn_wide<128|256>`), the unfused chain of stages 2-3."""
+@pytest.mark.parametrize("residual,wide", [(False, 1), (True, 1), (True, 3)])
+def test_base_waveform_route_vs_oracle(residual, wide, monkeypatch):
+    """HTSAT-base WITHOUT feature fusion (waveform -> log-mel -> encoder; C = 128 / 256 / 512 / 1024, head dim 32). wide = 1: the
+    default schedule (LayerNorm + GEMM chain for the FFNs); wide = 3: the opt-in fused FFN of stages 0-1 (`ffn_wide<128|256>`,
+    ARD_FUSED_FFN_WIDE=3, read when the handle is created)."""
+    monkeypatch.setenv("ARD_FUSED_FFN_WIDE", str(wide))
     _assert_all(G.check_encoder_vs_oracle("base", 2, residual))
 
 

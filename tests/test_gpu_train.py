@@ -50,8 +50,8 @@ def test_embedding_loss_lambda_grads_vs_oracle(layers, B, wseed):
 
 
 def test_base_model_lambda_grads_vs_oracle():
-    """The training step on HTSAT-base (C = 128 ... 1024): `gemm_dual` at K = 128 / 256 ... 1024, the gelu' GEMM pair at C >= 384,
-    `ffn_wide<128|256>` in the taped forward. Same bound as the tiny model's smooth-loss cases."""
+    """The training step on HTSAT-base (C = 128 ... 1024): `gemm_dual` at K = 128 / 256 ... 1024, the gelu' GEMM pair at C >= 384.
+    Same bound as the tiny model's smooth-loss cases."""
     m = G.check_embedding_grad_vs_oracle("base", 2, (0, 1, 2, 3), 0, 321)
     assert m["embedding"] < G.TOL_BF16, m
     for l in range(4):
