@@ -58,11 +58,14 @@ def finalize_head_spectra(accs, n_components=None):
     counts = torch.tensor([[float(a.n), 1.0 if r is not None else 0.0] for a, r in zip(accs, rows)], device=dev, dtype=torch.float64)
     n_loc = counts[:, 0].clone()
     if world > 1:
-        both = [counts.clone() for _ in range(world)]
-        dist.all_gather(both, counts)
-        n_all = torch.stack([b[:, 0] for b in both])                  # [world, heads]
+        # every exchange below is an allreduce (of a buffer that is zero outside this rank's slot): the collective the pass has
+        # already used. A first all_gather / gather makes NCCL set up new channels, which cost seconds at 8 ranks
+        both = torch.zeros((world,) + tuple(counts.shape), device=dev, dtype=torch.float64)
+        both[rank] = counts
+        dist.all_reduce(both)
+        n_all = both[:, :, 0]                                          # [world, heads]
         n_tot = n_all.sum(0)
-        parked = torch.stack([b[:, 1] for b in both]).min(0).values    # every rank still holds its rows
+        parked = both[:, :, 1].min(0).values                           # every rank still holds its rows
     else:
         n_all, n_tot, parked = n_loc[None], n_loc, counts[:, 1]
     gram = [bool(parked[i] > 0) and 1 < int(n_tot[i]) < D for i in range(len(accs))]
@@ -77,16 +80,13 @@ def finalize_head_spectra(accs, n_components=None):
         if gram[i]:
             r = rows[i]
             if world > 1:
-                nmax = int(n_all[:, i].max().item())
-                pad = torch.zeros((nmax, D), device=dev, dtype=torch.float32)
-                pad[:r.shape[0]] = r
-                # all_gather (the ring the allreduces already use) rather than gather to the owner: NCCL builds point-to-point
-                # channels lazily and the first gather paid ~2 s for them; the rows of one head are a few MB per rank
-                parts = [torch.empty_like(pad) for _ in range(world)]
-                dist.all_gather(parts, pad)
-                if rank == owner:
-                    r = torch.cat([parts[k][:int(n_all[k, i].item())] for k in range(world)])
-                del parts
+                offs = [0]
+                for k in range(world):
+                    offs.append(offs[-1] + int(n_all[k, i].item()))
+                allrows = torch.zeros((n_i, D), device=dev, dtype=torch.float32)
+                allrows[offs[rank]:offs[rank + 1]] = r
+                dist.all_reduce(allrows)                               # a few MB per head: every rank's rows in its own slot
+                r = allrows
             if rank == owner:
                 spectra[i] = _gram_spectrum(r, n_i, D)
         else:
