@@ -372,3 +372,35 @@ def test_reference_snapshot_recipe(tmp_path):
         assert os.path.exists(os.path.join(build_ref.DST, rel)), rel
     ign = open(os.path.join(ROOT, ".gitignore")).read()
     assert "oracle/_ref/" in ign                                   # reference sources never enter the history
+
+
+def test_gram_route_spectrum_equals_covariance_spectrum():
+    """analyze_attention._gram_spectrum (heads with fewer samples than dimensions): the n x n Gram matrix of the centred rows has the
+    non-zero eigenvalues of the D x D ddof=1 covariance; finalize_head_spectra takes that route for an accumulator that still holds
+    all of its rows and the moment route otherwise, and sets the global mean either way."""
+    from audio_residual_b200.analyze_attention import _gram_spectrum, _spectrum, finalize_head_spectra
+    g = torch.Generator().manual_seed(4)
+    n, D = 40, 96
+    X = torch.rand(n, D, generator=g) ** 2
+    Xd = X.double()
+    ref = _spectrum(n, Xd.sum(0), Xd.t() @ Xd)
+    got = _gram_spectrum(X, n, D)
+    assert got.shape == (D,) and torch.allclose(got[:n - 1], ref[:n - 1], rtol=1e-9, atol=1e-14) and float(got[n:].abs().max()) == 0.0
+
+    class Parked:                       # what finalize_head_spectra reads of a MomentAccumulator that has parked every row
+        def __init__(self, rows):
+            self.D, self.n, self._buf, self._fill = rows.shape[1], rows.shape[0], rows.clone(), rows.shape[0]
+            self._s1 = torch.zeros(self.D, dtype=torch.float64)
+
+        def parked_rows(self):
+            return self._buf[:self._fill]
+
+    class Moments:                      # ... and of one that has folded them
+        def __init__(self, rows):
+            r = rows.double()
+            self.D, self.n, self.s1, self.s2 = rows.shape[1], rows.shape[0], r.sum(0), r.t() @ r
+
+    a, b = Parked(X), Moments(X)
+    wa, wb = finalize_head_spectra([a, b], n_components=16)
+    assert wa.shape == (16,) and np.allclose(wa, wb, rtol=1e-9) and np.allclose(wa, ref[:16].numpy(), rtol=1e-9)
+    assert torch.allclose(a.mean_global, Xd.mean(0)) and torch.allclose(b.mean_global, Xd.mean(0))
