@@ -495,7 +495,8 @@ def measure(wl, B, K, Wm, dev, rank, world, dist, do_e2e=True, do_profile=True, 
             hf = torch.empty(w.wave.shape, dtype=torch.float32).pin_memory()
             hf.copy_(w.wave)
             f = lambda: w.clap.get_audio_embedding_from_data(hf, use_tensor=True).cpu()   # noqa: E731
-            f(); f()
+            for _ in range(8):
+                f()
             barrier()
             t0 = time.perf_counter()
             for _ in range(Ke):
