@@ -115,3 +115,97 @@ def test_head_sharded_spectra_match_single_process():
         X = rng.standard_normal((400, 12)) * np.linspace(2, 0.2, 12) + h
         ref = np.sort(np.linalg.eigvalsh(np.cov(X.T, ddof=1)))[::-1]
         assert np.allclose(spectra[h], ref, rtol=1e-9)
+
+
+def _gram_worker(rank, world, port, out):
+    """finalize_head_spectra with rank-sharded PARKED rows (fewer samples than dimensions): the rows travel, not the D x D moments."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from audio_residual_b200.analyze_attention import finalize_head_spectra
+
+    class Parked:         # what finalize_head_spectra reads of a MomentAccumulator that still holds every row
+        def __init__(self, rows):
+            self.D, self.n, self._buf, self._fill = rows.shape[1], rows.shape[0], rows, rows.shape[0]
+            self._s1 = torch.zeros(self.D, dtype=torch.float64)
+
+        def parked_rows(self):
+            return self._buf[:self._fill]
+
+        @property
+        def s1(self):         # the real accumulator folds its parked rows when the moments are read
+            return self._buf.double().sum(0)
+
+        @property
+        def s2(self):
+            return self._buf.double().t() @ self._buf.double()
+
+    class Moments:
+        def __init__(self, rows):
+            r = rows.double()
+            self.D, self.n, self.s1, self.s2 = rows.shape[1], rows.shape[0], r.sum(0), r.t() @ r
+
+    rng = np.random.default_rng(2)
+    accs = []
+    for h in range(4):
+        X = torch.from_numpy((rng.random((30, 64)) ** 2 + h).astype(np.float32))
+        lo, hi = (0, 11) if rank == 0 else (11, 30)                  # uneven shards
+        # heads 0-2 parked on every rank (Gram route); head 3 has been folded on rank 1 (moment route for the whole head)
+        accs.append(Moments(X[lo:hi]) if (h == 3 and rank == 1) else Parked(X[lo:hi]))
+    spectra = finalize_head_spectra(accs)
+    if rank == 0:
+        out.put(([a.n for a in accs], spectra, [a.mean_global.numpy() for a in accs]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gram_route_with_rank_sharded_rows():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gram_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ns, spectra, means = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(2)
+    assert ns == [30] * 4
+    for h in range(4):
+        X = (rng.random((30, 64)) ** 2 + h).astype(np.float32).astype(np.float64)
+        ref = np.sort(np.linalg.eigvalsh(np.cov(X.T, ddof=1)))[::-1]
+        assert np.allclose(spectra[h][:29], ref[:29], rtol=1e-8, atol=1e-12), h
+        assert np.allclose(means[h], X.mean(0))
+
+
+def _guard_worker(rank, world, port, out):
+    """bench.RankGuard: gloo agreement between ranks for the extra records."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    g = bench.RankGuard(dist, world)
+    res = [g.all_ok(True), g.all_ok(rank != 1), g.max(10.0 + rank)]
+    g.barrier()
+    if rank == 0:
+        out.put(res)
+    dist.destroy_process_group()
+
+
+def test_rank_guard_agreement():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_guard_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [True, False, 11.0]      # one rank's failure is seen by every rank; max over ranks
