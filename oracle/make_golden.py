@@ -249,3 +249,4 @@ if __name__ == "__main__":
     run_pca_case()
     run_case("tiny", False, 2, 0, "htsat_tiny_b2.npz")
     run_case("base", True, 2, 1, "htsat_base_fusion_b2.npz")
+    run_case("base", False, 2, 2, "htsat_base_b2.npz")          # HTSAT-base on the waveform route (no feature fusion)

@@ -99,6 +99,21 @@ def test_oracle_base_fusion_vs_golden():
     _check_dict(g, "plain", out, emb, tol=5e-5)
 
 
+def test_oracle_base_waveform_route_vs_golden():
+    """HTSAT-base without feature fusion (C = 128 ... 1024, head dim 32), plain and with ResiDual on all layers, against what the
+    real reference produced (oracle/make_golden.py run_case("base", False, ...))."""
+    g = np.load(os.path.join(GOLDEN, "htsat_base_b2.npz"))
+    seed = int(g["meta_seed"])
+    sd = W.make_state_dict("base", seed=seed)
+    wave = W.make_clips(int(g["meta_B"]), seed=1234)
+    with torch.no_grad():
+        out = O.htsat_forward({"waveform": wave}, sd, O.CONFIGS["base"])
+        _check_dict(g, "plain", out, O.audio_projection(out["embedding"], sd), tol=5e-5)
+        ores = {l: (mu, comp, lam.detach()) for l, (mu, comp, lam) in _ores("base", seed).items()}
+        out = O.htsat_forward({"waveform": wave}, sd, O.CONFIGS["base"], ores)
+        _check_dict(g, "residual", out, O.audio_projection(out["embedding"], sd), tol=5e-5)
+
+
 def test_quantize_and_padding():
     x = torch.tensor([-1.5, -1.0, -0.5, 0.0, 1e-5, 0.3333, 0.99999, 1.0, 2.0])
     q = O.quantize_tensor(x)

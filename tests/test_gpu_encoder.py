@@ -36,6 +36,11 @@ def test_base_fusion_vs_golden():
     _assert_all(m)
 
 
+def test_base_waveform_route_vs_golden():
+    """HTSAT-base on the waveform route, plain and ResiDual-patched, against the real reference's outputs (htsat_base_b2.npz)."""
+    _assert_all(G.check_encoder_vs_golden("htsat_base_b2.npz"))
+
+
 def test_fusion_featuriser_and_base_from_waveform():
     m = G.check_fusion_featuriser()
     assert m["mel_fusion"] < 1e-4 and m["channels_equal"] == 0.0, m
