@@ -268,7 +268,11 @@ class CLAP_Module(nn.Module):
             emb = emb.detach().cpu().numpy()
         return emb
 
-    h2d_adapt = os.environ.get("ARD_PIPE_ADAPT", "1") != "0"
+    # ARD_PIPE_ADAPT: 0 = fixed schedule, no event timing; 1 (default) = time every call's copies / encodes and fit the pipeline model
+    # (bench.py reports the fit per rank), keep the fixed schedule; 2 = also re-plan the chunk sizes from the fit. Re-planning is
+    # opt-in: on the 8-GPU box it was measured on, the slow ranks were not copy-bound (their copies ran at 35-43 GB/s inside the
+    # pipeline) and the re-planned ranks were no faster (15.4 vs 15.0 ms per call), while each re-plan costs an eager + a capture call.
+    h2d_adapt = int(os.environ.get("ARD_PIPE_ADAPT", "1") or 0)
     h2d_chunk = 64                        # host batches larger than this are copied in chunks overlapped with the encoder
     h2d_schedule = (24, 50, 80, 116, 156, 204, 256)   # chunk sizes in clips: a small first copy (nothing overlaps it), then growing
     h2d_schedule_pcm16 = (32, 80, 144, 256)            # int16 transport: copies take half as long, so chunks may grow faster
@@ -381,7 +385,7 @@ class CLAP_Module(nn.Module):
             if t < best_t:
                 best, best_t = list(sizes), t
         rates["predicted_ms"] = cur_t
-        if best_t >= 0.95 * cur_t:                             # re-plan only for a real gain: new chunk sizes cost an eager run + a capture
+        if self.h2d_adapt < 2 or best_t >= 0.95 * cur_t:                             # re-plan only for a real gain: new chunk sizes cost an eager run + a capture
             return
         rates["predicted_ms"] = best_t
         bounds, lo = [], 0

@@ -489,8 +489,8 @@ def measure(wl, B, K, Wm, dev, rank, world, dist, do_e2e=True, do_profile=True, 
                       "host_chunks_rank0": [hi - lo for lo, hi in getattr(w.clap, "_last_bounds", [])],
                       "host_pipe_fit_rank0": {k: round(float(v), 5) for k, v in (getattr(w.clap, "_pipe_rates", {}).get(host.dtype) or {}).items()
                                               if k in ("c", "a", "b", "predicted_ms")},
-                      "host_chunks_note": "chunk sizes (clips) of rank 0's last timed call: each rank fits copy(n) = c n and encode(n) = a + b n (ms) "
-                                          "to the CUDA-event timings of its previous call and takes the schedule its pipeline simulation predicts fastest"}
+                      "host_chunks_note": "chunk sizes (clips) of rank 0's last timed call; each rank fits copy(n) = c n and encode(n) = a + b n (ms) "
+                                          "to the CUDA-event timings of its previous call (per_rank); ARD_PIPE_ADAPT=2 also re-plans the chunks from the fit"}
         if wl == "infer":   # the same call with the fp32 host waveform (use_tensor=True): 1.92 MB per clip over PCIe
             hf = torch.empty(w.wave.shape, dtype=torch.float32).pin_memory()
             hf.copy_(w.wave)

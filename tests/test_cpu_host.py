@@ -321,6 +321,7 @@ def test_adaptive_chunk_schedule_from_measured_rates():
     chunks shrink and the tail tapers, and the prediction beats the fixed schedule by > 10 %."""
     from audio_residual_b200.clap import CLAP_Module
     m = CLAP_Module.__new__(CLAP_Module)
+    m.h2d_adapt = 2                                                  # re-planning is opt-in (ARD_PIPE_ADAPT=2); 1 only measures and fits
     fixed = CLAP_Module._chunk_bounds(m, 256, CLAP_Module.h2d_schedule_pcm16)
     assert m._pick_bounds(256, torch.int16) == fixed                 # nothing measured yet
     for n in (65, 256, 300, 1000):
@@ -347,6 +348,13 @@ def test_adaptive_chunk_schedule_from_measured_rates():
     assert sizes[-1] <= 64 and r["predicted_ms"] < 0.9 * t_fixed, (sizes, t_fixed)
     feed(sizes, 0.041, 0.55, 0.0375, calls=3)                        # same rates measured on the new schedule: it stays
     assert m._pick_bounds(256, torch.int16) == b and r["replans"][(256, torch.int16)] == 1
+    m2 = CLAP_Module.__new__(CLAP_Module)                            # default level 1: the fit is taken, the schedule stays fixed
+    m2.h2d_adapt = 1
+    m2._pipe_rates = {torch.int16: {}}
+    for _ in range(3):
+        m2._pipe_rates[torch.int16]["done"] = _fake_call([32, 80, 144], 0.041, 0.55, 0.0375)
+        m2._plan_next(256, torch.int16)
+    assert abs(m2._pipe_rates[torch.int16]["c"] - 0.041) < 1e-9 and m2._pick_bounds(256, torch.int16) == fixed
     # the simulation itself: copies back to back, an encode starts when its copy AND the previous encode are done
     assert abs(CLAP_Module._simulate([10, 10], 0.05, 1.0, 0.0, True) - (0.51 + 1.0 + 1.0)) < 1e-9        # copy 1 (0.51) hides under encode 0
     assert abs(CLAP_Module._simulate([10, 10], 0.5, 1.0, 0.0, True) - (2 * 5.01 + 1.0)) < 1e-9           # copy-bound: last copy + one encode
